@@ -1,0 +1,134 @@
+"""ctypes binding of libess_b200.so (the C ABI declared in include/ess_b200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is missing or a call
+fails, a RuntimeError is raised.  ctypes releases the GIL around every call; all calls are
+asynchronous on the CUDA stream passed in.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libess_b200.so')
+MAX_TAPS = 25
+
+EPI_LINEAR, EPI_LSTM, EPI_GRU_UR, EPI_GRU_OUT = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+
+
+class Src(C.Structure):
+    _fields_ = [('ptr', C.c_void_p), ('mean', C.c_void_p), ('rstd', C.c_void_p),
+                ('ld', C.c_int32), ('C', C.c_int32), ('ups', C.c_int32), ('relu', C.c_int32)]
+
+
+class Conv(C.Structure):
+    _fields_ = [('src', Src * 2),
+                ('w', C.c_void_p), ('bias', C.c_void_p), ('res_pre', C.c_void_p), ('res_post', C.c_void_p),
+                ('aux0', C.c_void_p), ('aux1', C.c_void_p), ('out', C.c_void_p), ('out2', C.c_void_p),
+                ('stats_partial', C.c_void_p), ('out_hi', C.c_void_p), ('out_lo', C.c_void_p),
+                ('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+                ('OH', C.c_int32), ('OW', C.c_int32), ('Cout', C.c_int32),
+                ('sy', C.c_int32), ('sx', C.c_int32),
+                ('OHf', C.c_int32), ('OWf', C.c_int32), ('osy', C.c_int32), ('ooy', C.c_int32),
+                ('osx', C.c_int32), ('oox', C.c_int32),
+                ('ldo', C.c_int32), ('ld_res', C.c_int32), ('ld_planes', C.c_int32), ('accumulate', C.c_int32),
+                ('epilogue', C.c_int32), ('act', C.c_int32), ('ntaps', C.c_int32),
+                ('dy', C.c_int8 * MAX_TAPS), ('dx', C.c_int8 * MAX_TAPS), ('widx', C.c_int8 * MAX_TAPS)]
+
+
+class Wgrad(C.Structure):
+    _fields_ = [('src', Src * 2),
+                ('dy_ptr', C.c_void_p), ('dw', C.c_void_p), ('dbias', C.c_void_p), ('workspace', C.c_void_p),
+                ('workspace_bytes', C.c_int64),
+                ('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('OH', C.c_int32), ('OW', C.c_int32),
+                ('Cout', C.c_int32), ('ld_dy', C.c_int32), ('sy', C.c_int32), ('sx', C.c_int32),
+                ('ntaps', C.c_int32),
+                ('dy', C.c_int8 * MAX_TAPS), ('dx', C.c_int8 * MAX_TAPS)]
+
+
+class TcView(C.Structure):
+    _fields_ = [('hi', C.c_void_p), ('lo', C.c_void_p),
+                ('stride_x', C.c_int64), ('stride_y', C.c_int64), ('stride_n', C.c_int64),
+                ('C', C.c_int32), ('W', C.c_int32), ('H', C.c_int32), ('reserved', C.c_int32)]
+
+
+class ConvTc(C.Structure):
+    _fields_ = [('views', TcView * 8),
+                ('w_hi', C.c_void_p), ('w_lo', C.c_void_p), ('bias', C.c_void_p), ('res_pre', C.c_void_p),
+                ('res_post', C.c_void_p), ('aux0', C.c_void_p), ('out', C.c_void_p), ('out2', C.c_void_p),
+                ('out_hi', C.c_void_p), ('out_lo', C.c_void_p),
+                ('n_views', C.c_int32), ('nseg', C.c_int32),
+                ('seg_C', C.c_int32 * 2), ('seg_view0', C.c_int32 * 2), ('seg_koff', C.c_int32 * 2),
+                ('k_per_tap', C.c_int32), ('n_w_taps', C.c_int32), ('w_rows', C.c_int32),
+                ('N', C.c_int32), ('OH', C.c_int32), ('OW', C.c_int32), ('Cout', C.c_int32),
+                ('OHf', C.c_int32), ('OWf', C.c_int32), ('osy', C.c_int32), ('ooy', C.c_int32),
+                ('osx', C.c_int32), ('oox', C.c_int32),
+                ('ldo', C.c_int32), ('ld_res', C.c_int32), ('ld_planes', C.c_int32),
+                ('epilogue', C.c_int32), ('act', C.c_int32), ('passes', C.c_int32), ('bw_log2', C.c_int32),
+                ('ntaps', C.c_int32),
+                ('dy', C.c_int8 * MAX_TAPS), ('dx', C.c_int8 * MAX_TAPS), ('view', C.c_int8 * MAX_TAPS),
+                ('widx', C.c_int8 * MAX_TAPS)]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> (restype, argtypes): every symbol include/ess_b200.h declares
+SIGNATURES = {
+    'essb_version': (_I, []),
+    'essb_build_arch': (C.c_char_p, []),
+    'essb_last_error': (C.c_char_p, []),
+    'essb_device_check': (_I, []),
+    'essb_conv_fp32': (_I, [C.POINTER(Conv), _P]),
+    'essb_conv_tiles_per_sample': (_I, [C.POINTER(Conv)]),
+    'essb_wgrad_workspace_bytes': (_L, [C.POINTER(Wgrad)]),
+    'essb_wgrad_fp32': (_I, [C.POINTER(Wgrad), _P]),
+    'essb_pack_weight': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'essb_in_finalize': (_I, [_P, _I, _I, _I, _L, _F, _P, _P, _P]),
+    'essb_norm_act_add': (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _I, _L, _I, _P]),
+    'essb_in_bwd_blocks': (_I, [_L]),
+    'essb_in_bwd_pass1': (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
+    'essb_in_bwd_pass2': (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _L, _I, _P]),
+    'essb_partial_reduce': (_I, [_P, _I, _I, _I, _P, _P]),
+    'essb_colsum': (_I, [_P, _I, _L, _I, _P, _P, _L, _P]),
+    'essb_upsample2_bwd': (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'essb_event_stats': (_I, [_P, _L, _I, _I, _L, _P, _P]),
+    'essb_event_prepare': (_I, [_P, _L, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'essb_nchw_to_nhwc': (_I, [_P, _P, _I, _I, _I, _L, _P]),
+    'essb_nhwc_to_nchw': (_I, [_P, _I, _P, _I, _I, _L, _P]),
+    'essb_bilinear_up2': (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    'essb_task_loss_fwd': (_I, [_P, _I, _P, _L, _I, _L, _P, _P]),
+    'essb_task_loss_finish': (_I, [_P, _I, _L, _I, _I, _P, _P]),
+    'essb_task_loss_bwd': (_I, [_P, _I, _P, _L, _I, _L, _P, _I, _I, _P, _P, _I, _P]),
+    'essb_confusion': (_I, [_P, _I, _P, _L, _I, _L, _P, _P]),
+    'essb_confusion_labels': (_I, [_P, _P, _L, _I, _L, _P, _P]),
+    'essb_split_bf16': (_I, [C.POINTER(Src), _I, _I, _I, _P, _P, _I, _I, _P]),
+    'essb_pack_weight_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'essb_conv_tc_run': (_I, [C.POINTER(ConvTc), _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises if it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('ess_b200: %s not found -- run `python -m ess_b200.build` (or '
+                               '__graft_entry__.build()); there is no CPU/PyTorch fallback' % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)   # AttributeError if the header and the library drift apart
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().essb_last_error().decode('utf-8', 'replace')
+        raise RuntimeError('ess_b200 %s failed (status %d): %s' % (what, rc, msg))
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)

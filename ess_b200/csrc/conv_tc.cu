@@ -1,0 +1,694 @@
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a ("bf16x3" fp32-parity mode and "bf16" mode).
+//
+// GEMM view of a gather-convolution on NHWC activations:
+//   M = 128 output pixels (a BH x BW spatial patch of one sample), N = BN <= 256 output channels,
+//   K = taps x input channels, consumed 64 channels of one tap per pipeline stage.
+// A operand: the activation is kept in HBM as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)); for
+//   tap (dy,dx) the A tile is the SAME 4-D TMA box shifted by (dy,dx) -- TMA zero-fills outside the
+//   image, which is exactly the convolution's zero padding, so no im2col buffer ever exists.
+//   Stride-2 convolutions address the input through parity-plane views (one tensor map per parity).
+// B operand: packed K-major weights [Cout][taps*Cin] as bf16 hi/lo planes, one 2-D TMA box per stage.
+// MMA: tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, fp32 accumulators in TMEM.  In the
+//   3-pass mode each K-step issues hi*hi + lo*hi + hi*lo (drops only lo*lo ~ 2^-16 relative), which
+//   restores fp32-level accuracy (logits 1.1e-4 vs 4.7e-2 for single-pass bf16).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+//   warps 2..5 = epilogue (TMEM lane quarter = warp % 4).  Two TMEM accumulator buffers let the
+//   epilogue of tile i overlap the main loop of tile i+1.  Persistent CTAs, one per SM.
+// Epilogues: LINEAR (bias / residual / ReLU / sigmoid / strided placement / bf16 planes out) and
+//   LSTM (sigma/tanh gates + cell/hidden update in registers: the 4C-channel `gates` tensor of
+//   e2vid/model/submodules.py:213 never reaches HBM).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_M = 128;
+constexpr int TC_KCH = 64;                      // channels per stage (128 B of bf16 = one swizzle row)
+constexpr int A_TILE_BYTES = TC_M * TC_KCH * 2; // 16 KB
+constexpr int MAX_VIEWS = 8;
+constexpr int MAX_STAGES = 8;
+
+struct TcParams {
+  CUtensorMap tmA_hi[MAX_VIEWS];
+  CUtensorMap tmA_lo[MAX_VIEWS];
+  CUtensorMap tmB_hi;
+  CUtensorMap tmB_lo;
+  // schedule
+  int n_items, n_tiles, tiles_x, tiles_y;
+  int bw_log2;             // BW = 1 << bw_log2, BH = 128 >> bw_log2
+  int BN;                  // N tile (multiple of 16, <= 256)
+  int stages, passes;
+  int stage_bytes, tx_bytes;  // bytes per pipeline stage / per-stage TMA transaction bytes
+  int off_alo, off_bhi, off_blo;  // tile offsets inside a stage
+  // K loop
+  int ntaps, nseg;
+  int seg_chunks[2];       // 64-channel chunks per segment
+  int seg_view0[2];        // first tensor-map index of the segment
+  int seg_koff[2];         // channel offset of the segment inside one tap's K range
+  int k_per_tap;           // total (padded) channels per tap in the packed weights
+  int8_t dy[ESSB_MAX_TAPS], dx[ESSB_MAX_TAPS], view[ESSB_MAX_TAPS], widx[ESSB_MAX_TAPS];
+  // epilogue
+  int N, OH, OW, Cout;
+  int OHf, OWf, osy, ooy, osx, oox;
+  int ldo, ld_res, ld_planes;
+  int act;
+  const float* bias;
+  const float* res_pre;
+  const float* res_post;
+  const float* aux0;
+  float* out;
+  float* out2;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+};
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B)
+//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B,
+// N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat16 v[8];
+};
+
+// ------------------------------------------------------------------------------------ the kernel
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* full_bar = bars;                    // [stages]
+  uint64_t* empty_bar = bars + MAX_STAGES;      // [stages]
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cpt = p.seg_chunks[0] + (p.nseg > 1 ? p.seg_chunks[1] : 0);
+  const int k_iters = p.ntaps * cpt;
+  const int BW = 1 << p.bw_log2, BH = TC_M >> p.bw_log2;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmB_hi);
+    if (p.passes == 3) tma_prefetch_desc(&p.tmB_lo);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer (one lane)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx_bytes = (uint32_t)p.tx_bytes;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int nt = item % p.n_tiles;
+        int mt = item / p.n_tiles;
+        const int txi = mt % p.tiles_x; mt /= p.tiles_x;
+        const int tyi = mt % p.tiles_y;
+        const int n = mt / p.tiles_y;
+        const int x0 = txi * BW, y0 = tyi * BH;
+        for (int it = 0; it < k_iters; ++it) {
+          const int tap = it / cpt;
+          const int r = it - tap * cpt;
+          const int seg = (r >= p.seg_chunks[0]) ? 1 : 0;
+          const int ch = (seg ? r - p.seg_chunks[0] : r) * TC_KCH;
+          const int v = p.seg_view0[seg] + p.view[tap];
+          const int kcoord = p.widx[tap] * p.k_per_tap + p.seg_koff[seg] + ch;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = stage_base + (size_t)s * p.stage_bytes;
+          mbar_expect_tx(&full_bar[s], tx_bytes);
+          const int cx = x0 + p.dx[tap], cy = y0 + p.dy[tap];
+          tma_load_4d(st, &p.tmA_hi[v], &full_bar[s], ch, cx, cy, n);
+          tma_load_2d(st + p.off_bhi, &p.tmB_hi, &full_bar[s], kcoord, nt * p.BN);
+          if (p.passes == 3) {
+            tma_load_4d(st + p.off_alo, &p.tmA_lo[v], &full_bar[s], ch, cx, cy, n);
+            tma_load_2d(st + p.off_blo, &p.tmB_lo, &full_bar[s], kcoord, nt * p.BN);
+          }
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer (one lane)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TC_M, p.BN);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t tph[2] = {0, 0};
+      int local = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+        const int buf = local & 1;
+        mbar_wait(&tempty_bar[buf], tph[buf] ^ 1);  // epilogue has drained this accumulator
+        tph[buf] ^= 1;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + (size_t)s * p.stage_bytes);
+          if (p.passes == 3) {
+            const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + p.off_alo);
+            const uint64_t b_hi = make_smem_desc(sa + p.off_bhi);
+            const uint64_t b_lo = make_smem_desc(sa + p.off_blo);
+#pragma unroll
+            for (int k = 0; k < TC_KCH / 16; ++k) {
+              const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes (>>4) inside the 128 B swizzle row
+              umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, (it | k) != 0);
+              umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            }
+          } else {
+            const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + p.off_bhi);
+#pragma unroll
+            for (int k = 0; k < TC_KCH / 16; ++k) {
+              const uint64_t ko = (uint64_t)(k * 2);
+              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, (it | k) != 0);
+            }
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ============================================================ epilogue warps (2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t tph[2] = {0, 0};
+    int local = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+      const int buf = local & 1;
+      const int nt = item % p.n_tiles;
+      int mt = item / p.n_tiles;
+      const int txi = mt % p.tiles_x; mt /= p.tiles_x;
+      const int tyi = mt % p.tiles_y;
+      const int n = mt / p.tiles_y;
+      const int m = q * 32 + lane;
+      const int oy = tyi * BH + (m >> p.bw_log2), ox = txi * BW + (m & (BW - 1));
+      const bool valid = oy < p.OH && ox < p.OW;
+      mbar_wait(&tfull_bar[buf], tph[buf]);
+      tph[buf] ^= 1;
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
+      const int n0 = nt * p.BN;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(t_addr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (!valid) {
+          // out-of-image rows of a partial tile: nothing to store
+        } else if constexpr (EPI == ESSB_EPI_LSTM) {
+          // columns co = 4*ch + {in, remember, out, cell}; 32 columns = 8 channels
+          const int hidden = p.Cout >> 2;
+          const int ch0 = (n0 + c0) >> 2;
+          const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
+          float cp[8];
+          if (p.aux0) {
+            const float4 c0v = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0);
+            const float4 c1v = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0 + 4);
+            cp[0] = c0v.x; cp[1] = c0v.y; cp[2] = c0v.z; cp[3] = c0v.w;
+            cp[4] = c1v.x; cp[5] = c1v.y; cp[6] = c1v.z; cp[7] = c1v.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cp[e] = 0.f;
+          }
+          float hv[8], cv[8];
+          bf16x8 hh, hl;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int co = n0 + c0 + e * 4;
+            float gi = __uint_as_float(r[e * 4 + 0]), gf = __uint_as_float(r[e * 4 + 1]);
+            float go = __uint_as_float(r[e * 4 + 2]), gc = __uint_as_float(r[e * 4 + 3]);
+            if (p.bias) {
+              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + co);
+              gi += b4.x; gf += b4.y; go += b4.z; gc += b4.w;
+            }
+            const float cell = essb_sigmoid(gf) * cp[e] + essb_sigmoid(gi) * tanhf(gc);
+            cv[e] = cell;
+            hv[e] = essb_sigmoid(go) * tanhf(cell);
+            split_bf16(hv[e], hh.v[e], hl.v[e]);
+          }
+          float* ho = p.out + pix * hidden + ch0;
+          float* co_ = p.out2 + pix * hidden + ch0;
+          *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+          *reinterpret_cast<float4*>(co_) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+          *reinterpret_cast<float4*>(co_ + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+          if (p.out_hi) {
+            *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0) = hh;
+            *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0) = hl;
+          }
+        } else {
+          const size_t opix = ((size_t)n * p.OHf + (oy * p.osy + p.ooy)) * p.OWf + (ox * p.osx + p.oox);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {  // 8 channels per group
+            const int co = n0 + c0 + g * 8;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]);
+            if (p.bias) {
+              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co);
+              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (p.res_pre) {
+              const float4 a0 = *reinterpret_cast<const float4*>(p.res_pre + opix * p.ld_res + co);
+              const float4 a1 = *reinterpret_cast<const float4*>(p.res_pre + opix * p.ld_res + co + 4);
+              v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+              v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+            }
+            if (p.act == ESSB_ACT_RELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            } else if (p.act == ESSB_ACT_SIGMOID) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = essb_sigmoid(v[e]);
+            }
+            if (p.res_post) {
+              const float4 a0 = *reinterpret_cast<const float4*>(p.res_post + opix * p.ld_res + co);
+              const float4 a1 = *reinterpret_cast<const float4*>(p.res_post + opix * p.ld_res + co + 4);
+              v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+              v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+            }
+            if (p.out) {
+              float* o = p.out + opix * p.ldo + co;
+              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            if (p.out_hi) {
+              bf16x8 hh, hl;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) split_bf16(v[e], hh.v[e], hl.v[e]);
+              *reinterpret_cast<bf16x8*>(p.out_hi + opix * p.ld_planes + co) = hh;
+              *reinterpret_cast<bf16x8*>(p.out_lo + opix * p.ld_planes + co) = hl;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// --------------------------------------------------------------------------- fp32 -> bf16 hi/lo
+__global__ void split_bf16_kernel(essb_src s, int N, int H, int W, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, int ld_out, int c_off, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int CQ = s.C >> 2;
+  const int c = (int)(idx % CQ) * 4;
+  const long long pix = idx / CQ;
+  const long long P = (long long)H * W;
+  const int n = (int)(pix / P);
+  const long long pp = pix - (long long)n * P;
+  const int y = (int)(pp / W), x = (int)(pp - (long long)y * W);
+  const int Hs = H >> s.ups, Ws = W >> s.ups;
+  const size_t sp = ((size_t)n * Hs + (y >> s.ups)) * Ws + (x >> s.ups);
+  float4 v = *reinterpret_cast<const float4*>(s.ptr + sp * s.ld + c);
+  if (s.mean) {
+    const float4 m = *reinterpret_cast<const float4*>(s.mean + (size_t)n * s.C + c);
+    const float4 r = *reinterpret_cast<const float4*>(s.rstd + (size_t)n * s.C + c);
+    v.x = (v.x - m.x) * r.x; v.y = (v.y - m.y) * r.y; v.z = (v.z - m.z) * r.z; v.w = (v.w - m.w) * r.w;
+  }
+  if (s.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  __nv_bfloat16 h[4], l[4];
+  split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+  __nv_bfloat16* ho = hi + pix * ld_out + c_off + c;
+  __nv_bfloat16* lo_ = lo + pix * ld_out + c_off + c;
+  *reinterpret_cast<uint2*>(ho) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(lo_) = *reinterpret_cast<uint2*>(l);
+}
+
+// packed K-major weights: out[np][t*KinP + k], np < NoutP (zero rows beyond Nout)
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Cout, int Cin,
+                                      int T, int transposed_layout, int swap_io, int flip, int interleave, int KinP,
+                                      int NoutP) {
+  const int Kin = swap_io ? Cout : Cin;
+  const int Nout = swap_io ? Cin : Cout;
+  const long long total = (long long)NoutP * T * KinP;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k = (int)(idx % KinP);
+  const long long r = idx / KinP;
+  const int t = (int)(r % T);
+  const int np = (int)(r / T);
+  float v = 0.f;
+  if (np < Nout && k < Kin) {
+    int co, ci;
+    if (swap_io) { co = k; ci = np; }
+    else {
+      ci = k;
+      co = np;
+      if (interleave > 1) {
+        const int G = Cout / interleave;
+        co = (np % interleave) * G + np / interleave;
+      }
+    }
+    const int ts = flip ? T - 1 - t : t;
+    const size_t src = transposed_layout ? ((size_t)ci * Cout + co) * T + ts : ((size_t)co * Cin + ci) * T + ts;
+    v = w[src];
+    if (scale && !swap_io) v *= scale[co];
+  }
+  __nv_bfloat16 h, l;
+  split_bf16(v, h, l);
+  hi[idx] = h;
+  lo[idx] = l;
+}
+
+// ------------------------------------------------------------------------ tensor-map encoding
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(sym);
+  }
+  return fn;
+}
+
+int encode_a_map(CUtensorMap* tm, const void* base, const essb_tc_view& v, int N, int BW, int BH) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    essb_set_error("conv_tc: cuTensorMapEncodeTiled unavailable");
+    return ESSB_ERR_DRIVER;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)v.stride_x * 2, (cuuint64_t)v.stride_y * 2, (cuuint64_t)v.stride_n * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_KCH, (cuuint32_t)BW, (cuuint32_t)BH, 1u};
+  cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    essb_set_error("conv_tc: cuTensorMapEncodeTiled(A) failed with %d (C=%d W=%d H=%d N=%d strides %lld %lld %lld)",
+                   (int)r, v.C, v.W, v.H, N, (long long)v.stride_x, (long long)v.stride_y, (long long)v.stride_n);
+    return ESSB_ERR_DRIVER;
+  }
+  return ESSB_OK;
+}
+
+int encode_b_map(CUtensorMap* tm, const void* base, long long ktot, int rows, int BN) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    essb_set_error("conv_tc: cuTensorMapEncodeTiled unavailable");
+    return ESSB_ERR_DRIVER;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_KCH, (cuuint32_t)BN};
+  cuuint32_t es[2] = {1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    essb_set_error("conv_tc: cuTensorMapEncodeTiled(B) failed with %d (ktot=%lld rows=%d BN=%d)", (int)r, ktot, rows, BN);
+    return ESSB_ERR_DRIVER;
+  }
+  return ESSB_OK;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+}  // namespace
+
+extern "C" int essb_split_bf16(const essb_src* src, int N, int H, int W, uint16_t* hi, uint16_t* lo, int ld_out,
+                               int c_off, void* stream) {
+  ESSB_REQUIRE(src && src->ptr && hi && lo && N > 0 && H > 0 && W > 0, "essb_split_bf16: bad arguments");
+  ESSB_REQUIRE(src->C % 4 == 0 && src->ld % 4 == 0 && essb_aligned16(src->ptr) && ld_out % 4 == 0 && c_off % 4 == 0,
+               "essb_split_bf16: C, ld, ld_out, c_off must be multiples of 4 and pointers 16B aligned");
+  ESSB_REQUIRE((src->mean == nullptr) == (src->rstd == nullptr), "essb_split_bf16: mean/rstd must come together");
+  const long long total = (long long)N * H * W * (src->C / 4);
+  split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      *src, N, H, W, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), ld_out, c_off, total);
+  ESSB_LAUNCH_CHECK("essb_split_bf16");
+  return ESSB_OK;
+}
+
+extern "C" int essb_pack_weight_tc(const float* w, const float* scale, uint16_t* hi, uint16_t* lo, int Cout, int Cin,
+                                   int T, int transposed_layout, int swap_io, int flip, int interleave, int KinP,
+                                   int NoutP, void* stream) {
+  ESSB_REQUIRE(w && hi && lo && Cout > 0 && Cin > 0 && T > 0, "essb_pack_weight_tc: bad arguments");
+  const int Kin = swap_io ? Cout : Cin, Nout = swap_io ? Cin : Cout;
+  ESSB_REQUIRE(KinP >= Kin && KinP % TC_KCH == 0 && NoutP >= Nout, "essb_pack_weight_tc: bad padding");
+  ESSB_REQUIRE(interleave <= 1 || (Cout % interleave == 0 && !swap_io), "essb_pack_weight_tc: bad interleave");
+  const long long total = (long long)NoutP * T * KinP;
+  pack_weight_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      w, scale, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), Cout, Cin, T,
+      transposed_layout, swap_io, flip, interleave, KinP, NoutP);
+  ESSB_LAUNCH_CHECK("essb_pack_weight_tc");
+  return ESSB_OK;
+}
+
+extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
+  ESSB_REQUIRE(d != nullptr, "essb_conv_tc_run: null descriptor");
+  ESSB_REQUIRE(d->n_views >= 1 && d->n_views <= MAX_VIEWS, "essb_conv_tc_run: n_views=%d", d->n_views);
+  ESSB_REQUIRE(d->nseg == 1 || d->nseg == 2, "essb_conv_tc_run: nseg=%d", d->nseg);
+  ESSB_REQUIRE(d->ntaps >= 1 && d->ntaps <= ESSB_MAX_TAPS, "essb_conv_tc_run: ntaps=%d", d->ntaps);
+  ESSB_REQUIRE(d->passes == 1 || d->passes == 3, "essb_conv_tc_run: passes must be 1 or 3");
+  ESSB_REQUIRE(d->N > 0 && d->OH > 0 && d->OW > 0 && d->Cout > 0, "essb_conv_tc_run: bad dims");
+  ESSB_REQUIRE(d->w_hi && (d->passes == 1 || d->w_lo), "essb_conv_tc_run: null weights");
+  ESSB_REQUIRE(d->bw_log2 >= 0 && d->bw_log2 <= 7, "essb_conv_tc_run: bw_log2=%d", d->bw_log2);
+  ESSB_REQUIRE(d->k_per_tap % TC_KCH == 0, "essb_conv_tc_run: k_per_tap must be a multiple of 64");
+  const int Ngemm = d->Cout;
+  int BN = Ngemm < 256 ? Ngemm : 256;
+  ESSB_REQUIRE(BN % 32 == 0 && Ngemm % BN == 0, "essb_conv_tc_run: Cout=%d must be 32/64/128 or a multiple of 256", Ngemm);
+  ESSB_REQUIRE(d->w_rows >= Ngemm, "essb_conv_tc_run: packed weight rows %d < Cout %d", d->w_rows, Ngemm);
+  if (d->epilogue == ESSB_EPI_LSTM) {
+    ESSB_REQUIRE(d->out && d->out2 && Ngemm % 4 == 0, "essb_conv_tc_run: LSTM needs out/out2");
+    ESSB_REQUIRE(!d->out_hi || (d->out_lo && d->ld_planes % 8 == 0), "essb_conv_tc_run: bad planes");
+  } else {
+    ESSB_REQUIRE(d->epilogue == ESSB_EPI_LINEAR, "essb_conv_tc_run: epilogue %d not supported on the tensor-core path", d->epilogue);
+    ESSB_REQUIRE(d->out || d->out_hi, "essb_conv_tc_run: no output");
+    ESSB_REQUIRE(!d->out || (d->ldo % 4 == 0 && essb_aligned16(d->out)), "essb_conv_tc_run: out must be 16B aligned, ldo %% 4 == 0");
+    ESSB_REQUIRE(!d->out_hi || (d->out_lo && d->ld_planes % 8 == 0), "essb_conv_tc_run: bad planes");
+    ESSB_REQUIRE(!(d->res_pre || d->res_post) || d->ld_res % 4 == 0, "essb_conv_tc_run: ld_res %% 4 != 0");
+  }
+
+  static thread_local TcParams p;  // 2.5 KB; filled per call, copied into the launch
+  const int BW = 1 << d->bw_log2, BH = TC_M >> d->bw_log2;
+  int rc;
+  for (int v = 0; v < d->n_views; ++v) {
+    const essb_tc_view& vw = d->views[v];
+    ESSB_REQUIRE(vw.hi && (d->passes == 1 || vw.lo), "essb_conv_tc_run: view %d has null planes", v);
+    ESSB_REQUIRE(vw.C % TC_KCH == 0, "essb_conv_tc_run: view %d channels %d not a multiple of 64", v, vw.C);
+    ESSB_REQUIRE(vw.stride_x % 8 == 0 && vw.stride_y % 8 == 0 && vw.stride_n % 8 == 0 && essb_aligned16(vw.hi) &&
+                     essb_aligned16(vw.lo),
+                 "essb_conv_tc_run: view %d strides must be multiples of 8 elements and bases 16B aligned", v);
+    if ((rc = encode_a_map(&p.tmA_hi[v], vw.hi, vw, d->N, BW, BH)) != ESSB_OK) return rc;
+    if (d->passes == 3 && (rc = encode_a_map(&p.tmA_lo[v], vw.lo, vw, d->N, BW, BH)) != ESSB_OK) return rc;
+  }
+  const long long ktot = (long long)d->n_w_taps * d->k_per_tap;
+  if ((rc = encode_b_map(&p.tmB_hi, d->w_hi, ktot, d->w_rows, BN)) != ESSB_OK) return rc;
+  if (d->passes == 3 && (rc = encode_b_map(&p.tmB_lo, d->w_lo, ktot, d->w_rows, BN)) != ESSB_OK) return rc;
+
+  p.tiles_x = (d->OW + BW - 1) / BW;
+  p.tiles_y = (d->OH + BH - 1) / BH;
+  p.n_tiles = Ngemm / BN;
+  p.n_items = d->N * p.tiles_x * p.tiles_y * p.n_tiles;
+  p.bw_log2 = d->bw_log2;
+  p.BN = BN;
+  p.passes = d->passes;
+  const int b_tile_bytes = BN * TC_KCH * 2;
+  if (d->passes == 3) {  // stage = [A_hi | A_lo | B_hi | B_lo]
+    p.off_alo = A_TILE_BYTES;
+    p.off_bhi = 2 * A_TILE_BYTES;
+    p.off_blo = 2 * A_TILE_BYTES + b_tile_bytes;
+    p.stage_bytes = 2 * (A_TILE_BYTES + b_tile_bytes);
+  } else {               // stage = [A_hi | B_hi]
+    p.off_alo = 0;
+    p.off_bhi = A_TILE_BYTES;
+    p.off_blo = 0;
+    p.stage_bytes = A_TILE_BYTES + b_tile_bytes;
+  }
+  p.tx_bytes = p.stage_bytes;
+  const int smem_budget = 200 * 1024;
+  int stages = smem_budget / p.stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  ESSB_REQUIRE(stages >= 2, "essb_conv_tc_run: tile does not fit two pipeline stages");
+  p.stages = stages;
+  p.ntaps = d->ntaps;
+  p.nseg = d->nseg;
+  for (int s = 0; s < 2; ++s) {
+    p.seg_chunks[s] = s < d->nseg ? d->seg_C[s] / TC_KCH : 0;
+    p.seg_view0[s] = d->seg_view0[s];
+    p.seg_koff[s] = d->seg_koff[s];
+    ESSB_REQUIRE(s >= d->nseg || (d->seg_C[s] > 0 && d->seg_C[s] % TC_KCH == 0), "essb_conv_tc_run: segment %d channels %d", s, d->seg_C[s]);
+  }
+  p.k_per_tap = d->k_per_tap;
+  for (int t = 0; t < d->ntaps; ++t) {
+    p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.view[t] = d->view[t]; p.widx[t] = d->widx[t];
+    ESSB_REQUIRE(d->widx[t] >= 0 && d->widx[t] < d->n_w_taps, "essb_conv_tc_run: widx out of range");
+    for (int s = 0; s < d->nseg; ++s)
+      ESSB_REQUIRE(d->seg_view0[s] + d->view[t] < d->n_views, "essb_conv_tc_run: view index out of range");
+  }
+  p.N = d->N; p.OH = d->OH; p.OW = d->OW; p.Cout = d->Cout;
+  p.OHf = d->OHf; p.OWf = d->OWf; p.osy = d->osy; p.ooy = d->ooy; p.osx = d->osx; p.oox = d->oox;
+  p.ldo = d->ldo; p.ld_res = d->ld_res; p.ld_planes = d->ld_planes; p.act = d->act;
+  p.bias = d->bias; p.res_pre = d->res_pre; p.res_post = d->res_post; p.aux0 = d->aux0;
+  p.out = d->out; p.out2 = d->out2;
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(d->out_hi);
+  p.out_lo = reinterpret_cast<__nv_bfloat16*>(d->out_lo);
+
+  size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // one CTA per SM: each CTA allocates all 512 TMEM columns
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+  cudaError_t e;
+  if (d->epilogue == ESSB_EPI_LSTM) {
+    e = cudaFuncSetAttribute(conv_tc_kernel<ESSB_EPI_LSTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) conv_tc_kernel<ESSB_EPI_LSTM><<<grid, TC_THREADS, smem_bytes, st>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(conv_tc_kernel<ESSB_EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) conv_tc_kernel<ESSB_EPI_LINEAR><<<grid, TC_THREADS, smem_bytes, st>>>(p);
+  }
+  if (e != cudaSuccess) {
+    essb_set_error("essb_conv_tc_run: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    return ESSB_ERR_LAUNCH;
+  }
+  ESSB_LAUNCH_CHECK("essb_conv_tc_run");
+  return ESSB_OK;
+}

@@ -1,0 +1,590 @@
+// Memory-bound helpers around the convolutions: weight packing, instance-norm statistics and
+// backward, event pre-processing, layout conversion.  All HBM-bound; coalesced float4 access,
+// grids sized from the element count.
+#include "common.cuh"
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+inline unsigned ew_blocks(long long items) {
+  long long b = (items + EW_THREADS - 1) / EW_THREADS;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+// ------------------------------------------------------------------------------ weight packing
+__global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                   float* __restrict__ out, int Cout, int Cin, int T, int transposed_layout,
+                                   int swap_io, int flip, int interleave) {
+  const int Kin = swap_io ? Cout : Cin;
+  const int Nout = swap_io ? Cin : Cout;
+  const int NoutP = (Nout + 3) & ~3;
+  const long long total = (long long)T * Kin * NoutP;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int np = (int)(idx % NoutP);
+  const long long r = idx / NoutP;
+  const int k = (int)(r % Kin);
+  const int t = (int)(r / Kin);
+  float v = 0.f;
+  if (np < Nout) {
+    int co, ci;
+    if (swap_io) { co = k; ci = np; }
+    else {
+      ci = k;
+      co = np;
+      if (interleave > 1) {  // packed co' = (co % G)*g + co / G  with G = Cout / g   =>  invert
+        const int G = Cout / interleave;
+        co = (np % interleave) * G + np / interleave;
+      }
+    }
+    const int ts = flip ? T - 1 - t : t;
+    const size_t src = transposed_layout ? ((size_t)ci * Cout + co) * T + ts : ((size_t)co * Cin + ci) * T + ts;
+    v = w[src];
+    if (scale && !swap_io) v *= scale[co];
+  }
+  out[idx] = v;
+}
+
+// --------------------------------------------------------------------- partial-sum reductions
+// One warp per (n, c): sum partial[n][b][c][0..1] over b in double, fixed order.
+__global__ void in_finalize_kernel(const float* __restrict__ partial, int N, int tiles, int C, double inv_count,
+                                   float eps, float* __restrict__ mean, float* __restrict__ rstd,
+                                   float* __restrict__ totals) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N * C) return;
+  const int n = warp / C, c = warp - n * C;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = lane; b < tiles; b += 32) {
+    const float* q = partial + (((size_t)n * tiles + b) * C + c) * 2;
+    s1 += (double)q[0];
+    s2 += (double)q[1];
+  }
+  s1 = warp_sum_d(s1);
+  s2 = warp_sum_d(s2);
+  if (lane == 0) {
+    if (totals) {
+      totals[((size_t)n * C + c) * 2 + 0] = (float)s1;
+      totals[((size_t)n * C + c) * 2 + 1] = (float)s2;
+    } else {
+      const double m = s1 * inv_count;
+      double var = s2 * inv_count - m * m;
+      if (var < 0.0) var = 0.0;
+      mean[(size_t)n * C + c] = (float)m;
+      rstd[(size_t)n * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------ elementwise IN ops
+__global__ void norm_act_add_kernel(const float* __restrict__ y, int ld_y, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, int relu, const float* __restrict__ res,
+                                    int ld_res, float* __restrict__ out, int ld_out, long long P, int C,
+                                    long long total /* N*P*C/4 */) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int CQ = C >> 2;
+  const int c = (int)(idx % CQ) * 4;
+  const long long pix = idx / CQ;
+  const int n = (int)(pix / P);
+  float4 v = *reinterpret_cast<const float4*>(y + pix * ld_y + c);
+  if (mean) {
+    const float4 m = *reinterpret_cast<const float4*>(mean + (size_t)n * C + c);
+    const float4 r = *reinterpret_cast<const float4*>(rstd + (size_t)n * C + c);
+    v.x = (v.x - m.x) * r.x; v.y = (v.y - m.y) * r.y; v.z = (v.z - m.z) * r.z; v.w = (v.w - m.w) * r.w;
+  }
+  if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  if (res) {
+    const float4 q = *reinterpret_cast<const float4*>(res + pix * ld_res + c);
+    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+  }
+  *reinterpret_cast<float4*>(out + pix * ld_out + c) = v;
+}
+
+constexpr int BWD_PIX_PER_BLOCK = 256;
+
+// pass 1 of the IN(+ReLU)(+upsample) backward.  grid = (blocks_per_sample, N, channel groups of 128)
+__global__ void __launch_bounds__(256) in_bwd_pass1_kernel(
+    const float* __restrict__ dA, int ld_dA, int ups, const float* __restrict__ extra, int ld_extra,
+    const float* __restrict__ y, int ld_y, const float* __restrict__ mean, const float* __restrict__ rstd,
+    int relu, float* __restrict__ g, float* __restrict__ partial, int H, int W, int C) {
+  __shared__ float red[8][32][8];
+  const int n = blockIdx.y, blk = blockIdx.x;
+  const int CQ = C >> 2;
+  const int cq_base = blockIdx.z * 32;
+  const int cq_left = CQ - cq_base;
+  // lanes per pixel: 32 when >=32 quads remain, else next power of two >= cq_left
+  int lpp = 32;
+  if (cq_left < 32) { lpp = 1; while (lpp < cq_left) lpp <<= 1; }
+  const int ppw = 32 / lpp;  // pixels per warp iteration
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane % lpp, sub = lane / lpp;
+  const bool cq_ok = q < cq_left;
+  const int c = (cq_base + q) * 4;
+  const long long P = (long long)H * W;
+  float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), r4 = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (cq_ok && mean) {
+    m4 = *reinterpret_cast<const float4*>(mean + (size_t)n * C + c);
+    r4 = *reinterpret_cast<const float4*>(rstd + (size_t)n * C + c);
+  }
+  float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long p_begin = (long long)blk * BWD_PIX_PER_BLOCK;
+  for (int i = warp * ppw + sub; i < BWD_PIX_PER_BLOCK; i += 8 * ppw) {
+    const long long pp = p_begin + i;
+    if (pp >= P || !cq_ok) continue;
+    const long long pix = (long long)n * P + pp;
+    float4 a;
+    if (ups) {
+      const int py = (int)(pp / W), px = (int)(pp - (long long)py * W);
+      const int W2 = W * 2;
+      const long long base = ((long long)n * (2 * H) + 2 * py) * W2 + 2 * px;
+      const float4 a0 = *reinterpret_cast<const float4*>(dA + base * ld_dA + c);
+      const float4 a1 = *reinterpret_cast<const float4*>(dA + (base + 1) * ld_dA + c);
+      const float4 a2 = *reinterpret_cast<const float4*>(dA + (base + W2) * ld_dA + c);
+      const float4 a3 = *reinterpret_cast<const float4*>(dA + (base + W2 + 1) * ld_dA + c);
+      a.x = (a0.x + a1.x) + (a2.x + a3.x); a.y = (a0.y + a1.y) + (a2.y + a3.y);
+      a.z = (a0.z + a1.z) + (a2.z + a3.z); a.w = (a0.w + a1.w) + (a2.w + a3.w);
+    } else {
+      a = *reinterpret_cast<const float4*>(dA + pix * ld_dA + c);
+    }
+    if (extra) {
+      const float4 e = *reinterpret_cast<const float4*>(extra + pix * ld_extra + c);
+      a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w;
+    }
+    const float4 yv = *reinterpret_cast<const float4*>(y + pix * ld_y + c);
+    const float xh[4] = {(yv.x - m4.x) * r4.x, (yv.y - m4.y) * r4.y, (yv.z - m4.z) * r4.z, (yv.w - m4.w) * r4.w};
+    float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (relu && !(xh[e] > 0.f)) av[e] = 0.f;
+      sg[e] += av[e];
+      sgx[e] += av[e] * xh[e];
+    }
+    *reinterpret_cast<float4*>(g + pix * C + c) = make_float4(av[0], av[1], av[2], av[3]);
+  }
+  // reduce over the `sub` lanes that share a channel quad, then over the 8 warps
+  for (int o = lpp; o < 32; o <<= 1) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      sg[e] += __shfl_xor_sync(0xffffffffu, sg[e], o);
+      sgx[e] += __shfl_xor_sync(0xffffffffu, sgx[e], o);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { red[warp][lane][e] = sg[e]; red[warp][lane][4 + e] = sgx[e]; }
+  __syncthreads();
+  if (warp == 0 && lane < lpp && cq_ok) {
+    float t[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float s = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) s += red[w8][lane][e];
+      t[e] = s;
+    }
+    float* dst = partial + (((size_t)n * gridDim.x + blk) * C + c) * 2;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dst[e * 2] = t[e]; dst[e * 2 + 1] = t[4 + e]; }
+  }
+}
+
+__global__ void in_bwd_pass2_kernel(const float* __restrict__ g, const float* __restrict__ y, int ld_y,
+                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const float* __restrict__ gsum, float* __restrict__ dy, long long P, int C,
+                                    float inv_p, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int CQ = C >> 2;
+  const int c = (int)(idx % CQ) * 4;
+  const long long pix = idx / CQ;
+  const int n = (int)(pix / P);
+  const float4 gv = *reinterpret_cast<const float4*>(g + pix * C + c);
+  const float4 yv = *reinterpret_cast<const float4*>(y + pix * ld_y + c);
+  const float4 m = *reinterpret_cast<const float4*>(mean + (size_t)n * C + c);
+  const float4 r = *reinterpret_cast<const float4*>(rstd + (size_t)n * C + c);
+  const float* gs = gsum + ((size_t)n * C + c) * 2;
+  const float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+  const float ya[4] = {yv.x, yv.y, yv.z, yv.w};
+  const float ma[4] = {m.x, m.y, m.z, m.w};
+  const float ra[4] = {r.x, r.y, r.z, r.w};
+  float o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float xh = (ya[e] - ma[e]) * ra[e];
+    o[e] = ra[e] * (ga[e] - gs[e * 2] * inv_p - xh * (gs[e * 2 + 1] * inv_p));
+  }
+  *reinterpret_cast<float4*>(dy + pix * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// out[n,y,x,c] (+)= sum of the 2x2 children of in
+__global__ void upsample2_bwd_kernel(const float* __restrict__ in, int ld_in, float* __restrict__ out, int ld_out,
+                                     int H, int W, int C, int accumulate, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int CQ = C >> 2;
+  const int c = (int)(idx % CQ) * 4;
+  const long long pix = idx / CQ;
+  const long long P = (long long)H * W;
+  const int n = (int)(pix / P);
+  const long long pp = pix - (long long)n * P;
+  const int py = (int)(pp / W), px = (int)(pp - (long long)py * W);
+  const int W2 = 2 * W;
+  const long long base = ((long long)n * (2 * H) + 2 * py) * W2 + 2 * px;
+  const float4 a0 = *reinterpret_cast<const float4*>(in + base * ld_in + c);
+  const float4 a1 = *reinterpret_cast<const float4*>(in + (base + 1) * ld_in + c);
+  const float4 a2 = *reinterpret_cast<const float4*>(in + (base + W2) * ld_in + c);
+  const float4 a3 = *reinterpret_cast<const float4*>(in + (base + W2 + 1) * ld_in + c);
+  float4 v = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                         (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+  float* o = out + pix * ld_out + c;
+  if (accumulate) {
+    const float4 q = *reinterpret_cast<const float4*>(o);
+    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+  }
+  *reinterpret_cast<float4*>(o) = v;
+}
+
+// ------------------------------------------------------------------------------- column sums
+__global__ void colsum_stage1(const float* __restrict__ x, int ld, long long rows, int C, long long rows_per_block,
+                              float* __restrict__ part) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + lane;
+    float s = 0.f;
+    if (c < C)
+      for (long long r = r0 + wy; r < r1; r += 8) s += x[r * ld + c];
+    red[wy][lane] = s;
+    __syncthreads();
+    if (wy == 0 && c < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][lane];
+      part[(size_t)blockIdx.x * C + c] = t;
+    }
+    __syncthreads();
+  }
+}
+__global__ void colsum_stage2(const float* __restrict__ part, int nblocks, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += (double)part[(size_t)b * C + c];
+  out[c] = (float)s;
+}
+
+// ------------------------------------------------------------------------- event pre-processing
+// stats[w][3] += (sum, sumsq, nnz) of window w; x is [B][T][count] with batch stride bstride.
+__global__ void event_stats_kernel(const float* __restrict__ x, long long bstride, int B, long long count,
+                                   double* __restrict__ stats) {
+  __shared__ double red[3][8];
+  const int w = blockIdx.y;
+  const long long total = (long long)B * count;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / count, r = i - b * count;
+    const float v = x[b * bstride + (long long)w * count + r];
+    s0 += (double)v;
+    s1 += (double)v * (double)v;
+    s2 += (v != 0.f) ? 1.0 : 0.0;
+  }
+  s0 = warp_sum_d(s0); s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  if (lane == 0) { red[0][wy] = s0; red[1][wy] = s1; red[2][wy] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[threadIdx.x][k];
+    atomicAdd(&stats[w * 3 + threadIdx.x], t);
+  }
+}
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+__global__ void event_prepare_kernel(const float* __restrict__ x, long long bstride, const double* __restrict__ stats,
+                                     int normalize, float* __restrict__ out, int ld_out, int C, int H, int W,
+                                     int Hp, int Wp, int pad_top, int pad_left, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = (int)(idx % Wp);
+  const long long r = idx / Wp;
+  const int oy = (int)(r % Hp);
+  const int n = (int)(r / Hp);
+  const int iy = reflect_idx(oy - pad_top, H), ix = reflect_idx(ox - pad_left, W);
+  float mean = 0.f, inv_std = 1.f;
+  bool do_norm = false;
+  if (normalize) {
+    const double nnz = stats[2];
+    if (nnz > 0.0) {
+      // fp32 arithmetic on the reduced sums, as the reference does (inference_utils.py:104-107)
+      const float fm = (float)stats[0] / (float)nnz;
+      const float fs = sqrtf((float)stats[1] / (float)nnz - fm * fm);
+      mean = fm;
+      inv_std = fs;
+      do_norm = true;
+    }
+  }
+  const float* src = x + (long long)n * bstride + (long long)iy * W + ix;
+  float* dst = out + idx * ld_out;
+  for (int c = 0; c < ld_out; ++c) {
+    float v = 0.f;
+    if (c < C) {
+      v = src[(long long)c * H * W];
+      if (do_norm) v = (v != 0.f) ? (v - mean) / inv_std : 0.f;
+    }
+    dst[c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------ layout kernels
+// [N][C][P] -> [N][P][ld]   (32x32 smem transpose)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int ld_out, int C,
+                                    long long P) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const long long pp = p0 + tx;
+    tile[j][tx] = (c < C && pp < P) ? in[((long long)n * C + c) * P + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const long long pp = p0 + j;
+    const int c = c0 + tx;
+    if (pp < P && c < C) out[((long long)n * P + pp) * ld_out + c] = tile[tx][j];
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int ld_in, float* __restrict__ out, int C,
+                                    long long P) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int j = ty; j < 32; j += 8) {
+    const long long pp = p0 + j;
+    const int c = c0 + tx;
+    tile[j][tx] = (c < C && pp < P) ? in[((long long)n * P + pp) * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const long long pp = p0 + tx;
+    if (c < C && pp < P) out[((long long)n * C + c) * P + pp] = tile[tx][j];
+  }
+}
+
+// bilinear x2, align_corners=False (ATen area_pixel_compute_source_index semantics)
+__global__ void bilinear_up2_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int C,
+                                    long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  long long r = idx / C;
+  const int ox = (int)(r % (2 * W)); r /= (2 * W);
+  const int oy = (int)(r % (2 * H));
+  const int n = (int)(r / (2 * H));
+  float sy = 0.5f * (oy + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+  float sx = 0.5f * (ox + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float ly1 = sy - y0, ly0 = 1.f - ly1, lx1 = sx - x0, lx0 = 1.f - lx1;
+  const float* b = in + (long long)n * H * W * C + c;
+  const float v00 = b[((long long)y0 * W + x0) * C], v01 = b[((long long)y0 * W + x1) * C];
+  const float v10 = b[((long long)y1 * W + x0) * C], v11 = b[((long long)y1 * W + x1) * C];
+  out[idx] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+}
+
+}  // namespace
+
+// =================================================================================== C ABI
+extern "C" int essb_pack_weight(const float* w, const float* scale, float* out, int Cout, int Cin, int T,
+                                int transposed_layout, int swap_io, int flip, int interleave, void* stream) {
+  ESSB_REQUIRE(w && out && Cout > 0 && Cin > 0 && T > 0, "essb_pack_weight: bad arguments");
+  ESSB_REQUIRE(interleave <= 1 || (Cout % interleave == 0 && !swap_io), "essb_pack_weight: bad interleave");
+  const int Kin = swap_io ? Cout : Cin;
+  const int NoutP = ((swap_io ? Cin : Cout) + 3) & ~3;
+  const long long total = (long long)T * Kin * NoutP;
+  pack_weight_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(w, scale, out, Cout, Cin, T,
+                                                                               transposed_layout, swap_io, flip,
+                                                                               interleave);
+  ESSB_LAUNCH_CHECK("essb_pack_weight");
+  return ESSB_OK;
+}
+
+extern "C" int essb_in_finalize(const float* partial, int N, int tiles, int C, int64_t count, float eps, float* mean,
+                                float* rstd, void* stream) {
+  ESSB_REQUIRE(partial && mean && rstd && N > 0 && tiles > 0 && C > 0 && count > 0, "essb_in_finalize: bad arguments");
+  const long long threads = (long long)N * C * 32;
+  in_finalize_kernel<<<ew_blocks(threads), EW_THREADS, 0, (cudaStream_t)stream>>>(partial, N, tiles, C,
+                                                                                 1.0 / (double)count, eps, mean, rstd,
+                                                                                 nullptr);
+  ESSB_LAUNCH_CHECK("essb_in_finalize");
+  return ESSB_OK;
+}
+
+extern "C" int essb_partial_reduce(const float* partial, int N, int blocks, int C, float* totals, void* stream) {
+  ESSB_REQUIRE(partial && totals && N > 0 && blocks > 0 && C > 0, "essb_partial_reduce: bad arguments");
+  const long long threads = (long long)N * C * 32;
+  in_finalize_kernel<<<ew_blocks(threads), EW_THREADS, 0, (cudaStream_t)stream>>>(partial, N, blocks, C, 0.0, 0.f,
+                                                                                 nullptr, nullptr, totals);
+  ESSB_LAUNCH_CHECK("essb_partial_reduce");
+  return ESSB_OK;
+}
+
+static int check_vec4(const void* p, int ld, const char* who) {
+  ESSB_REQUIRE(p == nullptr || (essb_aligned16(p) && ld % 4 == 0), "%s: tensors must be 16B aligned with ld %% 4 == 0", who);
+  return ESSB_OK;
+}
+
+extern "C" int essb_norm_act_add(const float* y, int ld_y, const float* mean, const float* rstd, int relu,
+                                 const float* res, int ld_res, float* out, int ld_out, int N, int64_t P, int C,
+                                 void* stream) {
+  ESSB_REQUIRE(y && out && N > 0 && P > 0 && C > 0 && C % 4 == 0, "essb_norm_act_add: bad arguments (C %% 4 == 0 required)");
+  int rc;
+  if ((rc = check_vec4(y, ld_y, "essb_norm_act_add")) || (rc = check_vec4(res, ld_res, "essb_norm_act_add")) ||
+      (rc = check_vec4(out, ld_out, "essb_norm_act_add")) || (rc = check_vec4(mean, 4, "essb_norm_act_add")))
+    return rc;
+  const long long total = (long long)N * P * (C / 4);
+  norm_act_add_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(y, ld_y, mean, rstd, relu, res,
+                                                                                ld_res, out, ld_out, P, C, total);
+  ESSB_LAUNCH_CHECK("essb_norm_act_add");
+  return ESSB_OK;
+}
+
+extern "C" int essb_in_bwd_blocks(int64_t P) { return (int)((P + BWD_PIX_PER_BLOCK - 1) / BWD_PIX_PER_BLOCK); }
+
+extern "C" int essb_in_bwd_pass1(const float* dA, int ld_dA, int ups, const float* extra, int ld_extra,
+                                 const float* y, int ld_y, const float* mean, const float* rstd, int relu, float* g,
+                                 float* partial, int N, int H, int W, int C, void* stream) {
+  ESSB_REQUIRE(dA && y && g && partial && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0,
+               "essb_in_bwd_pass1: bad arguments (C %% 4 == 0 required)");
+  ESSB_REQUIRE((mean == nullptr) == (rstd == nullptr), "essb_in_bwd_pass1: mean/rstd must come together");
+  int rc;
+  if ((rc = check_vec4(dA, ld_dA, "essb_in_bwd_pass1")) || (rc = check_vec4(extra, ld_extra, "essb_in_bwd_pass1")) ||
+      (rc = check_vec4(y, ld_y, "essb_in_bwd_pass1")) || (rc = check_vec4(g, 4, "essb_in_bwd_pass1")))
+    return rc;
+  const int blocks = essb_in_bwd_blocks((int64_t)H * W);
+  dim3 grid(blocks, N, (C / 4 + 31) / 32);
+  in_bwd_pass1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dA, ld_dA, ups, extra, ld_extra, y, ld_y, mean, rstd,
+                                                              relu, g, partial, H, W, C);
+  ESSB_LAUNCH_CHECK("essb_in_bwd_pass1");
+  return ESSB_OK;
+}
+
+extern "C" int essb_in_bwd_pass2(const float* g, const float* y, int ld_y, const float* mean, const float* rstd,
+                                 const float* gsum, float* dy, int N, int64_t P, int C, void* stream) {
+  ESSB_REQUIRE(g && y && mean && rstd && gsum && dy && N > 0 && P > 0 && C % 4 == 0, "essb_in_bwd_pass2: bad arguments");
+  int rc;
+  if ((rc = check_vec4(y, ld_y, "essb_in_bwd_pass2")) || (rc = check_vec4(g, 4, "essb_in_bwd_pass2")) ||
+      (rc = check_vec4(dy, 4, "essb_in_bwd_pass2")))
+    return rc;
+  const long long total = (long long)N * P * (C / 4);
+  in_bwd_pass2_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(g, y, ld_y, mean, rstd, gsum, dy, P,
+                                                                                C, 1.0f / (float)P, total);
+  ESSB_LAUNCH_CHECK("essb_in_bwd_pass2");
+  return ESSB_OK;
+}
+
+extern "C" int essb_upsample2_bwd(const float* in, int ld_in, float* out, int ld_out, int N, int H, int W, int C,
+                                  int accumulate, void* stream) {
+  ESSB_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "essb_upsample2_bwd: bad arguments");
+  int rc;
+  if ((rc = check_vec4(in, ld_in, "essb_upsample2_bwd")) || (rc = check_vec4(out, ld_out, "essb_upsample2_bwd")))
+    return rc;
+  const long long total = (long long)N * H * W * (C / 4);
+  upsample2_bwd_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(in, ld_in, out, ld_out, H, W, C,
+                                                                                 accumulate, total);
+  ESSB_LAUNCH_CHECK("essb_upsample2_bwd");
+  return ESSB_OK;
+}
+
+extern "C" int essb_colsum(const float* x, int ld, int64_t rows, int C, float* out, float* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  ESSB_REQUIRE(x && out && workspace && rows > 0 && C > 0, "essb_colsum: bad arguments");
+  long long nb = (rows + 511) / 512;
+  if (nb > 1024) nb = 1024;
+  const long long fit = workspace_bytes / ((long long)C * (long long)sizeof(float));
+  if (nb > fit) nb = fit;
+  if (nb < 1) {
+    essb_set_error("essb_colsum: workspace too small");
+    return ESSB_ERR_WORKSPACE;
+  }
+  const long long rpb = (rows + nb - 1) / nb;
+  nb = (rows + rpb - 1) / rpb;
+  colsum_stage1<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(x, ld, rows, C, rpb, workspace);
+  ESSB_LAUNCH_CHECK("essb_colsum stage1");
+  colsum_stage2<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(workspace, (int)nb, C, out);
+  ESSB_LAUNCH_CHECK("essb_colsum stage2");
+  return ESSB_OK;
+}
+
+extern "C" int essb_event_stats(const float* x, int64_t bstride, int B, int T, int64_t count, double* stats,
+                                void* stream) {
+  ESSB_REQUIRE(x && stats && B > 0 && T > 0 && count > 0, "essb_event_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 3 * T, st);
+  if (e != cudaSuccess) {
+    essb_set_error("essb_event_stats: memset failed: %s", cudaGetErrorString(e));
+    return ESSB_ERR_LAUNCH;
+  }
+  long long blocks = ((long long)B * count + 256 * 16 - 1) / (256 * 16);
+  if (blocks > 592) blocks = 592;
+  if (blocks < 1) blocks = 1;
+  dim3 grid((unsigned)blocks, T, 1);
+  event_stats_kernel<<<grid, 256, 0, st>>>(x, bstride, B, count, stats);
+  ESSB_LAUNCH_CHECK("essb_event_stats");
+  return ESSB_OK;
+}
+
+extern "C" int essb_event_prepare(const float* x, int64_t bstride, const double* stats, int normalize, float* out,
+                                  int ld_out, int B, int C, int H, int W, int Hp, int Wp, int pad_top, int pad_left,
+                                  void* stream) {
+  ESSB_REQUIRE(x && out && B > 0 && C > 0 && H > 0 && W > 0 && Hp >= H && Wp >= W && ld_out >= C,
+               "essb_event_prepare: bad arguments");
+  ESSB_REQUIRE(!normalize || stats, "essb_event_prepare: stats required when normalising");
+  ESSB_REQUIRE(pad_top < H && Hp - H - pad_top < H && pad_left < W && Wp - W - pad_left < W,
+               "essb_event_prepare: reflection padding must be smaller than the image");
+  const long long total = (long long)B * Hp * Wp;
+  event_prepare_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      x, bstride, stats, normalize, out, ld_out, C, H, W, Hp, Wp, pad_top, pad_left, total);
+  ESSB_LAUNCH_CHECK("essb_event_prepare");
+  return ESSB_OK;
+}
+
+extern "C" int essb_nchw_to_nhwc(const float* in, float* out, int ld_out, int N, int C, int64_t P, void* stream) {
+  ESSB_REQUIRE(in && out && N > 0 && C > 0 && P > 0 && ld_out >= C && N <= 65535, "essb_nchw_to_nhwc: bad arguments");
+  dim3 grid((unsigned)((P + 31) / 32), (C + 31) / 32, N), block(32, 8, 1);
+  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, ld_out, C, P);
+  ESSB_LAUNCH_CHECK("essb_nchw_to_nhwc");
+  return ESSB_OK;
+}
+
+extern "C" int essb_nhwc_to_nchw(const float* in, int ld_in, float* out, int N, int C, int64_t P, void* stream) {
+  ESSB_REQUIRE(in && out && N > 0 && C > 0 && P > 0 && ld_in >= C && N <= 65535, "essb_nhwc_to_nchw: bad arguments");
+  dim3 grid((unsigned)((P + 31) / 32), (C + 31) / 32, N), block(32, 8, 1);
+  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, ld_in, out, C, P);
+  ESSB_LAUNCH_CHECK("essb_nhwc_to_nchw");
+  return ESSB_OK;
+}
+
+extern "C" int essb_bilinear_up2(const float* in, float* out, int N, int H, int W, int C, void* stream) {
+  ESSB_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0, "essb_bilinear_up2: bad arguments");
+  const long long total = (long long)N * 4 * H * W * C;
+  bilinear_up2_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(in, out, H, W, C, total);
+  ESSB_LAUNCH_CHECK("essb_bilinear_up2");
+  return ESSB_OK;
+}

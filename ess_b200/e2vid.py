@@ -1,0 +1,452 @@
+"""Drop-in `E2VIDRecurrent` (reference: e2vid/model/model.py:69-100 -> e2vid/model/unet.py:117-181).
+
+Same constructor (`config` dict), attributes (`num_bins`, `num_encoders`, ...), `forward(event_tensor,
+prev_states) -> (img, states, latent)` signature and `state_dict` keys as the reference, so
+`e2vid.utils.loading_utils.load_model` (`eval(arch)(cfg)` + strict `load_state_dict`) and
+`ImageReconstructor` work unchanged.  The nn.Conv2d / nn.BatchNorm2d children are parameter holders
+only -- their forward is never called; all arithmetic runs in libess_b200.so:
+
+  mode "fp32"   : every conv on the exact-fp32 CUDA-core implicit-GEMM kernel (conv_fp32.cu)
+  mode "bf16x3" : encoder stride-2 convs and the fused ConvLSTM cells on the tcgen05/TMA kernel
+                  (conv_tc.cu) with the 3-product bf16 split (fp32-level accuracy)
+  mode "bf16"   : same kernels, single bf16 pass (fast, ~1e-2 relative; reported separately)
+
+Inference only (the reference freezes this network and runs it under no_grad,
+training/ess_supervised_trainer.py:44-47, e2vid/image_reconstructor.py:83); BatchNorm is applied in
+eval mode (running statistics folded into the conv weights).
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, EPI_GRU_OUT, EPI_GRU_UR, EPI_LINEAR, EPI_LSTM, ConvTc)
+from .ops import Seg
+
+BN_EPS = 1e-5
+MODES = ('fp32', 'bf16x3', 'bf16')
+
+
+def default_mode():
+    m = os.environ.get('ESS_B200_MODE', 'bf16x3')
+    if m not in MODES:
+        raise ValueError('ESS_B200_MODE must be one of %s' % (MODES,))
+    return m
+
+
+# ---------------------------------------------------------------------------- parameter holders
+class _ConvLayer(nn.Module):          # e2vid/model/submodules.py:7-31
+    def __init__(self, cin, cout, k, stride, pad, norm):
+        super().__init__()
+        self.conv2d = nn.Conv2d(cin, cout, k, stride, pad, bias=(norm != 'BN'))
+        if norm == 'BN':
+            self.norm_layer = nn.BatchNorm2d(cout)
+
+
+class _TransposedConvLayer(nn.Module):  # submodules.py:34-62
+    def __init__(self, cin, cout, k, pad, norm):
+        super().__init__()
+        self.transposed_conv2d = nn.ConvTranspose2d(cin, cout, k, stride=2, padding=pad, output_padding=1,
+                                                    bias=(norm != 'BN'))
+        if norm == 'BN':
+            self.norm_layer = nn.BatchNorm2d(cout)
+
+
+class _ConvLSTM(nn.Module):           # submodules.py:175-188
+    def __init__(self, c, hidden, k):
+        super().__init__()
+        self.Gates = nn.Conv2d(c + hidden, 4 * hidden, k, padding=k // 2)
+
+
+class _ConvGRU(nn.Module):            # submodules.py:233-253
+    def __init__(self, c, hidden, k):
+        super().__init__()
+        pad = k // 2
+        self.reset_gate = nn.Conv2d(c + hidden, hidden, k, padding=pad)
+        self.update_gate = nn.Conv2d(c + hidden, hidden, k, padding=pad)
+        self.out_gate = nn.Conv2d(c + hidden, hidden, k, padding=pad)
+        for m in (self.reset_gate, self.update_gate, self.out_gate):
+            nn.init.orthogonal_(m.weight)
+            nn.init.constant_(m.bias, 0.)
+
+
+class _RecurrentConvLayer(nn.Module):  # submodules.py:96-115
+    def __init__(self, cin, cout, block_type, norm):
+        super().__init__()
+        self.conv = _ConvLayer(cin, cout, 5, 2, 2, norm)
+        self.recurrent_block = (_ConvLSTM if block_type == 'convlstm' else _ConvGRU)(cout, cout, 3)
+
+
+class _ResidualBlock(nn.Module):      # submodules.py:140-155
+    def __init__(self, c, norm):
+        super().__init__()
+        bias = norm != 'BN'
+        self.conv1 = nn.Conv2d(c, c, 3, 1, 1, bias=bias)
+        if norm == 'BN':
+            self.bn1 = nn.BatchNorm2d(c)
+            self.bn2 = nn.BatchNorm2d(c)
+        self.conv2 = nn.Conv2d(c, c, 3, 1, 1, bias=bias)
+
+
+class _UNetRecurrent(nn.Module):      # unet.py:117-143
+    def __init__(self, cfg):
+        super().__init__()
+        base, ne, norm = cfg['base_num_channels'], cfg['num_encoders'], cfg['norm']
+        concat = cfg['skip_type'] != 'sum'
+        self.head = _ConvLayer(cfg['num_bins'], base, 5, 1, 2, None)
+        self.encoders = nn.ModuleList(
+            [_RecurrentConvLayer(base * 2 ** i, base * 2 ** (i + 1), cfg['recurrent_block_type'], norm)
+             for i in range(ne)])
+        cmax = base * 2 ** ne
+        self.resblocks = nn.ModuleList([_ResidualBlock(cmax, norm) for _ in range(cfg['num_residual_blocks'])])
+        self.decoders = nn.ModuleList()
+        for c in reversed([base * 2 ** (i + 1) for i in range(ne)]):
+            cin = 2 * c if concat else c
+            if cfg['use_upsample_conv']:
+                self.decoders.append(_ConvLayer(cin, c // 2, 5, 1, 2, norm))
+            else:
+                self.decoders.append(_TransposedConvLayer(cin, c // 2, 5, 2, norm))
+        self.pred = _ConvLayer(2 * base if concat else base, 1, 1, 1, 0, norm)
+
+
+def _bn_fold(conv_bias, bn, cout, device):
+    """Eval-mode BatchNorm -> (scale, bias) per output channel (submodules.py:19-20,26-27)."""
+    if bn is None:
+        return None, (conv_bias.detach().float().contiguous() if conv_bias is not None else None)
+    scale = (bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + BN_EPS))
+    bias = bn.bias.detach().float() - bn.running_mean.float() * scale
+    if conv_bias is not None:
+        bias = bias + conv_bias.detach().float() * scale
+    return scale.contiguous(), bias.contiguous()
+
+
+def _interleave(v, g):
+    """bias permutation matching essb_pack_weight(interleave=g): packed[ch*g + j] = v[j*G + ch]."""
+    G = v.numel() // g
+    return v.detach().float().view(g, G).t().contiguous().view(-1)
+
+
+class E2VIDRecurrent(nn.Module):
+    """Recurrent U-Net event encoder / image reconstructor (E2VID), B200-native."""
+
+    def __init__(self, config, mode=None):
+        super().__init__()
+        self.config = config
+        assert 'num_bins' in config
+        self.num_bins = int(config['num_bins'])                                   # model.py:13-14
+        self.skip_type = str(config.get('skip_type', 'sum'))
+        self.num_encoders = int(config.get('num_encoders', 4))
+        self.base_num_channels = int(config.get('base_num_channels', 32))
+        self.num_residual_blocks = int(config.get('num_residual_blocks', 2))
+        self.norm = str(config['norm']) if 'norm' in config else None
+        self.use_upsample_conv = bool(config.get('use_upsample_conv', True))
+        self.recurrent_block_type = str(config.get('recurrent_block_type', 'convlstm'))
+        if self.norm not in (None, 'BN'):
+            raise NotImplementedError("E2VIDRecurrent: norm=%r (only None and 'BN' are built)" % (self.norm,))
+        if self.recurrent_block_type not in ('convlstm', 'convgru'):
+            raise ValueError(self.recurrent_block_type)
+        if self.num_encoders < 3:
+            raise ValueError('UNetRecurrent.forward needs >= 3 encoders (latent dict, unet.py:172)')
+        if self.num_residual_blocks < 1:
+            raise NotImplementedError('num_residual_blocks == 0')
+        self.unetrecurrent = _UNetRecurrent(dict(
+            num_bins=self.num_bins, skip_type=self.skip_type, num_encoders=self.num_encoders,
+            base_num_channels=self.base_num_channels, num_residual_blocks=self.num_residual_blocks, norm=self.norm,
+            use_upsample_conv=self.use_upsample_conv, recurrent_block_type=self.recurrent_block_type))
+        self.mode = mode or default_mode()
+        self._packed = None
+        self._packed_key = None
+        self._planes = {}   # data_ptr of a returned hidden state -> (tensor, hi, lo) for the next window
+
+    # ------------------------------------------------------------------------------ weight packing
+    def _key(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers())) + (self.mode,)
+
+    def _pack(self):
+        key = self._key()
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        u = self.unetrecurrent
+        dev = u.head.conv2d.weight.device
+        P = {}
+        cpad = (self.num_bins + 7) // 8 * 8
+        wh = torch.zeros((self.base_num_channels, cpad, 5, 5), device=dev)
+        wh[:, :self.num_bins] = u.head.conv2d.weight.detach().float()
+        P['head'] = (ops.pack_weight(wh), u.head.conv2d.bias.detach().float().contiguous(), cpad)
+        tc = self.mode != 'fp32'
+        for i, enc in enumerate(u.encoders):
+            bn = getattr(enc.conv, 'norm_layer', None)
+            scale, bias = _bn_fold(enc.conv.conv2d.bias, bn, None, dev)
+            e = {'bias': bias, 'w': ops.pack_weight(enc.conv.conv2d.weight, scale)}
+            cin, cout = enc.conv.conv2d.in_channels, enc.conv.conv2d.out_channels
+            e['tc'] = None
+            if tc and cout % 64 == 0 and (cin % 64 == 0 or cin == 32):
+                w = enc.conv.conv2d.weight.detach().float()
+                fold = cin == 32
+                if fold:   # horizontal pixel pairs become one 64-channel super-pixel (see ops.parity_view)
+                    w6 = torch.zeros((cout, cin, 5, 6), device=dev)
+                    w6[..., :5] = w
+                    w = w6.view(cout, cin, 5, 3, 2).permute(0, 4, 1, 2, 3).reshape(cout, 2 * cin, 5, 3).contiguous()
+                hi, lo, kinp = ops.pack_weight_tc(w, scale)
+                e['tc'] = dict(hi=hi, lo=lo, k_per_tap=kinp, fold=fold, T=w.shape[2] * w.shape[3])
+            rb = enc.recurrent_block
+            C = cout
+            if self.recurrent_block_type == 'convlstm':
+                W = rb.Gates.weight
+                e['lstm_w'] = ops.pack_weight(W, interleave=4)
+                e['lstm_w_x'] = ops.pack_weight(W[:, :C].contiguous(), interleave=4)
+                e['lstm_b'] = _interleave(rb.Gates.bias, 4)
+                e['lstm_tc'] = None
+                if tc and C % 64 == 0:
+                    hi, lo, kinp = ops.pack_weight_tc(W, interleave=4)
+                    e['lstm_tc'] = dict(hi=hi, lo=lo, k_per_tap=kinp)
+            else:
+                wur = torch.cat([rb.update_gate.weight, rb.reset_gate.weight], 0).detach()
+                bur = torch.cat([rb.update_gate.bias, rb.reset_gate.bias], 0).detach()
+                e['gru_ur_w'] = ops.pack_weight(wur, interleave=2)
+                e['gru_ur_w_x'] = ops.pack_weight(wur[:, :C].contiguous(), interleave=2)
+                e['gru_ur_b'] = _interleave(bur, 2)
+                e['gru_o_w'] = ops.pack_weight(rb.out_gate.weight)
+                e['gru_o_w_x'] = ops.pack_weight(rb.out_gate.weight[:, :C].contiguous())
+                e['gru_o_b'] = rb.out_gate.bias.detach().float().contiguous()
+            P['enc%d' % i] = e
+        for j, rbk in enumerate(u.resblocks):
+            s1, b1 = _bn_fold(rbk.conv1.bias, getattr(rbk, 'bn1', None), None, dev)
+            s2, b2 = _bn_fold(rbk.conv2.bias, getattr(rbk, 'bn2', None), None, dev)
+            P['res%d' % j] = (ops.pack_weight(rbk.conv1.weight, s1), b1, ops.pack_weight(rbk.conv2.weight, s2), b2)
+        for i, dec in enumerate(u.decoders):
+            bn = getattr(dec, 'norm_layer', None)
+            if self.use_upsample_conv:
+                scale, bias = _bn_fold(dec.conv2d.bias, bn, None, dev)
+                P['dec%d' % i] = (ops.pack_weight(dec.conv2d.weight, scale), bias, dec.conv2d.out_channels)
+            else:
+                scale, bias = _bn_fold(dec.transposed_conv2d.bias, bn, None, dev)
+                P['dec%d' % i] = (ops.pack_weight(dec.transposed_conv2d.weight, scale, transposed_layout=True), bias,
+                                  dec.transposed_conv2d.out_channels)
+        scale, bias = _bn_fold(u.pred.conv2d.bias, getattr(u.pred, 'norm_layer', None), None, dev)
+        P['pred'] = (ops.pack_weight(u.pred.conv2d.weight, scale), bias)
+        self._packed, self._packed_key = P, key
+        return P
+
+    # --------------------------------------------------------------------------------- state helpers
+    @staticmethod
+    def _to_nhwc(t):
+        v = t.permute(0, 2, 3, 1)
+        return v if v.is_contiguous() else v.contiguous()
+
+    def _hidden_planes(self, h_nhwc):
+        ent = self._planes.get(h_nhwc.data_ptr())
+        if ent is not None and ent[0].data_ptr() == h_nhwc.data_ptr() and ent[0]._version == ent[3] \
+                and ent[0].shape == h_nhwc.shape:
+            return ent[1], ent[2]
+        N, H, W, _ = h_nhwc.shape
+        return ops.split_bf16(Seg(h_nhwc), N, H, W)
+
+    # --------------------------------------------------------------------------------------- forward
+    def forward(self, event_tensor, prev_states, with_image=True):
+        """event_tensor [N, num_bins, H, W] (H, W multiples of 2^num_encoders), prev_states None or a
+        list of (hidden, cell) tuples (ConvLSTM) / tensors (ConvGRU).  Returns (img [N,1,H,W] or None
+        when with_image=False, states, latent {1,2,4,8}) exactly as unet.py:145-181."""
+        ops.require_cuda(event_tensor)
+        N, Cb, H, W = event_tensor.shape
+        if Cb != self.num_bins:
+            raise RuntimeError('expected %d input channels, got %d' % (self.num_bins, Cb))
+        f = 2 ** self.num_encoders
+        if H % f or W % f:
+            raise RuntimeError('H, W must be multiples of %d (CropParameters pads to this)' % f)
+        with torch.no_grad():
+            cpad = (self.num_bins + 7) // 8 * 8
+            x = ops.nchw_to_nhwc(event_tensor, cpad)
+            return self.forward_nhwc(x, prev_states, with_image)
+
+    def forward_nhwc(self, x, prev_states, with_image=True):
+        """Same as forward() for an already pixel-major input [N, H, W, ceil8(num_bins)] (zero-padded
+        channels), as produced by the fused event pre-processing kernel."""
+        P = self._pack()
+        u = self.unetrecurrent
+        ne = self.num_encoders
+        lstm = self.recurrent_block_type == 'convlstm'
+        N, H, W, _ = x.shape
+        tc_mode = self.mode != 'fp32'
+        passes = 3 if self.mode == 'bf16x3' else 1
+        if prev_states is None:
+            prev_states = [None] * ne
+        base = self.base_num_channels
+
+        # head: conv5x5 + bias + ReLU (unet.py:131-132,153)
+        wh, bh, cpad = P['head']
+        want_planes = tc_mode and P['enc0']['tc'] is not None
+        planes = None
+        if want_planes:
+            planes = (torch.empty((N, H, W, base), device=x.device, dtype=torch.bfloat16),
+                      torch.empty((N, H, W, base), device=x.device, dtype=torch.bfloat16))
+        head, _, _, _ = ops.conv([Seg(x, C=cpad)], wh, bh, N, H, W, H, W, base, ops.taps_conv(5, 2), act=ACT_RELU,
+                                 planes=planes)
+
+        blocks, states = [], []
+        cur, cur_planes = head, planes
+        new_planes = {}
+        h_in, w_in = H, W
+        for i in range(ne):
+            e = P['enc%d' % i]
+            cin, cout = base * 2 ** i, base * 2 ** (i + 1)
+            oh, ow = h_in // 2, w_in // 2
+            st = prev_states[i]
+            use_tc = tc_mode and e['tc'] is not None and cur_planes is not None and \
+                (not lstm or e['lstm_tc'] is not None) and lstm
+            if use_tc:
+                xh = torch.empty((N, oh, ow, cout), device=x.device, dtype=torch.bfloat16)
+                xl = torch.empty_like(xh)
+                self._enc_conv_tc(e, cur_planes, N, h_in, w_in, cout, xh, xl, passes)
+                hp = cp = None
+                hp_planes = None
+                if st is not None:
+                    hp, cp = self._to_nhwc(st[0]), self._to_nhwc(st[1])
+                    hp_planes = self._hidden_planes(hp)
+                h, c, hh, hl = self._lstm_tc(e, (xh, xl), hp_planes, cp, N, oh, ow, cout, passes)
+                new_planes[h.data_ptr()] = (h, hh, hl, h._version)
+                cur, cur_planes = h, (hh, hl)
+                state = (ops.as_nchw(h), ops.as_nchw(c))
+            else:
+                if cur is None:
+                    raise RuntimeError('internal: fp32 activation missing')
+                xi, _, _, _ = ops.conv([Seg(cur)], e['w'], e['bias'], N, h_in, w_in, oh, ow, cout, ops.taps_conv(5, 2),
+                                       stride=2, act=ACT_RELU)
+                t3 = ops.taps_conv(3, 1)
+                if lstm:
+                    hp = cp = None
+                    if st is not None:
+                        hp, cp = self._to_nhwc(st[0]), self._to_nhwc(st[1])
+                    segs = [Seg(xi)] + ([Seg(hp)] if hp is not None else [])
+                    h, c, _, _ = ops.conv(segs, e['lstm_w'] if hp is not None else e['lstm_w_x'], e['lstm_b'], N, oh, ow,
+                                          oh, ow, 4 * cout, t3, epilogue=EPI_LSTM, aux0=cp)
+                    state = (ops.as_nchw(h), ops.as_nchw(c))
+                else:
+                    hp = self._to_nhwc(st) if st is not None else None
+                    segs = [Seg(xi)] + ([Seg(hp)] if hp is not None else [])
+                    upd, hr, _, _ = ops.conv(segs, e['gru_ur_w'] if hp is not None else e['gru_ur_w_x'], e['gru_ur_b'],
+                                             N, oh, ow, oh, ow, 2 * cout, t3, epilogue=EPI_GRU_UR, aux0=hp)
+                    segs = [Seg(xi)] + ([Seg(hr)] if hp is not None else [])
+                    h, _, _, _ = ops.conv(segs, e['gru_o_w'] if hp is not None else e['gru_o_w_x'], e['gru_o_b'], N, oh,
+                                          ow, oh, ow, cout, t3, epilogue=EPI_GRU_OUT, aux0=hp, aux1=upd)
+                    state = ops.as_nchw(h)
+                cur, cur_planes = h, None
+            blocks.append(cur)
+            states.append(state)
+            h_in, w_in = oh, ow
+        self._planes = new_planes
+
+        latent = {1: ops.as_nchw(head), 2: ops.as_nchw(blocks[0]), 4: ops.as_nchw(blocks[1]),
+                  8: ops.as_nchw(blocks[2])}                                       # unet.py:172
+        if not with_image:
+            return None, states, latent
+        img = self._image_decoder(P, head, blocks, N, h_in, w_in)
+        return ops.as_nchw(img), states, latent
+
+    # ----------------------------------------------------------------- image decoder (fp32 kernels)
+    def _image_decoder(self, P, head, blocks, N, h, w):
+        ne = self.num_encoders
+        concat = self.skip_type != 'sum'
+        base = self.base_num_channels
+        cmax = base * 2 ** ne
+        x = blocks[-1]
+        t3 = ops.taps_conv(3, 1)
+        nres = self.num_residual_blocks
+        for j in range(nres):                                                      # submodules.py:157-172
+            w1, b1, w2, b2 = P['res%d' % j]
+            t, _, _, _ = ops.conv([Seg(x)], w1, b1, N, h, w, h, w, cmax, t3, act=ACT_RELU)
+            post = blocks[ne - 1] if (j == nres - 1 and not concat) else None      # skip_sum, unet.py:175
+            x, _, _, _ = ops.conv([Seg(t)], w2, b2, N, h, w, h, w, cmax, t3, act=ACT_RELU, res_pre=x, res_post=post)
+        for i in range(ne):                                                        # unet.py:175-176
+            wd, bd, cout = P['dec%d' % i]
+            skip_next = blocks[ne - i - 2] if i < ne - 1 else head
+            post = None if concat else skip_next
+            segs = [Seg(x)] + ([Seg(blocks[ne - i - 1])] if concat else [])
+            if self.use_upsample_conv:                                             # submodules.py:83-93
+                if concat:
+                    raise NotImplementedError('skip_type=concat with UpsampleConvLayer')
+                xu = ops.bilinear_up2(x)
+                x, _, _, _ = ops.conv([Seg(xu)], wd, bd, N, 2 * h, 2 * w, 2 * h, 2 * w, cout, ops.taps_conv(5, 2),
+                                      act=ACT_RELU, res_post=post)
+            else:                                                                  # submodules.py:53-62
+                out = torch.empty((N, 2 * h, 2 * w, cout), device=x.device, dtype=torch.float32)
+                for py in range(2):
+                    for px in range(2):
+                        ops.conv(segs, wd, bd, N, h, w, h, w, cout, ops.taps_convT_phase(py, px), act=ACT_RELU,
+                                 out=out, out_place=(2 * h, 2 * w, 2, py, 2, px), res_post=post)
+                x = out
+            h, w = 2 * h, 2 * w
+        wp, bp = P['pred']
+        segs = [Seg(x)] + ([Seg(head)] if concat else [])
+        img, _, _, _ = ops.conv(segs, wp, bp, N, h, w, h, w, 1, ops.taps_conv(1, 0), act=ACT_SIGMOID)  # unet.py:179
+        return img
+
+    # -------------------------------------------------------------------------- tcgen05 launches
+    def _enc_conv_tc(self, e, in_planes, N, h_in, w_in, cout, out_hi, out_lo, passes):
+        """conv5x5 stride 2 pad 2 + folded BN + ReLU (submodules.py:107,111) through parity views."""
+        tcw = e['tc']
+        hi, lo = in_planes
+        d = ConvTc()
+        oh, ow = h_in // 2, w_in // 2
+        taps = []
+        if tcw['fold']:
+            for py in range(2):
+                ops.parity_view(d.views[py], hi, lo, py, 0, fold_x=True)
+            d.n_views = 2
+            for ky in range(5):
+                for j in range(3):
+                    taps.append(((ky - 2) // 2, j - 1, ky % 2, ky * 3 + j))
+            cin_eff = 64
+        else:
+            for py in range(2):
+                for px in range(2):
+                    ops.parity_view(d.views[py * 2 + px], hi, lo, py, px)
+            d.n_views = 4
+            for ky in range(5):
+                for kx in range(5):
+                    taps.append(((ky - 2) // 2, (kx - 2) // 2, (ky % 2) * 2 + (kx % 2), ky * 5 + kx))
+            cin_eff = hi.shape[-1]
+        d.nseg = 1
+        d.seg_C[0], d.seg_view0[0], d.seg_koff[0] = cin_eff, 0, 0
+        d.k_per_tap, d.n_w_taps, d.w_rows = tcw['k_per_tap'], tcw['T'], tcw['hi'].shape[0]
+        d.w_hi, d.w_lo, d.bias = ops._p(tcw['hi']), ops._p(tcw['lo']), ops._p(e['bias'])
+        d.N, d.OH, d.OW, d.Cout = N, oh, ow, cout
+        d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = oh, ow, 1, 0, 1, 0
+        d.out_hi, d.out_lo, d.ld_planes = ops._p(out_hi), ops._p(out_lo), cout
+        d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, ACT_RELU, passes, ops.pick_bw_log2(ow, oh)
+        d.ntaps = len(taps)
+        for t, (dy, dx, v, wi) in enumerate(taps):
+            d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, v, wi
+        ops.conv_tc(d)
+
+    def _lstm_tc(self, e, x_planes, h_planes, c_prev, N, oh, ow, C, passes):
+        """Fused ConvLSTM cell (submodules.py:190-230): gates GEMM + sigma/tanh + state update."""
+        tcw = e['lstm_tc']
+        d = ConvTc()
+        ops.dense_view(d.views[0], x_planes[0], x_planes[1])
+        d.n_views, d.nseg = 1, 1
+        d.seg_C[0], d.seg_view0[0], d.seg_koff[0] = C, 0, 0
+        if h_planes is not None:
+            ops.dense_view(d.views[1], h_planes[0], h_planes[1])
+            d.n_views, d.nseg = 2, 2
+            d.seg_C[1], d.seg_view0[1], d.seg_koff[1] = C, 1, C
+        d.k_per_tap, d.n_w_taps, d.w_rows = tcw['k_per_tap'], 9, tcw['hi'].shape[0]
+        d.w_hi, d.w_lo, d.bias = ops._p(tcw['hi']), ops._p(tcw['lo']), ops._p(e['lstm_b'])
+        dev = x_planes[0].device
+        h = torch.empty((N, oh, ow, C), device=dev, dtype=torch.float32)
+        c = torch.empty_like(h)
+        hh = torch.empty((N, oh, ow, C), device=dev, dtype=torch.bfloat16)
+        hl = torch.empty_like(hh)
+        d.aux0, d.out, d.out2 = ops._p(c_prev), ops._p(h), ops._p(c)
+        d.out_hi, d.out_lo, d.ld_planes = ops._p(hh), ops._p(hl), C
+        d.N, d.OH, d.OW, d.Cout = N, oh, ow, 4 * C
+        d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = oh, ow, 1, 0, 1, 0
+        d.ldo = C
+        d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LSTM, ACT_NONE, passes, ops.pick_bw_log2(ow, oh)
+        taps = ops.taps_conv(3, 1)
+        d.ntaps = len(taps)
+        for t, (dy, dx, wi) in enumerate(taps):
+            d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, 0, wi
+        ops.conv_tc(d)
+        return h, c, hh, hl

@@ -1,0 +1,374 @@
+"""Thin tensor-level wrappers over the C ABI (libess_b200.so).
+
+Activations are "pixel-major" NHWC fp32 tensors of shape [N, H, W, C] (contiguous).  PyTorch is used
+only to own device memory and streams; every arithmetic op on the hot path is a call into the
+library.  Nothing here falls back to torch ops: a missing library or a failing call raises.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, EPI_GRU_OUT, EPI_GRU_UR, EPI_LINEAR, EPI_LSTM, Conv, ConvTc,
+                   Src, TcView, Wgrad, call)
+
+IN_EPS = 1e-5
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, offset_elems=0):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr() + offset_elems * t.element_size())
+
+
+def require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('ess_b200 runs on CUDA (sm_100a) only; got a %s tensor -- there is no CPU '
+                               'fallback' % t.device)
+
+
+@dataclass
+class Seg:
+    """One input channel segment of a convolution (see essb_src in include/ess_b200.h)."""
+    t: torch.Tensor                 # [N, Hs, Ws, ld] fp32 NHWC (Hs = H >> ups)
+    C: Optional[int] = None         # channels used (default: all)
+    c_off: int = 0                  # first channel inside t
+    ups: int = 0
+    mean: Optional[torch.Tensor] = None   # [N, C]
+    rstd: Optional[torch.Tensor] = None
+    relu: bool = False
+
+    def fill(self, s: Src):
+        c = self.C if self.C is not None else self.t.shape[-1] - self.c_off
+        s.ptr = _p(self.t, self.c_off)
+        s.mean = _p(self.mean)
+        s.rstd = _p(self.rstd)
+        s.ld = self.t.shape[-1]
+        s.C = c
+        s.ups = self.ups
+        s.relu = 1 if self.relu else 0
+        return c
+
+
+def taps_conv(k, pad):
+    """(dy, dx, widx) of a k x k convolution with zero padding `pad` (weights in [.., ky, kx] order)."""
+    return [(ky - pad, kx - pad, ky * k + kx) for ky in range(k) for kx in range(k)]
+
+
+def taps_convT_phase(py, px, k=5, pad=2):
+    """Taps of output phase (py, px) of ConvTranspose2d(k, stride 2, pad, output_padding 1):
+    oy = 2*iy - pad + ky  =>  for oy = 2*oy' + py: ky = py + pad (mod 2), iy = oy' + (py + pad - ky)/2."""
+    out = []
+    for ky in range(k):
+        if (py + pad - ky) % 2:
+            continue
+        for kx in range(k):
+            if (px + pad - kx) % 2:
+                continue
+            out.append(((py + pad - ky) // 2, (px + pad - kx) // 2, ky * k + kx))
+    return out
+
+
+def _fill_taps(d, taps, with_widx=True):
+    d.ntaps = len(taps)
+    for i, tp in enumerate(taps):
+        d.dy[i], d.dx[i] = tp[0], tp[1]
+        if with_widx:
+            d.widx[i] = tp[2]
+
+
+def pack_weight(w, scale=None, transposed_layout=False, swap_io=False, flip=False, interleave=1):
+    """Reference-layout conv weight -> packed fp32 [T][Kin][NoutP] (essb_pack_weight)."""
+    require_cuda(w)
+    w = w.detach().contiguous().float()
+    if transposed_layout:
+        cin, cout = w.shape[0], w.shape[1]
+    else:
+        cout, cin = w.shape[0], w.shape[1]
+    T = w.shape[2] * w.shape[3]
+    kin, nout = (cout, cin) if swap_io else (cin, cout)
+    out = torch.empty((T, kin, (nout + 3) // 4 * 4), device=w.device, dtype=torch.float32)
+    call('essb_pack_weight', _p(w), _p(scale), _p(out), cout, cin, T, int(transposed_layout), int(swap_io),
+         int(flip), int(interleave), _stream())
+    return out
+
+
+def conv(segs: Sequence[Seg], w_packed, bias, N, H, W, OH, OW, Cout, taps, stride=1, epilogue=EPI_LINEAR,
+         act=ACT_NONE, out=None, out2=None, res_pre=None, res_post=None, aux0=None, aux1=None, want_stats=False,
+         out_place: Optional[Tuple[int, int, int, int, int, int]] = None, accumulate=False, planes=None):
+    """essb_conv_fp32.  Returns (out, out2, stats_partial, tiles)."""
+    d = Conv()
+    segs[0].fill(d.src[0])
+    if len(segs) > 1:
+        segs[1].fill(d.src[1])
+    dev = segs[0].t.device
+    d.w, d.bias = _p(w_packed), _p(bias)
+    d.N, d.H, d.W, d.OH, d.OW, d.Cout = N, H, W, OH, OW, Cout
+    d.sy = d.sx = stride
+    if out_place is None:
+        d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = OH, OW, 1, 0, 1, 0
+    else:
+        d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = out_place
+    if epilogue == EPI_LINEAR:
+        if out is None:
+            out = torch.empty((N, d.OHf, d.OWf, Cout), device=dev, dtype=torch.float32)
+        d.ldo = out.shape[-1]
+    else:
+        hidden = {EPI_LSTM: Cout // 4, EPI_GRU_UR: Cout // 2, EPI_GRU_OUT: Cout}[epilogue]
+        if out is None:
+            out = torch.empty((N, OH, OW, hidden), device=dev, dtype=torch.float32)
+        if out2 is None and epilogue in (EPI_LSTM, EPI_GRU_UR):
+            out2 = torch.empty((N, OH, OW, hidden), device=dev, dtype=torch.float32)
+        d.ldo = hidden
+    d.out, d.out2 = _p(out), _p(out2)
+    d.res_pre, d.res_post = _p(res_pre), _p(res_post)
+    r = res_pre if res_pre is not None else res_post
+    d.ld_res = r.shape[-1] if r is not None else 0
+    d.aux0, d.aux1 = _p(aux0), _p(aux1)
+    d.accumulate = int(accumulate)
+    d.epilogue, d.act = epilogue, act
+    _fill_taps(d, taps)
+    stats = None
+    tiles = _lib.lib().essb_conv_tiles_per_sample(C.byref(d))
+    if want_stats:
+        stats = torch.empty((N, tiles, Cout, 2), device=dev, dtype=torch.float32)
+        d.stats_partial = _p(stats)
+    if planes is not None:
+        d.out_hi, d.out_lo, d.ld_planes = _p(planes[0]), _p(planes[1]), planes[0].shape[-1]
+    call('essb_conv_fp32', C.byref(d), _stream())
+    return out, out2, stats, tiles
+
+
+def in_finalize(stats_partial, count):
+    N, tiles, Cc, _ = stats_partial.shape
+    mean = torch.empty((N, Cc), device=stats_partial.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    call('essb_in_finalize', _p(stats_partial), N, tiles, Cc, count, IN_EPS, _p(mean), _p(rstd), _stream())
+    return mean, rstd
+
+
+def norm_act_add(y, mean=None, rstd=None, relu=False, res=None, out=None, c_off=0, C_=None):
+    """out = act((y - mean) * rstd) + res over [N, H, W, C]."""
+    N, H, W = y.shape[:3]
+    Cc = C_ if C_ is not None else y.shape[-1] - c_off
+    if out is None:
+        out = torch.empty((N, H, W, Cc), device=y.device, dtype=torch.float32)
+    call('essb_norm_act_add', _p(y, c_off), y.shape[-1], _p(mean), _p(rstd), int(relu), _p(res),
+         res.shape[-1] if res is not None else 0, _p(out), out.shape[-1], N, H * W, Cc, _stream())
+    return out
+
+
+def in_backward(dA, y, mean, rstd, relu, ups=0, c_off=0, extra=None):
+    """Gradient w.r.t. y of  A = [upsample2]( relu?( (y-mean)*rstd ) )  given dA (channel slice
+    [c_off, c_off+C) of dA's last dim).  y: [N, H, W, C]."""
+    N, H, W, Cc = y.shape
+    dev = y.device
+    blocks = _lib.lib().essb_in_bwd_blocks(H * W)
+    g = torch.empty((N, H, W, Cc), device=dev, dtype=torch.float32)
+    partial = torch.empty((N, blocks, Cc, 2), device=dev, dtype=torch.float32)
+    call('essb_in_bwd_pass1', _p(dA, c_off), dA.shape[-1], ups, _p(extra), extra.shape[-1] if extra is not None else 0,
+         _p(y), Cc, _p(mean), _p(rstd), int(relu), _p(g), _p(partial), N, H, W, Cc, _stream())
+    totals = torch.empty((N, Cc, 2), device=dev, dtype=torch.float32)
+    call('essb_partial_reduce', _p(partial), N, blocks, Cc, _p(totals), _stream())
+    dy = torch.empty_like(g)
+    call('essb_in_bwd_pass2', _p(g), _p(y), Cc, _p(mean), _p(rstd), _p(totals), _p(dy), N, H * W, Cc, _stream())
+    return dy
+
+
+def upsample2_bwd(dA, H, W, Cc, c_off=0, out=None, accumulate=False):
+    """Sum of the 2x2 children: dA [N, 2H, 2W, ld] (channel slice) -> [N, H, W, C]."""
+    N = dA.shape[0]
+    if out is None:
+        out = torch.empty((N, H, W, Cc), device=dA.device, dtype=torch.float32)
+        accumulate = False
+    call('essb_upsample2_bwd', _p(dA, c_off), dA.shape[-1], _p(out), out.shape[-1], N, H, W, Cc, int(accumulate),
+         _stream())
+    return out
+
+
+def wgrad(segs: Sequence[Seg], dy, N, H, W, OH, OW, Cout, taps, stride=1, want_bias=True):
+    """essb_wgrad_fp32 -> (dW [Cout, Cin_total, ntaps], dbias [Cout] | None)."""
+    d = Wgrad()
+    cin = segs[0].fill(d.src[0])
+    if len(segs) > 1:
+        cin += segs[1].fill(d.src[1])
+    dev = dy.device
+    d.dy_ptr = _p(dy)
+    d.N, d.H, d.W, d.OH, d.OW, d.Cout, d.ld_dy = N, H, W, OH, OW, Cout, dy.shape[-1]
+    d.sy = d.sx = stride
+    _fill_taps(d, taps, with_widx=False)
+    dw = torch.empty((Cout, cin, len(taps)), device=dev, dtype=torch.float32)
+    db = torch.empty((Cout,), device=dev, dtype=torch.float32) if want_bias else None
+    d.dw, d.dbias = _p(dw), _p(db)
+    nbytes = _lib.lib().essb_wgrad_workspace_bytes(C.byref(d))
+    if nbytes < 0:
+        raise RuntimeError('essb_wgrad_workspace_bytes: unsupported segment layout')
+    nbytes = max(int(nbytes), 4 * 1024 * Cout)
+    ws = torch.empty((nbytes // 4 + 4,), device=dev, dtype=torch.float32)
+    d.workspace, d.workspace_bytes = _p(ws), ws.numel() * 4
+    call('essb_wgrad_fp32', C.byref(d), _stream())
+    return dw, db
+
+
+# ----------------------------------------------------------------------------- event pre-processing
+def event_stats(data, T, Cw):
+    """data [B, T*Cw, H, W] (contiguous per sample) -> stats [T, 3] double (sum, sumsq, nnz)."""
+    B, _, H, W = data.shape
+    if data.stride(1) != H * W or data.stride(2) != W or data.stride(3) != 1:
+        raise RuntimeError('event tensor must be contiguous within each sample')
+    stats = torch.empty((T, 3), device=data.device, dtype=torch.float64)
+    call('essb_event_stats', _p(data), data.stride(0), B, T, Cw * H * W, _p(stats), _stream())
+    return stats
+
+
+def event_prepare(window, stats_row, normalize, Hp, Wp, pad_top, pad_left, ld_out, out=None):
+    """window: [B, C, H, W] view (per-sample contiguous) -> NHWC [B, Hp, Wp, ld_out] normalised+padded."""
+    B, Cw, H, W = window.shape
+    if window.stride(1) != H * W or window.stride(2) != W or window.stride(3) != 1:
+        raise RuntimeError('event window must be contiguous within each sample')
+    if out is None:
+        out = torch.empty((B, Hp, Wp, ld_out), device=window.device, dtype=torch.float32)
+    call('essb_event_prepare', _p(window), window.stride(0), _p(stats_row), int(normalize), _p(out), ld_out, B, Cw, H,
+         W, Hp, Wp, pad_top, pad_left, _stream())
+    return out
+
+
+def nchw_to_nhwc(x, ld_out=None):
+    """[N, C, H, W] (any strides) -> pixel-major [N, H, W, ld]; zero-copy for channels_last inputs."""
+    N, Cc, H, W = x.shape
+    x = x.float()
+    v = x.permute(0, 2, 3, 1)
+    if (ld_out is None or ld_out == Cc) and v.is_contiguous():
+        return v
+    x = x.contiguous()
+    ld = ld_out or Cc
+    out = (torch.zeros if ld != Cc else torch.empty)((N, H, W, ld), device=x.device, dtype=torch.float32)
+    call('essb_nchw_to_nhwc', _p(x), _p(out), ld, N, Cc, H * W, _stream())
+    return out
+
+
+def as_nchw(t):
+    """Pixel-major [N, H, W, C] buffer -> logical NCHW view (channels_last strides, zero copy)."""
+    return t.permute(0, 3, 1, 2)
+
+
+def bilinear_up2(x):
+    N, H, W, Cc = x.shape
+    out = torch.empty((N, 2 * H, 2 * W, Cc), device=x.device, dtype=torch.float32)
+    call('essb_bilinear_up2', _p(x), _p(out), N, H, W, Cc, _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------- task loss
+def task_loss_sums(logits, target, K, ignore_index):
+    """logits pixel-major [N, H, W, ld>=K]; target int64 [N, H, W] -> sums [2 + 3K] double."""
+    npix = target.numel()
+    sums = torch.empty((2 + 3 * K,), device=logits.device, dtype=torch.float64)
+    call('essb_task_loss_fwd', _p(logits), logits.shape[-1], _p(target), npix, K, ignore_index, _p(sums), _stream())
+    return sums
+
+
+def task_loss_finish(sums, K, ignore_index, use_dice, use_ce):
+    loss = torch.empty((1,), device=sums.device, dtype=torch.float32)
+    call('essb_task_loss_finish', _p(sums), K, ignore_index, int(use_dice), int(use_ce), _p(loss), _stream())
+    return loss
+
+
+def task_loss_bwd(logits, target, K, ignore_index, sums, use_dice, use_ce, gscale):
+    dl = torch.empty(tuple(logits.shape[:3]) + (K,), device=logits.device, dtype=torch.float32)
+    call('essb_task_loss_bwd', _p(logits), logits.shape[-1], _p(target), target.numel(), K, ignore_index, _p(sums),
+         int(use_dice), int(use_ce), _p(gscale), _p(dl), K, _stream())
+    return dl
+
+
+def confusion_labels(pred, target, K, ignore_index, conf=None):
+    if conf is None:
+        conf = torch.zeros((K, K), device=pred.device, dtype=torch.int64)
+    call('essb_confusion_labels', _p(pred), _p(target), target.numel(), K, ignore_index, _p(conf), _stream())
+    return conf
+
+
+def confusion_logits(logits, target, K, ignore_index, conf=None):
+    if conf is None:
+        conf = torch.zeros((K, K), device=logits.device, dtype=torch.int64)
+    call('essb_confusion', _p(logits), logits.shape[-1], _p(target), target.numel(), K, ignore_index, _p(conf),
+         _stream())
+    return conf
+
+
+# --------------------------------------------------------------------------- tensor-core path helpers
+def split_bf16(seg: Seg, N, H, W, hi=None, lo=None, c_off=0, ld_out=None):
+    """fp32 (optionally normalised / ReLU'd / upsampled) -> bf16 hi/lo planes [N, H, W, ld_out]."""
+    s = Src()
+    c = seg.fill(s)
+    if hi is None:
+        ld_out = ld_out or c
+        hi = torch.empty((N, H, W, ld_out), device=seg.t.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi)
+    call('essb_split_bf16', C.byref(s), N, H, W, _p(hi), _p(lo), hi.shape[-1], c_off, _stream())
+    return hi, lo
+
+
+def pack_weight_tc(w, scale=None, transposed_layout=False, swap_io=False, flip=False, interleave=1, kin_pad=None,
+                   nout_pad=None):
+    """Reference-layout conv weight -> K-major bf16 hi/lo [NoutP][T*KinP] (essb_pack_weight_tc)."""
+    w = w.detach().contiguous().float()
+    if transposed_layout:
+        cin, cout = w.shape[0], w.shape[1]
+    else:
+        cout, cin = w.shape[0], w.shape[1]
+    T = w.shape[2] * w.shape[3]
+    kin, nout = (cout, cin) if swap_io else (cin, cout)
+    kinp = kin_pad or (kin + 63) // 64 * 64
+    noutp = nout_pad or nout
+    hi = torch.empty((noutp, T * kinp), device=w.device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    call('essb_pack_weight_tc', _p(w), _p(scale), _p(hi), _p(lo), cout, cin, T, int(transposed_layout), int(swap_io),
+         int(flip), int(interleave), kinp, noutp, _stream())
+    return hi, lo, kinp
+
+
+def dense_view(v: TcView, hi, lo, c_off=0, C_=None):
+    """TMA view of dense NHWC bf16 planes [N, H, W, ld]."""
+    N, H, W, ld = hi.shape
+    v.hi, v.lo = _p(hi, c_off), _p(lo, c_off)
+    v.stride_x, v.stride_y, v.stride_n = ld, W * ld, H * W * ld
+    v.C, v.W, v.H = (C_ if C_ is not None else ld - c_off), W, H
+
+
+def parity_view(v: TcView, hi, lo, py, px, fold_x=False):
+    """View of the (py, px) parity plane of NHWC planes [N, H, W, ld] for stride-2 convolutions.
+    fold_x: treat horizontal pixel pairs as one 2*ld-channel super-pixel (for ld = 32)."""
+    N, H, W, ld = hi.shape
+    if fold_x:
+        off = py * W * ld
+        v.hi, v.lo = _p(hi, off), _p(lo, off)
+        v.stride_x, v.stride_y, v.stride_n = 2 * ld, 2 * W * ld, H * W * ld
+        v.C, v.W, v.H = 2 * ld, W // 2, H // 2
+    else:
+        off = (py * W + px) * ld
+        v.hi, v.lo = _p(hi, off), _p(lo, off)
+        v.stride_x, v.stride_y, v.stride_n = 2 * ld, 2 * W * ld, H * W * ld
+        v.C, v.W, v.H = ld, W // 2, H // 2
+
+
+def pick_bw_log2(OW, OH):
+    """Spatial tile BW x (128/BW) (BW a power of two) minimising the padded pixel count."""
+    best, best_waste = 4, None
+    for b in (4, 3, 5, 6, 2):
+        bw, bh = 1 << b, 128 >> b
+        waste = ((OW + bw - 1) // bw * bw) * ((OH + bh - 1) // bh * bh) / float(OW * OH)
+        if best_waste is None or waste < best_waste - 1e-9:
+            best, best_waste = b, waste
+    return best
+
+
+def conv_tc(d: ConvTc):
+    call('essb_conv_tc_run', C.byref(d), _stream())

@@ -1,0 +1,105 @@
+"""`ImageReconstructor` equivalent (reference: e2vid/image_reconstructor.py:18-163, default options)
+and the fused T-window unroll.
+
+`update_reconstruction(event_tensor) -> (img, states, latent)` keeps the reference's per-window
+contract (normalise non-zeros over the whole batch tensor -> reflect-pad to a multiple of
+2^num_encoders -> model -> carry states in `last_states_for_each_channel['grayscale']`), all under
+no_grad.  Unlike the reference there is no host synchronisation: the `if num_nonzeros > 0` test
+(e2vid/utils/inference_utils.py:100) is a device-side select and the CudaTimer syncs are gone.
+
+`unroll(data, T, C)` is the fused form of the trainer loop (training/ess_supervised_trainer.py:126-130):
+statistics of all T windows in ONE launch, then T encoder steps, with the E2VID image decoder run on
+the last window only (the trainers overwrite `img_fake` every iteration) -- contract B of SURVEY.md s8d.
+`stats_reduce_fn` lets a data-parallel caller all-reduce the [T,3] statistics (global-batch semantics).
+"""
+import math
+
+import torch
+
+from . import ops
+
+
+def crop_padding(height, width, num_encoders):
+    """CropParameters.__init__ (e2vid/utils/inference_utils.py:311-330): (left, right, top, bottom)."""
+    f = 2 ** num_encoders
+    hc, wc = int(f * math.ceil(height / f)), int(f * math.ceil(width / f))
+    return (math.ceil(0.5 * (wc - width)), math.floor(0.5 * (wc - width)),
+            math.ceil(0.5 * (hc - height)), math.floor(0.5 * (hc - height)))
+
+
+class ImageReconstructor:
+    def __init__(self, model, height, width, num_bins, device=None, options=None, augmentation=False,
+                 standardization=False):
+        if augmentation:
+            raise NotImplementedError('augmentation=True is a CPU/PIL path in the reference; not on the hot path')
+        self.model = model
+        self.device = device
+        self.height, self.width, self.num_bins = height, width, num_bins
+        self.standardization = standardization
+        self.no_recurrent = bool(getattr(options, 'no_recurrent', False))
+        self.no_normalize = bool(getattr(options, 'no_normalize', False))
+        if getattr(options, 'flip', False) or getattr(options, 'hot_pixels_file', None) or \
+                getattr(options, 'color', False):
+            raise NotImplementedError('flip / hot_pixels_file / color options are not built')
+        self.last_states_for_each_channel = {'grayscale': None}
+        self.stats_reduce_fn = None
+
+    def _prepare(self, window, stats_row):
+        B, C, H, W = window.shape
+        left, right, top, bottom = crop_padding(H, W, self.model.num_encoders)
+        cpad = (C + 7) // 8 * 8
+        return ops.event_prepare(window, stats_row, not self.no_normalize, H + top + bottom, W + left + right, top,
+                                 left, cpad)
+
+    @staticmethod
+    def _per_sample_contiguous(t):
+        B, C, H, W = t.shape
+        if t.stride(1) == H * W and t.stride(2) == W and t.stride(3) == 1:
+            return t
+        return t.contiguous()
+
+    def update_reconstruction(self, event_tensor, event_tensor_id=None, stamp=None, with_image=True):
+        with torch.no_grad():
+            ev = event_tensor if event_tensor.is_cuda else event_tensor.to(self.device)
+            ops.require_cuda(ev)
+            ev = self._per_sample_contiguous(ev.float())
+            B, C, H, W = ev.shape
+            stats = None
+            if not self.no_normalize:
+                stats = ops.event_stats(ev, 1, C)
+                if self.stats_reduce_fn is not None:
+                    stats = self.stats_reduce_fn(stats)
+            x = self._prepare(ev, stats)
+            img, states, latent = self.model.forward_nhwc(x, self.last_states_for_each_channel['grayscale'],
+                                                          with_image=with_image)
+            self.last_states_for_each_channel['grayscale'] = None if self.no_recurrent else states
+            if self.standardization and img is not None:                 # image_reconstructor.py:129-134
+                b, h, w = img.size(0), img.size(2), img.size(3)
+                out = img.reshape(b, -1)
+                out = out - out.min(1, keepdim=True)[0]
+                out = out / out.max(1, keepdim=True)[0]
+                img = out.view(b, 1, h, w)
+        return img, states, latent
+
+    def unroll(self, data, num_windows, channels, image_on_last_only=True):
+        """data [B, T*C, H, W] -> (img, states, latent) of the last window; resets the state first."""
+        with torch.no_grad():
+            ops.require_cuda(data)
+            data = self._per_sample_contiguous(data.float())
+            self.last_states_for_each_channel = {'grayscale': None}
+            stats = None
+            if not self.no_normalize:
+                stats = ops.event_stats(data, num_windows, channels)
+                if self.stats_reduce_fn is not None:
+                    stats = self.stats_reduce_fn(stats)
+            states = None
+            img = latent = None
+            for i in range(num_windows):
+                win = data[:, i * channels:(i + 1) * channels]
+                x = self._prepare(win, stats[i] if stats is not None else None)
+                need_img = (i == num_windows - 1) or not image_on_last_only
+                img, states, latent = self.model.forward_nhwc(x, states, with_image=need_img)
+                if self.no_recurrent:
+                    states = None
+            self.last_states_for_each_channel['grayscale'] = states
+        return img, states, latent

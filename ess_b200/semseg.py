@@ -1,0 +1,312 @@
+"""Drop-in `SemSegE2VID` segmentation decoder (reference: models/style_networks.py:9-107) with a
+hand-scheduled forward AND backward on libess_b200.so kernels.
+
+Same constructor arguments, `forward(input_dict{1,2,4,8}) -> dict{8,4,2,1}`, parameter names
+(`decoder_scale_1.{0-4}.model.{0,3}.*`, `decoder_scale_1.5.model.0.*`, ... `decoder_scale_5.0.*`) and
+initialisation (N(0, 0.02) conv weights inside the IN blocks, style_networks.py:152-155) as the
+reference, so `utils/saver.py` checkpoints round-trip.
+
+Execution model: the decoder is a static list of nodes (a tiny graph executor instead of autograd
+tracing): `conv` nodes run the implicit-GEMM kernel whose loader applies InstanceNorm + ReLU +
+nearest x2 upsampling + channel concat on the fly and whose epilogue emits per-(n,c) sum / sumsq
+partials for the NEXT InstanceNorm; `mat` nodes materialise an IN(+ReLU)(+residual) result where the
+graph needs it as a tensor (INSResBlock outputs, the returned out[4] / out[2]).  The backward walks the
+same list in reverse: dgrad = the same gather kernel with mirrored taps and transposed weights
+(per input segment, skipped for segments that need no gradient), wgrad = split-K implicit GEMM,
+InstanceNorm/ReLU/upsample backward = two memory-bound passes.  One torch.autograd.Function wraps
+the whole decoder and honours `requires_grad` on every parameter and input individually
+(training/ess_trainer.py:133-137 freezes the parameters but still needs input gradients).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import ACT_NONE, EPI_LINEAR
+from .ops import Seg
+
+
+# --------------------------------------------------------------------------------- parameter holders
+class _ReLUINSConv2d(nn.Module):      # style_networks.py:158-169
+    def __init__(self, n_in, n_out):
+        super().__init__()
+        self.model = nn.Sequential(nn.Conv2d(n_in, n_out, 3, 1, 1, bias=True), nn.Identity(), nn.Identity())
+        self.model[0].weight.data.normal_(0.0, 0.02)
+
+
+class _INSResBlock(nn.Module):        # style_networks.py:172-193
+    def __init__(self, c):
+        super().__init__()
+        self.model = nn.Sequential(nn.Conv2d(c, c, 3, 1, 1), nn.Identity(), nn.Identity(), nn.Conv2d(c, c, 3, 1, 1),
+                                   nn.Identity())
+        self.model[0].weight.data.normal_(0.0, 0.02)
+        self.model[3].weight.data.normal_(0.0, 0.02)
+
+
+class _Conv(object):
+    __slots__ = ('out', 'srcs', 'w', 'b', 'cout', 'k', 'stats')
+
+    def __init__(self, out, srcs, w, b, cout, k, stats):
+        self.out, self.srcs, self.w, self.b, self.cout, self.k, self.stats = out, srcs, w, b, cout, k, stats
+
+
+class _Mat(object):
+    __slots__ = ('out', 'src', 'relu', 'res')
+
+    def __init__(self, out, src, relu, res):
+        self.out, self.src, self.relu, self.res = out, src, relu, res
+
+
+class SemSegE2VID(nn.Module):
+    def __init__(self, input_c, output_c, skip_connect=False, skip_type='sum', input_index_map=False):
+        super().__init__()
+        self.skip_connect = skip_connect
+        self.skip_type = skip_type
+        self.input_index_map = input_index_map
+        self.index_coords = None
+        self.input_c, self.output_c = input_c, output_c
+        tch = input_c
+        if skip_connect:
+            if skip_type != 'concat':
+                # style_networks.py:77-79: skip_sum keeps tch//2 channels but decoder_scale_2 expects tch
+                raise NotImplementedError("SemSegE2VID(skip_connect=True) is only shape-consistent with "
+                                          "skip_type='concat' (as in the reference)")
+            self.decoder_scale_1 = nn.Sequential(*([_INSResBlock(tch) for _ in range(5)] +
+                                                   [_ReLUINSConv2d(tch, tch // 2)]))
+            self.decoder_scale_2 = nn.Sequential(_ReLUINSConv2d(tch, tch // 2), _ReLUINSConv2d(tch // 2, tch // 4))
+            tch //= 2
+            self.decoder_scale_3 = nn.Sequential(_ReLUINSConv2d(tch, tch // 2), _ReLUINSConv2d(tch // 2, tch // 2))
+            tch //= 2
+            self.decoder_scale_4 = nn.Sequential(_ReLUINSConv2d(tch, tch // 2))
+            tch //= 2
+        else:
+            if input_index_map:
+                raise NotImplementedError('SemSegE2VID(input_index_map=True): the coordinate channels make C '
+                                          'not a multiple of 4; not built (unused by the reference YAMLs)')
+            self.decoder_scale_1 = nn.Sequential(*[_INSResBlock(tch) for _ in range(3)])
+            self.decoder_scale_2 = nn.Sequential(nn.Identity(), _ReLUINSConv2d(tch, tch // 2))
+            tch //= 2
+            self.decoder_scale_3 = nn.Sequential(nn.Identity(), _ReLUINSConv2d(tch, tch // 2))
+            tch //= 2
+            self.decoder_scale_4 = nn.Sequential(nn.Identity(), _ReLUINSConv2d(tch, tch // 2))
+            tch //= 2
+        self.decoder_scale_5 = nn.Sequential(nn.Conv2d(tch, output_c, 1, 1, 0))
+        self._build_program()
+
+    # ------------------------------------------------------------------------------- static graph
+    def _build_program(self):
+        """Tensor ids: 0 = input[8], 1 = input[4], 2 = input[2]; the rest are produced by nodes."""
+        nodes, outs = [], []
+        nid = [3]
+
+        def new():
+            nid[0] += 1
+            return nid[0] - 1
+
+        def conv(srcs, prefix, cout, k=3, stats=True):
+            o = new()
+            nodes.append(_Conv(o, srcs, prefix + '.weight', prefix + '.bias', cout, k, stats))
+            return o
+
+        def mat(src, relu, res=None):
+            o = new()
+            nodes.append(_Mat(o, src, relu, res))
+            return o
+
+        c = self.input_c
+        x = 0
+        nres = 5 if self.skip_connect else 3
+        for b in range(nres):                                            # INSResBlock
+            y1 = conv([(x, 'raw', 0)], 'decoder_scale_1.%d.model.0' % b, c)
+            y2 = conv([(y1, 'nr', 0)], 'decoder_scale_1.%d.model.3' % b, c)
+            x = mat(y2, False, x)
+        if self.skip_connect:
+            y = conv([(x, 'raw', 0)], 'decoder_scale_1.5.model.0', c // 2)
+            y = conv([(y, 'nr', 1), (1, 'raw', 0)], 'decoder_scale_2.0.model.0', c // 2)
+            y = conv([(y, 'nr', 0)], 'decoder_scale_2.1.model.0', c // 4)
+            o4 = mat(y, True)
+            outs.append(o4)
+            y = conv([(o4, 'raw', 1), (2, 'raw', 0)], 'decoder_scale_3.0.model.0', c // 4)
+            y = conv([(y, 'nr', 0)], 'decoder_scale_3.1.model.0', c // 4)
+            o2 = mat(y, True)
+            outs.append(o2)
+            y = conv([(o2, 'raw', 1)], 'decoder_scale_4.0.model.0', c // 8)
+            o1 = conv([(y, 'nr', 0)], 'decoder_scale_5.0', self.output_c, k=1, stats=False)
+            outs.append(o1)
+        else:
+            y = conv([(x, 'raw', 1)], 'decoder_scale_2.1.model.0', c // 2)
+            o4 = mat(y, True)
+            outs.append(o4)
+            y = conv([(o4, 'raw', 1)], 'decoder_scale_3.1.model.0', c // 4)
+            o2 = mat(y, True)
+            outs.append(o2)
+            y = conv([(o2, 'raw', 1)], 'decoder_scale_4.1.model.0', c // 8)
+            o1 = conv([(y, 'nr', 0)], 'decoder_scale_5.0', self.output_c, k=1, stats=False)
+            outs.append(o1)
+        self._nodes, self._outs = nodes, outs
+
+    def update_skip_dict(self, skips, x, sz_in):
+        rem, scale = sz_in % x.shape[3], sz_in // x.shape[3]
+        assert rem == 0
+        skips[scale] = x
+
+    def forward(self, input_dict):
+        sz_in = input_dict[1].shape[3]        # input_dict[1] is used for its width only (:70)
+        x8 = input_dict[8]
+        ops.require_cuda(x8)
+        names = [n for n, _ in self.named_parameters()]
+        params = [p for _, p in self.named_parameters()]
+        if self.skip_connect:
+            ins = (x8, input_dict[4], input_dict[2])
+        else:
+            ins = (x8, None, None)
+        res = _DecoderFn.apply(self, names, ins[0], ins[1], ins[2], *params)
+        out = {8: x8}
+        for t in res:
+            self.update_skip_dict(out, t, sz_in)
+        return out
+
+
+def _nhwc(t):
+    if t is None:
+        return None
+    v = t.detach().float().permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+def _taps(k):
+    return ops.taps_conv(k, k // 2)
+
+
+class _DecoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, names, x8, x4, x2, *params):
+        nodes = module._nodes
+        P = dict(zip(names, params))
+        T = {0: _nhwc(x8), 1: _nhwc(x4), 2: _nhwc(x2)}
+        S = {}
+        packed = {}
+        for nd in nodes:
+            if isinstance(nd, _Conv):
+                first = T[nd.srcs[0][0]]
+                N = first.shape[0]
+                ups0 = nd.srcs[0][2]
+                H, W = first.shape[1] << ups0, first.shape[2] << ups0
+                segs = []
+                for (sid, xf, ups) in nd.srcs:
+                    if xf == 'nr':
+                        segs.append(Seg(T[sid], ups=ups, mean=S[sid][0], rstd=S[sid][1], relu=True))
+                    else:
+                        segs.append(Seg(T[sid], ups=ups))
+                w = P[nd.w]
+                wp = ops.pack_weight(w)
+                packed[nd.out] = wp
+                y, _, st, _ = ops.conv(segs, wp, P[nd.b].detach().float().contiguous(), N, H, W, H, W, nd.cout,
+                                       _taps(nd.k), epilogue=EPI_LINEAR, act=ACT_NONE, want_stats=nd.stats)
+                T[nd.out] = y
+                if nd.stats:
+                    S[nd.out] = ops.in_finalize(st, H * W)
+            else:
+                src = T[nd.src]
+                T[nd.out] = ops.norm_act_add(src, S[nd.src][0], S[nd.src][1], relu=nd.relu,
+                                             res=T[nd.res] if nd.res is not None else None)
+        ctx.module, ctx.names = module, names
+        ctx.T, ctx.S = T, S
+        ctx.save_for_backward(*params)
+        outs = tuple(ops.as_nchw(T[o]) for o in module._outs)
+        return outs
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        module, names = ctx.module, ctx.names
+        nodes = module._nodes
+        params = ctx.saved_tensors
+        P = dict(zip(names, params))
+        T, S = ctx.T, ctx.S
+        nig = ctx.needs_input_grad          # (module, names, x8, x4, x2, *params)
+        need_in = {0: nig[2], 1: nig[3], 2: nig[4]}
+        need_p = {n: nig[5 + i] for i, n in enumerate(names)}
+
+        # which tensors carry gradient
+        need = dict(need_in)
+        for nd in nodes:
+            if isinstance(nd, _Conv):
+                need[nd.out] = need_p[nd.w] or need_p[nd.b] or any(need[s[0]] for s in nd.srcs)
+            else:
+                need[nd.out] = need[nd.src] or (nd.res is not None and need[nd.res])
+
+        G = {}   # tensor id -> [grad NHWC tensor, owned]
+
+        def add_grad(tid, g, owned):
+            if not need.get(tid, False):
+                return
+            if tid not in G:
+                G[tid] = [g, owned]
+            else:
+                cur = G[tid]
+                if not cur[1]:
+                    cur[0] = cur[0].clone()
+                    cur[1] = True
+                ops.norm_act_add(cur[0], res=g, out=cur[0])
+
+        for o, g in zip(module._outs, gouts):
+            if g is not None:
+                add_grad(o, _nhwc(g), False)
+
+        grads = {}
+        for nd in reversed(nodes):
+            if nd.out not in G:
+                continue
+            gy = G.pop(nd.out)[0]
+            if isinstance(nd, _Mat):
+                y = T[nd.src]
+                mean, rstd = S[nd.src]
+                if need[nd.src]:
+                    add_grad(nd.src, ops.in_backward(gy, y, mean, rstd, relu=nd.relu), True)
+                if nd.res is not None:
+                    add_grad(nd.res, gy, False)   # ownership not transferred: gy may alias a caller tensor
+                continue
+            first = T[nd.srcs[0][0]]
+            N = first.shape[0]
+            ups0 = nd.srcs[0][2]
+            H, W = first.shape[1] << ups0, first.shape[2] << ups0
+            w = P[nd.w]
+            taps = _taps(nd.k)
+            if need_p[nd.w] or need_p[nd.b]:
+                segs = []
+                for (sid, xf, ups) in nd.srcs:
+                    if xf == 'nr':
+                        segs.append(Seg(T[sid], ups=ups, mean=S[sid][0], rstd=S[sid][1], relu=True))
+                    else:
+                        segs.append(Seg(T[sid], ups=ups))
+                dw, db = ops.wgrad(segs, gy, N, H, W, H, W, nd.cout, taps, want_bias=need_p[nd.b])
+                if need_p[nd.w]:
+                    grads[nd.w] = dw.view(w.shape)
+                if need_p[nd.b]:
+                    grads[nd.b] = db
+            c_off = 0
+            dtaps = [(-dy, -dx, wi) for (dy, dx, wi) in taps]
+            for (sid, xf, ups) in nd.srcs:
+                src = T[sid]
+                cs = src.shape[-1]
+                if need[sid]:
+                    wseg = w.detach()[:, c_off:c_off + cs].contiguous()
+                    wp = ops.pack_weight(wseg, swap_io=True)
+                    dA, _, _, _ = ops.conv([Seg(gy)], wp, None, N, H, W, H, W, cs, dtaps)
+                    if xf == 'nr':
+                        add_grad(sid, ops.in_backward(dA, src, S[sid][0], S[sid][1], relu=True, ups=ups), True)
+                    elif ups:
+                        add_grad(sid, ops.upsample2_bwd(dA, H >> 1, W >> 1, cs), True)
+                    else:
+                        add_grad(sid, dA, True)
+                c_off += cs
+
+        def out_grad(tid, ref):
+            if tid in G and ref is not None:
+                return ops.as_nchw(G[tid][0]).to(ref.dtype)
+            return None
+
+        gx8 = out_grad(0, None if not nig[2] else T[0])
+        gx4 = out_grad(1, None if not nig[3] else T[1])
+        gx2 = out_grad(2, None if not nig[4] else T[2])
+        gparams = tuple(grads.get(n) for n in names)
+        return (None, None, gx8, gx4, gx2) + gparams

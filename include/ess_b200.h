@@ -1,0 +1,276 @@
+/* ess_b200 -- C ABI of the B200-native (sm_100a) kernels behind the ESS hot path.
+ *
+ * The reference (uzh-rpg/ess) has no FFI layer: every op below replaces an ATen/cuDNN library call
+ * reached from a reference nn.Module.  Each entry point cites the reference call site it replaces
+ * (paths relative to the reference root).  Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller
+ *     (PyTorch's caching allocator); the library never allocates, frees or retains device memory;
+ *   - asynchronous on the given `stream` (a cudaStream_t passed as void*), never synchronises;
+ *   - returns 0 on success, a negative essb_status otherwise; essb_last_error() gives a
+ *     thread-local message.  No exceptions cross the boundary; no exit();
+ *   - activations are fp32 NHWC ("pixel-major"): element (n, y, x, c) at ((n*H + y)*W + x)*ld + c
+ *     where `ld` (floats per pixel) may exceed C so that channel slices of wider tensors can be
+ *     addressed without copies.
+ */
+#ifndef ESS_B200_H
+#define ESS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESSB_VERSION 100
+#define ESSB_MAX_TAPS 25
+
+typedef enum essb_status {
+  ESSB_OK = 0,
+  ESSB_ERR_ARG = -1,      /* bad shape / alignment / null pointer */
+  ESSB_ERR_ARCH = -2,     /* device is not sm_100 */
+  ESSB_ERR_LAUNCH = -3,   /* cudaGetLastError() after launch */
+  ESSB_ERR_DRIVER = -4,   /* driver entry point (tensor map encode) unavailable */
+  ESSB_ERR_WORKSPACE = -5 /* workspace too small */
+} essb_status;
+
+/* ---- library info ----------------------------------------------------------------------- */
+int essb_version(void);
+const char* essb_build_arch(void);        /* "sm_100a" */
+const char* essb_last_error(void);
+int essb_device_check(void);              /* ESSB_OK iff current device is compute capability 10.x */
+
+/* ---- implicit-GEMM convolution --------------------------------------------------------- */
+/* One input channel segment.  A conv reads the channel-concatenation of up to two segments
+ * (replaces torch.cat in ConvLSTM.forward, e2vid/model/submodules.py:212, and skip_concat in
+ * SemSegE2VID.forward, models/style_networks.py:78,82) and can apply, while loading,
+ *   nearest x2 upsampling   (f.interpolate(scale_factor=2,'nearest'), style_networks.py:77,81,85)
+ *   instance normalisation  (nn.InstanceNorm2d(affine=False), style_networks.py:163,180,183)
+ *   ReLU                    (style_networks.py:164,181)
+ * so none of those intermediate tensors is ever written to HBM. */
+typedef struct essb_src {
+  const float* ptr;   /* NHWC fp32, source dims (H>>ups, W>>ups); NULL => segment absent */
+  const float* mean;  /* [N, C] or NULL */
+  const float* rstd;  /* [N, C] or NULL */
+  int32_t ld;         /* floats per pixel in memory */
+  int32_t C;          /* channels in this segment */
+  int32_t ups;        /* 0 or 1 */
+  int32_t relu;       /* apply max(.,0) after normalisation */
+} essb_src;
+
+typedef enum essb_epilogue {
+  ESSB_EPI_LINEAR = 0, /* out = post( act(acc + bias + res_pre) ) + res_post                      */
+  ESSB_EPI_LSTM = 1,   /* ConvLSTM gates, e2vid/model/submodules.py:216-228 (Cout = 4*hidden,
+                          packed gate-interleaved: co = 4*ch + {in, remember, out, cell})          */
+  ESSB_EPI_GRU_UR = 2, /* ConvGRU update/reset, submodules.py:267-268 (co = 2*ch + {update,reset});
+                          writes update -> out, prev_state*reset -> out2                            */
+  ESSB_EPI_GRU_OUT = 3 /* ConvGRU out gate + blend, submodules.py:269-271                          */
+} essb_epilogue;
+
+typedef enum essb_act { ESSB_ACT_NONE = 0, ESSB_ACT_RELU = 1, ESSB_ACT_SIGMOID = 2 } essb_act;
+
+/* Generic gather-convolution launch:
+ *   acc[n,oy,ox,co] = sum_t sum_ci  A[n, oy*sy + dy[t], ox*sx + dx[t], ci] * w[widx[t]][ci][co]
+ * with A the (upsampled / normalised / ReLU'd / concatenated) virtual input of dims H x W, zero
+ * outside.  The result for (oy,ox) in [0,OH)x[0,OW) is stored at pixel (oy*osy+ooy, ox*osx+oox) of
+ * an OHf x OWf output image -- strided output implements the four sub-pixel phases of
+ * ConvTranspose2d(k5,s2,p2,op1) (e2vid/model/submodules.py:39-40).
+ * Replaces nn.Conv2d / nn.ConvTranspose2d forward AND their autograd input-gradient
+ * (dgrad = the same gather with flipped taps and transposed weights). */
+typedef struct essb_conv {
+  essb_src src[2];
+  const float* w;        /* packed weights [n_w_taps][Cin_total][CoutP], CoutP = Cout rounded up to 4 */
+  const float* bias;     /* [Cout] or NULL */
+  const float* res_pre;  /* LINEAR: added before the activation (ResidualBlock, submodules.py:170) or NULL */
+  const float* res_post; /* LINEAR: added after the activation (skip_sum, e2vid/model/unet.py:175,179) or NULL */
+  const float* aux0;     /* LSTM: prev cell [N,OH,OW,hidden] or NULL(=0). GRU_*: prev state or NULL(=0) */
+  const float* aux1;     /* GRU_OUT: update gate [N,OH,OW,hidden] */
+  float* out;            /* LINEAR: result. LSTM: hidden. GRU_UR: update. GRU_OUT: new state */
+  float* out2;           /* LSTM: cell. GRU_UR: prev_state*reset. else NULL */
+  float* stats_partial;  /* LINEAR only: per-tile (sum, sumsq) partials [N][tiles][Cout][2] or NULL */
+  uint16_t* out_hi;      /* LINEAR only, optional: bf16 hi/lo planes of the result (operand format of */
+  uint16_t* out_lo;      /*   the tensor-core path), pixel pitch ld_planes; needs Cout % 4 == 0      */
+  int32_t N, H, W;       /* virtual input dims */
+  int32_t OH, OW;        /* output grid of this launch */
+  int32_t Cout;          /* GEMM N (for LSTM = 4*hidden, GRU_UR = 2*hidden) */
+  int32_t sy, sx;        /* input step per output pixel */
+  int32_t OHf, OWf, osy, ooy, osx, oox; /* output image dims and phase placement */
+  int32_t ldo;           /* floats per output pixel (out, out2, res_*, aux* all share it for LINEAR;
+                            for LSTM/GRU all state tensors are dense [.., hidden]) */
+  int32_t ld_res;        /* floats per pixel of res_pre / res_post */
+  int32_t ld_planes;     /* elements per pixel of out_hi / out_lo */
+  int32_t accumulate;    /* LINEAR: out += result (used to sum gradient contributions) */
+  int32_t epilogue;      /* essb_epilogue */
+  int32_t act;           /* essb_act (LINEAR) */
+  int32_t ntaps;
+  int8_t dy[ESSB_MAX_TAPS];
+  int8_t dx[ESSB_MAX_TAPS];
+  int8_t widx[ESSB_MAX_TAPS];
+} essb_conv;
+
+/* fp32 CUDA-core path (exact fp32 FMA accumulation; parity reference mode "fp32"). */
+int essb_conv_fp32(const essb_conv* d, void* stream);
+int essb_conv_tiles_per_sample(const essb_conv* d); /* tiles dimension of stats_partial */
+
+/* Weight gradient of the same gather-convolution (autograd of nn.Conv2d w.r.t. weight/bias):
+ *   dW[co][ci][t] = sum_{n,oy,ox} A[n, oy*sy+dy[t], ox*sx+dx[t], ci] * dY[n,oy,ox,co]
+ * written in the reference parameter layout [Cout, Cin, KH*KW] (tap index = position in dy/dx);
+ * dbias[co] = sum dY.  `workspace` holds split-K partials. */
+typedef struct essb_wgrad {
+  essb_src src[2];
+  const float* dy_ptr;   /* [N, OH, OW, ld_dy] */
+  float* dw;             /* [Cout, Cin_total, ntaps] */
+  float* dbias;          /* [Cout] or NULL */
+  float* workspace;
+  int64_t workspace_bytes;
+  int32_t N, H, W, OH, OW, Cout, ld_dy, sy, sx;
+  int32_t ntaps;
+  int8_t dy[ESSB_MAX_TAPS];
+  int8_t dx[ESSB_MAX_TAPS];
+} essb_wgrad;
+int64_t essb_wgrad_workspace_bytes(const essb_wgrad* d);
+int essb_wgrad_fp32(const essb_wgrad* d, void* stream);
+
+/* Weight packing: reference layout -> packed [T][Cin][CoutP].
+ *   transposed_layout = 0: w is nn.Conv2d weight  [Cout, Cin, T]
+ *   transposed_layout = 1: w is nn.ConvTranspose2d weight [Cin, Cout, T]
+ *   swap_io: pack for dgrad (roles of Cin/Cout exchanged); flip: reverse tap order (dgrad)
+ *   scale[Cout] (or NULL): eval-mode BatchNorm fold, gamma/sqrt(var+eps) (submodules.py:19-20,26-27)
+ *   interleave g > 1: packed output channel co' = (co % (Cout/g))*g + co / (Cout/g)
+ *                     (gate-interleaving for ESSB_EPI_LSTM / GRU_UR) */
+int essb_pack_weight(const float* w, const float* scale, float* out, int Cout, int Cin, int T,
+                     int transposed_layout, int swap_io, int flip, int interleave, void* stream);
+
+/* ---- instance-norm helpers (nn.InstanceNorm2d fwd/bwd, style_networks.py:163,180,183) ---- */
+/* partial [N][tiles][C][2] -> mean, rstd [N][C]; biased variance, eps inside the sqrt. */
+int essb_in_finalize(const float* partial, int N, int tiles, int C, int64_t count, float eps,
+                     float* mean, float* rstd, void* stream);
+/* out = act((y - mean)*rstd) + res   (materialises an IN(+ReLU)(+residual) output, e.g. the
+ * INSResBlock output `out += residual`, style_networks.py:190-193).  mean==NULL => identity norm. */
+int essb_norm_act_add(const float* y, int ld_y, const float* mean, const float* rstd, int relu,
+                      const float* res, int ld_res, float* out, int ld_out, int N, int64_t P, int C,
+                      void* stream);
+/* Backward through  A = relu?(IN(y))  (optionally followed by nearest x2 upsampling), two passes.
+ * pass 1: g = [relu mask] * (sum over the 2^ups x 2^ups children of dA) (+ extra);  writes g and
+ *         per-block partial sums of g and g*xhat  -> partial [N][blocks][C][2]
+ * pass 2: dy = rstd * (g - mean_p(g) - xhat * mean_p(g*xhat))                                    */
+int essb_in_bwd_blocks(int64_t P);
+int essb_in_bwd_pass1(const float* dA, int ld_dA, int ups, const float* extra, int ld_extra,
+                      const float* y, int ld_y, const float* mean, const float* rstd, int relu,
+                      float* g, float* partial, int N, int H, int W, int C, void* stream);
+int essb_in_bwd_pass2(const float* g, const float* y, int ld_y, const float* mean, const float* rstd,
+                      const float* gsum /* [N][C][2] totals */, float* dy, int N, int64_t P, int C,
+                      void* stream);
+/* totals[N][C][2] = sum over blocks of partial (fixed order => deterministic) */
+int essb_partial_reduce(const float* partial, int N, int blocks, int C, float* totals, void* stream);
+/* out[c] = sum over rows of x[rows][ld] (bias gradients) */
+int essb_colsum(const float* x, int ld, int64_t rows, int C, float* out, float* workspace,
+                int64_t workspace_bytes, void* stream);
+/* g_child -> parent:  out[n,y,x,c] = sum over the 2x2 children of in (backward of nearest x2) */
+int essb_upsample2_bwd(const float* in, int ld_in, float* out, int ld_out, int N, int H, int W, int C,
+                       int accumulate, void* stream);
+
+/* ---- event pre-processing (e2vid/utils/inference_utils.py:84-109, 311-338) --------------- */
+/* stats[w][3] = (sum x, sum x^2, count of non-zeros) of window w for ALL T windows in one launch;
+ * x is [B][T][count] with batch stride `bstride` floats (count = C*H*W of one window).  One launch
+ * before the unroll removes the reference's per-window blocking `if num_nonzeros > 0` D2H sync. */
+int essb_event_stats(const float* x, int64_t bstride, int B, int T, int64_t count, double* stats,
+                     void* stream);
+/* Normalise non-zeros to mean 0 / std 1 using stats (no-op scale if nnz == 0), reflect-pad to
+ * (Hp, Wp) with (pad_top, pad_left), convert NCHW -> NHWC with channel pitch ld_out (extra
+ * channels zero-filled).  x is a [B, C, H, W] slice with batch stride `bstride` floats. */
+int essb_event_prepare(const float* x, int64_t bstride, const double* stats, int normalize,
+                       float* out, int ld_out, int B, int C, int H, int W, int Hp, int Wp,
+                       int pad_top, int pad_left, void* stream);
+
+/* ---- layout plumbing ---------------------------------------------------------------------- */
+int essb_nchw_to_nhwc(const float* in, float* out, int ld_out, int N, int C, int64_t P, void* stream);
+int essb_nhwc_to_nchw(const float* in, int ld_in, float* out, int N, int C, int64_t P, void* stream);
+/* bilinear x2 upsampling, align_corners=False (UpsampleConvLayer, e2vid/model/submodules.py:84) */
+int essb_bilinear_up2(const float* in, float* out, int N, int H, int W, int C, void* stream);
+
+/* ---- task loss: Dice + cross-entropy (utils/loss_functions.py:6-24, 63-135) ---------------- */
+/* logits NHWC [N*P][ld] fp32, target int64 [N*P].  sums layout (double):
+ *   [0] = sum of -log softmax[target] over valid pixels, [1] = valid pixel count,
+ *   [2 + k] = I_k = sum p_k t_k, [2 + K + k] = S_k = sum p_k^2, [2 + 2K + k] = T_k = sum t_k.
+ * essb_task_loss_fwd zeroes and fills `sums`; _finish writes loss[0] = dice*use_dice + ce*use_ce.
+ * Between the two a data-parallel caller all-reduces `sums` (global-batch semantics). */
+int essb_task_loss_fwd(const float* logits, int ld, const int64_t* target, int64_t npix, int K,
+                       int64_t ignore_index, double* sums, void* stream);
+int essb_task_loss_finish(const double* sums, int K, int64_t ignore_index, int use_dice, int use_ce,
+                          float* loss, void* stream);
+/* dlogits = gscale[0] * dLoss/dlogits  (gscale: device scalar, the upstream gradient). */
+int essb_task_loss_bwd(const float* logits, int ld, const int64_t* target, int64_t npix, int K,
+                       int64_t ignore_index, const double* sums, int use_dice, int use_ce,
+                       const float* gscale, float* dlogits, int ld_d, void* stream);
+/* argmax over channels + confusion matrix conf[y][y_hat] (evaluation/metrics.py:4-24), int64. */
+int essb_confusion(const float* logits, int ld, const int64_t* target, int64_t npix, int K,
+                   int64_t ignore_index, int64_t* conf, void* stream);
+/* same from already-computed label predictions (MetricsSemseg.update_batch, metrics.py:50-56) */
+int essb_confusion_labels(const int64_t* pred, const int64_t* target, int64_t npix, int K,
+                          int64_t ignore_index, int64_t* conf, void* stream);
+
+/* ---- tcgen05 / TMA tensor-core path (sm_100a) --------------------------------------------- */
+/* Split an fp32 tensor into bf16 hi/lo planes: hi = bf16(x), lo = bf16(x - hi)  (x ~= hi + lo to
+ * 2^-17 relative).  Optionally applies the same normalise/ReLU/upsample transform as essb_src. */
+int essb_split_bf16(const essb_src* src, int N, int H, int W, uint16_t* hi, uint16_t* lo, int ld_out,
+                    int c_off, void* stream);
+/* Pack conv weights for the tensor-core path: K-major [NoutP][T*KinP] bf16 hi and lo planes
+ * (same transposed_layout / swap_io / flip / interleave / scale semantics as essb_pack_weight;
+ * KinP = input channels padded to a multiple of 64, rows beyond Nout are zero). */
+int essb_pack_weight_tc(const float* w, const float* scale, uint16_t* hi, uint16_t* lo, int Cout,
+                        int Cin, int T, int transposed_layout, int swap_io, int flip, int interleave,
+                        int KinP, int NoutP, void* stream);
+
+/* One TMA view of an A operand: bf16 hi/lo NHWC planes addressed as view[n][y][x][c] with element
+ * strides (stride_n, stride_y, stride_x, 1).  A dense NHWC tensor is one view; a stride-2 conv
+ * reads its input through four parity views (base shifted by (py*W+px)*ld, strides doubled). */
+typedef struct essb_tc_view {
+  const uint16_t* hi;
+  const uint16_t* lo;        /* may be NULL when passes == 1 */
+  int64_t stride_x, stride_y, stride_n;  /* in elements; multiples of 8 */
+  int32_t C, W, H;           /* view extent: channels (multiple of 64), width, height */
+  int32_t reserved;
+} essb_tc_view;
+
+/* tcgen05 gather-convolution (same GEMM semantics as essb_conv; operands pre-split to bf16 hi/lo):
+ *   acc[n,oy,ox,co] = sum_t sum_seg sum_c  view[seg_view0[seg] + view[t]][n, oy+dy[t], ox+dx[t], c]
+ *                                          * W[co][widx[t]*k_per_tap + seg_koff[seg] + c]
+ * Epilogues: ESSB_EPI_LINEAR (bias, res_pre, act, res_post, strided placement, fp32 and/or bf16
+ * hi/lo outputs) and ESSB_EPI_LSTM (as essb_conv; additionally writes the hidden state as bf16
+ * planes so the next window's MMA can consume it without a conversion pass). */
+typedef struct essb_conv_tc {
+  essb_tc_view views[8];
+  const uint16_t* w_hi;  /* [w_rows][n_w_taps * k_per_tap] */
+  const uint16_t* w_lo;
+  const float* bias;
+  const float* res_pre;
+  const float* res_post;
+  const float* aux0;     /* LSTM: previous cell or NULL */
+  float* out;            /* LINEAR: fp32 result or NULL; LSTM: hidden */
+  float* out2;           /* LSTM: cell */
+  uint16_t* out_hi;      /* optional bf16 planes of the result (LSTM: of the hidden state) */
+  uint16_t* out_lo;
+  int32_t n_views, nseg;
+  int32_t seg_C[2];      /* channels consumed per segment (multiples of 64) */
+  int32_t seg_view0[2];
+  int32_t seg_koff[2];
+  int32_t k_per_tap, n_w_taps, w_rows;
+  int32_t N, OH, OW, Cout;
+  int32_t OHf, OWf, osy, ooy, osx, oox;
+  int32_t ldo, ld_res, ld_planes;
+  int32_t epilogue, act;
+  int32_t passes;        /* 3 = bf16x3 split (fp32-parity mode), 1 = single bf16 pass */
+  int32_t bw_log2;       /* spatial tile: BW = 1<<bw_log2 columns x 128/BW rows */
+  int32_t ntaps;
+  int8_t dy[ESSB_MAX_TAPS];
+  int8_t dx[ESSB_MAX_TAPS];
+  int8_t view[ESSB_MAX_TAPS];
+  int8_t widx[ESSB_MAX_TAPS];
+} essb_conv_tc;
+int essb_conv_tc_run(const essb_conv_tc* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESS_B200_H */

@@ -1,0 +1,139 @@
+"""Pins the oracle: against the committed golden fixture (generated from the reference) and, where
+/root/reference is present (build container only), against the live imported reference modules."""
+import pytest
+import torch
+
+from helpers import O, rel_err
+from oracle import ref_shim
+
+
+def test_oracle_matches_golden(golden):
+    d = golden['dims']
+    img, states, latent = O.encoder_unroll(golden['e2vid_sd'], golden['cfg'], golden['data'], d['T'], d['C'])
+    assert rel_err(img, golden['img']) < 1e-5
+    for k in (1, 2, 4, 8):
+        assert rel_err(latent[k], golden['latent'][k]) < 1e-5
+    for (h, c), (gh, gc) in zip(states, golden['states']):
+        assert rel_err(h, gh) < 1e-5 and rel_err(c, gc) < 1e-5
+    lat = {k: v for k, v in golden['latent'].items()}
+    pred = O.semseg_forward(golden['semseg_sd'], lat)
+    for k in (1, 2, 4):
+        assert rel_err(pred[k], golden['pred'][k]) < 1e-5
+    loss = O.task_loss(golden['pred'][1], golden['labels'], d['K'])
+    assert abs(float(loss) - float(golden['loss'])) < 1e-5
+    conf = O.confusion_matrix(golden['pred'][1].argmax(1), golden['labels'], d['K'], 255)
+    assert torch.equal(conf, golden['confusion'])
+    miou, _, acc = O.confusion_to_iou(conf)
+    assert abs(float(miou) - float(golden['mean_iou'])) < 1e-9 and abs(float(acc) - float(golden['acc'])) < 1e-9
+
+
+def test_oracle_gradients_match_golden(golden):
+    d = golden['dims']
+    params = {k: v.clone().requires_grad_(True) for k, v in golden['semseg_sd'].items()}
+    pred = O.semseg_forward(params, golden['latent'])
+    loss = O.task_loss(pred[1], golden['labels'], d['K'])
+    grads = torch.autograd.grad(loss, list(params.values()))
+    for (n, g) in zip(params.keys(), grads):
+        ref = golden['grads'][n]
+        # biases that feed an InstanceNorm have an exactly-zero true gradient: pure rounding noise
+        # (|g| ~ 1e-6), hence the absolute term
+        assert (g - ref).abs().max() <= 1e-4 * ref.abs().max() + 5e-6, n
+
+
+def test_edge_cases_event_normalize():
+    z = torch.zeros(2, 3, 8, 8)
+    assert torch.equal(O.event_normalize(z), z)           # no non-zeros: unchanged (inference_utils.py:100)
+    x = torch.zeros(1, 1, 4, 4)
+    x[0, 0, 1, 1], x[0, 0, 2, 2] = 2.0, 4.0
+    y = O.event_normalize(x)
+    assert y[0, 0, 0, 0] == 0 and abs(float(y[0, 0, 1, 1]) + 1) < 1e-6 and abs(float(y[0, 0, 2, 2]) - 1) < 1e-6
+    assert O.crop_padding(200, 346, 3) == (3, 3, 0, 0)    # DDD17 raw width 346 -> 352
+    assert O.crop_padding(440, 640, 3) == (0, 0, 0, 0)
+
+
+needs_ref = pytest.mark.skipif(not ref_shim.available(), reason='/root/reference not present')
+
+
+@needs_ref
+def test_oracle_vs_live_reference_lightweight():
+    ref_shim.install()
+    from e2vid.image_reconstructor import ImageReconstructor
+    m = ref_shim.make_reference_e2vid()
+    B, T, C, H, W = 1, 2, 5, 32, 40
+    torch.manual_seed(0)
+    data = torch.randn(B, T * C, H, W) * (torch.rand(B, T * C, H, W) < 0.2)
+    rec = ImageReconstructor(m, H, W, C, 'cpu', ref_shim.e2vid_options())
+    for i in range(T):
+        img, st, lat = rec.update_reconstruction(data[:, i * C:(i + 1) * C])
+    img2, st2, lat2 = O.encoder_unroll(m.state_dict(), ref_shim.E2VID_LIGHTWEIGHT_CFG, data, T, C)
+    assert rel_err(img2, img) < 1e-6
+    for k in lat:
+        assert rel_err(lat2[k], lat[k]) < 1e-6
+
+
+@needs_ref
+@pytest.mark.parametrize('variant', ['convgru', 'upsample_conv', 'no_norm', 'reflect_pad'])
+def test_oracle_vs_live_reference_variants(variant):
+    ref_shim.install()
+    from e2vid.image_reconstructor import ImageReconstructor
+    cfg = dict(ref_shim.E2VID_LIGHTWEIGHT_CFG, base_num_channels=8, num_bins=3)
+    H, W = 32, 40
+    if variant == 'convgru':
+        cfg['recurrent_block_type'] = 'convgru'
+    elif variant == 'upsample_conv':
+        cfg['use_upsample_conv'] = True
+    elif variant == 'no_norm':
+        cfg.pop('norm')
+    else:
+        H, W = 30, 43
+    m = ref_shim.make_reference_e2vid(cfg)
+    torch.manual_seed(1)
+    data = torch.randn(2, 6, H, W) * (torch.rand(2, 6, H, W) < 0.3)
+    rec = ImageReconstructor(m, H, W, 3, 'cpu', ref_shim.e2vid_options())
+    for i in range(2):
+        img, st, lat = rec.update_reconstruction(data[:, i * 3:(i + 1) * 3])
+    img2, st2, lat2 = O.encoder_unroll(m.state_dict(), cfg, data, 2, 3)
+    assert rel_err(img2, img) < 1e-6
+    assert rel_err(lat2[8], lat[8]) < 1e-6
+
+
+@needs_ref
+def test_oracle_vs_live_reference_semseg_variants():
+    ref_shim.install()
+    from models.style_networks import SemSegE2VID
+    from utils.loss_functions import TaskLoss, symJSDivLoss
+    torch.manual_seed(3)
+    lat = {1: torch.randn(2, 8, 32, 32), 2: torch.randn(2, 16, 16, 16), 4: torch.randn(2, 32, 8, 8),
+           8: torch.randn(2, 64, 4, 4)}
+    for kw in (dict(skip_connect=True, skip_type='concat'), dict(skip_connect=False), ):
+        dec = SemSegE2VID(input_c=64, output_c=5, **kw)
+        out = dec(lat)
+        out2 = O.semseg_forward(dec.state_dict(), lat, **kw)
+        assert set(out.keys()) == set(out2.keys())
+        for k in out:
+            assert rel_err(out2[k], out[k]) < 1e-6
+    lab = torch.randint(0, 5, (2, 32, 32))
+    lab[0, :3] = 255
+    for losses in (['dice', 'cross_entropy'], ['dice'], ['cross_entropy']):
+        tl = TaskLoss(losses=losses, num_classes=5, ignore_index=255)
+        assert abs(float(tl(out[1], lab)) - float(O.task_loss(out2[1], lab, 5, 255, losses))) < 1e-6
+    a, b = torch.randn(2, 5, 8, 8), torch.randn(2, 5, 8, 8)
+    assert abs(float(symJSDivLoss()(a, b)) - float(O.sym_js_div_loss(a, b))) < 1e-7
+
+
+@needs_ref
+def test_reference_trainer_runs_with_shim():
+    """The real ESSSupervisedModel.train_step executes on CPU through the shim (config 1 plumbing)."""
+    import os
+    cfg = dict(ref_shim.E2VID_LIGHTWEIGHT_CFG, num_bins=1, base_num_channels=32)
+    m = ref_shim.make_reference_e2vid(cfg)
+    path = ref_shim.save_synthetic_checkpoint(m, cfg)
+    try:
+        t = ref_shim.make_supervised_trainer(ref_shim.supervised_settings(path, (64, 64), 11, 2, 1))
+        torch.manual_seed(0)
+        data = torch.randn(2, 2, 64, 64) * (torch.rand(2, 2, 64, 64) < 0.2)
+        labels = torch.randint(0, 11, (2, 64, 64))
+        losses = [float(t.train_step([data, labels])[2]) for _ in range(3)]
+        assert all(torch.isfinite(torch.tensor(losses)))
+    finally:
+        os.remove(path)
