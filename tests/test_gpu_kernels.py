@@ -1,0 +1,251 @@
+"""Kernel-level parity tests (`-m gpu`): every C-ABI kernel vs the CPU oracle / plain torch fp32 ops on
+identical seeded inputs.  Tolerance: 1e-3 max-norm relative (BASELINE.json north_star) unless noted;
+the exact-fp32 kernels are expected (and asserted) to be far tighter."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import O, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3        # the contract
+TIGHT = 2e-5      # what exact-fp32 kernels actually achieve (accumulation-order noise)
+
+
+def _ops():
+    from ess_b200 import ops
+    return ops
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().cuda()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).cpu()
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout,k,stride', [
+    (2, 16, 24, 16, 32, 3, 1),
+    (1, 55, 80, 64, 128, 3, 1),       # odd DSEC 1/8 extent, Cout > 64 (TN=8 path)
+    (2, 20, 12, 8, 64, 5, 2),
+    (1, 16, 16, 5, 32, 5, 1),         # C=5 head: scalar-load path
+    (2, 9, 7, 32, 11, 1, 1),          # 1x1 classifier, Cout not a multiple of 4
+    (1, 24, 40, 20, 72, 3, 1),        # channel tail in the K-step (20 = 16 + 4) and Cout tail
+])
+def test_conv_fp32_linear(N, H, W, Cin, Cout, k, stride):
+    ops = _ops()
+    from ess_b200._lib import ACT_RELU
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) * 0.1
+    b = torch.randn(Cout, generator=g)
+    pad = k // 2
+    ref = torch.relu(F.conv2d(x, w, b, stride=stride, padding=pad))
+    OH, OW = ref.shape[2:]
+    wp = ops.pack_weight(w.cuda())
+    out, _, _, _ = ops.conv([ops.Seg(nhwc(x))], wp, b.cuda(), N, H, W, OH, OW, Cout, ops.taps_conv(k, pad),
+                            stride=stride, act=ACT_RELU)
+    assert rel_err(nchw(out), ref) < TIGHT
+
+
+def test_conv_fp32_fused_loader_and_stats():
+    """two segments: [upsample2(relu(IN(y))), skip] -> conv3x3, with IN statistics from the epilogue."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    N, H, W, C0, C1, Cout = 2, 12, 20, 32, 16, 48
+    y = torch.randn(N, C0, H // 2, W // 2, generator=g) * 2 + 0.5
+    skip = torch.randn(N, C1, H, W, generator=g)
+    w = torch.randn(Cout, C0 + C1, 3, 3, generator=g) * 0.05
+    b = torch.randn(Cout, generator=g)
+    a = torch.relu(F.instance_norm(y, eps=1e-5))
+    a = a.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    ref = F.conv2d(torch.cat([a, skip], 1), w, b, padding=1)
+    mean = y.mean((2, 3)).cuda()
+    rstd = (1.0 / torch.sqrt(y.var((2, 3), unbiased=False) + 1e-5)).cuda()
+    segs = [ops.Seg(nhwc(y), ups=1, mean=mean.contiguous(), rstd=rstd.contiguous(), relu=True), ops.Seg(nhwc(skip))]
+    out, _, st, tiles = ops.conv(segs, ops.pack_weight(w.cuda()), b.cuda(), N, H, W, H, W, Cout, ops.taps_conv(3, 1),
+                                 want_stats=True)
+    assert rel_err(nchw(out), ref) < TIGHT
+    m2, r2 = ops.in_finalize(st, H * W)
+    assert rel_err(m2.cpu(), ref.mean((2, 3))) < TIGHT
+    assert rel_err(r2.cpu(), 1.0 / torch.sqrt(ref.var((2, 3), unbiased=False) + 1e-5)) < 1e-4
+
+
+def test_conv_transposed_phases():
+    ops = _ops()
+    from ess_b200._lib import ACT_RELU
+    g = torch.Generator().manual_seed(2)
+    N, H, W, Cin, Cout = 2, 7, 10, 32, 16
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cin, Cout, 5, 5, generator=g) * 0.1
+    skip = torch.randn(N, Cout, 2 * H, 2 * W, generator=g)
+    ref = torch.relu(F.conv_transpose2d(x, w, None, stride=2, padding=2, output_padding=1)) + skip
+    wp = ops.pack_weight(w.cuda(), transposed_layout=True)
+    out = torch.empty((N, 2 * H, 2 * W, Cout), device='cuda')
+    xs, sk = nhwc(x), nhwc(skip)
+    for py in range(2):
+        for px in range(2):
+            ops.conv([ops.Seg(xs)], wp, None, N, H, W, H, W, Cout, ops.taps_convT_phase(py, px), act=ACT_RELU, out=out,
+                     out_place=(2 * H, 2 * W, 2, py, 2, px), res_post=sk)
+    assert rel_err(nchw(out), ref) < TIGHT
+
+
+@pytest.mark.parametrize('with_state', [False, True])
+def test_convlstm_fp32(with_state):
+    ops = _ops()
+    from ess_b200._lib import EPI_LSTM
+    from ess_b200.e2vid import _interleave
+    g = torch.Generator().manual_seed(3)
+    N, H, W, C = 2, 11, 13, 32
+    x = torch.randn(N, C, H, W, generator=g)
+    w = torch.randn(4 * C, 2 * C, 3, 3, generator=g) * 0.05
+    b = torch.randn(4 * C, generator=g) * 0.1
+    prev = (torch.randn(N, C, H, W, generator=g), torch.randn(N, C, H, W, generator=g)) if with_state else None
+    h_ref, c_ref = O.convlstm(x, prev, {'p.Gates.weight': w, 'p.Gates.bias': b}, 'p')
+    wc = w.cuda()
+    if with_state:
+        segs = [ops.Seg(nhwc(x)), ops.Seg(nhwc(prev[0]))]
+        wp, cp = ops.pack_weight(wc, interleave=4), nhwc(prev[1])
+    else:
+        segs = [ops.Seg(nhwc(x))]
+        wp, cp = ops.pack_weight(wc[:, :C].contiguous(), interleave=4), None
+    h, c, _, _ = ops.conv(segs, wp, _interleave(b.cuda(), 4), N, H, W, H, W, 4 * C, ops.taps_conv(3, 1),
+                          epilogue=EPI_LSTM, aux0=cp)
+    assert rel_err(nchw(h), h_ref) < TIGHT and rel_err(nchw(c), c_ref) < TIGHT
+
+
+def test_wgrad_fp32():
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    N, H, W, C0, C1, Cout = 2, 14, 18, 64, 32, 40
+    a0 = torch.randn(N, C0, H // 2, W // 2, generator=g)
+    a1 = torch.randn(N, C1, H, W, generator=g)
+    dy = torch.randn(N, Cout, H, W, generator=g)
+    w = torch.zeros(Cout, C0 + C1, 3, 3, requires_grad=True)
+    b = torch.zeros(Cout, requires_grad=True)
+    a = torch.cat([a0.repeat_interleave(2, 2).repeat_interleave(2, 3), a1], 1)
+    out = F.conv2d(a, w, b, padding=1)
+    gw, gb = torch.autograd.grad(out, [w, b], dy)
+    segs = [ops.Seg(nhwc(a0), ups=1), ops.Seg(nhwc(a1))]
+    dw, db = ops.wgrad(segs, nhwc(dy), N, H, W, H, W, Cout, ops.taps_conv(3, 1))
+    assert rel_err(dw.view(Cout, C0 + C1, 3, 3).cpu(), gw) < TIGHT
+    assert rel_err(db.cpu(), gb) < TIGHT
+
+
+def test_dgrad_via_gather_conv():
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    N, H, W, Cin, Cout = 2, 10, 9, 24, 32
+    x = torch.randn(N, Cin, H, W, generator=g, requires_grad=True)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * 0.1
+    dy = torch.randn(N, Cout, H, W, generator=g)
+    gx, = torch.autograd.grad(F.conv2d(x, w, None, padding=1), [x], dy)
+    wp = ops.pack_weight(w.cuda(), swap_io=True)
+    dtaps = [(-a, -b_, t) for (a, b_, t) in ops.taps_conv(3, 1)]
+    dA, _, _, _ = ops.conv([ops.Seg(nhwc(dy))], wp, None, N, H, W, H, W, Cin, dtaps)
+    assert rel_err(nchw(dA), gx) < TIGHT
+
+
+@pytest.mark.parametrize('relu,ups,C', [(True, 0, 32), (False, 0, 256), (True, 1, 64), (True, 0, 128)])
+def test_instance_norm_backward(relu, ups, C):
+    ops = _ops()
+    g = torch.Generator().manual_seed(6)
+    N, H, W = 2, 9, 14
+    y = (torch.randn(N, C, H, W, generator=g) * 1.7 + 0.3).requires_grad_(True)
+    a = F.instance_norm(y, eps=1e-5)
+    if relu:
+        a = torch.relu(a)
+    if ups:
+        a = a.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    dA = torch.randn(a.shape, generator=g)
+    gy, = torch.autograd.grad(a, [y], dA)
+    yd = y.detach()
+    mean = yd.mean((2, 3)).cuda().contiguous()
+    rstd = (1.0 / torch.sqrt(yd.var((2, 3), unbiased=False) + 1e-5)).cuda().contiguous()
+    out = ops.in_backward(nhwc(dA), nhwc(yd), mean, rstd, relu=relu, ups=ups)
+    assert rel_err(nchw(out), gy) < 1e-4
+    # forward materialisation
+    res = torch.randn(N, C, H, W, generator=g)
+    fwd = ops.norm_act_add(nhwc(yd), mean, rstd, relu=relu, res=nhwc(res))
+    ref = F.instance_norm(yd, eps=1e-5)
+    ref = (torch.relu(ref) if relu else ref) + res
+    assert rel_err(nchw(fwd), ref) < TIGHT
+
+
+@pytest.mark.parametrize('K,losses', [(11, ('dice', 'cross_entropy')), (6, ('dice',)), (19, ('cross_entropy',)),
+                                      (3, ('dice', 'cross_entropy'))])
+def test_task_loss_kernels(K, losses):
+    ops = _ops()
+    g = torch.Generator().manual_seed(7)
+    N, H, W = 2, 17, 23
+    logits = (torch.randn(N, K, H, W, generator=g) * 3).requires_grad_(True)
+    target = torch.randint(0, K, (N, H, W), generator=g)
+    target[:, :3] = 255
+    ref = O.task_loss(logits, target, K, 255, losses)
+    gref, = torch.autograd.grad(ref * 0.7, [logits])
+    lg = nhwc(logits.detach())
+    sums = ops.task_loss_sums(lg, target.cuda(), K, 255)
+    loss = ops.task_loss_finish(sums, K, 255, 'dice' in losses, 'cross_entropy' in losses)
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    dl = ops.task_loss_bwd(lg, target.cuda(), K, 255, sums, 'dice' in losses, 'cross_entropy' in losses,
+                           torch.tensor([0.7], device='cuda'))
+    assert rel_err(nchw(dl), gref) < 1e-4
+    conf = ops.confusion_logits(lg, target.cuda(), K, 255)
+    assert torch.equal(conf.cpu(), O.confusion_matrix(logits.detach().argmax(1), target, K, 255))   # bit-exact
+    conf2 = ops.confusion_labels(logits.detach().argmax(1).cuda(), target.cuda(), K, 255)
+    assert torch.equal(conf2.cpu(), conf.cpu())
+
+
+def test_task_loss_all_ignored_and_module():
+    import ess_b200
+    crit = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], num_classes=4, ignore_index=255)
+    logits = torch.randn(1, 4, 6, 6, device='cuda', requires_grad=True)
+    target = torch.randint(0, 4, (1, 6, 6), device='cuda')
+    loss = crit(logits, target)
+    loss.backward()
+    ref_logits = logits.detach().cpu().requires_grad_(True)
+    ref = O.task_loss(ref_logits, target.cpu(), 4, 255)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5
+    assert rel_err(logits.grad, ref_logits.grad) < 1e-4
+
+
+@pytest.mark.parametrize('H,W,C', [(16, 24, 5), (30, 43, 3), (200, 346, 5)])
+def test_event_prepare(H, W, C):
+    ops = _ops()
+    from ess_b200.reconstructor import crop_padding
+    g = torch.Generator().manual_seed(8)
+    B, T = 2, 3
+    data = torch.randn(B, T * C, H, W, generator=g) * (torch.rand(B, T * C, H, W, generator=g) < 0.2)
+    dd = data.cuda()
+    stats = ops.event_stats(dd, T, C)
+    left, right, top, bottom = crop_padding(H, W, 3)
+    assert (left, right, top, bottom) == O.crop_padding(H, W, 3)
+    for i in range(T):
+        win = data[:, i * C:(i + 1) * C]
+        ref = O.reflect_pad(O.event_normalize(win), 3)
+        out = ops.event_prepare(dd[:, i * C:(i + 1) * C], stats[i], True, H + top + bottom, W + left + right, top, left,
+                                8)
+        assert rel_err(nchw(out)[:, :C], ref) < 1e-5
+        assert float(out[..., C:].abs().max()) == 0.0
+    # all-zero window: passes through unchanged (inference_utils.py:100)
+    z = torch.zeros(1, C, H, W, device='cuda')
+    st = ops.event_stats(z, 1, C)
+    out = ops.event_prepare(z, st[0], True, H + top + bottom, W + left + right, top, left, 8)
+    assert float(out.abs().max()) == 0.0
+
+
+def test_layout_and_bilinear():
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 5, 7, 9, generator=g)
+    out = ops.nchw_to_nhwc(x.cuda(), 8)
+    assert torch.equal(out[..., :5].cpu(), x.permute(0, 2, 3, 1)) and float(out[..., 5:].abs().max()) == 0
+    y = torch.randn(2, 6, 5, 7, generator=g)
+    up = ops.bilinear_up2(nhwc(y))
+    ref = F.interpolate(y, scale_factor=2, mode='bilinear', align_corners=False)
+    assert rel_err(nchw(up), ref) < 1e-6
+    ch = torch.randn(2, 8, 6, 4, generator=g)
+    s = ops.upsample2_bwd(nhwc(ch), 3, 2, 8)
+    assert rel_err(nchw(s), F.avg_pool2d(ch, 2) * 4) < 1e-6

@@ -1,0 +1,199 @@
+"""Module-level parity (`-m gpu`): the drop-in nn.Modules vs the golden fixture (generated from the
+reference) and vs the CPU oracle with identical state_dicts.  Calls go through the reference-facing
+module surface -> C ABI."""
+import pytest
+import torch
+
+from helpers import (E2VID_CFG, O, make_e2vid, make_events, make_labels, make_latents, make_semseg, rel_err, sd_cpu)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def test_golden_end_to_end_fp32(golden):
+    """tiny config of tests/golden: reconstructor T-loop -> decoder -> loss -> grads -> mIoU."""
+    import ess_b200
+    d = golden['dims']
+    m = ess_b200.E2VIDRecurrent(golden['cfg'], mode='fp32')
+    m.load_state_dict(golden['e2vid_sd'])
+    m = m.cuda().eval()
+    rec = ess_b200.ImageReconstructor(m, d['H'], d['W'], d['C'], 'cuda')
+    data = golden['data'].cuda()
+    for i in range(d['T']):
+        img, states, latent = rec.update_reconstruction(data[:, i * d['C']:(i + 1) * d['C']])
+    assert rel_err(img, golden['img']) < TOL
+    for k in (1, 2, 4, 8):
+        assert latent[k].shape == golden['latent'][k].shape
+        assert rel_err(latent[k], golden['latent'][k]) < TOL
+    for (h, c), (gh, gc) in zip(states, golden['states']):
+        assert rel_err(h, gh) < TOL and rel_err(c, gc) < TOL
+    # fused unroll == per-window loop
+    img2, states2, latent2 = rec.unroll(data, d['T'], d['C'])
+    assert rel_err(img2, golden['img']) < TOL and rel_err(latent2[8], golden['latent'][8]) < TOL
+
+    dec = ess_b200.SemSegE2VID(golden['cfg']['base_num_channels'] * 8, d['K'], skip_connect=True, skip_type='concat')
+    dec.load_state_dict(golden['semseg_sd'])
+    dec = dec.cuda()
+    lat = {k: v.cuda() for k, v in golden['latent'].items()}
+    pred = dec(lat)
+    assert set(pred.keys()) == {8, 4, 2, 1}
+    for k in (1, 2, 4):
+        assert rel_err(pred[k], golden['pred'][k]) < TOL
+    crit = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], gamma=2.0, num_classes=d['K'], ignore_index=255,
+                             reduction='mean')
+    loss = crit(pred[1], golden['labels'].cuda())
+    assert abs(float(loss) - float(golden['loss'])) < TOL * abs(float(golden['loss']))
+    loss.backward()
+    for n, p in dec.named_parameters():
+        ref = golden['grads'][n]
+        assert p.grad is not None, n
+        # abs term: conv biases in front of an InstanceNorm have zero true gradient (rounding noise only)
+        assert (p.grad.cpu() - ref).abs().max() <= TOL * ref.abs().max() + 5e-6, n
+    met = ess_b200.MetricsSemseg(d['K'], 255, ['c%d' % i for i in range(d['K'])])
+    met.update_batch(pred[1].argmax(1), golden['labels'].cuda())
+    s = met.get_metrics_summary()
+    assert torch.equal(s['cm'], golden['confusion'])                    # integer work: bit-exact
+    assert abs(float(s['mean_iou']) - float(golden['mean_iou'])) < 1e-9
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-3), ('bf16x3', 1e-3), ('bf16', 6e-2)])
+def test_e2vid_lightweight_vs_oracle(mode, tol):
+    """E2VID-lightweight architecture (10.7 M params), 3 windows, all three precision modes."""
+    import ess_b200
+    B, T, C, H, W = 2, 3, 5, 64, 96
+    m = make_e2vid(mode=mode)
+    sd = sd_cpu(m)
+    data = make_events(B, T, C, H, W)
+    img_r, st_r, lat_r = O.encoder_unroll(sd, E2VID_CFG, data, T, C)
+    m = m.cuda()
+    rec = ess_b200.ImageReconstructor(m, H, W, C, 'cuda')
+    for i in range(T):
+        img, st, lat = rec.update_reconstruction(data[:, i * C:(i + 1) * C].cuda())
+    errs = {k: rel_err(lat[k], lat_r[k]) for k in (1, 2, 4, 8)}
+    errs['img'] = rel_err(img, img_r)
+    errs['c2'] = rel_err(st[2][1], st_r[2][1])
+    print(mode, errs)
+    assert max(errs.values()) < tol, errs
+
+
+@pytest.mark.parametrize('variant', ['convgru', 'upsample_conv', 'no_norm', 'reflect_pad', 'concat'])
+def test_e2vid_variants_fp32(variant):
+    import ess_b200
+    cfg = dict(E2VID_CFG, base_num_channels=8, num_bins=3)
+    H, W = 32, 40
+    if variant == 'convgru':
+        cfg['recurrent_block_type'] = 'convgru'
+    elif variant == 'upsample_conv':
+        cfg['use_upsample_conv'] = True
+    elif variant == 'no_norm':
+        cfg.pop('norm')
+    elif variant == 'concat':
+        cfg['skip_type'] = 'concat'
+    else:
+        H, W = 30, 43
+    m = make_e2vid(cfg, mode='fp32')
+    sd = sd_cpu(m)
+    data = make_events(2, 2, 3, H, W)
+    img_r, st_r, lat_r = O.encoder_unroll(sd, cfg, data, 2, 3)
+    m = m.cuda()
+    rec = ess_b200.ImageReconstructor(m, H, W, 3, 'cuda')
+    img, st, lat = rec.unroll(data.cuda(), 2, 3)
+    assert img.shape == img_r.shape
+    assert rel_err(img, img_r) < TOL and rel_err(lat[8], lat_r[8]) < TOL and rel_err(lat[1], lat_r[1]) < TOL
+
+
+def _oracle_semseg_grads(dec, lat, labels, K, want_inputs=False, **kw):
+    params = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in dec.state_dict().items()}
+    lat_c = {k: v.detach().cpu().clone().requires_grad_(want_inputs) for k, v in lat.items()}
+    pred = O.semseg_forward(params, lat_c, **kw)
+    loss = O.task_loss(pred[1], labels.cpu(), K)
+    wrt = list(params.values()) + ([lat_c[8], lat_c[4], lat_c[2]] if want_inputs and kw.get('skip_connect', True)
+                                   else ([lat_c[8]] if want_inputs else []))
+    grads = torch.autograd.grad(loss, wrt)
+    return pred, loss, dict(zip(list(params.keys()) + ['in8', 'in4', 'in2'][:len(wrt) - len(params)], grads))
+
+
+@pytest.mark.parametrize('K,H,W', [(11, 64, 96), (6, 40, 56)])
+def test_semseg_forward_backward_vs_oracle(K, H, W):
+    import ess_b200
+    B = 2
+    dec = make_semseg(K).cuda()
+    lat = make_latents(B, H, W, device='cuda')
+    labels = make_labels(B, H, W, K).cuda()
+    pred_r, loss_r, g_r = _oracle_semseg_grads(dec, lat, labels, K, skip_connect=True, skip_type='concat')
+    pred = dec(lat)
+    crit = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255)
+    loss = crit(pred[1], labels)
+    loss.backward()
+    for k in (1, 2, 4):
+        assert rel_err(pred[k], pred_r[k]) < TOL
+    assert abs(float(loss) - float(loss_r)) < TOL * abs(float(loss_r))
+    worst = 0.0
+    for n, p in dec.named_parameters():
+        ref = g_r[n]
+        err = float((p.grad.cpu() - ref).abs().max() / (ref.abs().max() + 1e-12))
+        if n.endswith('bias') and not n.startswith('decoder_scale_5'):
+            assert float((p.grad.cpu() - ref).abs().max()) < 5e-6, n      # zero true gradient
+        else:
+            worst = max(worst, err)
+            assert err < 5e-3, (n, err)      # per-layer wgrad: fp32 ordering noise through ReLU/IN chain
+    print('worst weight-grad rel err', worst)
+
+
+def test_semseg_input_grads_with_frozen_params():
+    """UDA usage (training/ess_trainer.py:133-137): parameters frozen, gradients flow to the inputs."""
+    import ess_b200
+    K, B, H, W = 6, 1, 32, 48
+    dec = make_semseg(K).cuda()
+    lat = make_latents(B, H, W, device='cuda')
+    labels = make_labels(B, H, W, K).cuda()
+    _, _, g_r = _oracle_semseg_grads(dec, lat, labels, K, want_inputs=True, skip_connect=True, skip_type='concat')
+    for p in dec.parameters():
+        p.requires_grad = False
+    lat_g = {k: v.clone().requires_grad_(k != 1) for k, v in lat.items()}
+    pred = dec(lat_g)
+    crit = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255)
+    crit(pred[1], labels).backward()
+    assert all(p.grad is None for p in dec.parameters())
+    for key, name in ((8, 'in8'), (4, 'in4'), (2, 'in2')):
+        assert rel_err(lat_g[key].grad, g_r[name]) < 5e-3, key
+    # and under no_grad nothing is recorded
+    with torch.no_grad():
+        out = dec(lat)
+    assert not out[1].requires_grad
+
+
+def test_semseg_no_skip_variant():
+    import ess_b200
+    K, B, H, W = 5, 2, 32, 32
+    dec = make_semseg(K, skip_connect=False, skip_type='sum').cuda()
+    lat = make_latents(B, H, W, device='cuda')
+    labels = make_labels(B, H, W, K).cuda()
+    pred_r, loss_r, g_r = _oracle_semseg_grads(dec, lat, labels, K, skip_connect=False, skip_type='sum')
+    pred = dec(lat)
+    assert set(pred.keys()) == set(pred_r.keys())
+    for k in pred_r:
+        assert rel_err(pred[k], pred_r[k]) < TOL
+    crit = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255)
+    crit(pred[1], labels).backward()
+    n = 'decoder_scale_5.0.weight'
+    assert rel_err(dict(dec.named_parameters())[n].grad, g_r[n]) < 5e-3
+
+
+def test_full_size_properties_dsec():
+    """BASELINE.json full size (440x640, C=5): properties that need no CPU oracle -- the tcgen05 path
+    agrees with the exact-fp32 path, states carry, an all-zero window leaves zero-input statistics."""
+    import ess_b200
+    B, T, C, H, W = 1, 2, 5, 440, 640
+    data = make_events(B, T, C, H, W).cuda()
+    outs = {}
+    for mode in ('fp32', 'bf16x3'):
+        m = make_e2vid(mode=mode).cuda()
+        rec = ess_b200.ImageReconstructor(m, H, W, C, 'cuda')
+        img, st, lat = rec.unroll(data, T, C)
+        outs[mode] = (img, st, lat)
+        assert lat[8].shape == (B, 256, 55, 80) and lat[1].shape == (B, 32, 440, 640) and img.shape == (B, 1, H, W)
+        assert bool(torch.isfinite(lat[8]).all()) and float(img.min()) >= 0 and float(img.max()) <= 1
+    for k in (1, 2, 4, 8):
+        assert rel_err(outs['bf16x3'][2][k], outs['fp32'][2][k]) < TOL, k
+    assert rel_err(outs['bf16x3'][0], outs['fp32'][0]) < TOL

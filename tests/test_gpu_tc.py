@@ -1,0 +1,90 @@
+"""tcgen05 / TMA convolution kernel (`-m gpu`): parity against the CPU oracle in both precision modes.
+bf16x3 (3-product split) must meet the 1e-3 contract; single-pass bf16 is checked against a looser
+bound and reported as a separate mode."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import O, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().cuda()
+
+
+def nchw(x):
+    return x.float().permute(0, 3, 1, 2).cpu()
+
+
+def planes_of(x_nchw):
+    from ess_b200 import ops
+    t = nhwc(x_nchw)
+    N, H, W, C = t.shape
+    return ops.split_bf16(ops.Seg(t), N, H, W)
+
+
+def test_split_bf16_roundtrip():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 64, 5, 7, generator=g) * 3
+    hi, lo = planes_of(x)
+    rec = hi.float() + lo.float()
+    assert rel_err(nchw(rec), x) < 2 ** -15
+
+
+@pytest.mark.parametrize('passes,tol', [(3, 1e-3), (1, 3e-2)])
+@pytest.mark.parametrize('N,H,W,C,with_state', [(1, 8, 16, 64, True), (2, 13, 20, 64, False), (1, 7, 10, 128, True),
+                                                (1, 55, 80, 64, True)])
+def test_convlstm_tc(passes, tol, N, H, W, C, with_state):
+    import ess_b200
+    from ess_b200.e2vid import _interleave
+    from ess_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, C, H, W, generator=g)
+    w = torch.randn(4 * C, 2 * C, 3, 3, generator=g) * 0.03
+    b = torch.randn(4 * C, generator=g) * 0.1
+    prev = (torch.randn(N, C, H, W, generator=g), torch.randn(N, C, H, W, generator=g)) if with_state else None
+    h_ref, c_ref = O.convlstm(x, prev, {'p.Gates.weight': w, 'p.Gates.bias': b}, 'p')
+    m = ess_b200.E2VIDRecurrent.__new__(ess_b200.E2VIDRecurrent)
+    hi, lo, kinp = ops.pack_weight_tc(w.cuda(), interleave=4)
+    e = dict(lstm_tc=dict(hi=hi, lo=lo, k_per_tap=kinp), lstm_b=_interleave(b.cuda(), 4))
+    xp = planes_of(x)
+    hp = planes_of(prev[0]) if with_state else None
+    cp = nhwc(prev[1]) if with_state else None
+    h, c, hh, hl = ess_b200.E2VIDRecurrent._lstm_tc(m, e, xp, hp, cp, N, H, W, C, passes)
+    torch.cuda.synchronize()
+    assert rel_err(nchw(h), h_ref) < tol, rel_err(nchw(h), h_ref)
+    assert rel_err(nchw(c), c_ref) < tol
+    assert rel_err(nchw(hh.float() + hl.float()), h_ref) < max(tol, 1e-4)
+
+
+@pytest.mark.parametrize('passes,tol', [(3, 1e-3), (1, 3e-2)])
+@pytest.mark.parametrize('Cin,Cout,H,W', [(32, 64, 16, 32), (64, 128, 24, 16), (128, 256, 14, 22), (32, 64, 110, 160)])
+def test_encoder_conv_tc(passes, tol, Cin, Cout, H, W):
+    """conv5x5 stride 2 + folded BN + ReLU through parity views (and the 32-channel pixel-pair fold)."""
+    import ess_b200
+    from ess_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    N = 2
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 5, 5, generator=g) * 0.05
+    scale = torch.rand(Cout, generator=g) + 0.5
+    bias = torch.randn(Cout, generator=g) * 0.1
+    ref = torch.relu(F.conv2d(x, w * scale.view(-1, 1, 1, 1), bias, stride=2, padding=2))
+    wd = w.cuda()
+    fold = Cin == 32
+    if fold:
+        w6 = torch.zeros((Cout, Cin, 5, 6), device='cuda')
+        w6[..., :5] = wd
+        wd = w6.view(Cout, Cin, 5, 3, 2).permute(0, 4, 1, 2, 3).reshape(Cout, 2 * Cin, 5, 3).contiguous()
+    hi, lo, kinp = ops.pack_weight_tc(wd, scale.cuda())
+    e = dict(tc=dict(hi=hi, lo=lo, k_per_tap=kinp, fold=fold, T=wd.shape[2] * wd.shape[3]), bias=bias.cuda())
+    m = ess_b200.E2VIDRecurrent.__new__(ess_b200.E2VIDRecurrent)
+    oh, ow = H // 2, W // 2
+    out_hi = torch.empty((N, oh, ow, Cout), device='cuda', dtype=torch.bfloat16)
+    out_lo = torch.empty_like(out_hi)
+    ess_b200.E2VIDRecurrent._enc_conv_tc(m, e, planes_of(x), N, H, W, Cout, out_hi, out_lo, passes)
+    torch.cuda.synchronize()
+    got = nchw(out_hi.float() + out_lo.float())
+    assert rel_err(got, ref) < tol, rel_err(got, ref)
