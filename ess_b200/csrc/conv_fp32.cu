@@ -396,7 +396,7 @@ constexpr int WG_K = 16;   // pixels per K-step
 struct WgradParams {
   essb_wgrad d;
   int cin_total;
-  int ci_tiles, co_tiles, splits;
+  int ci_tiles, ci_tiles0, co_tiles, splits;  // ci tiles are per segment (never straddle the boundary)
   long long pix_total;      // N*OH*OW
   long long pix_per_split;  // multiple of WG_K
   int vec0, vec1, vec_dy;
@@ -414,11 +414,12 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_fp32_kernel(const __grid_const
   const int cit = b % p.ci_tiles; b /= p.ci_tiles;
   const int tap = b;
   const int split = blockIdx.y;
-  const int ci0 = cit * WG_T, co0 = cot * WG_T;
-  // the ci tile lies entirely inside one segment (host guarantees tiles do not straddle)
-  const int seg = ci0 >= d.src[0].C ? 1 : 0;
+  const int co0 = cot * WG_T;
+  // ci tiles are enumerated per segment, so a tile lies entirely inside one segment
+  const int seg = cit >= p.ci_tiles0 ? 1 : 0;
   const essb_src& s = d.src[seg];
-  const int cseg0 = ci0 - (seg ? d.src[0].C : 0);
+  const int cseg0 = (seg ? cit - p.ci_tiles0 : cit) * WG_T;
+  const int ci0 = (seg ? d.src[0].C : 0) + cseg0;
   const int vec = seg ? p.vec1 : p.vec0;
   const int dyv = d.dy[tap], dxv = d.dx[tap];
   const int npix = d.OH * d.OW;
@@ -513,16 +514,15 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
 }
 
 struct WgradPlan {
-  int ci_tiles, co_tiles, splits;
+  int ci_tiles, ci_tiles0, co_tiles, splits;
   long long pix_per_split;
 };
 
 int wgrad_plan(const essb_wgrad& d, WgradPlan* pl) {
   const int c0 = d.src[0].C, c1 = d.src[1].ptr ? d.src[1].C : 0;
-  // ci tiles never straddle the segment boundary: segment 0 is padded up to a tile multiple
   const int t0 = (c0 + WG_T - 1) / WG_T, t1 = (c1 + WG_T - 1) / WG_T;
-  if (c1 > 0 && c0 % WG_T != 0) return -1;
   pl->ci_tiles = t0 + t1;
+  pl->ci_tiles0 = t0;
   pl->co_tiles = (d.Cout + WG_T - 1) / WG_T;
   const long long pix = (long long)d.N * d.OH * d.OW;
   const long long base = (long long)d.ntaps * pl->ci_tiles * pl->co_tiles;
@@ -562,9 +562,10 @@ extern "C" int essb_wgrad_fp32(const essb_wgrad* dp, void* stream) {
   if ((rc = check_src(d.src[0], d.H, d.W, "essb_wgrad_fp32 src0")) != ESSB_OK) return rc;
   if ((rc = check_src(d.src[1], d.H, d.W, "essb_wgrad_fp32 src1")) != ESSB_OK) return rc;
   WgradPlan pl;
-  ESSB_REQUIRE(wgrad_plan(d, &pl) == 0, "essb_wgrad_fp32: segment 0 channels (%d) must be a multiple of 64 when two segments are used", d.src[0].C);
+  ESSB_REQUIRE(wgrad_plan(d, &pl) == 0, "essb_wgrad_fp32: bad plan");
   p.cin_total = d.src[0].C + d.src[1].C;
   p.ci_tiles = pl.ci_tiles;
+  p.ci_tiles0 = pl.ci_tiles0;
   p.co_tiles = pl.co_tiles;
   p.splits = pl.splits;
   p.pix_total = (long long)d.N * d.OH * d.OW;

@@ -102,9 +102,9 @@ def test_e2vid_variants_fp32(variant):
     assert rel_err(img, img_r) < TOL and rel_err(lat[8], lat_r[8]) < TOL and rel_err(lat[1], lat_r[1]) < TOL
 
 
-def _oracle_semseg_grads(dec, lat, labels, K, want_inputs=False, **kw):
-    params = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in dec.state_dict().items()}
-    lat_c = {k: v.detach().cpu().clone().requires_grad_(want_inputs) for k, v in lat.items()}
+def _oracle_semseg_grads(dec, lat, labels, K, want_inputs=False, dtype=torch.float32, **kw):
+    params = {k: v.detach().cpu().to(dtype).clone().requires_grad_(True) for k, v in dec.state_dict().items()}
+    lat_c = {k: v.detach().cpu().to(dtype).clone().requires_grad_(want_inputs) for k, v in lat.items()}
     pred = O.semseg_forward(params, lat_c, **kw)
     loss = O.task_loss(pred[1], labels.cpu(), K)
     wrt = list(params.values()) + ([lat_c[8], lat_c[4], lat_c[2]] if want_inputs and kw.get('skip_connect', True)
@@ -121,6 +121,7 @@ def test_semseg_forward_backward_vs_oracle(K, H, W):
     lat = make_latents(B, H, W, device='cuda')
     labels = make_labels(B, H, W, K).cuda()
     pred_r, loss_r, g_r = _oracle_semseg_grads(dec, lat, labels, K, skip_connect=True, skip_type='concat')
+    _, _, g_64 = _oracle_semseg_grads(dec, lat, labels, K, dtype=torch.float64, skip_connect=True, skip_type='concat')
     pred = dec(lat)
     crit = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255)
     loss = crit(pred[1], labels)
@@ -128,16 +129,22 @@ def test_semseg_forward_backward_vs_oracle(K, H, W):
     for k in (1, 2, 4):
         assert rel_err(pred[k], pred_r[k]) < TOL
     assert abs(float(loss) - float(loss_r)) < TOL * abs(float(loss_r))
-    worst = 0.0
+    # End-to-end weight gradients are chaotic (ReLU sign flips behind InstanceNorm): the reference's own
+    # fp32 run differs from its fp64 run by up to ~7e-3.  Criterion used there:
+    #   err(new, fp64) <= max(1e-3, c * err(ref_fp32, fp64)) per layer, max-norm relative (c = 2 there;
+    #   3 here because both sides are single draws of the same rounding-noise distribution).
+    worst = (0.0, 0.0)
     for n, p in dec.named_parameters():
-        ref = g_r[n]
-        err = float((p.grad.cpu() - ref).abs().max() / (ref.abs().max() + 1e-12))
+        r64 = g_64[n]
+        scale = float(r64.abs().max()) + 1e-12
+        e_new = float((p.grad.cpu().double() - r64).abs().max()) / scale
+        e_ref = float((g_r[n].double() - r64).abs().max()) / scale
         if n.endswith('bias') and not n.startswith('decoder_scale_5'):
-            assert float((p.grad.cpu() - ref).abs().max()) < 5e-6, n      # zero true gradient
+            assert float((p.grad.cpu().double() - r64).abs().max()) < 5e-6, n      # zero true gradient
         else:
-            worst = max(worst, err)
-            assert err < 5e-3, (n, err)      # per-layer wgrad: fp32 ordering noise through ReLU/IN chain
-    print('worst weight-grad rel err', worst)
+            worst = max(worst, (e_new, e_ref))
+            assert e_new <= max(1e-3, 3 * e_ref), (n, e_new, e_ref)   # per-kernel exactness: test_gpu_kernels.py
+    print('worst weight-grad rel err vs fp64 (ours, reference-fp32):', worst)
 
 
 def test_semseg_input_grads_with_frozen_params():
