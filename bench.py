@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ESS hot path on B200 (contract: see the task statement).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--mode bf16x3|bf16|fp32]
+
+Metric (BASELINE.json): samples/s of one supervised training iteration -- frozen E2VID encoder unrolled
+over T event windows (forward) + SemSegE2VID decoder forward + Dice/CE loss + backward (+ RAdam step)
+-- on synthetic [B, T*C, H, W] voxel grids.  Workload at every N: BASELINE.json configs[2] "DSEC shape
+640x440, 5 bins, 11 classes, batch=8, ess_supervised" per GPU (weak scaling: 8 samples per GPU; for
+N > 1 the minibatch is sharded by sample with global-batch semantics, ess_b200/dp.py).
+
+One JSON line on rank 0.  `value` = device-resident inputs; `e2e` = the same step through the public
+module API with HOST (pinned) inputs: H2D copy of the events + labels and D2H read of the loss inside
+the timed region.  `--impl reference` times the CPU restatement of the reference (oracle/, "port":
+the reference is pure Python/PyTorch and cannot travel to the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+E2VID_CFG = dict(num_bins=5, skip_type='sum', recurrent_block_type='convlstm', num_encoders=3, base_num_channels=32,
+                 num_residual_blocks=2, norm='BN', use_upsample_conv=False)
+WORK = dict(B=8, T=20, C=5, H=440, W=640, K=11)
+METRIC = 'samples/sec fwd+bwd 640x440x5bin voxel grids'
+
+
+def flops_per_sample(T, C, H, W, K, contract='B'):
+    """Algorithmic FLOPs (2*MAC) of one sample, SURVEY.md s8d / BASELINE.md s3."""
+    P = H * W
+    f_enc = (1600 * C + 519168) * P
+    f_img = 150592 * P
+    f_seg = (331776 + 64 * K) * P
+    if contract == 'A':
+        return T * (f_enc + f_img) + 3 * f_seg
+    return T * f_enc + f_img + 3 * f_seg
+
+
+def synth_inputs(B, T, C, H, W, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    data = torch.randn(B, T * C, H, W, generator=g) * (torch.rand(B, T * C, H, W, generator=g) < 0.2)
+    labels = torch.randint(0, K, (B, H, W), generator=g)
+    labels[:, :5] = 255
+    return data, labels
+
+
+def randomize_bn_(module, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    for m in module.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+            with torch.no_grad():
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(bf16=p.get('bf16_tflops_sustained', 1401.6), bf16_burst=p.get('bf16_tflops', 1645.8),
+                    hbm=p.get('hbm_gbs', 6549.8), source='measured')
+    return dict(bf16=1400.0, bf16_burst=1590.0, hbm=6650.0, source='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        os.remove(self.path)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_sample(windows=2, threads=None):
+    """Times the oracle (CPU restatement of the reference path) on a bounded sample of the workload:
+    B=1, `windows` of the 20 event windows (image decoder on the last one) + the full decoder
+    forward/backward, then extrapolates linearly in T to one full sample.  Returns samples/s."""
+    from oracle import ess_oracle as O
+    w = WORK
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(6)
+    import ess_b200
+    m = ess_b200.E2VIDRecurrent(dict(E2VID_CFG), mode='fp32')      # parameter container only (CPU tensors)
+    randomize_bn_(m)
+    dec = ess_b200.SemSegE2VID(256, w['K'], skip_connect=True, skip_type='concat')
+    e_sd = {k: v.detach() for k, v in m.state_dict().items()}
+    d_sd = {k: v.detach() for k, v in dec.state_dict().items()}
+    data, labels = synth_inputs(1, windows, w['C'], w['H'], w['W'], w['K'], 1234)
+    states = None
+    t_win = []
+    with torch.no_grad():
+        for i in range(windows):
+            t0 = time.perf_counter()
+            ev = data[:, i * w['C']:(i + 1) * w['C']]
+            _, states, latent = O.reconstructor_step(e_sd, E2VID_CFG, ev, states, with_image=False)
+            t_win.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        O.reconstructor_step(e_sd, E2VID_CFG, data[:, :w['C']], states, with_image=True)
+        t_img = max(time.perf_counter() - t0 - min(t_win), 0.0)
+    t0 = time.perf_counter()
+    params = {k: v.clone().requires_grad_(True) for k, v in d_sd.items()}
+    pred = O.semseg_forward(params, {k: v.detach() for k, v in latent.items()})
+    loss = O.task_loss(pred[1], labels, w['K'])
+    torch.autograd.grad(loss, list(params.values()))
+    t_dec = time.perf_counter() - t0
+    t_window = min(t_win[1:]) if len(t_win) > 1 else t_win[0]     # first window has no recurrent input
+    t_sample = w['T'] * t_window + t_img + t_dec
+    return 1.0 / t_sample, dict(t_window_s=t_window, t_image_decoder_s=t_img, t_decoder_fwd_bwd_s=t_dec)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, parts = cpu_reference_sample(windows=2)
+        if i >= args.warmup:
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    sample = 'B=1: 2 of T=20 event windows + image decoder once + full SemSeg decoder fwd/bwd at 440x640, ' \
+             'extrapolated linearly in T to one sample; all host threads'
+    line = dict(impl='reference', metric=METRIC, value=value, unit='samples/s', n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1000.0 / value, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload='DSEC 440x640, C=5 bins, T=20 windows, K=11, ess_supervised (contract B: image on '
+                                     'last window)', batch_per_gpu=WORK['B'], parallelism='cpu'),
+                cpu_baseline=dict(value=value, unit='samples/s', cores=torch.get_num_threads(), kind='port',
+                                  sample=sample, parts=parts),
+                e2e=dict(value=value, unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--mode', default=os.environ.get('ESS_B200_MODE', 'bf16x3'), choices=['bf16x3', 'bf16', 'fp32'])
+    ap.add_argument('--batch', type=int, default=WORK['B'], help='samples per GPU')
+    ap.add_argument('--windows', type=int, default=WORK['T'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-optimizer', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import ess_b200
+    from ess_b200 import _lib, dp
+    from ess_b200.optim import RAdam
+    rank, world, local = dp.init_from_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product arm')
+    dev = torch.device('cuda', local)
+    _lib.check(_lib.lib().essb_device_check(), 'device check')
+    w = dict(WORK, B=args.batch, T=args.windows)
+    B, T, C, H, W, K = w['B'], w['T'], w['C'], w['H'], w['W'], w['K']
+
+    torch.manual_seed(6)
+    e2vid = ess_b200.E2VIDRecurrent(dict(E2VID_CFG), mode=args.mode)
+    randomize_bn_(e2vid)
+    e2vid = e2vid.to(dev).eval()
+    for p in e2vid.parameters():
+        p.requires_grad = False
+    dec = ess_b200.SemSegE2VID(256, K, skip_connect=True, skip_type='concat').to(dev)
+    crit = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], gamma=2.0, num_classes=K, ignore_index=255)
+    rec = ess_b200.ImageReconstructor(e2vid, H, W, C, dev)
+    bucket = None
+    if world > 1:
+        dp.attach(rec, crit)
+        bucket = dp.GradBucket(dec.parameters())
+    opt = None if args.no_optimizer else RAdam([p for p in dec.parameters() if p.requires_grad], lr=5e-4,
+                                               weight_decay=0., betas=(0., 0.999))
+
+    # two distinct device-resident batches (901 MB each >> 126 MB L2) alternate between timed steps
+    host = [synth_inputs(B, T, C, H, W, K, 1234 + 17 * rank + i) for i in range(2)]
+    host = [(d.pin_memory(), l.pin_memory()) for d, l in host]
+    devb = [(d.to(dev), l.to(dev)) for d, l in host]
+    stage_d = torch.empty_like(devb[0][0])
+    stage_l = torch.empty_like(devb[0][1])
+
+    def step(data, labels):
+        if bucket is not None:
+            bucket.zero_()
+        else:
+            for p in dec.parameters():
+                p.grad = None
+        _, _, latent = rec.unroll(data, T, C)                     # ess_supervised_trainer.py:126-130
+        latent = {k: v.detach() for k, v in latent.items()}       # :145-146
+        pred = dec(latent)                                        # :148
+        loss = crit(pred[1], labels)                              # :149
+        loss.backward()                                           # :103
+        if bucket is not None:
+            bucket.allreduce_()
+        if opt is not None:
+            opt.step()                                            # :106
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms)
+
+    for i in range(args.warmup):
+        step(*devb[i & 1])
+    clocks = ClockSampler(local)
+    clocks.start()
+    _lib.PROFILE = []
+    launches0 = _lib.launch_count
+    ms_dev = timed(lambda i: step(*devb[i & 1]), args.steps)
+    launches = _lib.launch_count - launches0
+    prof = _lib.PROFILE
+    _lib.PROFILE = None
+
+    def e2e_step(i):
+        d, l = host[i & 1]
+        stage_d.copy_(d, non_blocking=True)
+        stage_l.copy_(l, non_blocking=True)
+        loss = step(stage_d, stage_l)
+        return float(loss.item())
+
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+    clk = clocks.stop()
+
+    samples = args.steps * B * world
+    value = samples / (ms_dev / 1e3)
+    e2e_value = samples / (ms_e2e / 1e3)
+    peaks = load_peaks()
+
+    # roofline of the dominant kernel (the fused tcgen05 ConvLSTM cell): algorithmic FLOPs per launch /
+    # mean launch duration from CUDA events recorded on the launching stream inside the timed region
+    roof = None
+    by_tag = {}
+    for tag, fl, a, b in prof:
+        t = by_tag.setdefault(tag, [0.0, 0.0, 0])
+        t[0] += fl
+        t[1] += a.elapsed_time(b) / 1e3
+        t[2] += 1
+    if 'lstm_tc' in by_tag:
+        fl, sec, n = by_tag['lstm_tc']
+        ach = fl / sec / 1e12
+        roof = dict(kernel='conv_tc_kernel<LSTM> (fused ConvLSTM cell, %d launches)' % n, bound='tensor', achieved=ach,
+                    peak=peaks['bf16'], unit='TFLOP/s', frac=ach / peaks['bf16'], traffic=None,
+                    peak_source='%s bf16 dense sustained (MEASURED_PEAKS.json)' % peaks['source'],
+                    note='algorithmic FLOPs (2*MAC, no credit for the 3 split passes): in bf16x3 mode the tensor pipe '
+                         'executes 3x this, so the mode ceiling is peak/3',
+                    mean_launch_ms=sec / n * 1e3, share_of_step=sec * 1e3 / ms_dev,
+                    mma_frac_of_peak=ach * (3 if args.mode == 'bf16x3' else 1) / peaks['bf16'])
+        if 'enc_tc' in by_tag:
+            fl2, sec2, n2 = by_tag['enc_tc']
+            roof['enc_tc'] = dict(achieved=fl2 / sec2 / 1e12, mean_launch_ms=sec2 / n2 * 1e3, launches=n2,
+                                  share_of_step=sec2 * 1e3 / ms_dev)
+    elif args.mode == 'fp32':
+        roof = dict(kernel='conv_fp32_kernel', bound='tensor', achieved=None, peak=peaks['bf16'], unit='TFLOP/s',
+                    frac=None, traffic=None)
+
+    line = dict(metric=METRIC, value=value, unit='samples/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype={'bf16x3': 'bf16x3-split (f32 accumulate, f32 epilogues)', 'bf16': 'bf16 (f32 accumulate)',
+                       'fp32': 'f32'}[args.mode],
+                data='synthetic',
+                config=dict(workload='DSEC 440x640, C=5 bins, T=%d windows, K=11, ess_supervised (contract B: E2VID image '
+                                     'decoder on the last window only)' % T,
+                            batch_per_gpu=B, global_batch=B * world, parallelism='dp%d' % world, mode=args.mode,
+                            optimizer='none' if opt is None else 'RAdam (fused kernel)',
+                            l2_policy='two alternating 901 MB input batches (inputs larger than the 126 MB L2)',
+                            gflop_per_sample=flops_per_sample(T, C, H, W, K) / 1e9),
+                tflops=value * flops_per_sample(T, C, H, W, K) / 1e12,
+                e2e=dict(value=e2e_value, unit='samples/s', ms_per_step=ms_e2e / args.steps,
+                         h2d_bytes_per_step=stage_d.numel() * 4 + stage_l.numel() * 8, d2h_bytes_per_step=4),
+                gpu_launches=launches, clocks=dict(sm_mhz=clk['sm_mhz'], sm_max_mhz=clk['sm_max_mhz'],
+                                                   reasons=clk['reasons'], samples=clk['samples']),
+                roofline=roof)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cores = os.cpu_count() or 1
+            v, parts = cpu_reference_sample(windows=2, threads=cores)
+            line['cpu_baseline'] = dict(value=v, unit='samples/s', cores=torch.get_num_threads(), kind='port',
+                                        sample='B=1: 2 of T=20 windows + image decoder once + SemSeg decoder fwd/bwd at '
+                                               '440x640 through oracle/ess_oracle.py, extrapolated linearly in T',
+                                        parts=parts)
+        except Exception as ex:   # the baseline must never take the measurement down
+            line['cpu_baseline'] = dict(value=None, error=repr(ex))
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -100,6 +100,7 @@ SIGNATURES = {
     'essb_task_loss_bwd': (_I, [_P, _I, _P, _L, _I, _L, _P, _I, _I, _P, _P, _I, _P]),
     'essb_confusion': (_I, [_P, _I, _P, _L, _I, _L, _P, _P]),
     'essb_confusion_labels': (_I, [_P, _P, _L, _I, _L, _P, _P]),
+    'essb_radam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P]),
     'essb_split_bf16': (_I, [C.POINTER(Src), _I, _I, _I, _P, _P, _I, _I, _P]),
     'essb_pack_weight_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'essb_conv_tc_run': (_I, [C.POINTER(ConvTc), _P]),
@@ -130,5 +131,13 @@ def check(rc, what=''):
         raise RuntimeError('ess_b200 %s failed (status %d): %s' % (what, rc, msg))
 
 
+# kernels launched per successful API call (for bench.py's `gpu_launches` claim)
+_LAUNCHES = {'essb_wgrad_fp32': 4, 'essb_colsum': 2}
+launch_count = 0
+PROFILE = None   # when a list: (tag, algorithmic_flops, start_event, end_event) per profiled launch
+
+
 def call(name, *args):
+    global launch_count
     check(getattr(lib(), name)(*args), name)
+    launch_count += _LAUNCHES.get(name, 1)

@@ -408,9 +408,36 @@ __global__ void bilinear_up2_kernel(const float* __restrict__ in, float* __restr
   out[idx] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
 }
 
+// ------------------------------------------------------------------------------------ RAdam
+__global__ void radam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, float beta1, float beta2, float step_lr, float eps,
+                             float wd_lr, int rectified) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+  v[i] = vi;
+  m[i] = mi;
+  float pi = p[i];
+  if (wd_lr != 0.f) pi += -wd_lr * pi;
+  if (rectified) pi += -step_lr * (mi / (sqrtf(vi) + eps));
+  else pi += -step_lr * mi;
+  p[i] = pi;
+}
+
 }  // namespace
 
 // =================================================================================== C ABI
+extern "C" int essb_radam_step(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2,
+                               float step_lr, float eps, float wd_lr, int rectified, void* stream) {
+  ESSB_REQUIRE(p && g && m && v && n > 0, "essb_radam_step: bad arguments");
+  radam_kernel<<<ew_blocks(n), EW_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, n, beta1, beta2, step_lr, eps, wd_lr,
+                                                                     rectified);
+  ESSB_LAUNCH_CHECK("essb_radam_step");
+  return ESSB_OK;
+}
+
 extern "C" int essb_pack_weight(const float* w, const float* scale, float* out, int Cout, int Cin, int T,
                                 int transposed_layout, int swap_io, int flip, int interleave, void* stream) {
   ESSB_REQUIRE(w && out && Cout > 0 && Cin > 0 && T > 0, "essb_pack_weight: bad arguments");

@@ -418,7 +418,7 @@ class E2VIDRecurrent(nn.Module):
         d.ntaps = len(taps)
         for t, (dy, dx, v, wi) in enumerate(taps):
             d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, v, wi
-        ops.conv_tc(d)
+        ops.conv_tc(d, tag='enc_tc')
 
     def _lstm_tc(self, e, x_planes, h_planes, c_prev, N, oh, ow, C, passes):
         """Fused ConvLSTM cell (submodules.py:190-230): gates GEMM + sigma/tanh + state update."""
@@ -448,5 +448,5 @@ class E2VIDRecurrent(nn.Module):
         d.ntaps = len(taps)
         for t, (dy, dx, wi) in enumerate(taps):
             d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, 0, wi
-        ops.conv_tc(d)
+        ops.conv_tc(d, tag='lstm_tc')
         return h, c, hh, hl

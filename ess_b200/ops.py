@@ -370,5 +370,17 @@ def pick_bw_log2(OW, OH):
     return best
 
 
-def conv_tc(d: ConvTc):
+def conv_tc(d: ConvTc, tag=None):
+    """essb_conv_tc_run; when _lib.PROFILE is a list, brackets the launch with CUDA events on the
+    launching stream and records (tag, algorithmic FLOPs, start, end)."""
+    prof = _lib.PROFILE
+    if prof is None:
+        call('essb_conv_tc_run', C.byref(d), _stream())
+        return
+    k = sum(d.seg_C[s] for s in range(d.nseg)) * d.ntaps
+    flops = 2.0 * d.N * d.OH * d.OW * d.Cout * k
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     call('essb_conv_tc_run', C.byref(d), _stream())
+    e1.record()
+    prof.append((tag or 'conv_tc', flops, e0, e1))

@@ -210,6 +210,12 @@ int essb_confusion(const float* logits, int ld, const int64_t* target, int64_t n
 int essb_confusion_labels(const int64_t* pred, const int64_t* target, int64_t npix, int K,
                           int64_t ignore_index, int64_t* conf, void* stream);
 
+/* ---- optimizer (utils/radam.py:15-80, one fused elementwise update per tensor) ------------------ */
+/* v = b2*v + (1-b2)*g^2; m = b1*m + (1-b1)*g; p -= wd_lr*p; p -= step_lr * (rectified ? m/(sqrt(v)+eps) : m)
+ * with step_lr = step_size*lr and wd_lr = weight_decay*lr computed on the host exactly as radam.py:53-75. */
+int essb_radam_step(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2,
+                    float step_lr, float eps, float wd_lr, int rectified, void* stream);
+
 /* ---- tcgen05 / TMA tensor-core path (sm_100a) --------------------------------------------- */
 /* Split an fp32 tensor into bf16 hi/lo planes: hi = bf16(x), lo = bf16(x - hi)  (x ~= hi + lo to
  * 2^-17 relative).  Optionally applies the same normalise/ReLU/upsample transform as essb_src. */

@@ -355,3 +355,29 @@ def supervised_step(e2vid_sd, e2vid_cfg, semseg_sd, data, labels, num_windows, c
     loss = task_loss(pred[1], labels, num_classes, ignore_index)
     grads = torch.autograd.grad(loss, list(params.values()))
     return loss.detach(), pred[1].detach(), dict(zip(params.keys(), grads))
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer: RAdam (utils/radam.py:15-80), restated functionally for one tensor
+# ------------------------------------------------------------------------------------------------
+def radam_step(p, grad, state, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    """One RAdam update of tensor `p` in place; `state` = dict(step, exp_avg, exp_avg_sq) (radam.py:33-75)."""
+    beta1, beta2 = betas
+    if not state:
+        state.update(step=0, exp_avg=torch.zeros_like(p), exp_avg_sq=torch.zeros_like(p))
+    state['exp_avg_sq'].mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    state['exp_avg'].mul_(beta1).add_(grad, alpha=1 - beta1)
+    state['step'] += 1
+    t = state['step']
+    beta2_t = beta2 ** t
+    n_max = 2 / (1 - beta2) - 1
+    n_sma = n_max - 2 * t * beta2_t / (1 - beta2_t)
+    if weight_decay != 0:
+        p.add_(p, alpha=-weight_decay * lr)
+    if n_sma >= 5:
+        step_size = math.sqrt((1 - beta2_t) * (n_sma - 4) / (n_max - 4) * (n_sma - 2) / n_sma * n_max /
+                              (n_max - 2)) / (1 - beta1 ** t)
+        p.addcdiv_(state['exp_avg'], state['exp_avg_sq'].sqrt().add_(eps), value=-step_size * lr)
+    else:
+        p.add_(state['exp_avg'], alpha=-1.0 / (1 - beta1 ** t) * lr)
+    return p

@@ -249,3 +249,18 @@ def test_layout_and_bilinear():
     ch = torch.randn(2, 8, 6, 4, generator=g)
     s = ops.upsample2_bwd(nhwc(ch), 3, 2, 8)
     assert rel_err(nchw(s), F.avg_pool2d(ch, 2) * 4) < 1e-6
+
+
+def test_radam_kernel_vs_oracle():
+    import ess_b200.optim
+    torch.manual_seed(0)
+    w = torch.nn.Parameter(torch.randn(33, 17, device='cuda'))
+    w2 = w.detach().cpu().clone()
+    opt = ess_b200.optim.RAdam([w], lr=5e-4, weight_decay=0., betas=(0., 0.999))
+    state = {}
+    for i in range(9):       # crosses the N_sma >= 5 rectification switch (radam.py:60-66)
+        g = torch.randn(33, 17)
+        w.grad = g.cuda()
+        opt.step()
+        O.radam_step(w2, g, state, 5e-4, (0., 0.999))
+        assert rel_err(w.detach(), w2) < 1e-6, i

@@ -137,3 +137,20 @@ def test_reference_trainer_runs_with_shim():
         assert all(torch.isfinite(torch.tensor(losses)))
     finally:
         os.remove(path)
+
+
+@needs_ref
+def test_oracle_radam_vs_live_reference():
+    ref_shim.install()
+    from utils.radam import RAdam
+    torch.manual_seed(0)
+    w = torch.nn.Parameter(torch.randn(7, 5))
+    w2 = w.detach().clone()
+    opt = RAdam([w], lr=5e-4, weight_decay=0., betas=(0., 0.999))
+    state = {}
+    for i in range(9):       # crosses the N_sma >= 5 switch
+        g = torch.randn(7, 5)
+        w.grad = g.clone()
+        opt.step()
+        O.radam_step(w2, g, state, 5e-4, (0., 0.999))
+        assert torch.allclose(w2, w.detach(), rtol=1e-6, atol=1e-8), i
