@@ -85,6 +85,7 @@ SIGNATURES = {
     'essb_in_finalize': (_I, [_P, _I, _I, _I, _L, _F, _P, _P, _P]),
     'essb_norm_act_add': (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _I, _L, _I, _P]),
     'essb_in_bwd_blocks': (_I, [_L]),
+    'essb_in_stats': (_I, [_P, _I, _P, _I, _L, _I, _P]),
     'essb_in_bwd_pass1': (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
     'essb_in_bwd_pass2': (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _L, _I, _P]),
     'essb_partial_reduce': (_I, [_P, _I, _I, _I, _P, _P]),

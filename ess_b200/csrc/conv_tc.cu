@@ -11,8 +11,8 @@
 // MMA: tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, fp32 accumulators in TMEM.  In the
 //   3-pass mode each K-step issues hi*hi + lo*hi + hi*lo (drops only lo*lo ~ 2^-16 relative), which
 //   restores fp32-level accuracy (logits 1.1e-4 vs 4.7e-2 for single-pass bf16).
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-//   warps 2..5 = epilogue (TMEM lane quarter = warp % 4).  Two TMEM accumulator buffers let the
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+//   warps 2..9 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter split the columns).  Two TMEM accumulator buffers let the
 //   epilogue of tile i overlap the main loop of tile i+1.  Persistent CTAs, one per SM.
 // Epilogues: LINEAR (bias / residual / ReLU / sigmoid / strided placement / bf16 planes out) and
 //   LSTM (sigma/tanh gates + cell/hidden update in registers: the 4C-channel `gates` tensor of
@@ -24,7 +24,7 @@
 
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;               // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TC_M = 128;
 constexpr int TC_KCH = 64;                      // channels per stage (128 B of bf16 = one swizzle row)
 constexpr int A_TILE_BYTES = TC_M * TC_KCH * 2; // 16 KB
@@ -162,6 +162,10 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+// fast gate non-linearities (MUFU.EX2 + MUFU.RCP; ~1e-6 absolute error, far inside the 1e-3 contract)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 2.f * sigmoid_fast(2.f * x) - 1.f; }
+
 struct alignas(16) bf16x8 {
   __nv_bfloat16 v[8];
 };
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[b], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
     tma_prefetch_desc(&p.tmB_hi);
@@ -287,8 +291,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
   } else {
-    // ============================================================ epilogue warps (2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ============================================================ epilogue warps (2..9)
+    // TMEM lane quarter = warp % 4 (hardware rule); the two warps that share a quarter split the
+    // accumulator columns in interleaved 32-column chunks (half 0: 0, 64, ..; half 1: 32, 96, ..).
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     uint32_t tph[2] = {0, 0};
     int local = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
@@ -301,12 +308,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int m = q * 32 + lane;
       const int oy = tyi * BH + (m >> p.bw_log2), ox = txi * BW + (m & (BW - 1));
       const bool valid = oy < p.OH && ox < p.OW;
+      const int n0 = nt * p.BN;
+      const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
+      // LSTM: the previous cell state does not depend on the MMA -> fetch it BEFORE waiting for the
+      // accumulator so its latency hides under the main loop of this tile
+      float cp[4][8];
+      if constexpr (EPI == ESSB_EPI_LSTM) {
+        const int hidden = p.Cout >> 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = half * 32 + j * 64;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) cp[j][e] = 0.f;
+          if (valid && p.aux0 && c0 < p.BN) {
+            const float* src = p.aux0 + pix * hidden + ((n0 + c0) >> 2);
+            const float4 c0v = *reinterpret_cast<const float4*>(src);
+            const float4 c1v = *reinterpret_cast<const float4*>(src + 4);
+            cp[j][0] = c0v.x; cp[j][1] = c0v.y; cp[j][2] = c0v.z; cp[j][3] = c0v.w;
+            cp[j][4] = c1v.x; cp[j][5] = c1v.y; cp[j][6] = c1v.z; cp[j][7] = c1v.w;
+          }
+        }
+      }
       mbar_wait(&tfull_bar[buf], tph[buf]);
       tph[buf] ^= 1;
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
-      const int n0 = nt * p.BN;
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c0 = half * 32 + j * 64;
+        if (c0 >= p.BN) break;  // warp-uniform
         uint32_t r[32];
         __syncwarp();
         tmem_ld32(t_addr + (uint32_t)c0, r);
@@ -317,17 +347,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           // columns co = 4*ch + {in, remember, out, cell}; 32 columns = 8 channels
           const int hidden = p.Cout >> 2;
           const int ch0 = (n0 + c0) >> 2;
-          const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
-          float cp[8];
-          if (p.aux0) {
-            const float4 c0v = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0);
-            const float4 c1v = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0 + 4);
-            cp[0] = c0v.x; cp[1] = c0v.y; cp[2] = c0v.z; cp[3] = c0v.w;
-            cp[4] = c1v.x; cp[5] = c1v.y; cp[6] = c1v.z; cp[7] = c1v.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) cp[e] = 0.f;
-          }
           float hv[8], cv[8];
           bf16x8 hh, hl;
 #pragma unroll
@@ -339,9 +358,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const float4 b4 = *reinterpret_cast<const float4*>(p.bias + co);
               gi += b4.x; gf += b4.y; go += b4.z; gc += b4.w;
             }
-            const float cell = essb_sigmoid(gf) * cp[e] + essb_sigmoid(gi) * tanhf(gc);
+            const float cell = sigmoid_fast(gf) * cp[j][e] + sigmoid_fast(gi) * tanh_fast(gc);
             cv[e] = cell;
-            hv[e] = essb_sigmoid(go) * tanhf(cell);
+            hv[e] = sigmoid_fast(go) * tanh_fast(cell);
             split_bf16(hv[e], hh.v[e], hl.v[e]);
           }
           float* ho = p.out + pix * hidden + ch0;

@@ -190,6 +190,53 @@ __global__ void __launch_bounds__(256) in_bwd_pass1_kernel(
   }
 }
 
+// per-block (sum, sumsq) of y over pixels: partial [N][blocks][C][2].  Same thread mapping as pass 1.
+__global__ void __launch_bounds__(256) in_stats_kernel(const float* __restrict__ y, int ld_y,
+                                                       float* __restrict__ partial, long long P, int C) {
+  __shared__ float red[8][32][8];
+  const int n = blockIdx.y, blk = blockIdx.x;
+  const int CQ = C >> 2;
+  const int cq_base = blockIdx.z * 32;
+  const int cq_left = CQ - cq_base;
+  int lpp = 32;
+  if (cq_left < 32) { lpp = 1; while (lpp < cq_left) lpp <<= 1; }
+  const int ppw = 32 / lpp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane % lpp, sub = lane / lpp;
+  const bool cq_ok = q < cq_left;
+  const int c = (cq_base + q) * 4;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long p_begin = (long long)blk * BWD_PIX_PER_BLOCK;
+  for (int i = warp * ppw + sub; i < BWD_PIX_PER_BLOCK; i += 8 * ppw) {
+    const long long pp = p_begin + i;
+    if (pp >= P || !cq_ok) continue;
+    const float4 v = *reinterpret_cast<const float4*>(y + ((long long)n * P + pp) * ld_y + c);
+    s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+    s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
+  }
+  for (int o = lpp; o < 32; o <<= 1) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
+      s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { red[warp][lane][e] = s1[e]; red[warp][lane][4 + e] = s2[e]; }
+  __syncthreads();
+  if (warp == 0 && lane < lpp && cq_ok) {
+    float* dst = partial + (((size_t)n * gridDim.x + blk) * C + c) * 2;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) { a += red[w8][lane][e]; b += red[w8][lane][4 + e]; }
+      dst[e * 2] = a;
+      dst[e * 2 + 1] = b;
+    }
+  }
+}
+
 __global__ void in_bwd_pass2_kernel(const float* __restrict__ g, const float* __restrict__ y, int ld_y,
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ gsum, float* __restrict__ dy, long long P, int C,
@@ -489,6 +536,17 @@ extern "C" int essb_norm_act_add(const float* y, int ld_y, const float* mean, co
   norm_act_add_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(y, ld_y, mean, rstd, relu, res,
                                                                                 ld_res, out, ld_out, P, C, total);
   ESSB_LAUNCH_CHECK("essb_norm_act_add");
+  return ESSB_OK;
+}
+
+extern "C" int essb_in_stats(const float* y, int ld_y, float* partial, int N, int64_t P, int C, void* stream) {
+  ESSB_REQUIRE(y && partial && N > 0 && P > 0 && C > 0 && C % 4 == 0, "essb_in_stats: bad arguments (C %% 4 == 0)");
+  int rc;
+  if ((rc = check_vec4(y, ld_y, "essb_in_stats"))) return rc;
+  const int blocks = (int)((P + BWD_PIX_PER_BLOCK - 1) / BWD_PIX_PER_BLOCK);
+  dim3 grid(blocks, N, (C / 4 + 31) / 32);
+  in_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, ld_y, partial, P, C);
+  ESSB_LAUNCH_CHECK("essb_in_stats");
   return ESSB_OK;
 }
 

@@ -370,6 +370,40 @@ def pick_bw_log2(OW, OH):
     return best
 
 
+def in_stats(y, count=None):
+    """InstanceNorm statistics (mean, rstd) of a pixel-major tensor [N, H, W, C] (separate pass)."""
+    N, H, W, Cc = y.shape
+    blocks = _lib.lib().essb_in_bwd_blocks(H * W)
+    partial = torch.empty((N, blocks, Cc, 2), device=y.device, dtype=torch.float32)
+    call('essb_in_stats', _p(y), Cc, _p(partial), N, H * W, Cc, _stream())
+    return in_finalize(partial, count or H * W)
+
+
+def conv_tc_dense(planes, w_hi, w_lo, k_per_tap, taps, N, H, W, Cout, passes, bias=None, out=None, act=ACT_NONE,
+                  tag=None):
+    """Stride-1 gather-convolution on the tcgen05 kernel over ONE dense bf16 hi/lo plane pair
+    [N, H, W, Cin] (Cin a multiple of 64; concatenated inputs are laid out side by side by
+    split_bf16(c_off=...)).  Returns the fp32 result [N, H, W, Cout]."""
+    hi, lo = planes
+    d = ConvTc()
+    dense_view(d.views[0], hi, lo)
+    d.n_views, d.nseg = 1, 1
+    d.seg_C[0], d.seg_view0[0], d.seg_koff[0] = hi.shape[-1], 0, 0
+    d.k_per_tap, d.n_w_taps, d.w_rows = k_per_tap, w_hi.shape[1] // k_per_tap, w_hi.shape[0]
+    d.w_hi, d.w_lo, d.bias = _p(w_hi), _p(w_lo), _p(bias)
+    if out is None:
+        out = torch.empty((N, H, W, Cout), device=hi.device, dtype=torch.float32)
+    d.out, d.ldo = _p(out), out.shape[-1]
+    d.N, d.OH, d.OW, d.Cout = N, H, W, Cout
+    d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = H, W, 1, 0, 1, 0
+    d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, act, passes, pick_bw_log2(W, H)
+    d.ntaps = len(taps)
+    for t, (dy, dx, wi) in enumerate(taps):
+        d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, 0, wi
+    conv_tc(d, tag=tag)
+    return out
+
+
 def conv_tc(d: ConvTc, tag=None):
     """essb_conv_tc_run; when _lib.PROFILE is a list, brackets the launch with CUDA events on the
     launching stream and records (tag, algorithmic FLOPs, start, end)."""

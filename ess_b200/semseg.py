@@ -90,6 +90,10 @@ class SemSegE2VID(nn.Module):
             self.decoder_scale_4 = nn.Sequential(nn.Identity(), _ReLUINSConv2d(tch, tch // 2))
             tch //= 2
         self.decoder_scale_5 = nn.Sequential(nn.Conv2d(tch, output_c, 1, 1, 0))
+        # precision mode of the 3x3 convolutions (forward + dgrad): 'fp32' (CUDA cores, exact),
+        # 'bf16x3' (tcgen05, fp32-parity split) or 'bf16'; constructor signature stays the reference's
+        from .e2vid import default_mode
+        self.mode = default_mode()
         self._build_program()
 
     # ------------------------------------------------------------------------------- static graph
@@ -184,7 +188,9 @@ class _DecoderFn(torch.autograd.Function):
         P = dict(zip(names, params))
         T = {0: _nhwc(x8), 1: _nhwc(x4), 2: _nhwc(x2)}
         S = {}
-        packed = {}
+        tc = module.mode != 'fp32'
+        passes = 3 if module.mode == 'bf16x3' else 1
+        ctx.mode = module.mode
         for nd in nodes:
             if isinstance(nd, _Conv):
                 first = T[nd.srcs[0][0]]
@@ -198,13 +204,30 @@ class _DecoderFn(torch.autograd.Function):
                     else:
                         segs.append(Seg(T[sid], ups=ups))
                 w = P[nd.w]
-                wp = ops.pack_weight(w)
-                packed[nd.out] = wp
-                y, _, st, _ = ops.conv(segs, wp, P[nd.b].detach().float().contiguous(), N, H, W, H, W, nd.cout,
-                                       _taps(nd.k), epilogue=EPI_LINEAR, act=ACT_NONE, want_stats=nd.stats)
-                T[nd.out] = y
-                if nd.stats:
-                    S[nd.out] = ops.in_finalize(st, H * W)
+                bias = P[nd.b].detach().float().contiguous()
+                cin_total = w.shape[1]
+                if tc and nd.k == 3 and cin_total % 64 == 0 and nd.cout in (32, 64, 128, 256):
+                    # tensor-core path: operand planes = the transformed (IN/ReLU/upsample/concat) input
+                    hi = torch.empty((N, H, W, cin_total), device=first.device, dtype=torch.bfloat16)
+                    lo = torch.empty_like(hi)
+                    c_off = 0
+                    for sg in segs:
+                        ops.split_bf16(sg, N, H, W, hi, lo, c_off)
+                        c_off += sg.C if sg.C is not None else sg.t.shape[-1]
+                    w_hi, w_lo, kinp = ops.pack_weight_tc(w)
+                    y = ops.conv_tc_dense((hi, lo), w_hi, w_lo, kinp, _taps(nd.k), N, H, W, nd.cout, passes, bias=bias,
+                                          tag='seg_fwd')
+                    del hi, lo
+                    T[nd.out] = y
+                    if nd.stats:
+                        S[nd.out] = ops.in_stats(y)
+                else:
+                    wp = ops.pack_weight(w)
+                    y, _, st, _ = ops.conv(segs, wp, bias, N, H, W, H, W, nd.cout, _taps(nd.k), epilogue=EPI_LINEAR,
+                                           act=ACT_NONE, want_stats=nd.stats)
+                    T[nd.out] = y
+                    if nd.stats:
+                        S[nd.out] = ops.in_finalize(st, H * W)
             else:
                 src = T[nd.src]
                 T[nd.out] = ops.norm_act_add(src, S[nd.src][0], S[nd.src][1], relu=nd.relu,
@@ -285,13 +308,26 @@ class _DecoderFn(torch.autograd.Function):
                     grads[nd.b] = db
             c_off = 0
             dtaps = [(-dy, -dx, wi) for (dy, dx, wi) in taps]
+            tc = ctx.mode != 'fp32' and nd.k == 3 and nd.cout % 32 == 0
+            passes = 3 if ctx.mode == 'bf16x3' else 1
+            gplanes = None
             for (sid, xf, ups) in nd.srcs:
                 src = T[sid]
                 cs = src.shape[-1]
                 if need[sid]:
                     wseg = w.detach()[:, c_off:c_off + cs].contiguous()
-                    wp = ops.pack_weight(wseg, swap_io=True)
-                    dA, _, _, _ = ops.conv([Seg(gy)], wp, None, N, H, W, H, W, cs, dtaps)
+                    if tc and cs in (64, 128, 256):
+                        kinp = (nd.cout + 63) // 64 * 64
+                        if gplanes is None:       # bf16 hi/lo planes of dY, channel-padded to 64 with zeros
+                            alloc = torch.zeros if kinp != nd.cout else torch.empty
+                            gplanes = (alloc((N, H, W, kinp), device=gy.device, dtype=torch.bfloat16),
+                                       alloc((N, H, W, kinp), device=gy.device, dtype=torch.bfloat16))
+                            ops.split_bf16(Seg(gy), N, H, W, gplanes[0], gplanes[1], 0)
+                        w_hi, w_lo, _ = ops.pack_weight_tc(wseg, swap_io=True, kin_pad=kinp)
+                        dA = ops.conv_tc_dense(gplanes, w_hi, w_lo, kinp, dtaps, N, H, W, cs, passes, tag='seg_dgrad')
+                    else:
+                        wp = ops.pack_weight(wseg, swap_io=True)
+                        dA, _, _, _ = ops.conv([Seg(gy)], wp, None, N, H, W, H, W, cs, dtaps)
                     if xf == 'nr':
                         add_grad(sid, ops.in_backward(dA, src, S[sid][0], S[sid][1], relu=True, ups=ups), True)
                     elif ups:

@@ -155,6 +155,9 @@ int essb_norm_act_add(const float* y, int ld_y, const float* mean, const float* 
  *         per-block partial sums of g and g*xhat  -> partial [N][blocks][C][2]
  * pass 2: dy = rstd * (g - mean_p(g) - xhat * mean_p(g*xhat))                                    */
 int essb_in_bwd_blocks(int64_t P);
+/* per-block (sum, sumsq) partials of y [N][P][ld_y] -> partial [N][essb_in_bwd_blocks(P)][C][2]; used
+ * on the tensor-core path, whose conv epilogue does not emit the statistics itself. */
+int essb_in_stats(const float* y, int ld_y, float* partial, int N, int64_t P, int C, void* stream);
 int essb_in_bwd_pass1(const float* dA, int ld_dA, int ups, const float* extra, int ld_extra,
                       const float* y, int ld_y, const float* mean, const float* rstd, int relu,
                       float* g, float* partial, int N, int H, int W, int C, void* stream);

@@ -113,11 +113,13 @@ def _oracle_semseg_grads(dec, lat, labels, K, want_inputs=False, dtype=torch.flo
     return pred, loss, dict(zip(list(params.keys()) + ['in8', 'in4', 'in2'][:len(wrt) - len(params)], grads))
 
 
+@pytest.mark.parametrize('mode', ['fp32', 'bf16x3'])
 @pytest.mark.parametrize('K,H,W', [(11, 64, 96), (6, 40, 56)])
-def test_semseg_forward_backward_vs_oracle(K, H, W):
+def test_semseg_forward_backward_vs_oracle(K, H, W, mode):
     import ess_b200
     B = 2
     dec = make_semseg(K).cuda()
+    dec.mode = mode          # fp32: CUDA-core kernels; bf16x3: tcgen05 forward + dgrad (wgrad stays fp32)
     lat = make_latents(B, H, W, device='cuda')
     labels = make_labels(B, H, W, K).cuda()
     pred_r, loss_r, g_r = _oracle_semseg_grads(dec, lat, labels, K, skip_connect=True, skip_type='concat')
@@ -143,7 +145,13 @@ def test_semseg_forward_backward_vs_oracle(K, H, W):
             assert float((p.grad.cpu().double() - r64).abs().max()) < 5e-6, n      # zero true gradient
         else:
             worst = max(worst, (e_new, e_ref))
-            assert e_new <= max(1e-3, 3 * e_ref), (n, e_new, e_ref)   # per-kernel exactness: test_gpu_kernels.py
+            # A single ReLU sign flip (an activation within ~1e-6 of zero) moves a handful of entries by
+            # ~1/sqrt(H*W) in max-norm, so the max-norm bound carries the fp64-anchored slack while the
+            # relative L2 error over the whole tensor must meet the 1e-3 contract outright.
+            # Per-kernel exactness (no chaos) is asserted in tests/test_gpu_kernels.py.
+            l2 = float((p.grad.cpu().double() - r64).norm() / r64.norm())
+            assert l2 < 1e-3, (n, l2)
+            assert e_new <= max(2e-2, 3 * e_ref), (n, e_new, e_ref)
     print('worst weight-grad rel err vs fp64 (ours, reference-fp32):', worst)
 
 
