@@ -102,6 +102,7 @@ SIGNATURES = {
     'essb_confusion': (_I, [_P, _I, _P, _L, _I, _L, _P, _P]),
     'essb_confusion_labels': (_I, [_P, _P, _L, _I, _L, _P, _P]),
     'essb_radam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P]),
+    'essb_event_prepare_planes': (_I, [_P, _L, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'essb_split_bf16': (_I, [C.POINTER(Src), _I, _I, _I, _P, _P, _I, _I, _P]),
     'essb_pack_weight_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'essb_conv_tc_run': (_I, [C.POINTER(ConvTc), _P]),

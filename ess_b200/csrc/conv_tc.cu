@@ -464,6 +464,59 @@ __global__ void split_bf16_kernel(essb_src s, int N, int H, int W, __nv_bfloat16
   *reinterpret_cast<uint2*>(lo_) = *reinterpret_cast<uint2*>(l);
 }
 
+// Event pre-processing straight into the head convolution's operand format: normalise (as
+// event_prepare_kernel in pointwise.cu), reflect-pad to (Hp, Wp), NCHW -> pixel-major with `cpad`
+// channels, split to bf16 hi/lo, and store at offset (off_y, off_x) inside a zero-bordered buffer
+// [B][Hb][Wb][cpad].  The zero border is the 5x5 convolution's padding, so the head conv can read
+// 8-pixel x cpad-channel row windows as ONE contiguous K-chunk through an overlapping TMA view.
+__device__ __forceinline__ int reflect_idx_tc(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+template <int CPAD>
+__global__ void event_prepare_planes_kernel(const float* __restrict__ x, long long bstride,
+                                            const double* __restrict__ stats, int normalize,
+                                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int C, int H,
+                                            int W, int Hp, int Wp, int pad_top, int pad_left, int Hb, int Wb, int off_y,
+                                            int off_x, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = (int)(idx % Wp);
+  const long long r = idx / Wp;
+  const int oy = (int)(r % Hp);
+  const int n = (int)(r / Hp);
+  const int iy = reflect_idx_tc(oy - pad_top, H), ix = reflect_idx_tc(ox - pad_left, W);
+  float mean = 0.f, stdv = 1.f;
+  bool do_norm = false;
+  if (normalize) {
+    const double nnz = stats[2];
+    if (nnz > 0.0) {
+      const float fm = (float)stats[0] / (float)nnz;
+      stdv = sqrtf((float)stats[1] / (float)nnz - fm * fm);
+      mean = fm;
+      do_norm = true;
+    }
+  }
+  const float* src = x + (long long)n * bstride + (long long)iy * W + ix;
+  __align__(16) __nv_bfloat16 h[CPAD], l[CPAD];
+#pragma unroll
+  for (int c = 0; c < CPAD; ++c) {
+    float v = 0.f;
+    if (c < C) {
+      v = src[(long long)c * H * W];
+      if (do_norm) v = (v != 0.f) ? (v - mean) / stdv : 0.f;
+    }
+    split_bf16(v, h[c], l[c]);
+  }
+  const size_t dst = (((size_t)n * Hb + oy + off_y) * Wb + ox + off_x) * CPAD;
+#pragma unroll
+  for (int c = 0; c < CPAD; c += 8) {
+    *reinterpret_cast<uint4*>(hi + dst + c) = *reinterpret_cast<const uint4*>(h + c);
+    *reinterpret_cast<uint4*>(lo + dst + c) = *reinterpret_cast<const uint4*>(l + c);
+  }
+}
+
 // packed K-major weights: out[np][t*KinP + k], np < NoutP (zero rows beyond Nout)
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Cout, int Cin,
@@ -584,6 +637,30 @@ extern "C" int essb_split_bf16(const essb_src* src, int N, int H, int W, uint16_
   split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       *src, N, H, W, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), ld_out, c_off, total);
   ESSB_LAUNCH_CHECK("essb_split_bf16");
+  return ESSB_OK;
+}
+
+extern "C" int essb_event_prepare_planes(const float* x, int64_t bstride, const double* stats, int normalize,
+                                         uint16_t* hi, uint16_t* lo, int cpad, int B, int C, int H, int W, int Hp, int Wp,
+                                         int pad_top, int pad_left, int Hb, int Wb, int off_y, int off_x, void* stream) {
+  ESSB_REQUIRE(x && hi && lo && B > 0 && C > 0 && H > 0 && W > 0 && Hp >= H && Wp >= W, "essb_event_prepare_planes: bad arguments");
+  ESSB_REQUIRE((cpad == 8 || cpad == 16) && C <= cpad, "essb_event_prepare_planes: cpad must be 8 or 16 and >= C");
+  ESSB_REQUIRE(!normalize || stats, "essb_event_prepare_planes: stats required when normalising");
+  ESSB_REQUIRE(off_y >= 0 && off_x >= 0 && Hp + off_y <= Hb && Wp + off_x <= Wb, "essb_event_prepare_planes: image does not fit the padded buffer");
+  ESSB_REQUIRE(pad_top < H && Hp - H - pad_top < H && pad_left < W && Wp - W - pad_left < W,
+               "essb_event_prepare_planes: reflection padding must be smaller than the image");
+  ESSB_REQUIRE(essb_aligned16(hi) && essb_aligned16(lo), "essb_event_prepare_planes: planes must be 16B aligned");
+  const long long total = (long long)B * Hp * Wp;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(hi);
+  __nv_bfloat16* l = reinterpret_cast<__nv_bfloat16*>(lo);
+  if (cpad == 8)
+    event_prepare_planes_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, bstride, stats, normalize, h, l, C, H, W, Hp,
+                                                                          Wp, pad_top, pad_left, Hb, Wb, off_y, off_x, total);
+  else
+    event_prepare_planes_kernel<16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, bstride, stats, normalize, h, l, C, H, W, Hp,
+                                                                           Wp, pad_top, pad_left, Hb, Wb, off_y, off_x, total);
+  ESSB_LAUNCH_CHECK("essb_event_prepare_planes");
   return ESSB_OK;
 }
 

@@ -240,6 +240,36 @@ def event_prepare(window, stats_row, normalize, Hp, Wp, pad_top, pad_left, ld_ou
     return out
 
 
+HEAD_PAD_BEFORE, HEAD_PAD_AFTER_Y, HEAD_PAD_AFTER_X = 2, 2, 6
+
+
+def head_planes_alloc(B, Hp, Wp, cpad, device):
+    """Zero-bordered bf16 hi/lo buffers [B, Hp+4, Wp+8, cpad] for the tensor-core head convolution."""
+    shape = (B, Hp + HEAD_PAD_BEFORE + HEAD_PAD_AFTER_Y, Wp + HEAD_PAD_BEFORE + HEAD_PAD_AFTER_X, cpad)
+    return (torch.zeros(shape, device=device, dtype=torch.bfloat16), torch.zeros(shape, device=device, dtype=torch.bfloat16))
+
+
+def event_prepare_planes(window, stats_row, normalize, Hp, Wp, pad_top, pad_left, planes):
+    """Like event_prepare but writes bf16 hi/lo planes into the interior of a head_planes_alloc buffer."""
+    B, Cw, H, W = window.shape
+    if window.stride(1) != H * W or window.stride(2) != W or window.stride(3) != 1:
+        raise RuntimeError('event window must be contiguous within each sample')
+    hi, lo = planes
+    call('essb_event_prepare_planes', _p(window), window.stride(0), _p(stats_row), int(normalize), _p(hi), _p(lo),
+         hi.shape[3], B, Cw, H, W, Hp, Wp, pad_top, pad_left, hi.shape[1], hi.shape[2], HEAD_PAD_BEFORE,
+         HEAD_PAD_BEFORE, _stream())
+    return planes
+
+
+def window_view(v: TcView, hi, lo, Hp, Wp):
+    """Overlapping-stride TMA view of a head_planes_alloc buffer: view pixel (x, y) is the 8-pixel x cpad
+    row window starting at padded pixel (x, y), i.e. image pixels (x-2 .. x+5, y-2) for tap row 0."""
+    N, Hb, Wb, cpad = hi.shape
+    v.hi, v.lo = _p(hi), _p(lo)
+    v.stride_x, v.stride_y, v.stride_n = cpad, Wb * cpad, Hb * Wb * cpad
+    v.C, v.W, v.H = 8 * cpad, Wp, Hb
+
+
 def nchw_to_nhwc(x, ld_out=None):
     """[N, C, H, W] (any strides) -> pixel-major [N, H, W, ld]; zero-copy for channels_last inputs."""
     N, Cc, H, W = x.shape

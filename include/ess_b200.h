@@ -224,6 +224,16 @@ int essb_radam_step(float* p, const float* g, float* m, float* v, int64_t n, flo
  * 2^-17 relative).  Optionally applies the same normalise/ReLU/upsample transform as essb_src. */
 int essb_split_bf16(const essb_src* src, int N, int H, int W, uint16_t* hi, uint16_t* lo, int ld_out,
                     int c_off, void* stream);
+/* Event pre-processing (same arithmetic as essb_event_prepare) written directly in the head
+ * convolution's tensor-core operand format: bf16 hi/lo planes with `cpad` (8 or 16) channels per
+ * pixel, stored at (off_y, off_x) inside a caller-zeroed bordered buffer [B][Hb][Wb][cpad].  With a
+ * border of 2 rows/columns before and >= 2 rows / 6 columns after, the head conv5x5 (C=5, unet.py:131)
+ * reads, per kernel row, the 8-pixel window starting at x-2 as ONE contiguous 8*cpad-element K-chunk
+ * through an overlapping-stride TMA view (element stride of x = cpad). */
+int essb_event_prepare_planes(const float* x, int64_t bstride, const double* stats, int normalize,
+                              uint16_t* hi, uint16_t* lo, int cpad, int B, int C, int H, int W, int Hp,
+                              int Wp, int pad_top, int pad_left, int Hb, int Wb, int off_y, int off_x,
+                              void* stream);
 /* Pack conv weights for the tensor-core path: K-major [NoutP][T*KinP] bf16 hi and lo planes
  * (same transposed_layout / swap_io / flip / interleave / scale semantics as essb_pack_weight;
  * KinP = input channels padded to a multiple of 64, rows beyond Nout are zero). */
