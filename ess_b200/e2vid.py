@@ -175,6 +175,15 @@ class E2VIDRecurrent(nn.Module):
         wh[:, :self.num_bins] = u.head.conv2d.weight.detach().float()
         P['head'] = (ops.pack_weight(wh), u.head.conv2d.bias.detach().float().contiguous(), cpad)
         tc = self.mode != 'fp32'
+        P['head_tc'] = None
+        if tc and cpad in (8, 16) and self.base_num_channels % 32 == 0 and self.base_num_channels <= 256:
+            # per kernel row ky the head conv reads the 8-pixel x cpad-channel window starting at x-2 as one
+            # contiguous K-chunk (ops.window_view): virtual weight [Cout][8*cpad][ky], zero for kx >= 5
+            wv = torch.zeros((self.base_num_channels, 8, cpad, 5), device=dev)
+            wv[:, :5, :self.num_bins] = u.head.conv2d.weight.detach().float().permute(0, 3, 1, 2)  # [co,kx,ci,ky]
+            wv = wv.reshape(self.base_num_channels, 8 * cpad, 5, 1).contiguous()
+            hi, lo, kinp = ops.pack_weight_tc(wv)
+            P['head_tc'] = dict(hi=hi, lo=lo, k_per_tap=kinp, cpad=cpad)
         for i, enc in enumerate(u.encoders):
             bn = getattr(enc.conv, 'norm_layer', None)
             scale, bias = _bn_fold(enc.conv.conv2d.bias, bn, None, dev)
@@ -256,33 +265,83 @@ class E2VIDRecurrent(nn.Module):
         if H % f or W % f:
             raise RuntimeError('H, W must be multiples of %d (CropParameters pads to this)' % f)
         with torch.no_grad():
+            buf = self.head_planes_buffer(N, H, W, event_tensor.device)
+            if buf is not None:      # tensor-core head: convert straight into its operand format
+                ev = event_tensor.float().contiguous()
+                ops.event_prepare_planes(ev, None, False, H, W, 0, 0, buf)
+                return self.forward_planes(buf, H, W, prev_states, with_image)
             cpad = (self.num_bins + 7) // 8 * 8
             x = ops.nchw_to_nhwc(event_tensor, cpad)
             return self.forward_nhwc(x, prev_states, with_image)
 
+    def head_planes_buffer(self, N, H, W, device):
+        """Cached zero-bordered bf16 hi/lo input buffer of the tensor-core head conv for an [N, *, H, W]
+        input (see ops.head_planes_alloc), or None when the head runs on the fp32 kernel."""
+        P = self._pack()
+        if P['head_tc'] is None:
+            return None
+        key = (N, H, W, str(device))
+        buf = self._in_planes.get(key) if hasattr(self, '_in_planes') else None
+        if buf is None:
+            buf = ops.head_planes_alloc(N, H, W, P['head_tc']['cpad'], device)
+            self._in_planes = {key: buf}
+        return buf
+
+    def forward_planes(self, in_planes, H, W, prev_states, with_image=True):
+        """forward() for an input already in the head conv's operand format (essb_event_prepare_planes)."""
+        return self._forward_impl(None, in_planes, in_planes[0].shape[0], H, W, prev_states, with_image)
+
     def forward_nhwc(self, x, prev_states, with_image=True):
         """Same as forward() for an already pixel-major input [N, H, W, ceil8(num_bins)] (zero-padded
         channels), as produced by the fused event pre-processing kernel."""
+        return self._forward_impl(x, None, x.shape[0], x.shape[1], x.shape[2], prev_states, with_image)
+
+    def _head_tc(self, P, in_planes, N, H, W, head, planes, passes):
+        """head conv5x5 + bias + ReLU (unet.py:131-132,153) on the tcgen05 kernel: 5 taps (kernel rows), each
+        one 8*cpad-element K-chunk read through the overlapping-stride window view."""
+        tcw = P['head_tc']
+        base = self.base_num_channels
+        d = ConvTc()
+        ops.window_view(d.views[0], in_planes[0], in_planes[1], H, W)
+        d.n_views, d.nseg = 1, 1
+        d.seg_C[0], d.seg_view0[0], d.seg_koff[0] = 8 * tcw['cpad'], 0, 0
+        d.k_per_tap, d.n_w_taps, d.w_rows = tcw['k_per_tap'], 5, tcw['hi'].shape[0]
+        d.w_hi, d.w_lo, d.bias = ops._p(tcw['hi']), ops._p(tcw['lo']), ops._p(P['head'][1])
+        d.out, d.ldo = ops._p(head), base
+        d.out_hi, d.out_lo, d.ld_planes = ops._p(planes[0]), ops._p(planes[1]), base
+        d.N, d.OH, d.OW, d.Cout = N, H, W, base
+        d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = H, W, 1, 0, 1, 0
+        d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, ACT_RELU, passes, ops.pick_bw_log2(W, H)
+        d.ntaps = 5
+        for ky in range(5):
+            d.dy[ky], d.dx[ky], d.view[ky], d.widx[ky] = ky, 0, 0, ky
+        ops.conv_tc(d, tag='head_tc')
+
+    def _forward_impl(self, x, in_planes, N, H, W, prev_states, with_image):
         P = self._pack()
         u = self.unetrecurrent
         ne = self.num_encoders
         lstm = self.recurrent_block_type == 'convlstm'
-        N, H, W, _ = x.shape
         tc_mode = self.mode != 'fp32'
         passes = 3 if self.mode == 'bf16x3' else 1
         if prev_states is None:
             prev_states = [None] * ne
         base = self.base_num_channels
+        dev = x.device if x is not None else in_planes[0].device
 
         # head: conv5x5 + bias + ReLU (unet.py:131-132,153)
         wh, bh, cpad = P['head']
         want_planes = tc_mode and P['enc0']['tc'] is not None
         planes = None
-        if want_planes:
-            planes = (torch.empty((N, H, W, base), device=x.device, dtype=torch.bfloat16),
-                      torch.empty((N, H, W, base), device=x.device, dtype=torch.bfloat16))
-        head, _, _, _ = ops.conv([Seg(x, C=cpad)], wh, bh, N, H, W, H, W, base, ops.taps_conv(5, 2), act=ACT_RELU,
-                                 planes=planes)
+        if want_planes or in_planes is not None:
+            planes = (torch.empty((N, H, W, base), device=dev, dtype=torch.bfloat16),
+                      torch.empty((N, H, W, base), device=dev, dtype=torch.bfloat16))
+        if in_planes is not None:
+            head = torch.empty((N, H, W, base), device=dev, dtype=torch.float32)
+            self._head_tc(P, in_planes, N, H, W, head, planes, passes)
+        else:
+            head, _, _, _ = ops.conv([Seg(x, C=cpad)], wh, bh, N, H, W, H, W, base, ops.taps_conv(5, 2), act=ACT_RELU,
+                                     planes=planes)
 
         blocks, states = [], []
         cur, cur_planes = head, planes
@@ -296,7 +355,7 @@ class E2VIDRecurrent(nn.Module):
             use_tc = tc_mode and e['tc'] is not None and cur_planes is not None and \
                 (not lstm or e['lstm_tc'] is not None) and lstm
             if use_tc:
-                xh = torch.empty((N, oh, ow, cout), device=x.device, dtype=torch.bfloat16)
+                xh = torch.empty((N, oh, ow, cout), device=dev, dtype=torch.bfloat16)
                 xl = torch.empty_like(xh)
                 self._enc_conv_tc(e, cur_planes, N, h_in, w_in, cout, xh, xl, passes)
                 hp = cp = None

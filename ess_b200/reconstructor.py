@@ -44,12 +44,17 @@ class ImageReconstructor:
         self.last_states_for_each_channel = {'grayscale': None}
         self.stats_reduce_fn = None
 
-    def _prepare(self, window, stats_row):
+    def _step(self, window, stats_row, states, with_image):
+        """normalise + reflect-pad + layout/precision conversion (one kernel) -> model."""
         B, C, H, W = window.shape
         left, right, top, bottom = crop_padding(H, W, self.model.num_encoders)
-        cpad = (C + 7) // 8 * 8
-        return ops.event_prepare(window, stats_row, not self.no_normalize, H + top + bottom, W + left + right, top,
-                                 left, cpad)
+        Hp, Wp = H + top + bottom, W + left + right
+        buf = self.model.head_planes_buffer(B, Hp, Wp, window.device)
+        if buf is not None:      # tensor-core head conv: write its bf16 hi/lo operand planes directly
+            ops.event_prepare_planes(window, stats_row, not self.no_normalize, Hp, Wp, top, left, buf)
+            return self.model.forward_planes(buf, Hp, Wp, states, with_image=with_image)
+        x = ops.event_prepare(window, stats_row, not self.no_normalize, Hp, Wp, top, left, (C + 7) // 8 * 8)
+        return self.model.forward_nhwc(x, states, with_image=with_image)
 
     @staticmethod
     def _per_sample_contiguous(t):
@@ -69,9 +74,7 @@ class ImageReconstructor:
                 stats = ops.event_stats(ev, 1, C)
                 if self.stats_reduce_fn is not None:
                     stats = self.stats_reduce_fn(stats)
-            x = self._prepare(ev, stats)
-            img, states, latent = self.model.forward_nhwc(x, self.last_states_for_each_channel['grayscale'],
-                                                          with_image=with_image)
+            img, states, latent = self._step(ev, stats, self.last_states_for_each_channel['grayscale'], with_image)
             self.last_states_for_each_channel['grayscale'] = None if self.no_recurrent else states
             if self.standardization and img is not None:                 # image_reconstructor.py:129-134
                 b, h, w = img.size(0), img.size(2), img.size(3)
@@ -96,9 +99,8 @@ class ImageReconstructor:
             img = latent = None
             for i in range(num_windows):
                 win = data[:, i * channels:(i + 1) * channels]
-                x = self._prepare(win, stats[i] if stats is not None else None)
                 need_img = (i == num_windows - 1) or not image_on_last_only
-                img, states, latent = self.model.forward_nhwc(x, states, with_image=need_img)
+                img, states, latent = self._step(win, stats[i] if stats is not None else None, states, need_img)
                 if self.no_recurrent:
                     states = None
             self.last_states_for_each_channel['grayscale'] = states

@@ -220,3 +220,28 @@ def test_full_size_properties_dsec():
     for k in (1, 2, 4, 8):
         assert rel_err(outs['bf16x3'][2][k], outs['fp32'][2][k]) < TOL, k
     assert rel_err(outs['bf16x3'][0], outs['fp32'][0]) < TOL
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16x3'])
+def test_e2vid_module_forward_signature(mode):
+    """E2VIDRecurrent.forward(event_tensor NCHW, prev_states) itself (no reconstructor): two chained calls,
+    states passed back in, outputs are logical-NCHW tensors of the reference's shapes."""
+    B, C, H, W = 1, 5, 32, 64
+    m = make_e2vid(mode=mode)
+    sd = sd_cpu(m)
+    ev = make_events(B, 2, C, H, W)
+    r1 = O.e2vid_recurrent_forward(sd, E2VID_CFG, ev[:, :C], None)
+    r2 = O.e2vid_recurrent_forward(sd, E2VID_CFG, ev[:, C:], r1[1])
+    m = m.cuda()
+    o1 = m(ev[:, :C].cuda(), None)
+    o2 = m(ev[:, C:].cuda(), o1[1])
+    assert o2[0].shape == (B, 1, H, W) and o2[2][8].shape == (B, 256, H // 8, W // 8)
+    assert rel_err(o2[0], r2[0]) < TOL
+    for k in (1, 2, 4, 8):
+        assert rel_err(o2[2][k], r2[2][k]) < TOL
+    for (h, c), (hr, cr) in zip(o2[1], r2[1]):
+        assert rel_err(h, hr) < TOL and rel_err(c, cr) < TOL
+    # states handed back as plain contiguous NCHW copies (not our channels_last views) also work
+    st = [(h.contiguous(), c.contiguous()) for (h, c) in o1[1]]
+    o2b = m(ev[:, C:].cuda(), st)
+    assert rel_err(o2b[2][8], r2[2][8]) < TOL
