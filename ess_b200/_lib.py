@@ -69,6 +69,14 @@ class ConvTc(C.Structure):
                 ('widx', C.c_int8 * MAX_TAPS)]
 
 
+class WgradTc(C.Structure):
+    _fields_ = [('a_hi', C.c_void_p), ('a_lo', C.c_void_p), ('g_hi', C.c_void_p), ('g_lo', C.c_void_p),
+                ('dw', C.c_void_p), ('workspace', C.c_void_p), ('workspace_bytes', C.c_int64),
+                ('a_ld', C.c_int32), ('Cin', C.c_int32), ('g_ld', C.c_int32), ('Cout', C.c_int32),
+                ('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('passes', C.c_int32), ('ntaps', C.c_int32),
+                ('dy', C.c_int8 * MAX_TAPS), ('dx', C.c_int8 * MAX_TAPS)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes): every symbol include/ess_b200.h declares
@@ -106,6 +114,8 @@ SIGNATURES = {
     'essb_split_bf16': (_I, [C.POINTER(Src), _I, _I, _I, _P, _P, _I, _I, _P]),
     'essb_pack_weight_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'essb_conv_tc_run': (_I, [C.POINTER(ConvTc), _P]),
+    'essb_wgrad_tc_workspace_bytes': (_L, [C.POINTER(WgradTc)]),
+    'essb_wgrad_tc_run': (_I, [C.POINTER(WgradTc), _P]),
 }
 
 _lib = None
@@ -134,7 +144,7 @@ def check(rc, what=''):
 
 
 # kernels launched per successful API call (for bench.py's `gpu_launches` claim)
-_LAUNCHES = {'essb_wgrad_fp32': 4, 'essb_colsum': 2}
+_LAUNCHES = {'essb_wgrad_fp32': 4, 'essb_colsum': 2, 'essb_wgrad_tc_run': 2}
 launch_count = 0
 PROFILE = None   # when a list: (tag, algorithmic_flops, start_event, end_event) per profiled launch
 

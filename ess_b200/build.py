@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libess_b200.so')
-SOURCES = ['api.cu', 'conv_fp32.cu', 'conv_tc.cu', 'pointwise.cu', 'loss.cu']
+SOURCES = ['api.cu', 'conv_fp32.cu', 'conv_tc.cu', 'wgrad_tc.cu', 'pointwise.cu', 'loss.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-I' + os.path.join(ROOT, 'include')]
 
@@ -35,7 +35,8 @@ def build_library(force=False, verbose=False):
     """Compile every CUDA source for sm_100a and link the shared library. Returns its path."""
     objdir = os.path.join(HERE, 'build')
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(ROOT, 'include', 'ess_b200.h'), os.path.join(CSRC, 'common.cuh')]
+    headers = [os.path.join(ROOT, 'include', 'ess_b200.h'), os.path.join(CSRC, 'common.cuh'),
+               os.path.join(CSRC, 'tc_ptx.cuh')]
     nvcc = _nvcc()
 
     def compile_one(src):

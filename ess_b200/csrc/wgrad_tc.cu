@@ -1,0 +1,364 @@
+// tcgen05 / TMA weight-gradient of a stride-1 gather-convolution (autograd of nn.Conv2d w.r.t. weight):
+//     dW[co][ci][t] = sum_{n,y,x} A[n, y+dy_t, x+dx_t, ci] * dY[n, y, x, co]
+// GEMM per tap: D[ci (M=128), co (N<=256)] += A_t^T[ci][pixel] * dY[pixel][co], K = pixels.
+// Both operands are "MN-major" for this GEMM (channels contiguous, pixels strided), which is exactly
+// how a 4-D TMA box [64 pixels][64 channels] of the NHWC bf16 planes lands in shared memory with
+// SWIZZLE_128B: rows of 128 B (64 channels) stacked along K.  The UMMA descriptors are therefore
+// MN-major / SWIZZLE_128B: SBO = 1024 B (8-pixel K atom), LBO = 8192 B (next 64-channel block).
+// The tap shift of A is, as in conv_tc.cu, just a shifted TMA box with hardware zero fill.
+// Work item = (split-K range of 64-pixel patches, tap, 128-wide ci tile); partial results go to a
+// workspace [split][tap][ci][co] and are reduced in fixed order (deterministic).
+// bf16x3: D += A_lo*G_hi + A_hi*G_lo + A_hi*G_hi, fp32 accumulation in TMEM.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int WG_THREADS = 320;
+constexpr int WG_PIX = 64;                 // pixels (K) per pipeline stage
+constexpr int WG_BOX_BYTES = WG_PIX * 128; // one [64 px][64 ch] bf16 box = 8 KB
+constexpr int WG_MAX_STAGES = 8;
+
+struct WgTcParams {
+  CUtensorMap tmA_hi, tmA_lo, tmG_hi, tmG_lo;
+  int n_items, m_tiles, splits, ntaps;
+  int patches_total, patches_per_split, tiles_x, tiles_y;
+  int bw_log2;           // patch = BW x (64/BW) pixels
+  int nb;                // 64-channel boxes of dY (N = 64*nb)
+  int stages, passes, stage_bytes;
+  int off_alo, off_ghi, off_glo;
+  int cin, cout;
+  float* partial;
+  int8_t dy[ESSB_MAX_TAPS], dx[ESSB_MAX_TAPS];
+};
+
+// MN-major SWIZZLE_128B descriptor: [0,14) start>>4, [16,30) LBO>>4 (stride between 64-element blocks
+// along M/N), [32,46) SBO>>4 (stride between 8-row groups along K), version 1, layout SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(WG_BOX_BYTES >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + WG_MAX_STAGES;
+  uint64_t* tfull_bar = bars + 2 * WG_MAX_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BW = 1 << p.bw_log2, BH = WG_PIX >> p.bw_log2;
+  const int BN = 64 * p.nb;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int per_split = p.ntaps * p.m_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int split = item / per_split;
+        const int r = item - split * per_split;
+        const int tap = r / p.m_tiles, mt = r - tap * p.m_tiles;
+        const int p0 = split * p.patches_per_split;
+        const int p1 = min(p0 + p.patches_per_split, p.patches_total);
+        for (int pp = p0; pp < p1; ++pp) {
+          int q = pp;
+          const int txi = q % p.tiles_x; q /= p.tiles_x;
+          const int tyi = q % p.tiles_y;
+          const int n = q / p.tiles_y;
+          const int x0 = txi * BW, y0 = tyi * BH;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + (size_t)s * p.stage_bytes;
+          mbar_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
+          const int ax = x0 + p.dx[tap], ay = y0 + p.dy[tap];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            tma_load_4d(st + j * WG_BOX_BYTES, &p.tmA_hi, &full_bar[s], mt * 128 + j * 64, ax, ay, n);
+            if (p.passes == 3)
+              tma_load_4d(st + p.off_alo + j * WG_BOX_BYTES, &p.tmA_lo, &full_bar[s], mt * 128 + j * 64, ax, ay, n);
+          }
+          for (int j = 0; j < p.nb; ++j) {
+            tma_load_4d(st + p.off_ghi + j * WG_BOX_BYTES, &p.tmG_hi, &full_bar[s], j * 64, x0, y0, n);
+            if (p.passes == 3)
+              tma_load_4d(st + p.off_glo + j * WG_BOX_BYTES, &p.tmG_lo, &full_bar[s], j * 64, x0, y0, n);
+          }
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_mn(128, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t tph[2] = {0, 0};
+      int local = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+        const int split = item / per_split;
+        const int p0 = split * p.patches_per_split;
+        const int p1 = min(p0 + p.patches_per_split, p.patches_total);
+        const int buf = local & 1;
+        mbar_wait(&tempty_bar[buf], tph[buf] ^ 1);
+        tph[buf] ^= 1;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+        for (int pp = p0; pp < p1; ++pp) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
+          const uint64_t a_hi = make_smem_desc_mn(sa), g_hi = make_smem_desc_mn(sa + p.off_ghi);
+          const uint64_t a_lo = make_smem_desc_mn(sa + p.off_alo), g_lo = make_smem_desc_mn(sa + p.off_glo);
+#pragma unroll
+          for (int k = 0; k < WG_PIX / 16; ++k) {
+            const uint64_t ko = (uint64_t)(k * (16 * 128 >> 4));  // 16 pixel rows of 128 B
+            const uint32_t first = (pp != p0 || k != 0) ? 1u : 0u;
+            if (p.passes == 3) {
+              umma_bf16(d_tmem, a_lo + ko, g_hi + ko, idesc, first);
+              umma_bf16(d_tmem, a_hi + ko, g_lo + ko, idesc, 1u);
+              umma_bf16(d_tmem, a_hi + ko, g_hi + ko, idesc, 1u);
+            } else {
+              umma_bf16(d_tmem, a_hi + ko, g_hi + ko, idesc, first);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint32_t tph[2] = {0, 0};
+    int local = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+      const int split = item / per_split;
+      const int r = item - split * per_split;
+      const int tap = r / p.m_tiles, mt = r - tap * p.m_tiles;
+      const int buf = local & 1;
+      const int ci = mt * 128 + q * 32 + lane;
+      mbar_wait(&tfull_bar[buf], tph[buf]);
+      tph[buf] ^= 1;
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
+      float* dst = p.partial + (((size_t)split * p.ntaps + tap) * p.cin + ci) * p.cout;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c0 = half * 32 + j * 64;
+        if (c0 >= BN) break;
+        uint32_t rr[32];
+        __syncwarp();
+        tmem_ld32(t_addr + (uint32_t)c0, rr);
+        tmem_ld_wait();
+        if (ci < p.cin && c0 < p.cout) {   // cout is a multiple of 32
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(dst + c0 + e) =
+                make_float4(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]),
+                            __uint_as_float(rr[e + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// dw[co][ci][tap] = sum_split partial[split][tap][ci][co]
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int splits, int ntaps,
+                                       int cin, int cout) {
+  const long long total = (long long)ntaps * cin * cout;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int co = (int)(idx % cout);
+  const long long r = idx / cout;
+  const int ci = (int)(r % cin);
+  const int tap = (int)(r / cin);
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp) s += part[(size_t)sp * total + idx];
+  dw[((size_t)co * cin + ci) * ntaps + tap] = s;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled wg_get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(sym);
+  }
+  return fn;
+}
+
+int wg_encode(CUtensorMap* tm, const void* base, int C, int ld, int N, int H, int W, int BW, int BH) {
+  PFN_encodeTiled enc = wg_get_encode();
+  if (!enc) {
+    essb_set_error("wgrad_tc: cuTensorMapEncodeTiled unavailable");
+    return ESSB_ERR_DRIVER;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {64u, (cuuint32_t)BW, (cuuint32_t)BH, 1u};
+  cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    essb_set_error("wgrad_tc: cuTensorMapEncodeTiled failed with %d", (int)r);
+    return ESSB_ERR_DRIVER;
+  }
+  return ESSB_OK;
+}
+
+struct WgPlan {
+  int m_tiles, splits, patches_total, patches_per_split, tiles_x, tiles_y, bw_log2, nb;
+};
+
+int wg_plan(const essb_wgrad_tc& d, WgPlan* pl) {
+  if (d.Cin <= 0 || d.Cout <= 0 || d.Cout % 32 != 0 || d.Cout > 256 || d.g_ld % 64 != 0 || d.g_ld < d.Cout) return -1;
+  pl->m_tiles = (d.Cin + 127) / 128;
+  pl->nb = (d.Cout + 63) / 64;
+  int best = 4;
+  double best_waste = 1e30;
+  for (int b = 2; b <= 6; ++b) {
+    const int bw = 1 << b, bh = WG_PIX >> b;
+    const double waste = (double)((d.W + bw - 1) / bw * bw) * ((d.H + bh - 1) / bh * bh) / ((double)d.W * d.H);
+    if (waste < best_waste - 1e-9) { best_waste = waste; best = b; }
+  }
+  pl->bw_log2 = best;
+  const int BW = 1 << best, BH = WG_PIX >> best;
+  pl->tiles_x = (d.W + BW - 1) / BW;
+  pl->tiles_y = (d.H + BH - 1) / BH;
+  pl->patches_total = d.N * pl->tiles_x * pl->tiles_y;
+  const int per_split = d.ntaps * pl->m_tiles;
+  int splits = (2 * 148 + per_split - 1) / per_split;
+  const int max_splits = (pl->patches_total + 3) / 4;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  pl->patches_per_split = (pl->patches_total + splits - 1) / splits;
+  pl->splits = (pl->patches_total + pl->patches_per_split - 1) / pl->patches_per_split;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t essb_wgrad_tc_workspace_bytes(const essb_wgrad_tc* d) {
+  WgPlan pl;
+  if (!d || wg_plan(*d, &pl) != 0) return -1;
+  return (int64_t)pl.splits * d->ntaps * d->Cin * d->Cout * (int64_t)sizeof(float);
+}
+
+extern "C" int essb_wgrad_tc_run(const essb_wgrad_tc* d, void* stream) {
+  ESSB_REQUIRE(d != nullptr, "essb_wgrad_tc_run: null descriptor");
+  ESSB_REQUIRE(d->a_hi && d->g_hi && d->dw && d->workspace, "essb_wgrad_tc_run: null tensor");
+  ESSB_REQUIRE(d->passes == 1 || (d->passes == 3 && d->a_lo && d->g_lo), "essb_wgrad_tc_run: passes must be 1 or 3 (with lo planes)");
+  ESSB_REQUIRE(d->ntaps >= 1 && d->ntaps <= ESSB_MAX_TAPS, "essb_wgrad_tc_run: ntaps=%d", d->ntaps);
+  ESSB_REQUIRE(d->a_ld % 8 == 0 && d->g_ld % 8 == 0 && d->a_ld >= d->Cin, "essb_wgrad_tc_run: plane pitches must be multiples of 8");
+  ESSB_REQUIRE(essb_aligned16(d->a_hi) && essb_aligned16(d->a_lo) && essb_aligned16(d->g_hi) && essb_aligned16(d->g_lo) &&
+                   essb_aligned16(d->workspace),
+               "essb_wgrad_tc_run: pointers must be 16B aligned");
+  WgPlan pl;
+  ESSB_REQUIRE(wg_plan(*d, &pl) == 0, "essb_wgrad_tc_run: unsupported shape (Cout %% 32 == 0, Cout <= 256, g_ld %% 64 == 0 required)");
+  const int64_t need = (int64_t)pl.splits * d->ntaps * d->Cin * d->Cout * (int64_t)sizeof(float);
+  if (d->workspace_bytes < need) {
+    essb_set_error("essb_wgrad_tc_run: workspace %lld < %lld bytes", (long long)d->workspace_bytes, (long long)need);
+    return ESSB_ERR_WORKSPACE;
+  }
+  static thread_local WgTcParams p;
+  const int BW = 1 << pl.bw_log2, BH = WG_PIX >> pl.bw_log2;
+  int rc;
+  if ((rc = wg_encode(&p.tmA_hi, d->a_hi, d->Cin, d->a_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK) return rc;
+  if ((rc = wg_encode(&p.tmG_hi, d->g_hi, d->g_ld, d->g_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK) return rc;
+  if (d->passes == 3) {
+    if ((rc = wg_encode(&p.tmA_lo, d->a_lo, d->Cin, d->a_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK) return rc;
+    if ((rc = wg_encode(&p.tmG_lo, d->g_lo, d->g_ld, d->g_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK) return rc;
+  }
+  p.m_tiles = pl.m_tiles; p.splits = pl.splits; p.ntaps = d->ntaps;
+  p.n_items = pl.splits * d->ntaps * pl.m_tiles;
+  p.patches_total = pl.patches_total; p.patches_per_split = pl.patches_per_split;
+  p.tiles_x = pl.tiles_x; p.tiles_y = pl.tiles_y; p.bw_log2 = pl.bw_log2; p.nb = pl.nb;
+  p.passes = d->passes;
+  const int a_bytes = 2 * WG_BOX_BYTES, g_bytes = pl.nb * WG_BOX_BYTES;
+  if (d->passes == 3) {
+    p.off_alo = a_bytes; p.off_ghi = 2 * a_bytes; p.off_glo = 2 * a_bytes + g_bytes;
+    p.stage_bytes = 2 * (a_bytes + g_bytes);
+  } else {
+    p.off_alo = 0; p.off_ghi = a_bytes; p.off_glo = 0;
+    p.stage_bytes = a_bytes + g_bytes;
+  }
+  int stages = (200 * 1024) / p.stage_bytes;
+  if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
+  ESSB_REQUIRE(stages >= 2, "essb_wgrad_tc_run: tile does not fit two stages");
+  p.stages = stages;
+  p.cin = d->Cin; p.cout = d->Cout; p.partial = d->workspace;
+  for (int t = 0; t < d->ntaps; ++t) { p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; }
+  size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024 + 256;
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) {
+    essb_set_error("essb_wgrad_tc_run: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    return ESSB_ERR_LAUNCH;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.n_items < sms ? p.n_items : sms;
+  wgrad_tc_kernel<<<grid, WG_THREADS, smem_bytes, st>>>(p);
+  ESSB_LAUNCH_CHECK("essb_wgrad_tc_run");
+  const long long total = (long long)d->ntaps * d->Cin * d->Cout;
+  wgrad_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d->workspace, d->dw, pl.splits, d->ntaps, d->Cin,
+                                                                          d->Cout);
+  ESSB_LAUNCH_CHECK("essb_wgrad_tc_reduce");
+  return ESSB_OK;
+}

@@ -434,6 +434,44 @@ def conv_tc_dense(planes, w_hi, w_lo, k_per_tap, taps, N, H, W, Cout, passes, bi
     return out
 
 
+def wgrad_tc(a_planes, g_planes, Cin, Cout, taps, N, H, W, passes, tag='seg_wgrad'):
+    """essb_wgrad_tc_run: dW [Cout, Cin, ntaps] from the bf16 planes of the conv input and of dY."""
+    d = _lib.WgradTc()
+    d.a_hi, d.a_lo, d.g_hi, d.g_lo = _p(a_planes[0]), _p(a_planes[1]), _p(g_planes[0]), _p(g_planes[1])
+    d.a_ld, d.Cin, d.g_ld, d.Cout = a_planes[0].shape[-1], Cin, g_planes[0].shape[-1], Cout
+    d.N, d.H, d.W, d.passes = N, H, W, passes
+    d.ntaps = len(taps)
+    for i, tp in enumerate(taps):
+        d.dy[i], d.dx[i] = tp[0], tp[1]
+    dev = a_planes[0].device
+    dw = torch.empty((Cout, Cin, len(taps)), device=dev, dtype=torch.float32)
+    nbytes = _lib.lib().essb_wgrad_tc_workspace_bytes(C.byref(d))
+    if nbytes < 0:
+        raise RuntimeError('essb_wgrad_tc: unsupported shape')
+    ws = torch.empty((int(nbytes) // 4 + 4,), device=dev, dtype=torch.float32)
+    d.dw, d.workspace, d.workspace_bytes = _p(dw), _p(ws), ws.numel() * 4
+    prof = _lib.PROFILE
+    if prof is None:
+        call('essb_wgrad_tc_run', C.byref(d), _stream())
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call('essb_wgrad_tc_run', C.byref(d), _stream())
+        e1.record()
+        prof.append((tag, 2.0 * N * H * W * Cout * Cin * len(taps), e0, e1))
+    return dw
+
+
+def colsum(x, Cc=None):
+    """Column sums over all pixels of a pixel-major tensor [N, H, W, ld] -> [C] (bias gradients)."""
+    rows = x.shape[0] * x.shape[1] * x.shape[2]
+    Cc = Cc or x.shape[-1]
+    out = torch.empty((Cc,), device=x.device, dtype=torch.float32)
+    ws = torch.empty((1024 * Cc,), device=x.device, dtype=torch.float32)
+    call('essb_colsum', _p(x), x.shape[-1], rows, Cc, _p(out), _p(ws), ws.numel() * 4, _stream())
+    return out
+
+
 def conv_tc(d: ConvTc, tag=None):
     """essb_conv_tc_run; when _lib.PROFILE is a list, brackets the launch with CUDA events on the
     launching stream and records (tag, algorithmic FLOPs, start, end)."""

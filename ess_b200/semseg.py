@@ -294,6 +294,19 @@ class _DecoderFn(torch.autograd.Function):
             H, W = first.shape[1] << ups0, first.shape[2] << ups0
             w = P[nd.w]
             taps = _taps(nd.k)
+            tc = ctx.mode != 'fp32' and nd.k == 3 and nd.cout % 32 == 0
+            passes = 3 if ctx.mode == 'bf16x3' else 1
+            gplanes = None
+
+            def dy_planes():
+                """bf16 hi/lo planes of dY (channel-padded to a multiple of 64 with zeros), built once per node"""
+                kinp = (nd.cout + 63) // 64 * 64
+                alloc = torch.zeros if kinp != nd.cout else torch.empty
+                pl = (alloc((N, H, W, kinp), device=gy.device, dtype=torch.bfloat16),
+                      alloc((N, H, W, kinp), device=gy.device, dtype=torch.bfloat16))
+                ops.split_bf16(Seg(gy), N, H, W, pl[0], pl[1], 0)
+                return pl
+
             if need_p[nd.w] or need_p[nd.b]:
                 segs = []
                 for (sid, xf, ups) in nd.srcs:
@@ -301,16 +314,29 @@ class _DecoderFn(torch.autograd.Function):
                         segs.append(Seg(T[sid], ups=ups, mean=S[sid][0], rstd=S[sid][1], relu=True))
                     else:
                         segs.append(Seg(T[sid], ups=ups))
-                dw, db = ops.wgrad(segs, gy, N, H, W, H, W, nd.cout, taps, want_bias=need_p[nd.b])
-                if need_p[nd.w]:
-                    grads[nd.w] = dw.view(w.shape)
-                if need_p[nd.b]:
-                    grads[nd.b] = db
+                cin_total = w.shape[1]
+                if tc and cin_total % 64 == 0 and nd.cout <= 256:
+                    # tensor-core wgrad: re-create the conv's operand planes (cheaper than keeping them alive)
+                    hi = torch.empty((N, H, W, cin_total), device=gy.device, dtype=torch.bfloat16)
+                    lo = torch.empty_like(hi)
+                    co = 0
+                    for sg in segs:
+                        ops.split_bf16(sg, N, H, W, hi, lo, co)
+                        co += sg.C if sg.C is not None else sg.t.shape[-1]
+                    gplanes = dy_planes()
+                    if need_p[nd.w]:
+                        grads[nd.w] = ops.wgrad_tc((hi, lo), gplanes, cin_total, nd.cout, taps, N, H, W, passes).view(w.shape)
+                    del hi, lo
+                    if need_p[nd.b]:
+                        grads[nd.b] = ops.colsum(gy, nd.cout)
+                else:
+                    dw, db = ops.wgrad(segs, gy, N, H, W, H, W, nd.cout, taps, want_bias=need_p[nd.b])
+                    if need_p[nd.w]:
+                        grads[nd.w] = dw.view(w.shape)
+                    if need_p[nd.b]:
+                        grads[nd.b] = db
             c_off = 0
             dtaps = [(-dy, -dx, wi) for (dy, dx, wi) in taps]
-            tc = ctx.mode != 'fp32' and nd.k == 3 and nd.cout % 32 == 0
-            passes = 3 if ctx.mode == 'bf16x3' else 1
-            gplanes = None
             for (sid, xf, ups) in nd.srcs:
                 src = T[sid]
                 cs = src.shape[-1]
@@ -318,11 +344,8 @@ class _DecoderFn(torch.autograd.Function):
                     wseg = w.detach()[:, c_off:c_off + cs].contiguous()
                     if tc and cs in (64, 128, 256):
                         kinp = (nd.cout + 63) // 64 * 64
-                        if gplanes is None:       # bf16 hi/lo planes of dY, channel-padded to 64 with zeros
-                            alloc = torch.zeros if kinp != nd.cout else torch.empty
-                            gplanes = (alloc((N, H, W, kinp), device=gy.device, dtype=torch.bfloat16),
-                                       alloc((N, H, W, kinp), device=gy.device, dtype=torch.bfloat16))
-                            ops.split_bf16(Seg(gy), N, H, W, gplanes[0], gplanes[1], 0)
+                        if gplanes is None:
+                            gplanes = dy_planes()
                         w_hi, w_lo, _ = ops.pack_weight_tc(wseg, swap_io=True, kin_pad=kinp)
                         dA = ops.conv_tc_dense(gplanes, w_hi, w_lo, kinp, dtaps, N, H, W, cs, passes, tag='seg_dgrad')
                     else:

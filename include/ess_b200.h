@@ -289,6 +289,28 @@ typedef struct essb_conv_tc {
 } essb_conv_tc;
 int essb_conv_tc_run(const essb_conv_tc* d, void* stream);
 
+/* tcgen05 weight gradient of a stride-1 gather-convolution (autograd of nn.Conv2d w.r.t. weight,
+ * same definition as essb_wgrad_fp32): operands are the bf16 hi/lo planes of the (transformed,
+ * concatenated) conv input A [N,H,W,a_ld] and of dY [N,H,W,g_ld] (g_ld a multiple of 64 >= Cout,
+ * zero padded).  dw is written in the reference layout [Cout][Cin][ntaps]. */
+typedef struct essb_wgrad_tc {
+  const uint16_t* a_hi;
+  const uint16_t* a_lo;
+  const uint16_t* g_hi;
+  const uint16_t* g_lo;
+  float* dw;
+  float* workspace;
+  int64_t workspace_bytes;
+  int32_t a_ld, Cin, g_ld, Cout;
+  int32_t N, H, W;
+  int32_t passes;
+  int32_t ntaps;
+  int8_t dy[ESSB_MAX_TAPS];
+  int8_t dx[ESSB_MAX_TAPS];
+} essb_wgrad_tc;
+int64_t essb_wgrad_tc_workspace_bytes(const essb_wgrad_tc* d);
+int essb_wgrad_tc_run(const essb_wgrad_tc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

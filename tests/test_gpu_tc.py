@@ -88,3 +88,25 @@ def test_encoder_conv_tc(passes, tol, Cin, Cout, H, W):
     torch.cuda.synchronize()
     got = nchw(out_hi.float() + out_lo.float())
     assert rel_err(got, ref) < tol, rel_err(got, ref)
+
+
+@pytest.mark.parametrize('passes,tol', [(3, 1e-3), (1, 3e-2)])
+@pytest.mark.parametrize('N,H,W,Cin,Cout', [(2, 12, 20, 64, 64), (1, 55, 80, 256, 128), (2, 9, 14, 192, 256),
+                                            (1, 40, 64, 64, 32), (2, 16, 16, 128, 96)])
+def test_wgrad_tc(passes, tol, N, H, W, Cin, Cout):
+    """tcgen05 weight gradient (MN-major operands, split-K over pixels) vs autograd of F.conv2d."""
+    from ess_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(N, Cin, H, W, generator=g)
+    dy = torch.randn(N, Cout, H, W, generator=g)
+    w = torch.zeros(Cout, Cin, 3, 3, requires_grad=True)
+    gw, = torch.autograd.grad(F.conv2d(a, w, None, padding=1), [w], dy)
+    ap = planes_of(a)
+    kinp = (Cout + 63) // 64 * 64
+    gh = torch.zeros((N, H, W, kinp), device='cuda', dtype=torch.bfloat16)
+    gl = torch.zeros_like(gh)
+    ops.split_bf16(ops.Seg(nhwc(dy)), N, H, W, gh, gl, 0)
+    dw = ops.wgrad_tc(ap, (gh, gl), Cin, Cout, ops.taps_conv(3, 1), N, H, W, passes)
+    torch.cuda.synchronize()
+    err = rel_err(dw.view(Cout, Cin, 3, 3).cpu(), gw)
+    assert err < tol, err
