@@ -224,6 +224,8 @@ class E2VIDRecurrent(nn.Module):
             s1, b1 = _bn_fold(rbk.conv1.bias, getattr(rbk, 'bn1', None), None, dev)
             s2, b2 = _bn_fold(rbk.conv2.bias, getattr(rbk, 'bn2', None), None, dev)
             P['res%d' % j] = (ops.pack_weight(rbk.conv1.weight, s1), b1, ops.pack_weight(rbk.conv2.weight, s2), b2)
+            if tc:
+                P['res%d_tc' % j] = ops.pack_weight_tc(rbk.conv1.weight, s1) + ops.pack_weight_tc(rbk.conv2.weight, s2)
         for i, dec in enumerate(u.decoders):
             bn = getattr(dec, 'norm_layer', None)
             if self.use_upsample_conv:
@@ -233,6 +235,8 @@ class E2VIDRecurrent(nn.Module):
                 scale, bias = _bn_fold(dec.transposed_conv2d.bias, bn, None, dev)
                 P['dec%d' % i] = (ops.pack_weight(dec.transposed_conv2d.weight, scale, transposed_layout=True), bias,
                                   dec.transposed_conv2d.out_channels)
+                if tc:
+                    P['dec%d_tc' % i] = ops.pack_weight_tc(dec.transposed_conv2d.weight, scale, transposed_layout=True)
         scale, bias = _bn_fold(u.pred.conv2d.bias, getattr(u.pred, 'norm_layer', None), None, dev)
         P['pred'] = (ops.pack_weight(u.pred.conv2d.weight, scale), bias)
         self._packed, self._packed_key = P, key
@@ -400,8 +404,57 @@ class E2VIDRecurrent(nn.Module):
                   8: ops.as_nchw(blocks[2])}                                       # unet.py:172
         if not with_image:
             return None, states, latent
-        img = self._image_decoder(P, head, blocks, N, h_in, w_in)
+        cmax = base * 2 ** ne
+        if tc_mode and cur_planes is not None and self.skip_type == 'sum' and not self.use_upsample_conv \
+                and base % 32 == 0 and cmax <= 256 * 4 and base * 2 % 64 == 0:
+            img = self._image_decoder_tc(P, head, blocks, cur_planes, N, h_in, w_in, passes)
+        else:
+            img = self._image_decoder(P, head, blocks, N, h_in, w_in)
         return ops.as_nchw(img), states, latent
+
+    # --------------------------------------------------------- image decoder on the tcgen05 kernel
+    def _image_decoder_tc(self, P, head, blocks, planes, N, h, w, passes):
+        """2 ResidualBlocks + 3 TransposedConvLayers (4 sub-pixel phases each, strided epilogue stores) on the
+        tensor-core kernel; activations travel between layers as bf16 hi/lo planes written by the epilogues;
+        the skip sums (unet.py:175,179) are epilogue adds.  The 1x1 prediction conv stays on the fp32 kernel."""
+        ne, base = self.num_encoders, self.base_num_channels
+        cmax = base * 2 ** ne
+        dev = head.device
+        t3 = ops.taps_conv(3, 1)
+
+        def new_planes(hh, ww, c):
+            return (torch.empty((N, hh, ww, c), device=dev, dtype=torch.bfloat16),
+                    torch.empty((N, hh, ww, c), device=dev, dtype=torch.bfloat16))
+
+        x, xp = blocks[-1], planes
+        nres = self.num_residual_blocks
+        for j in range(nres):
+            hi1, lo1, k1, hi2, lo2, k2 = P['res%d_tc' % j]
+            b1, b2 = P['res%d' % j][1], P['res%d' % j][3]
+            tp = new_planes(h, w, cmax)
+            ops.conv_tc_dense(xp, hi1, lo1, k1, t3, N, h, w, cmax, passes, bias=b1, act=ACT_RELU, want_out=False,
+                              out_planes=tp, tag='img_tc')
+            post = blocks[ne - 1] if j == nres - 1 else None
+            np_ = new_planes(h, w, cmax)
+            x = ops.conv_tc_dense(tp, hi2, lo2, k2, t3, N, h, w, cmax, passes, bias=b2, act=ACT_RELU, res_pre=x,
+                                  res_post=post, out_planes=np_, tag='img_tc')
+            xp = np_
+        for i in range(ne):
+            hi, lo, k = P['dec%d_tc' % i]
+            bd, cout = P['dec%d' % i][1], P['dec%d' % i][2]
+            skip_next = blocks[ne - i - 2] if i < ne - 1 else head
+            out = torch.empty((N, 2 * h, 2 * w, cout), device=dev, dtype=torch.float32)
+            op = new_planes(2 * h, 2 * w, cout) if i < ne - 1 else None
+            for py in range(2):
+                for px in range(2):
+                    ops.conv_tc_dense(xp, hi, lo, k, ops.taps_convT_phase(py, px), N, h, w, cout, passes, bias=bd,
+                                      act=ACT_RELU, out=out, out_place=(2 * h, 2 * w, 2, py, 2, px), res_post=skip_next,
+                                      out_planes=op, tag='img_tc')
+            x, xp = out, op
+            h, w = 2 * h, 2 * w
+        wp, bp = P['pred']
+        img, _, _, _ = ops.conv([Seg(x)], wp, bp, N, h, w, h, w, 1, ops.taps_conv(1, 0), act=ACT_SIGMOID)  # unet.py:179
+        return img
 
     # ----------------------------------------------------------------- image decoder (fp32 kernels)
     def _image_decoder(self, P, head, blocks, N, h, w):

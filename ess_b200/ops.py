@@ -410,10 +410,12 @@ def in_stats(y, count=None):
 
 
 def conv_tc_dense(planes, w_hi, w_lo, k_per_tap, taps, N, H, W, Cout, passes, bias=None, out=None, act=ACT_NONE,
-                  tag=None):
+                  tag=None, res_pre=None, res_post=None, out_planes=None, want_out=True, out_place=None):
     """Stride-1 gather-convolution on the tcgen05 kernel over ONE dense bf16 hi/lo plane pair
     [N, H, W, Cin] (Cin a multiple of 64; concatenated inputs are laid out side by side by
-    split_bf16(c_off=...)).  Returns the fp32 result [N, H, W, Cout]."""
+    split_bf16(c_off=...)).  Returns the fp32 result [N, H, W, Cout] (None when want_out=False and
+    only the bf16 `out_planes` are produced).  out_place = (OHf, OWf, osy, ooy, osx, oox) scatters the
+    result into a larger image (transposed-conv phases)."""
     hi, lo = planes
     d = ConvTc()
     dense_view(d.views[0], hi, lo)
@@ -421,11 +423,19 @@ def conv_tc_dense(planes, w_hi, w_lo, k_per_tap, taps, N, H, W, Cout, passes, bi
     d.seg_C[0], d.seg_view0[0], d.seg_koff[0] = hi.shape[-1], 0, 0
     d.k_per_tap, d.n_w_taps, d.w_rows = k_per_tap, w_hi.shape[1] // k_per_tap, w_hi.shape[0]
     d.w_hi, d.w_lo, d.bias = _p(w_hi), _p(w_lo), _p(bias)
-    if out is None:
-        out = torch.empty((N, H, W, Cout), device=hi.device, dtype=torch.float32)
-    d.out, d.ldo = _p(out), out.shape[-1]
+    if out_place is None:
+        out_place = (H, W, 1, 0, 1, 0)
+    if out is None and want_out:
+        out = torch.empty((N, out_place[0], out_place[1], Cout), device=hi.device, dtype=torch.float32)
+    if out is not None:
+        d.out, d.ldo = _p(out), out.shape[-1]
+    if out_planes is not None:
+        d.out_hi, d.out_lo, d.ld_planes = _p(out_planes[0]), _p(out_planes[1]), out_planes[0].shape[-1]
+    d.res_pre, d.res_post = _p(res_pre), _p(res_post)
+    r = res_pre if res_pre is not None else res_post
+    d.ld_res = r.shape[-1] if r is not None else 0
     d.N, d.OH, d.OW, d.Cout = N, H, W, Cout
-    d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = H, W, 1, 0, 1, 0
+    d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = out_place
     d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, act, passes, pick_bw_log2(W, H)
     d.ntaps = len(taps)
     for t, (dy, dx, wi) in enumerate(taps):
