@@ -251,3 +251,55 @@ def test_e2vid_module_forward_signature(mode):
     st = [(h.contiguous(), c.contiguous()) for (h, c) in o1[1]]
     o2b = m(ev[:, C:].cuda(), st)
     assert rel_err(o2b[2][8], r2[2][8]) < TOL
+
+
+def test_training_trajectory_and_miou_parity():
+    """Learnable synthetic task: labels = argmax of a fixed random 'teacher' decoder on the
+    same latents.  Train the decoder for 25 RAdam steps with our modules (GPU, bf16x3) and with the oracle
+    (CPU fp32, oracle.radam_step), same init, same data: loss curves and final mIoU must agree."""
+    import ess_b200
+    from ess_b200.optim import RAdam
+    K, B, H, W, steps = 5, 2, 32, 48, 25
+    lat = make_latents(B, H, W, seed=11)
+    teacher = make_semseg(K, seed=123)
+    with torch.no_grad():
+        labels = O.semseg_forward(sd_cpu(teacher), lat)[1].argmax(1)
+    labels[:, :2] = 255
+    dec = make_semseg(K, seed=6)
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in dec.state_dict().items()}
+    states = {k: {} for k in params}
+    ref_losses = []
+    for _ in range(steps):
+        pred = O.semseg_forward(params, lat)
+        loss = O.task_loss(pred[1], labels, K)
+        grads = torch.autograd.grad(loss, list(params.values()))
+        ref_losses.append(float(loss))
+        with torch.no_grad():
+            for (k, p), g in zip(params.items(), grads):
+                O.radam_step(p, g, states[k], 5e-4, (0., 0.999))
+    with torch.no_grad():
+        conf_ref = O.confusion_matrix(O.semseg_forward(params, lat)[1].argmax(1), labels, K, 255)
+    miou_ref = float(O.confusion_to_iou(conf_ref)[0])
+
+    dec = dec.cuda()
+    crit = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255)
+    opt = RAdam(dec.parameters(), lr=5e-4, weight_decay=0., betas=(0., 0.999))
+    lat_d = {k: v.cuda() for k, v in lat.items()}
+    lab_d = labels.cuda()
+    losses = []
+    for _ in range(steps):
+        opt.zero_grad()
+        loss = crit(dec(lat_d)[1], lab_d)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    met = ess_b200.MetricsSemseg(K, 255, ['c%d' % i for i in range(K)])
+    with torch.no_grad():
+        met.update_batch(dec(lat_d)[1].argmax(1), lab_d)
+    miou = float(met.get_metrics_summary()['mean_iou'])
+    print('loss first/last ours %.5f/%.5f oracle %.5f/%.5f; mIoU ours %.3f oracle %.3f' %
+          (losses[0], losses[-1], ref_losses[0], ref_losses[-1], miou, miou_ref))
+    assert losses[-1] < losses[0] and ref_losses[-1] < ref_losses[0]          # both actually learn
+    assert abs(losses[0] - ref_losses[0]) < 1e-3 * ref_losses[0]
+    assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 1e-2 * ref_losses[0]   # trajectories track
+    assert abs(miou - miou_ref) < 1.0                                             # mIoU in percent points
