@@ -33,6 +33,17 @@ WORK = dict(B=8, T=20, C=5, H=440, W=640, K=11)
 METRIC = 'samples/sec fwd+bwd 640x440x5bin voxel grids'
 
 
+# stdout must carry exactly ONE JSON line (the driver parses it): keep a private handle on the real stdout
+# and send everything else any library prints (NCCL banners, torchrun notices, warnings) to stderr.
+_REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + '\n')
+    _REAL_STDOUT.flush()
+
+
 def flops_per_sample(T, C, H, W, K, contract='B'):
     """Algorithmic FLOPs (2*MAC) of one sample, SURVEY.md s8d / BASELINE.md s3."""
     P = H * W
@@ -188,7 +199,7 @@ def run_reference(args):
                 cpu_baseline=dict(value=value, unit='samples/s', cores=torch.get_num_threads(), kind='port',
                                   sample=sample, parts=parts),
                 e2e=dict(value=value, unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -213,6 +224,9 @@ def main():
     import ess_b200
     from ess_b200 import _lib, dp
     from ess_b200.optim import RAdam
+    # stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'
     rank, world, local = dp.init_from_env()
     if not torch.cuda.is_available():
         raise RuntimeError('bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product arm')
@@ -394,7 +408,7 @@ def main():
         except Exception as ex:   # the baseline must never take the measurement down
             line['cpu_baseline'] = dict(value=None, error=repr(ex))
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0

@@ -303,3 +303,44 @@ def test_training_trajectory_and_miou_parity():
     assert abs(losses[0] - ref_losses[0]) < 1e-3 * ref_losses[0]
     assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 1e-2 * ref_losses[0]   # trajectories track
     assert abs(miou - miou_ref) < 1.0                                             # mIoU in percent points
+
+
+def test_e2vid_ten_bins_config5():
+    """BASELINE config 5 uses C=10 voxel bins: the tensor-core head conv then runs with 16-channel pixels
+    (two 64-wide K chunks per kernel row)."""
+    import ess_b200
+    cfg = dict(E2VID_CFG, num_bins=10)
+    B, T, C, H, W = 1, 2, 10, 32, 64
+    m = make_e2vid(cfg, mode='bf16x3')
+    sd = sd_cpu(m)
+    data = make_events(B, T, C, H, W)
+    img_r, st_r, lat_r = O.encoder_unroll(sd, cfg, data, T, C)
+    m = m.cuda()
+    rec = ess_b200.ImageReconstructor(m, H, W, C, 'cuda')
+    img, st, lat = rec.unroll(data.cuda(), T, C)
+    assert rel_err(img, img_r) < TOL
+    for k in (1, 2, 4, 8):
+        assert rel_err(lat[k], lat_r[k]) < TOL, k
+
+
+def test_ddd17_shape_config2():
+    """BASELINE config 2: raw DDD17 width 346 is reflect-padded to 352 (L3/R3) and the logits stay at the
+    padded size; K=6.  Checked against the oracle at B=1, T=2 (CPU finishes in seconds)."""
+    import ess_b200
+    B, T, C, H, W, K = 1, 2, 5, 200, 346, 6
+    m = make_e2vid(mode='bf16x3')
+    sd = sd_cpu(m)
+    data = make_events(B, T, C, H, W)
+    img_r, st_r, lat_r = O.encoder_unroll(sd, E2VID_CFG, data, T, C)
+    m = m.cuda()
+    rec = ess_b200.ImageReconstructor(m, H, W, C, 'cuda')
+    img, st, lat = rec.unroll(data.cuda(), T, C)
+    assert img.shape == (B, 1, 200, 352) and lat[8].shape == (B, 256, 25, 44)
+    assert rel_err(img, img_r) < TOL
+    for k in (1, 2, 4, 8):
+        assert rel_err(lat[k], lat_r[k]) < TOL, k
+    dec = make_semseg(K).cuda()
+    pred = dec({k: v.detach() for k, v in lat.items()})
+    pred_r = O.semseg_forward(sd_cpu(dec), lat_r)
+    assert pred[1].shape == (B, K, 200, 352)
+    assert rel_err(pred[1], pred_r[1]) < TOL
