@@ -8,5 +8,7 @@ from .loss import TaskLoss                                         # noqa: F401
 from .metrics import MetricsSemseg                                 # noqa: F401
 from .reconstructor import ImageReconstructor                      # noqa: F401
 from .semseg import SemSegE2VID                                    # noqa: F401
+from .style_encoder import StyleEncoderE2VID                       # noqa: F401
+from .uda_losses import L1Loss, symJSDivLoss                       # noqa: F401
 
-__all__ = ['E2VIDRecurrent', 'SemSegE2VID', 'TaskLoss', 'MetricsSemseg', 'ImageReconstructor', 'lib', 'LIB_PATH']
+__all__ = ['E2VIDRecurrent', 'SemSegE2VID', 'StyleEncoderE2VID', 'L1Loss', 'symJSDivLoss', 'TaskLoss', 'MetricsSemseg', 'ImageReconstructor', 'lib', 'LIB_PATH']

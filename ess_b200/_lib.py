@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libess_b200.so')
-MAX_TAPS = 25
+MAX_TAPS = 49
 
 EPI_LINEAR, EPI_LSTM, EPI_GRU_UR, EPI_GRU_OUT = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
@@ -109,6 +109,13 @@ SIGNATURES = {
     'essb_task_loss_bwd': (_I, [_P, _I, _P, _L, _I, _L, _P, _I, _I, _P, _P, _I, _P]),
     'essb_confusion': (_I, [_P, _I, _P, _L, _I, _L, _P, _P]),
     'essb_confusion_labels': (_I, [_P, _P, _L, _I, _L, _P, _P]),
+    'essb_affine_act': (_I, [_P, _I, _P, _P, _P, _I, _I, _P, _I, _L, _I, _P]),
+    'essb_bn_bwd_blocks': (_I, [_L]),
+    'essb_bn_bwd_pass1': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _L, _I, _P]),
+    'essb_bn_bwd_pass2': (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _L, _I, _P]),
+    'essb_l1_fwd': (_I, [_P, _P, _L, _P, _P]),
+    'essb_l1_bwd': (_I, [_P, _P, _L, _P, _P, _P]),
+    'essb_jsdiv': (_I, [_P, _I, _P, _I, _L, _I, _P, _P, _P, _I, _P]),
     'essb_radam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P]),
     'essb_event_prepare_planes': (_I, [_P, _L, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'essb_split_bf16': (_I, [C.POINTER(Src), _I, _I, _I, _P, _P, _I, _I, _P]),

@@ -472,6 +472,75 @@ def wgrad_tc(a_planes, g_planes, Cin, Cout, taps, N, H, W, passes, tag='seg_wgra
     return dw
 
 
+def dgrad_phase_taps(k, pad, stride):
+    """Input-gradient of a k x k / stride s / padding `pad` convolution as gather-convs over dY, one per
+    output phase:  dx[s*i'+p] = sum_{k = p+pad (mod s)} dy[i' + (p+pad-k)/s] * w[k].
+    Returns {(py, px): [(dy, dx, widx), ...]} (an empty list = that phase is identically zero)."""
+    out = {}
+    for py in range(stride):
+        for px in range(stride):
+            taps = []
+            for ky in range(k):
+                if (py + pad - ky) % stride:
+                    continue
+                for kx in range(k):
+                    if (px + pad - kx) % stride:
+                        continue
+                    taps.append(((py + pad - ky) // stride, (px + pad - kx) // stride, ky * k + kx))
+            out[(py, px)] = taps
+    return out
+
+
+def affine_act(x, a, b, res=None, relu=False, out=None):
+    """out = relu?(x * a[c] + b[c] + res) over a pixel-major tensor [..., C]."""
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    if out is None:
+        out = torch.empty_like(x)
+    call('essb_affine_act', _p(x), Cc, _p(a), _p(b), _p(res), Cc if res is not None else 0, int(relu), _p(out), Cc,
+         rows, Cc, _stream())
+    return out
+
+
+def bn_backward(dout, mask_src, x, mean, rstd, gamma):
+    """Train-mode BatchNorm backward.  Returns (dx, dgamma, dbeta, g) with g = dout * (mask_src > 0)."""
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    dev = x.device
+    blocks = _lib.lib().essb_bn_bwd_blocks(rows)
+    g = torch.empty_like(x)
+    partial = torch.empty((1, blocks, Cc, 2), device=dev, dtype=torch.float32)
+    call('essb_bn_bwd_pass1', _p(dout), Cc, _p(mask_src), Cc if mask_src is not None else 0, _p(x), Cc, _p(mean),
+         _p(rstd), _p(g), _p(partial), rows, Cc, _stream())
+    totals = torch.empty((1, Cc, 2), device=dev, dtype=torch.float32)
+    call('essb_partial_reduce', _p(partial), 1, blocks, Cc, _p(totals), _stream())
+    dx = torch.empty_like(x)
+    call('essb_bn_bwd_pass2', _p(g), _p(x), Cc, _p(mean), _p(rstd), _p(gamma), _p(totals), _p(dx), rows, Cc, _stream())
+    return dx, totals[0, :, 1].contiguous(), totals[0, :, 0].contiguous(), g
+
+
+def l1_sum(a, b):
+    sums = torch.empty((1,), device=a.device, dtype=torch.float64)
+    call('essb_l1_fwd', _p(a), _p(b), a.numel(), _p(sums), _stream())
+    return sums
+
+
+def l1_bwd(a, b, gscale):
+    da = torch.empty_like(a)
+    call('essb_l1_bwd', _p(a), _p(b), a.numel(), _p(gscale), _p(da), _stream())
+    return da
+
+
+def jsdiv(predict, target, K, want_sum=True, gscale=None, want_grad=False):
+    """symJSDivLoss kernels on pixel-major logits [N, H, W, ld]; returns (sums | None, dpredict | None)."""
+    rows = predict.numel() // predict.shape[-1]
+    sums = torch.empty((1,), device=predict.device, dtype=torch.float64) if want_sum else None
+    dp = torch.empty(tuple(predict.shape[:-1]) + (K,), device=predict.device, dtype=torch.float32) if want_grad else None
+    call('essb_jsdiv', _p(predict), predict.shape[-1], _p(target), target.shape[-1], rows, K, _p(sums), _p(gscale),
+         _p(dp), K, _stream())
+    return sums, dp
+
+
 def colsum(x, Cc=None):
     """Column sums over all pixels of a pixel-major tensor [N, H, W, ld] -> [C] (bias gradients)."""
     rows = x.shape[0] * x.shape[1] * x.shape[2]

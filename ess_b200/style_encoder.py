@@ -1,0 +1,162 @@
+"""Drop-in `StyleEncoderE2VID` (reference: models/style_networks.py:110-145) -- the UDA image encoder:
+ResNet-18 stem (conv7x7 s2 + BN + ReLU, no max-pool) + layer1..3 with BatchNorm in TRAIN mode
+(training/ess_trainer.py:159-162), forward and backward on libess_b200.so kernels.
+
+Same constructor (`input_dim`, `skip_connect`), `forward(x) -> {1: x, 2, 4, 8}` and `state_dict` keys
+(`encoder_scale_1.0.weight`, `encoder_scale_1.1.*`, `encoder_scale_1.3.{0,1}.*`, `encoder_scale_{2,3}.{0,1}.*`)
+as the reference.  The torchvision modules are parameter/buffer holders only.  The reference builds its
+holders from `resnet18(pretrained=True)` (ImageNet weights, needs network access); here they start from
+torchvision's random init -- load a checkpoint for pretrained weights.
+
+Execution: two small autograd Functions on pixel-major fp32 tensors -- a bias-free gather convolution
+(forward; input gradient as per-phase gather-convs over dY; weight gradient as split-K implicit GEMM)
+and train-mode BatchNorm fused with the BasicBlock residual add and ReLU (batch statistics in one
+memory pass, apply in one pass; backward in two passes).  Convolutions run on the exact-fp32 CUDA-core
+kernel (the tcgen05 path for this encoder is the next widening step).
+"""
+import torch
+import torch.nn as nn
+import torchvision.models as tvm
+
+from . import ops
+from ._lib import ACT_NONE
+from .ops import Seg
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+class _ConvFn(torch.autograd.Function):
+    """y = conv2d(x, w, stride, padding) without bias; x, y pixel-major [N, H, W, C]."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, pad):
+        N, H, W, Cin = x.shape
+        Cout, _, k, _ = w.shape
+        OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        wp = ops.pack_weight(w)
+        y, _, _, _ = ops.conv([Seg(x)], wp, None, N, H, W, OH, OW, Cout, ops.taps_conv(k, pad), stride=stride,
+                              act=ACT_NONE)
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        stride, pad = ctx.cfg
+        N, H, W, Cin = x.shape
+        Cout, _, k, _ = w.shape
+        gy = gy.contiguous()
+        OH, OW = gy.shape[1], gy.shape[2]
+        gx = gw = None
+        if ctx.needs_input_grad[1]:
+            dw, _ = ops.wgrad([Seg(x)], gy, N, H, W, OH, OW, Cout, ops.taps_conv(k, pad), stride=stride, want_bias=False)
+            gw = dw.view(w.shape)
+        if ctx.needs_input_grad[0]:
+            if H != OH * stride or W != OW * stride:
+                raise RuntimeError('conv input gradient needs H, W divisible by the stride')
+            wp = ops.pack_weight(w.detach(), swap_io=True)
+            phases = ops.dgrad_phase_taps(k, pad, stride)
+            alloc = torch.zeros if any(not t for t in phases.values()) else torch.empty
+            gx = alloc((N, H, W, Cin), device=x.device, dtype=torch.float32)
+            for (py, px), taps in phases.items():
+                if taps:
+                    ops.conv([Seg(gy)], wp, None, N, OH, OW, OH, OW, Cin, taps, out=gx,
+                             out_place=(H, W, stride, py, stride, px))
+        return gx, gw, None, None
+
+
+class _BNFn(torch.autograd.Function):
+    """out = relu?(BatchNorm_train(x) + res): batch statistics over all N*H*W rows per channel."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, res, relu, bn):
+        N, H, W, Cc = x.shape
+        rows = N * H * W
+        mean, rstd = ops.in_stats(x.view(1, 1, rows, Cc))          # biased variance, eps inside the sqrt
+        mean, rstd = mean.view(-1), rstd.view(-1)
+        if bn is not None and bn.track_running_stats:              # nn.BatchNorm2d running statistics update
+            with torch.no_grad():
+                var_b = 1.0 / (rstd * rstd) - BN_EPS
+                var_u = var_b * (rows / max(rows - 1, 1))
+                bn.running_mean.mul_(1 - BN_MOMENTUM).add_(mean, alpha=BN_MOMENTUM)
+                bn.running_var.mul_(1 - BN_MOMENTUM).add_(var_u, alpha=BN_MOMENTUM)
+                bn.num_batches_tracked += 1
+        g = gamma.detach().float()
+        a = (g * rstd).contiguous()
+        b = (beta.detach().float() - mean * a).contiguous()
+        out = ops.affine_act(x, a, b, res=res, relu=relu)
+        ctx.save_for_backward(x, mean, rstd, g.contiguous(), out if relu else None)
+        ctx.has_res = res is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, mean, rstd, gamma, out = ctx.saved_tensors
+        dx, dgamma, dbeta, g = ops.bn_backward(gout.contiguous(), out, x, mean, rstd, gamma)
+        return dx, dgamma, dbeta, (g if ctx.has_res else None), None, None
+
+
+def _bn_apply(x, bn, res, relu, training):
+    if training:
+        return _BNFn.apply(x, bn.weight, bn.bias, res, relu, bn)
+    if torch.is_grad_enabled() and (x.requires_grad or bn.weight.requires_grad):
+        raise NotImplementedError('StyleEncoderE2VID in eval mode is forward-only (use torch.no_grad())')
+    a = (bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + BN_EPS)).contiguous()
+    b = (bn.bias.detach().float() - bn.running_mean.float() * a).contiguous()
+    return ops.affine_act(x, a, b, res=res, relu=relu)
+
+
+class StyleEncoderE2VID(nn.Module):
+    def __init__(self, input_dim, skip_connect=False):
+        super().__init__()
+        self.skip_connect = skip_connect
+        r = tvm.resnet18(weights=None)
+        conv_list = [nn.Conv2d(input_dim, 64, kernel_size=(7, 7), stride=(2, 2), padding=(3, 3), bias=False)]
+        conv_list += list(r.children())[1:3]          # bn1, relu
+        conv_list += list(r.children())[4:5]          # layer1 (max-pool skipped, as in the reference)
+        self.encoder_scale_1 = nn.Sequential(*conv_list)
+        self.encoder_scale_2 = list(r.children())[5]  # layer2
+        self.encoder_scale_3 = list(r.children())[6]  # layer3
+
+    def update_skip_dict(self, skips, x, sz_in):
+        rem, scale = sz_in % x.shape[3], sz_in // x.shape[3]
+        assert rem == 0
+        skips[scale] = x
+
+    def _block(self, x, blk):
+        """torchvision BasicBlock: conv-bn-relu-conv-bn (+ downsample) + add + relu."""
+        tr = self.training
+        s = blk.conv1.stride[0]
+        y = _ConvFn.apply(x, blk.conv1.weight, s, 1)
+        y = _bn_apply(y, blk.bn1, None, True, tr)
+        y = _ConvFn.apply(y, blk.conv2.weight, 1, 1)
+        identity = x
+        if blk.downsample is not None:
+            identity = _ConvFn.apply(x, blk.downsample[0].weight, blk.downsample[0].stride[0], 0)
+            identity = _bn_apply(identity, blk.downsample[1], None, False, tr)
+        return _bn_apply(y, blk.bn2, identity, True, tr)
+
+    def forward(self, x):
+        ops.require_cuda(x)
+        out = {1: x}
+        sz_in = x.shape[3]
+        if x.shape[2] % 8 or x.shape[3] % 8:
+            raise RuntimeError('StyleEncoderE2VID: H, W must be multiples of 8')
+        t = x.float().permute(0, 2, 3, 1).contiguous()           # C = input_dim pixel-major
+        e1 = self.encoder_scale_1
+        y = _ConvFn.apply(t, e1[0].weight, 2, 3)
+        y = _bn_apply(y, e1[1], None, True, self.training)
+        for blk in e1[3]:
+            y = self._block(y, blk)
+        if self.skip_connect:
+            self.update_skip_dict(out, y.permute(0, 3, 1, 2), sz_in)
+        for blk in self.encoder_scale_2:
+            y = self._block(y, blk)
+        if self.skip_connect:
+            self.update_skip_dict(out, y.permute(0, 3, 1, 2), sz_in)
+        for blk in self.encoder_scale_3:
+            y = self._block(y, blk)
+        self.update_skip_dict(out, y.permute(0, 3, 1, 2), sz_in)
+        return out

@@ -23,7 +23,7 @@ extern "C" {
 #endif
 
 #define ESSB_VERSION 100
-#define ESSB_MAX_TAPS 25
+#define ESSB_MAX_TAPS 49   /* up to a 7x7 filter (ResNet stem of StyleEncoderE2VID) */
 
 typedef enum essb_status {
   ESSB_OK = 0,
@@ -212,6 +212,30 @@ int essb_confusion(const float* logits, int ld, const int64_t* target, int64_t n
 /* same from already-computed label predictions (MetricsSemseg.update_batch, metrics.py:50-56) */
 int essb_confusion_labels(const int64_t* pred, const int64_t* target, int64_t npix, int K,
                           int64_t ignore_index, int64_t* conf, void* stream);
+
+/* ---- train-mode BatchNorm + UDA consistency losses (UDA companion path) ----
+ * StyleEncoderE2VID = ResNet-18 stem + layer1-3 with BatchNorm in TRAIN mode (models/style_networks.py:
+ * 110-145, training/ess_trainer.py:159-162).  Per-channel batch statistics reuse essb_in_stats /
+ * essb_in_finalize / essb_partial_reduce with N = 1 over rows = N*H*W. */
+/* out = relu?(x * a[c] + b[c] + res)   (BN apply with folded gamma/beta, BasicBlock residual add) */
+int essb_affine_act(const float* x, int ld_x, const float* a, const float* b, const float* res, int ld_res,
+                    int relu, float* out, int ld_out, int64_t rows, int C, void* stream);
+int essb_bn_bwd_blocks(int64_t rows);
+/* g = dout * (mask > 0) (mask = the block's post-ReLU output, or NULL); partial [blocks][C][2] = sums of
+ * g and g*xhat per block.  dbeta = sum g, dgamma = sum g*xhat after essb_partial_reduce. */
+int essb_bn_bwd_pass1(const float* dout, int ld_d, const float* mask, int ld_m, const float* x, int ld_x,
+                      const float* mean, const float* rstd, float* g, float* partial, int64_t rows, int C,
+                      void* stream);
+/* dx = gamma * rstd * (g - sum(g)/M - xhat * sum(g*xhat)/M), totals = [C][2] */
+int essb_bn_bwd_pass2(const float* g, const float* x, int ld_x, const float* mean, const float* rstd,
+                      const float* gamma, const float* totals, float* dx, int64_t rows, int C, void* stream);
+/* torch.nn.L1Loss (mean): sums[0] = sum |a-b|;  da = gscale[0]/n * sign(a-b) */
+int essb_l1_fwd(const float* a, const float* b, int64_t n, double* sums, void* stream);
+int essb_l1_bwd(const float* a, const float* b, int64_t n, const float* gscale, float* da, void* stream);
+/* symJSDivLoss (utils/loss_functions.py:27-37) on pixel-major logits [rows][K]: sums[0] = rows*K * loss
+ * (when sums != NULL); dpredict = gscale[0] * dLoss/dpredict (when dpredict != NULL; target gets none). */
+int essb_jsdiv(const float* predict, int ld_p, const float* target, int ld_t, int64_t rows, int K,
+               double* sums, const float* gscale, float* dpredict, int ld_d, void* stream);
 
 /* ---- optimizer (utils/radam.py:15-80, one fused elementwise update per tensor) ------------------ */
 /* v = b2*v + (1-b2)*g^2; m = b1*m + (1-b1)*g; p -= wd_lr*p; p -= step_lr * (rectified ? m/(sqrt(v)+eps) : m)

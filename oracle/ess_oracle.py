@@ -381,3 +381,111 @@ def radam_step(p, grad, state, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.
     else:
         p.add_(state['exp_avg'], alpha=-1.0 / (1 - beta1 ** t) * lr)
     return p
+
+
+# ------------------------------------------------------------------------------------------------
+# UDA companion path: StyleEncoderE2VID + ESSModel.train_step (DSEC branch)
+# ------------------------------------------------------------------------------------------------
+def _bn(x, sd, prefix, training, stats_out=None):
+    """nn.BatchNorm2d (torchvision ResNet), train mode = batch statistics (+ running-stat update
+    returned through stats_out), eval mode = running statistics."""
+    if training:
+        if stats_out is not None:
+            m = x.shape[0] * x.shape[2] * x.shape[3]
+            mean = x.mean((0, 2, 3))
+            var_u = x.var((0, 2, 3), unbiased=True) if m > 1 else x.var((0, 2, 3), unbiased=False)
+            stats_out[prefix] = (0.9 * sd[prefix + '.running_mean'] + 0.1 * mean.detach(),
+                                 0.9 * sd[prefix + '.running_var'] + 0.1 * var_u.detach())
+        return F.batch_norm(x, None, None, sd[prefix + '.weight'], sd[prefix + '.bias'], training=True, eps=BN_EPS)
+    return F.batch_norm(x, sd[prefix + '.running_mean'], sd[prefix + '.running_var'], sd[prefix + '.weight'],
+                        sd[prefix + '.bias'], training=False, eps=BN_EPS)
+
+
+def _basic_block(x, sd, prefix, stride, training, stats_out):
+    """torchvision.models.resnet.BasicBlock.forward."""
+    out = F.conv2d(x, sd[prefix + '.conv1.weight'], None, stride=stride, padding=1)
+    out = torch.relu(_bn(out, sd, prefix + '.bn1', training, stats_out))
+    out = F.conv2d(out, sd[prefix + '.conv2.weight'], None, stride=1, padding=1)
+    out = _bn(out, sd, prefix + '.bn2', training, stats_out)
+    identity = x
+    if prefix + '.downsample.0.weight' in sd:
+        identity = F.conv2d(x, sd[prefix + '.downsample.0.weight'], None, stride=stride)
+        identity = _bn(identity, sd, prefix + '.downsample.1', training, stats_out)
+    return torch.relu(out + identity)
+
+
+def style_encoder_forward(sd, x, skip_connect=True, training=True, stats_out=None):
+    """StyleEncoderE2VID.forward (models/style_networks.py:128-145): conv7x7 s2 -> bn1 -> relu -> layer1
+    (encoder_scale_1), layer2 (encoder_scale_2), layer3 (encoder_scale_3); out keys by width ratio."""
+    out = {1: x}
+    sz_in = x.shape[3]
+
+    def put(t):
+        assert sz_in % t.shape[3] == 0
+        out[sz_in // t.shape[3]] = t
+
+    y = F.conv2d(x, sd['encoder_scale_1.0.weight'], None, stride=2, padding=3)
+    y = torch.relu(_bn(y, sd, 'encoder_scale_1.1', training, stats_out))
+    for b in range(2):
+        y = _basic_block(y, sd, 'encoder_scale_1.3.%d' % b, 1, training, stats_out)
+    if skip_connect:
+        put(y)
+    for b in range(2):
+        y = _basic_block(y, sd, 'encoder_scale_2.%d' % b, 2 if b == 0 else 1, training, stats_out)
+    if skip_connect:
+        put(y)
+    for b in range(2):
+        y = _basic_block(y, sd, 'encoder_scale_3.%d' % b, 2 if b == 0 else 1, training, stats_out)
+    put(y)
+    return out
+
+
+def uda_step(e2vid_sd, e2vid_cfg, enc_sd, dec_sd, img_a, labels_a, data_b, num_windows, channels, num_classes,
+             ignore_index=255, w_task=1.0, w_kl=1.0, w_cycle=1.0, w_cycle_task=1.0):
+    """ESSModel.train_step, DSEC branch, train_on_event_labels=False (training/ess_trainer.py:103-148 with
+    img_train_step :150-180, event_train_step :257-301, trainCycleStep :211-255, TasktrainCycleStep :303-330).
+    Returns (losses dict, grads of the image encoder dict, grads of the decoder dict)."""
+    enc = {k: v.detach().clone().requires_grad_(v.is_floating_point() and 'running' not in k) for k, v in enc_sd.items()}
+    dec = {k: v.detach().clone().requires_grad_(True) for k, v in dec_sd.items()}
+    enc_params = [v for v in enc.values() if v.requires_grad]
+    dec_params = list(dec.values())
+    g_enc = [torch.zeros_like(p) for p in enc_params]
+    g_dec = [torch.zeros_like(p) for p in dec_params]
+    l1 = torch.nn.functional.l1_loss
+
+    def accumulate(loss, params, grads):
+        gs = torch.autograd.grad(loss, params, allow_unused=True, retain_graph=False)
+        for a, g in zip(grads, gs):
+            if g is not None:
+                a += g
+
+    # ---- images: encoder forward (train-mode BN), latents detached for DSEC (:188), decoder + task loss
+    lat_fake = style_encoder_forward(enc, img_a, True, True)
+    pred_a = semseg_forward(dec, {k: v.detach() for k, v in lat_fake.items()})
+    t_img = task_loss(pred_a[1], labels_a, num_classes, ignore_index) * w_task
+    accumulate(t_img, dec_params, g_dec)                                  # :120-125 (encoder params frozen)
+
+    # ---- events: T windows through the frozen E2VID (no_grad, :277-280)
+    img_fake, _, lat_real = encoder_unroll(e2vid_sd, e2vid_cfg, data_b, num_windows, channels, True)
+    lat_real = {k: v.detach() for k, v in lat_real.items()}
+    lat_fake = style_encoder_forward(enc, img_fake.detach(), True, True)  # :282
+    # trainCycleStep (:211-255)
+    e_loss = (l1(lat_fake[2], lat_real[2]) + l1(lat_fake[4], lat_real[4]) + l1(lat_fake[8], lat_real[8])) * w_cycle
+    pred_second = semseg_forward(dec, lat_fake)
+    with torch.no_grad():
+        pred_first_ng = semseg_forward(dec, lat_real)
+    e_loss = e_loss + sym_js_div_loss(pred_second[1], pred_first_ng[1])
+    e_loss = e_loss + l1(pred_second[2], pred_first_ng[2]) * w_cycle_task
+    e_loss = e_loss + l1(pred_second[4], pred_first_ng[4]) * w_cycle_task
+    # TasktrainCycleStep (:303-330)
+    pred_first = semseg_forward(dec, lat_real)
+    with torch.no_grad():
+        pred_second_ng = semseg_forward(dec, {k: v.detach() for k, v in lat_fake.items()})
+    t_loss = sym_js_div_loss(pred_first[1], pred_second_ng[1]) * w_kl
+    t_loss = t_loss + l1(pred_first[2], pred_second_ng[2]) * w_cycle_task
+    t_loss = t_loss + l1(pred_first[4], pred_second_ng[4]) * w_cycle_task
+    accumulate(e_loss, enc_params, g_enc)          # :133-137: back_end frozen for e_loss -> encoder grads only
+    accumulate(t_loss, dec_params, g_dec)          # :138
+    losses = dict(task_img=float(t_img), e_loss=float(e_loss), t_loss=float(t_loss))
+    names_e = [k for k, v in enc.items() if v.requires_grad]
+    return losses, dict(zip(names_e, g_enc)), dict(zip(dec.keys(), g_dec))

@@ -210,3 +210,38 @@ def make_supervised_trainer(settings, device='cpu'):
         t.init_fn()
     t.visualize_epoch = lambda: False
     return t
+
+
+def uda_settings(ckpt_path, img_size, num_classes, T, C, device='cpu'):
+    """Fields of config/settings.py read by ESSModel.init_fn / train_step (DSEC branch, settings_DSEC.yaml)."""
+    s = supervised_settings(ckpt_path, img_size, num_classes, T, C, device)
+    s.dataset_name_b = 'DSEC_events'
+    s.input_channels_a = 1
+    s.skip_connect_encoder = True
+    s.lr_front = 5e-4
+    s.weight_KL_loss = 1.0
+    s.weight_cycle_loss = 1.0
+    s.weight_cycle_task_loss = 1.0
+    s.require_paired_data_train_a = False
+    s.train_on_event_labels = False
+    s.semseg_label_val_b = True
+    return s
+
+
+def make_uda_trainer(settings, device='cpu'):
+    """ESSModel (training/ess_trainer.py) without BaseTrainer.__init__."""
+    install()
+    import io
+    import torch
+    from training.ess_trainer import ESSModel
+    t = object.__new__(ESSModel)
+    t.settings = settings
+    t.device = torch.device(device)
+    t.is_training = True
+    t.step_count = 0
+    t.epoch_count = 0
+    t.do_val_training_epoch = False
+    with contextlib.redirect_stdout(io.StringIO()):
+        t.init_fn()
+    t.visualize_epoch = lambda: False
+    return t

@@ -154,3 +154,36 @@ def test_oracle_radam_vs_live_reference():
         opt.step()
         O.radam_step(w2, g, state, 5e-4, (0., 0.999))
         assert torch.allclose(w2, w.detach(), rtol=1e-6, atol=1e-8), i
+
+
+@needs_ref
+def test_oracle_uda_step_vs_live_reference_trainer():
+    """oracle.uda_step restates ESSModel.train_step (DSEC branch): same losses and the same gradients on the
+    image encoder and on the decoder as the UNMODIFIED reference trainer run through the shim."""
+    import os
+    cfg = dict(ref_shim.E2VID_LIGHTWEIGHT_CFG, num_bins=2)
+    m = ref_shim.make_reference_e2vid(cfg)
+    path = ref_shim.save_synthetic_checkpoint(m, cfg)
+    try:
+        H, W, K, T, C, B = 32, 48, 5, 2, 2, 2
+        t = ref_shim.make_uda_trainer(ref_shim.uda_settings(path, (H, W), K, T, C))
+        enc_sd = {k: v.detach().clone() for k, v in t.front_end_sensor_a.state_dict().items()}
+        dec_sd = {k: v.detach().clone() for k, v in t.task_backend.state_dict().items()}
+        e2vid_sd = {k: v.detach().clone() for k, v in t.front_end_sensor_b.state_dict().items()}
+        g = torch.Generator().manual_seed(0)
+        img_a = torch.rand(B, 1, H, W, generator=g)
+        labels_a = torch.randint(0, K, (B, H, W), generator=g)
+        labels_a[:, :2] = 255
+        data_b = torch.randn(B, T * C, H, W, generator=g) * (torch.rand(B, T * C, H, W, generator=g) < 0.3)
+        labels_b = torch.randint(0, K, (B, H, W), generator=g)
+        losses, _, final = t.train_step([[img_a, labels_a], [data_b, labels_b]])
+        ol, g_enc, g_dec = O.uda_step(e2vid_sd, cfg, enc_sd, dec_sd, img_a, labels_a, data_b, T, C, K)
+        assert abs(ol['task_img'] - float(losses['semseg_sensor_a_loss'])) < 1e-5
+        assert abs(ol['task_img'] + ol['e_loss'] + ol['t_loss'] - float(final)) < 1e-4
+        for n, p in t.front_end_sensor_a.named_parameters():
+            assert p.grad is not None, n
+            assert (p.grad - g_enc[n]).abs().max() <= 1e-4 * g_enc[n].abs().max() + 1e-7, n
+        for n, p in t.task_backend.named_parameters():
+            assert (p.grad - g_dec[n]).abs().max() <= 1e-4 * g_dec[n].abs().max() + 5e-6, n
+    finally:
+        os.remove(path)

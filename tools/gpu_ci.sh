@@ -3,7 +3,7 @@
 # others), each under a timeout, logging into gpurun_out/.  Usage: bash tools/gpu_ci.sh [files...]
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-FILES=${@:-"tests/test_gpu_kernels.py tests/test_gpu_tc.py tests/test_gpu_modules.py"}
+FILES=${@:-"tests/test_gpu_kernels.py tests/test_gpu_tc.py tests/test_gpu_modules.py tests/test_gpu_uda.py tests/test_gpu_dp.py"}
 rc=0
 for f in $FILES; do
   name=$(basename $f .py)
