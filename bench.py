@@ -372,10 +372,11 @@ def main():
                          'executes 3x this, so the mode ceiling is peak/3',
                     mean_launch_ms=sec / n * 1e3, share_of_step=sec * 1e3 / ms_dev,
                     mma_frac_of_peak=ach * (3 if args.mode == 'bf16x3' else 1) / peaks['bf16'])
-        if 'enc_tc' in by_tag:
-            fl2, sec2, n2 = by_tag['enc_tc']
-            roof['enc_tc'] = dict(achieved=fl2 / sec2 / 1e12, mean_launch_ms=sec2 / n2 * 1e3, launches=n2,
-                                  share_of_step=sec2 * 1e3 / ms_dev)
+        # the other tcgen05 launches of the step, by role (algorithmic TFLOP/s, share of the timed region)
+        roof['other_tc_kernels'] = {
+            tag: dict(achieved=fl2 / sec2 / 1e12, mean_launch_ms=sec2 / n2 * 1e3, launches=n2,
+                      share_of_step=sec2 * 1e3 / ms_dev)
+            for tag, (fl2, sec2, n2) in sorted(by_tag.items()) if tag != 'lstm_tc'}
     elif args.mode == 'fp32':
         roof = dict(kernel='conv_fp32_kernel', bound='tensor', achieved=None, peak=peaks['bf16'], unit='TFLOP/s',
                     frac=None, traffic=None)

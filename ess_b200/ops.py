@@ -551,6 +551,37 @@ def colsum(x, Cc=None):
     return out
 
 
+def conv_tc_s2(planes, w_hi, w_lo, k_per_tap, k, pad, N, H, W, Cout, passes, bias=None, act=ACT_NONE, tag=None):
+    """k x k stride-2 convolution on the tcgen05 kernel: the input planes [N, H, W, Cin] (Cin a multiple of
+    64, H and W even) are addressed through four parity views; tap offset k-pad = 2a + p selects view p and
+    plane offset a.  Returns the fp32 result [N, H/2, W/2, Cout]."""
+    hi, lo = planes
+    d = ConvTc()
+    for py in range(2):
+        for px in range(2):
+            parity_view(d.views[py * 2 + px], hi, lo, py, px)
+    d.n_views, d.nseg = 4, 1
+    d.seg_C[0], d.seg_view0[0], d.seg_koff[0] = hi.shape[-1], 0, 0
+    d.k_per_tap, d.n_w_taps, d.w_rows = k_per_tap, k * k, w_hi.shape[0]
+    d.w_hi, d.w_lo, d.bias = _p(w_hi), _p(w_lo), _p(bias)
+    OH, OW = H // 2, W // 2
+    out = torch.empty((N, OH, OW, Cout), device=hi.device, dtype=torch.float32)
+    d.out, d.ldo = _p(out), Cout
+    d.N, d.OH, d.OW, d.Cout = N, OH, OW, Cout
+    d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = OH, OW, 1, 0, 1, 0
+    d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, act, passes, pick_bw_log2(OW, OH)
+    t = 0
+    for ky in range(k):
+        for kx in range(k):
+            oy, ox = ky - pad, kx - pad
+            py, px = oy % 2, ox % 2
+            d.dy[t], d.dx[t], d.view[t], d.widx[t] = (oy - py) // 2, (ox - px) // 2, py * 2 + px, ky * k + kx
+            t += 1
+    d.ntaps = t
+    conv_tc(d, tag=tag)
+    return out
+
+
 def conv_tc(d: ConvTc, tag=None):
     """essb_conv_tc_run; when _lib.PROFILE is a list, brackets the launch with CUDA events on the
     launching stream and records (tag, algorithmic FLOPs, start, end)."""

@@ -11,8 +11,10 @@ torchvision's random init -- load a checkpoint for pretrained weights.
 Execution: two small autograd Functions on pixel-major fp32 tensors -- a bias-free gather convolution
 (forward; input gradient as per-phase gather-convs over dY; weight gradient as split-K implicit GEMM)
 and train-mode BatchNorm fused with the BasicBlock residual add and ReLU (batch statistics in one
-memory pass, apply in one pass; backward in two passes).  Convolutions run on the exact-fp32 CUDA-core
-kernel (the tcgen05 path for this encoder is the next widening step).
+memory pass, apply in one pass; backward in two passes).  In the tensor-core modes every 3x3 / 1x1 convolution
+runs on the tcgen05 kernels (stride 2 through parity views; input gradients of strided convs as per-phase
+gathers with strided stores); the 1-channel 7x7 stem and the stride-2 weight gradients stay on the exact-fp32
+CUDA-core kernels.
 """
 import torch
 import torch.nn as nn
@@ -26,45 +28,76 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
 
+def _tc_ok(mode, k, cin, cout):
+    return mode != 'fp32' and k in (1, 3) and cin % 64 == 0 and cout in (64, 128, 256)
+
+
 class _ConvFn(torch.autograd.Function):
-    """y = conv2d(x, w, stride, padding) without bias; x, y pixel-major [N, H, W, C]."""
+    """y = conv2d(x, w, stride, padding) without bias; x, y pixel-major [N, H, W, C].
+    mode 'fp32': exact CUDA-core kernels; 'bf16x3' / 'bf16': tcgen05 kernels wherever the shape allows
+    (3x3 / 1x1 with Cin % 64 == 0: forward, input gradient; weight gradient for stride 1)."""
 
     @staticmethod
-    def forward(ctx, x, w, stride, pad):
+    def forward(ctx, x, w, stride, pad, mode):
         N, H, W, Cin = x.shape
         Cout, _, k, _ = w.shape
         OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-        wp = ops.pack_weight(w)
-        y, _, _, _ = ops.conv([Seg(x)], wp, None, N, H, W, OH, OW, Cout, ops.taps_conv(k, pad), stride=stride,
-                              act=ACT_NONE)
+        passes = 3 if mode == 'bf16x3' else 1
+        if _tc_ok(mode, k, Cin, Cout) and (stride == 1 or (stride == 2 and H % 2 == 0 and W % 2 == 0)):
+            planes = ops.split_bf16(Seg(x), N, H, W)
+            w_hi, w_lo, kinp = ops.pack_weight_tc(w)
+            if stride == 1:
+                y = ops.conv_tc_dense(planes, w_hi, w_lo, kinp, ops.taps_conv(k, pad), N, H, W, Cout, passes, tag='uda_fwd')
+            else:
+                y = ops.conv_tc_s2(planes, w_hi, w_lo, kinp, k, pad, N, H, W, Cout, passes, tag='uda_fwd')
+        else:
+            wp = ops.pack_weight(w)
+            y, _, _, _ = ops.conv([Seg(x)], wp, None, N, H, W, OH, OW, Cout, ops.taps_conv(k, pad), stride=stride,
+                                  act=ACT_NONE)
         ctx.save_for_backward(x, w)
-        ctx.cfg = (stride, pad)
+        ctx.cfg = (stride, pad, mode)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
-        stride, pad = ctx.cfg
+        stride, pad, mode = ctx.cfg
         N, H, W, Cin = x.shape
         Cout, _, k, _ = w.shape
         gy = gy.contiguous()
         OH, OW = gy.shape[1], gy.shape[2]
+        passes = 3 if mode == 'bf16x3' else 1
+        tc = _tc_ok(mode, k, Cin, Cout)
+        gplanes = ops.split_bf16(Seg(gy), N, OH, OW) if tc else None          # Cout is a multiple of 64
         gx = gw = None
         if ctx.needs_input_grad[1]:
-            dw, _ = ops.wgrad([Seg(x)], gy, N, H, W, OH, OW, Cout, ops.taps_conv(k, pad), stride=stride, want_bias=False)
-            gw = dw.view(w.shape)
+            if tc and stride == 1:
+                planes = ops.split_bf16(Seg(x), N, H, W)
+                gw = ops.wgrad_tc(planes, gplanes, Cin, Cout, ops.taps_conv(k, pad), N, H, W, passes,
+                                  tag='uda_wgrad').view(w.shape)
+            else:
+                dw, _ = ops.wgrad([Seg(x)], gy, N, H, W, OH, OW, Cout, ops.taps_conv(k, pad), stride=stride,
+                                  want_bias=False)
+                gw = dw.view(w.shape)
         if ctx.needs_input_grad[0]:
             if H != OH * stride or W != OW * stride:
                 raise RuntimeError('conv input gradient needs H, W divisible by the stride')
-            wp = ops.pack_weight(w.detach(), swap_io=True)
             phases = ops.dgrad_phase_taps(k, pad, stride)
             alloc = torch.zeros if any(not t for t in phases.values()) else torch.empty
             gx = alloc((N, H, W, Cin), device=x.device, dtype=torch.float32)
-            for (py, px), taps in phases.items():
-                if taps:
-                    ops.conv([Seg(gy)], wp, None, N, OH, OW, OH, OW, Cin, taps, out=gx,
-                             out_place=(H, W, stride, py, stride, px))
-        return gx, gw, None, None
+            if tc:
+                w_hi, w_lo, kinp = ops.pack_weight_tc(w.detach(), swap_io=True)
+                for (py, px), taps in phases.items():
+                    if taps:
+                        ops.conv_tc_dense(gplanes, w_hi, w_lo, kinp, taps, N, OH, OW, Cin, passes, out=gx,
+                                          out_place=(H, W, stride, py, stride, px), tag='uda_dgrad')
+            else:
+                wp = ops.pack_weight(w.detach(), swap_io=True)
+                for (py, px), taps in phases.items():
+                    if taps:
+                        ops.conv([Seg(gy)], wp, None, N, OH, OW, OH, OW, Cin, taps, out=gx,
+                                 out_place=(H, W, stride, py, stride, px))
+        return gx, gw, None, None, None
 
 
 class _BNFn(torch.autograd.Function):
@@ -119,6 +152,8 @@ class StyleEncoderE2VID(nn.Module):
         self.encoder_scale_1 = nn.Sequential(*conv_list)
         self.encoder_scale_2 = list(r.children())[5]  # layer2
         self.encoder_scale_3 = list(r.children())[6]  # layer3
+        from .e2vid import default_mode
+        self.mode = default_mode()    # 'fp32' | 'bf16x3' | 'bf16' (same meaning as in E2VIDRecurrent / SemSegE2VID)
 
     def update_skip_dict(self, skips, x, sz_in):
         rem, scale = sz_in % x.shape[3], sz_in // x.shape[3]
@@ -129,12 +164,12 @@ class StyleEncoderE2VID(nn.Module):
         """torchvision BasicBlock: conv-bn-relu-conv-bn (+ downsample) + add + relu."""
         tr = self.training
         s = blk.conv1.stride[0]
-        y = _ConvFn.apply(x, blk.conv1.weight, s, 1)
+        y = _ConvFn.apply(x, blk.conv1.weight, s, 1, self.mode)
         y = _bn_apply(y, blk.bn1, None, True, tr)
-        y = _ConvFn.apply(y, blk.conv2.weight, 1, 1)
+        y = _ConvFn.apply(y, blk.conv2.weight, 1, 1, self.mode)
         identity = x
         if blk.downsample is not None:
-            identity = _ConvFn.apply(x, blk.downsample[0].weight, blk.downsample[0].stride[0], 0)
+            identity = _ConvFn.apply(x, blk.downsample[0].weight, blk.downsample[0].stride[0], 0, self.mode)
             identity = _bn_apply(identity, blk.downsample[1], None, False, tr)
         return _bn_apply(y, blk.bn2, identity, True, tr)
 
@@ -146,7 +181,7 @@ class StyleEncoderE2VID(nn.Module):
             raise RuntimeError('StyleEncoderE2VID: H, W must be multiples of 8')
         t = x.float().permute(0, 2, 3, 1).contiguous()           # C = input_dim pixel-major
         e1 = self.encoder_scale_1
-        y = _ConvFn.apply(t, e1[0].weight, 2, 3)
+        y = _ConvFn.apply(t, e1[0].weight, 2, 3, self.mode)
         y = _bn_apply(y, e1[1], None, True, self.training)
         for blk in e1[3]:
             y = self._block(y, blk)

@@ -89,9 +89,11 @@ def _make_style_encoder(seed=3):
     return m
 
 
-def test_style_encoder_forward_backward_vs_oracle():
+@pytest.mark.parametrize('mode', ['fp32', 'bf16x3'])
+def test_style_encoder_forward_backward_vs_oracle(mode):
     B, H, W = 2, 64, 96
     m = _make_style_encoder()
+    m.mode = mode
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     g = torch.Generator().manual_seed(5)
     x = torch.rand(B, 1, H, W, generator=g)
