@@ -116,6 +116,8 @@ SIGNATURES = {
     'essb_l1_fwd': (_I, [_P, _P, _L, _P, _P]),
     'essb_l1_bwd': (_I, [_P, _P, _L, _P, _P, _P]),
     'essb_jsdiv': (_I, [_P, _I, _P, _I, _L, _I, _P, _P, _P, _I, _P]),
+    'essb_voxel_grid_dsec': (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P, _P]),
+    'essb_voxel_grid_ddd17': (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
     'essb_radam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P]),
     'essb_event_prepare_planes': (_I, [_P, _L, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'essb_split_bf16': (_I, [C.POINTER(Src), _I, _I, _I, _P, _P, _I, _I, _P]),

@@ -237,6 +237,16 @@ int essb_l1_bwd(const float* a, const float* b, int64_t n, const float* gscale, 
 int essb_jsdiv(const float* predict, int ld_p, const float* target, int ld_t, int64_t rows, int K,
                double* sums, const float* gscale, float* dpredict, int ld_d, void* stream);
 
+/* ---- events -> voxel grid (the tensor-building step in front of the path) ------ */
+/* VoxelGrid.convert without normalisation (DSEC/dataset/representations.py:15-44): x, y, pol, t are float
+ * device arrays of n events (time-sorted); grid [C][H][W] is zeroed and filled by trilinear scatter. */
+int essb_voxel_grid_dsec(const float* x, const float* y, const float* pol, const float* t, int64_t n, int C,
+                         int H, int W, float* grid, void* stream);
+/* generate_voxel_grid (datasets/data_util.py:54-126): events = n rows of double [x, y, t, polarity in {0,1}];
+ * grid [2C][H][W] (separate_pol: positive then negative) or [C][H][W] (positive - negative). */
+int essb_voxel_grid_ddd17(const double* events, int64_t n, int C, int H, int W, int separate_pol, float* grid,
+                          void* stream);
+
 /* ---- optimizer (utils/radam.py:15-80, one fused elementwise update per tensor) ------------------ */
 /* v = b2*v + (1-b2)*g^2; m = b1*m + (1-b1)*g; p -= wd_lr*p; p -= step_lr * (rectified ? m/(sqrt(v)+eps) : m)
  * with step_lr = step_size*lr and wd_lr = weight_decay*lr computed on the host exactly as radam.py:53-75. */

@@ -489,3 +489,56 @@ def uda_step(e2vid_sd, e2vid_cfg, enc_sd, dec_sd, img_a, labels_a, data_b, num_w
     losses = dict(task_img=float(t_img), e_loss=float(e_loss), t_loss=float(t_loss))
     names_e = [k for k, v in enc.items() if v.requires_grad]
     return losses, dict(zip(names_e, g_enc)), dict(zip(dec.keys(), g_dec))
+
+
+# ------------------------------------------------------------------------------------------------
+# events -> voxel grid
+# ------------------------------------------------------------------------------------------------
+def voxel_grid_dsec(x, y, pol, time, channels, height, width):
+    """VoxelGrid.convert with normalize=False (DSEC/dataset/representations.py:15-44)."""
+    C, H, W = channels, height, width
+    grid = torch.zeros((C, H, W), dtype=torch.float)
+    t_norm = (C - 1) * (time - time[0]) / (time[-1] - time[0])
+    x0, y0, t0 = x.int(), y.int(), t_norm.int()
+    value = 2 * pol - 1
+    for xlim in [x0, x0 + 1]:
+        for ylim in [y0, y0 + 1]:
+            for tlim in [t0, t0 + 1]:
+                mask = (xlim < W) & (xlim >= 0) & (ylim < H) & (ylim >= 0) & (tlim >= 0) & (tlim < C)
+                w = value * (1 - (xlim - x).abs()) * (1 - (ylim - y).abs()) * (1 - (tlim - t_norm).abs())
+                index = H * W * tlim.long() + W * ylim.long() + xlim.long()
+                grid.put_(index[mask], w[mask], accumulate=True)
+    return grid
+
+
+def voxel_grid_ddd17(events, shape, nr_temporal_bins, separate_pol=True):
+    """generate_voxel_grid (datasets/data_util.py:54-126) restated with numpy; `events` = [N,4] float64 rows
+    [x, y, t, polarity].  (The reference function itself uses `np.int`, removed in numpy >= 1.24, so it cannot
+    run in this image: this restatement is unpinned against live reference output.)"""
+    import numpy as np
+    events = np.array(events, dtype=np.float64)
+    height, width = shape
+    n = nr_temporal_bins
+    pos = np.zeros((n, height, width), np.float32).ravel()
+    neg = np.zeros((n, height, width), np.float32).ravel()
+    first, last = events[0, 2], events[-1, 2]
+    dT = last - first
+    if dT == 0:
+        dT = 1.0
+    xs, ys = events[:, 0].astype(np.int64), events[:, 1].astype(np.int64)
+    ts = (n - 1) * (events[:, 2] - first) / dT
+    pols = events[:, 3].copy()
+    pols[pols == 0] = -1
+    tis = ts.astype(np.int64)
+    dts = ts - tis
+    vl, vr = np.abs(pols) * (1.0 - dts), np.abs(pols) * dts
+    valid = (xs < width) & (xs >= 0) & (ys < height) & (ys >= 0) & (ts >= 0) & (ts < n)
+    for grid, sel in ((pos, pols == 1), (neg, pols != 1)):
+        m = (tis < n) & sel & valid
+        np.add.at(grid, xs[m] + ys[m] * width + tis[m] * width * height, vl[m])
+        m = ((tis + 1) < n) & sel & valid
+        np.add.at(grid, xs[m] + ys[m] * width + (tis[m] + 1) * width * height, vr[m])
+    pos, neg = pos.reshape(n, height, width), neg.reshape(n, height, width)
+    if separate_pol:
+        return torch.from_numpy(np.concatenate([pos, neg], 0))
+    return torch.from_numpy(pos - neg)

@@ -264,3 +264,26 @@ def test_radam_kernel_vs_oracle():
         opt.step()
         O.radam_step(w2, g, state, 5e-4, (0., 0.999))
         assert rel_err(w.detach(), w2) < 1e-6, i
+
+
+def test_voxel_grids():
+    from ess_b200.voxel import VoxelGrid, generate_voxel_grid
+    g = torch.Generator().manual_seed(0)
+    n, C, H, W = 20000, 5, 40, 64
+    x = torch.rand(n, generator=g) * (W + 1) - 0.7
+    y = torch.rand(n, generator=g) * (H + 1) - 0.7
+    pol = (torch.rand(n, generator=g) > 0.5).float()
+    t = torch.sort(torch.rand(n, generator=g))[0] * 1e3
+    ref = O.voxel_grid_dsec(x, y, pol, t, C, H, W)
+    out = VoxelGrid(C, H, W, False).convert(x.cuda(), y.cuda(), pol.cuda(), t.cuda())
+    assert float((out.cpu() - ref).abs().max()) < 1e-4          # float atomics: summation-order noise only
+    ev = torch.stack([torch.floor(torch.rand(n, generator=g) * (W + 2)) - 1, torch.floor(torch.rand(n, generator=g) * (H + 2)) - 1,
+                      torch.sort(torch.rand(n, generator=g))[0] * 50.0, (torch.rand(n, generator=g) > 0.5).float()], 1).double()
+    for sep in (True, False):
+        ref = O.voxel_grid_ddd17(ev.numpy(), (H, W), C, separate_pol=sep)
+        out = generate_voxel_grid(ev.cuda(), (H, W), C, separate_pol=sep)
+        assert out.shape == ref.shape and float((out.cpu() - ref).abs().max()) < 1e-4
+    # degenerate: all events share one timestamp (deltaT == 0 branch, data_util.py:75-76)
+    ev2 = ev.clone()
+    ev2[:, 2] = 7.0
+    assert float((generate_voxel_grid(ev2.cuda(), (H, W), C).cpu() - O.voxel_grid_ddd17(ev2.numpy(), (H, W), C)).abs().max()) < 1e-4

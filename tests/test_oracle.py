@@ -187,3 +187,17 @@ def test_oracle_uda_step_vs_live_reference_trainer():
             assert (p.grad - g_dec[n]).abs().max() <= 1e-4 * g_dec[n].abs().max() + 5e-6, n
     finally:
         os.remove(path)
+
+
+@needs_ref
+def test_oracle_voxel_grid_dsec_vs_live_reference():
+    ref_shim.install()
+    from DSEC.dataset.representations import VoxelGrid
+    g = torch.Generator().manual_seed(0)
+    n, C, H, W = 5000, 5, 24, 32
+    x = torch.rand(n, generator=g) * (W + 1) - 0.7          # includes out-of-range and negative-fraction coordinates
+    y = torch.rand(n, generator=g) * (H + 1) - 0.7
+    pol = (torch.rand(n, generator=g) > 0.5).float()
+    t = torch.sort(torch.rand(n, generator=g))[0] * 1e3
+    ref = VoxelGrid(C, H, W, normalize=False).convert(x, y, pol, t)
+    assert torch.allclose(O.voxel_grid_dsec(x, y, pol, t, C, H, W), ref, rtol=0, atol=1e-5)
