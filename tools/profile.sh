@@ -11,7 +11,7 @@ echo "launch list exit $?"
 # (2) full capture of the dominant kernel (fused ConvLSTM cell on tcgen05): the three pyramid levels of one
 #     window after warm-up (conv_tc_kernel<1> = LSTM epilogue instantiation)
 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k 'regex:conv_tc_kernel<1>' -s 9 -c 3 \
+    -k 'regex:conv_tc_kernel<.int.1>' -s 9 -c 3 \
     -o gpurun_out/prof_lstm_$R -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --windows 4 \
     > gpurun_out/prof_lstm_$R.log 2>&1
 echo "full capture exit $?"

@@ -33,7 +33,7 @@ def launches():
     T = sum(v[1] for v in tot.values())
     with open(os.path.join(P, '%s_launches%s.txt' % (R, SUF)), 'w') as f:
         f.write('# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 3 '
-                '--no-cpu-baseline\n# %d launches over 6 bench steps (3 warm-up + 1 timed + 2 end-to-end); per-launch '
+                '--no-cpu-baseline\n# %d launches over the whole bench run (warm-up + timed + end-to-end steps); per-launch '
                 'times are cold-cache and serialised: compare SHARES\n' % len(rows))
         f.write('%-44s %7s %11s %7s %10s\n' % ('kernel', 'count', 'total ms', 'share', 'avg ms'))
         for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
