@@ -215,6 +215,8 @@ def main():
     ap.add_argument('--windows', type=int, default=WORK['T'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-optimizer', action='store_true')
+    ap.add_argument('--torch-gpu-baseline', action='store_true',
+                    help='also time the oracle (the reference op stream as plain PyTorch/cuDNN ops, TF32 default) on this GPU')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -365,8 +367,14 @@ def main():
     if 'lstm_tc' in by_tag:
         fl, sec, n = by_tag['lstm_tc']
         ach = fl / sec / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+        if os.path.exists(tpath) and (B, T, H, W) == (WORK['B'], WORK['T'], WORK['H'], WORK['W']):
+            traffic = json.load(open(tpath)).get('lstm_tc', {}).get('mean_dram_bytes_per_launch')
         roof = dict(kernel='conv_tc_kernel<LSTM> (fused ConvLSTM cell, %d launches)' % n, bound='tensor', achieved=ach,
-                    peak=peaks['bf16'], unit='TFLOP/s', frac=ach / peaks['bf16'], traffic=None,
+                    peak=peaks['bf16'], unit='TFLOP/s', frac=ach / peaks['bf16'], traffic=traffic,
+                    traffic_note='mean DRAM bytes per launch from the committed ncu --set full capture '
+                                 '(profiles/ncu_traffic.json); algorithmic bytes are 865/433/216 MB for the 3 levels',
                     peak_source='%s bf16 dense sustained (MEASURED_PEAKS.json)' % peaks['source'],
                     note='algorithmic FLOPs (2*MAC, no credit for the 3 split passes): in bf16x3 mode the tensor pipe '
                          'executes 3x this, so the mode ceiling is peak/3',
@@ -408,6 +416,53 @@ def main():
                                         parts=parts)
         except Exception as ex:   # the baseline must never take the measurement down
             line['cpu_baseline'] = dict(value=None, error=repr(ex))
+    if rank == 0 and world == 1 and args.torch_gpu_baseline:
+        # Secondary baseline of SURVEY.md s8d: the reference's op stream through PyTorch/ATen/cuDNN on this B200
+        # (cudnn.allow_tf32 = True, torch's default): the oracle's functions run on CUDA tensors.  Bounded
+        # sample: B=8, 3 windows (+ image decoder once) + decoder fwd/bwd, extrapolated linearly in T.
+        try:
+            from oracle import ess_oracle as O
+            e_sd = {k: v.detach() for k, v in e2vid.state_dict().items()}
+            d_sd = {k: v.detach() for k, v in dec.state_dict().items()}
+            d0, l0 = devb[0]
+
+            def enc_windows(nw, with_img):
+                st = None
+                for i in range(nw):
+                    _, st, lat = O.reconstructor_step(e_sd, E2VID_CFG, d0[:, i * C:(i + 1) * C], st,
+                                                      with_image=(with_img and i == nw - 1))
+                return lat
+
+            def dec_step(lat):
+                params = {k: v.clone().requires_grad_(True) for k, v in d_sd.items()}
+                pred = O.semseg_forward(params, {k: v.detach() for k, v in lat.items()})
+                torch.autograd.grad(O.task_loss(pred[1], l0, K), list(params.values()))
+
+            def tm(fn, n=3):
+                fn()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) / n
+
+            with torch.no_grad():
+                t3 = tm(lambda: enc_windows(3, False))
+                t1 = tm(lambda: enc_windows(1, False))
+                t3i = tm(lambda: enc_windows(3, True))
+                lat = enc_windows(2, False)
+            t_win = (t3 - t1) / 2.0
+            t_dec = tm(lambda: dec_step(lat))
+            ms = T * t_win + (t3i - t3) + t_dec
+            line['torch_gpu_baseline'] = dict(value=B / (ms / 1e3), unit='samples/s', ms_per_step=ms,
+                                              kind='oracle ops (PyTorch/ATen/cuDNN, allow_tf32 default) on this GPU',
+                                              parts=dict(ms_window=t_win, ms_image_decoder=t3i - t3, ms_decoder_fwd_bwd=t_dec),
+                                              sample='B=%d: 3 windows + image decoder once + decoder fwd/bwd, linear in T' % B)
+        except Exception as ex:
+            line['torch_gpu_baseline'] = dict(value=None, error=repr(ex))
     if rank == 0:
         emit(line)
     if world > 1:

@@ -292,7 +292,8 @@ def dice_loss(predict, target, num_classes, ignore_index):
     but the mean still divides by K (:135)."""
     mask = target != ignore_index
     tgt = target * mask
-    onehot = torch.zeros((target.shape[0], num_classes) + tuple(target.shape[1:]), dtype=predict.dtype)
+    onehot = torch.zeros((target.shape[0], num_classes) + tuple(target.shape[1:]), dtype=predict.dtype,
+                         device=predict.device)
     onehot.scatter_(1, tgt.unsqueeze(1), 1)
     onehot = onehot * mask.unsqueeze(1)
     p = F.softmax(predict, dim=1) * mask.unsqueeze(1)
