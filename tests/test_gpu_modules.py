@@ -344,3 +344,22 @@ def test_ddd17_shape_config2():
     pred_r = O.semseg_forward(sd_cpu(dec), lat_r)
     assert pred[1].shape == (B, K, 200, 352)
     assert rel_err(pred[1], pred_r[1]) < TOL
+
+
+def test_convgru_in_tensor_core_mode():
+    """ConvGRU checkpoints (`recurrent_block_type='convgru'`, model.py:77-80) in bf16x3 mode: the head conv runs on
+    tcgen05, the GRU cells (no tcgen05 epilogue yet) and their encoder convs on the exact-fp32 kernels."""
+    import ess_b200
+    cfg = dict(E2VID_CFG, recurrent_block_type='convgru')
+    B, T, C, H, W = 1, 2, 5, 32, 64
+    m = make_e2vid(cfg, mode='bf16x3')
+    sd = sd_cpu(m)
+    data = make_events(B, T, C, H, W)
+    img_r, st_r, lat_r = O.encoder_unroll(sd, cfg, data, T, C)
+    m = m.cuda()
+    rec = ess_b200.ImageReconstructor(m, H, W, C, 'cuda')
+    img, st, lat = rec.unroll(data.cuda(), T, C)
+    assert torch.is_tensor(st[0]) and st[0].shape == st_r[0].shape      # GRU state is a tensor, not a tuple
+    assert rel_err(img, img_r) < TOL
+    for k in (1, 2, 4, 8):
+        assert rel_err(lat[k], lat_r[k]) < TOL, k
