@@ -54,8 +54,8 @@ class TcView(C.Structure):
 class ConvTc(C.Structure):
     _fields_ = [('views', TcView * 8),
                 ('w_hi', C.c_void_p), ('w_lo', C.c_void_p), ('bias', C.c_void_p), ('res_pre', C.c_void_p),
-                ('res_post', C.c_void_p), ('aux0', C.c_void_p), ('out', C.c_void_p), ('out2', C.c_void_p),
-                ('out_hi', C.c_void_p), ('out_lo', C.c_void_p),
+                ('res_post', C.c_void_p), ('aux0', C.c_void_p), ('aux1', C.c_void_p), ('out', C.c_void_p),
+                ('out2', C.c_void_p), ('out_hi', C.c_void_p), ('out_lo', C.c_void_p),
                 ('n_views', C.c_int32), ('nseg', C.c_int32),
                 ('seg_C', C.c_int32 * 2), ('seg_view0', C.c_int32 * 2), ('seg_koff', C.c_int32 * 2),
                 ('k_per_tap', C.c_int32), ('n_w_taps', C.c_int32), ('w_rows', C.c_int32),

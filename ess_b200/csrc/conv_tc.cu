@@ -60,6 +60,7 @@ struct TcParams {
   const float* res_pre;
   const float* res_post;
   const float* aux0;
+  const float* aux1;
   float* out;
   float* out2;
   __nv_bfloat16* out_hi;
@@ -268,6 +269,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (p.out_hi) {
             *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0) = hh;
             *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0) = hl;
+          }
+        } else if constexpr (EPI == ESSB_EPI_GRU_UR) {
+          // ConvGRU update / reset gates (submodules.py:267-268): columns co = 2*ch + {update, reset};
+          // 32 columns = 16 channels.  Writes update (fp32) and prev_state*reset as bf16 planes (the A
+          // operand of the out-gate convolution).
+          const int hidden = p.Cout >> 1;
+          const int ch0 = (n0 + c0) >> 1;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float uv[8];
+            bf16x8 hh, hl;
+            float hp[8];
+            if (p.aux0) {
+              const float4 a0 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0 + g * 8);
+              const float4 a1 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0 + g * 8 + 4);
+              hp[0] = a0.x; hp[1] = a0.y; hp[2] = a0.z; hp[3] = a0.w; hp[4] = a1.x; hp[5] = a1.y; hp[6] = a1.z; hp[7] = a1.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) hp[e] = 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int col = g * 16 + e * 2;
+              float gu = __uint_as_float(r[col]), gr = __uint_as_float(r[col + 1]);
+              if (p.bias) { gu += p.bias[n0 + c0 + col]; gr += p.bias[n0 + c0 + col + 1]; }
+              uv[e] = sigmoid_fast(gu);
+              split_bf16(hp[e] * sigmoid_fast(gr), hh.v[e], hl.v[e]);
+            }
+            float* uo = p.out + pix * hidden + ch0 + g * 8;
+            *reinterpret_cast<float4*>(uo) = make_float4(uv[0], uv[1], uv[2], uv[3]);
+            *reinterpret_cast<float4*>(uo + 4) = make_float4(uv[4], uv[5], uv[6], uv[7]);
+            *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0 + g * 8) = hh;
+            *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0 + g * 8) = hl;
+          }
+        } else if constexpr (EPI == ESSB_EPI_GRU_OUT) {
+          // ConvGRU out gate + blend (submodules.py:269-271): h' = h*(1-u) + tanh(acc + b)*u
+          const int hidden = p.Cout;
+          const int ch0 = n0 + c0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int ch = ch0 + g * 8;
+            float hv[8], hp[8], uu[8];
+            const float4 u0 = *reinterpret_cast<const float4*>(p.aux1 + pix * hidden + ch);
+            const float4 u1 = *reinterpret_cast<const float4*>(p.aux1 + pix * hidden + ch + 4);
+            uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w; uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
+            if (p.aux0) {
+              const float4 a0 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch);
+              const float4 a1 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch + 4);
+              hp[0] = a0.x; hp[1] = a0.y; hp[2] = a0.z; hp[3] = a0.w; hp[4] = a1.x; hp[5] = a1.y; hp[6] = a1.z; hp[7] = a1.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) hp[e] = 0.f;
+            }
+            bf16x8 hh, hl;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = __uint_as_float(r[g * 8 + e]);
+              if (p.bias) x += p.bias[ch + e];
+              hv[e] = hp[e] * (1.f - uu[e]) + tanh_fast(x) * uu[e];
+              split_bf16(hv[e], hh.v[e], hl.v[e]);
+            }
+            float* ho = p.out + pix * hidden + ch;
+            *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+            if (p.out_hi) {
+              *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch) = hh;
+              *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch) = hl;
+            }
           }
         } else {
           const size_t opix = ((size_t)n * p.OHf + (oy * p.osy + p.ooy)) * p.OWf + (ox * p.osx + p.oox);
@@ -592,8 +661,13 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   if (d->epilogue == ESSB_EPI_LSTM) {
     ESSB_REQUIRE(d->out && d->out2 && Ngemm % 4 == 0, "essb_conv_tc_run: LSTM needs out/out2");
     ESSB_REQUIRE(!d->out_hi || (d->out_lo && d->ld_planes % 8 == 0), "essb_conv_tc_run: bad planes");
+  } else if (d->epilogue == ESSB_EPI_GRU_UR) {
+    ESSB_REQUIRE(d->out && d->out_hi && d->out_lo && d->ld_planes % 8 == 0, "essb_conv_tc_run: GRU_UR needs out (update) and the bf16 planes of prev_state*reset");
+  } else if (d->epilogue == ESSB_EPI_GRU_OUT) {
+    ESSB_REQUIRE(d->out && d->aux1, "essb_conv_tc_run: GRU_OUT needs out and the update gate in aux1");
+    ESSB_REQUIRE(!d->out_hi || (d->out_lo && d->ld_planes % 8 == 0), "essb_conv_tc_run: bad planes");
   } else {
-    ESSB_REQUIRE(d->epilogue == ESSB_EPI_LINEAR, "essb_conv_tc_run: epilogue %d not supported on the tensor-core path", d->epilogue);
+    ESSB_REQUIRE(d->epilogue == ESSB_EPI_LINEAR, "essb_conv_tc_run: unknown epilogue %d", d->epilogue);
     ESSB_REQUIRE(d->out || d->out_hi, "essb_conv_tc_run: no output");
     ESSB_REQUIRE(!d->out || (d->ldo % 4 == 0 && essb_aligned16(d->out)), "essb_conv_tc_run: out must be 16B aligned, ldo %% 4 == 0");
     ESSB_REQUIRE(!d->out_hi || (d->out_lo && d->ld_planes % 8 == 0), "essb_conv_tc_run: bad planes");
@@ -660,7 +734,7 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   p.N = d->N; p.OH = d->OH; p.OW = d->OW; p.Cout = d->Cout;
   p.OHf = d->OHf; p.OWf = d->OWf; p.osy = d->osy; p.ooy = d->ooy; p.osx = d->osx; p.oox = d->oox;
   p.ldo = d->ldo; p.ld_res = d->ld_res; p.ld_planes = d->ld_planes; p.act = d->act;
-  p.bias = d->bias; p.res_pre = d->res_pre; p.res_post = d->res_post; p.aux0 = d->aux0;
+  p.bias = d->bias; p.res_pre = d->res_pre; p.res_post = d->res_post; p.aux0 = d->aux0; p.aux1 = d->aux1;
   p.out = d->out; p.out2 = d->out2;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(d->out_hi);
   p.out_lo = reinterpret_cast<__nv_bfloat16*>(d->out_lo);
@@ -673,6 +747,12 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   if (d->epilogue == ESSB_EPI_LSTM) {
     e = cudaFuncSetAttribute(conv_tc_kernel<ESSB_EPI_LSTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e == cudaSuccess) conv_tc_kernel<ESSB_EPI_LSTM><<<grid, TC_THREADS, smem_bytes, st>>>(p);
+  } else if (d->epilogue == ESSB_EPI_GRU_UR) {
+    e = cudaFuncSetAttribute(conv_tc_kernel<ESSB_EPI_GRU_UR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) conv_tc_kernel<ESSB_EPI_GRU_UR><<<grid, TC_THREADS, smem_bytes, st>>>(p);
+  } else if (d->epilogue == ESSB_EPI_GRU_OUT) {
+    e = cudaFuncSetAttribute(conv_tc_kernel<ESSB_EPI_GRU_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) conv_tc_kernel<ESSB_EPI_GRU_OUT><<<grid, TC_THREADS, smem_bytes, st>>>(p);
   } else {
     e = cudaFuncSetAttribute(conv_tc_kernel<ESSB_EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e == cudaSuccess) conv_tc_kernel<ESSB_EPI_LINEAR><<<grid, TC_THREADS, smem_bytes, st>>>(p);

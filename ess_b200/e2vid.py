@@ -219,6 +219,11 @@ class E2VIDRecurrent(nn.Module):
                 e['gru_o_w'] = ops.pack_weight(rb.out_gate.weight)
                 e['gru_o_w_x'] = ops.pack_weight(rb.out_gate.weight[:, :C].contiguous())
                 e['gru_o_b'] = rb.out_gate.bias.detach().float().contiguous()
+                e['gru_tc'] = None
+                if tc and C % 64 == 0:
+                    uh, ul, kinp = ops.pack_weight_tc(wur, interleave=2)
+                    oh_, ol_, _ = ops.pack_weight_tc(rb.out_gate.weight)
+                    e['gru_tc'] = dict(ur_hi=uh, ur_lo=ul, o_hi=oh_, o_lo=ol_, k_per_tap=kinp)
             P['enc%d' % i] = e
         for j, rbk in enumerate(u.resblocks):
             s1, b1 = _bn_fold(rbk.conv1.bias, getattr(rbk, 'bn1', None), None, dev)
@@ -357,8 +362,18 @@ class E2VIDRecurrent(nn.Module):
             oh, ow = h_in // 2, w_in // 2
             st = prev_states[i]
             use_tc = tc_mode and e['tc'] is not None and cur_planes is not None and \
-                (not lstm or e['lstm_tc'] is not None) and lstm
-            if use_tc:
+                (e['lstm_tc'] if lstm else e['gru_tc']) is not None
+            if use_tc and not lstm:
+                xh = torch.empty((N, oh, ow, cout), device=dev, dtype=torch.bfloat16)
+                xl = torch.empty_like(xh)
+                self._enc_conv_tc(e, cur_planes, N, h_in, w_in, cout, xh, xl, passes)
+                hp = self._to_nhwc(st) if st is not None else None
+                hp_planes = self._hidden_planes(hp) if hp is not None else None
+                h, hh, hl = self._gru_tc(e, (xh, xl), hp, hp_planes, N, oh, ow, cout, passes)
+                new_planes[h.data_ptr()] = (h, hh, hl, h._version)
+                cur, cur_planes = h, (hh, hl)
+                state = ops.as_nchw(h)
+            elif use_tc:
                 xh = torch.empty((N, oh, ow, cout), device=dev, dtype=torch.bfloat16)
                 xl = torch.empty_like(xh)
                 self._enc_conv_tc(e, cur_planes, N, h_in, w_in, cout, xh, xl, passes)
@@ -531,6 +546,51 @@ class E2VIDRecurrent(nn.Module):
         for t, (dy, dx, v, wi) in enumerate(taps):
             d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, v, wi
         ops.conv_tc(d, tag='enc_tc')
+
+    def _gru_tc(self, e, x_planes, h_prev, h_planes, N, oh, ow, C, passes):
+        """ConvGRU cell (submodules.py:255-273) as two tcgen05 launches: [update, reset] gates (epilogue writes
+        update and the bf16 planes of prev_state*reset), then the out gate over [x, prev_state*reset] whose
+        epilogue blends h' = h*(1-u) + tanh(.)*u."""
+        tcw = e['gru_tc']
+        dev = x_planes[0].device
+        taps = ops.taps_conv(3, 1)
+
+        def base(d, second):
+            ops.dense_view(d.views[0], x_planes[0], x_planes[1])
+            d.n_views, d.nseg = 1, 1
+            d.seg_C[0], d.seg_view0[0], d.seg_koff[0] = C, 0, 0
+            if second is not None:
+                ops.dense_view(d.views[1], second[0], second[1])
+                d.n_views, d.nseg = 2, 2
+                d.seg_C[1], d.seg_view0[1], d.seg_koff[1] = C, 1, C
+            d.k_per_tap, d.n_w_taps = tcw['k_per_tap'], 9
+            d.N, d.OH, d.OW = N, oh, ow
+            d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = oh, ow, 1, 0, 1, 0
+            d.ldo, d.ld_planes = C, C
+            d.act, d.passes, d.bw_log2 = ACT_NONE, passes, ops.pick_bw_log2(ow, oh)
+            d.ntaps = len(taps)
+            for t, (dy, dx, wi) in enumerate(taps):
+                d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, 0, wi
+
+        upd = torch.empty((N, oh, ow, C), device=dev, dtype=torch.float32)
+        hr = (torch.empty((N, oh, ow, C), device=dev, dtype=torch.bfloat16),
+              torch.empty((N, oh, ow, C), device=dev, dtype=torch.bfloat16))
+        d = ConvTc()
+        base(d, h_planes)
+        d.w_hi, d.w_lo, d.w_rows, d.bias = ops._p(tcw['ur_hi']), ops._p(tcw['ur_lo']), tcw['ur_hi'].shape[0], ops._p(e['gru_ur_b'])
+        d.aux0, d.out, d.out_hi, d.out_lo = ops._p(h_prev), ops._p(upd), ops._p(hr[0]), ops._p(hr[1])
+        d.Cout, d.epilogue = 2 * C, EPI_GRU_UR
+        ops.conv_tc(d, tag='gru_tc')
+        h = torch.empty((N, oh, ow, C), device=dev, dtype=torch.float32)
+        hh = torch.empty((N, oh, ow, C), device=dev, dtype=torch.bfloat16)
+        hl = torch.empty_like(hh)
+        d = ConvTc()
+        base(d, hr if h_planes is not None else None)          # prev_state = 0  =>  prev_state*reset = 0: skip that K half
+        d.w_hi, d.w_lo, d.w_rows, d.bias = ops._p(tcw['o_hi']), ops._p(tcw['o_lo']), tcw['o_hi'].shape[0], ops._p(e['gru_o_b'])
+        d.aux0, d.aux1, d.out, d.out_hi, d.out_lo = ops._p(h_prev), ops._p(upd), ops._p(h), ops._p(hh), ops._p(hl)
+        d.Cout, d.epilogue = C, EPI_GRU_OUT
+        ops.conv_tc(d, tag='gru_tc')
+        return h, hh, hl
 
     def _lstm_tc(self, e, x_planes, h_planes, c_prev, N, oh, ow, C, passes):
         """Fused ConvLSTM cell (submodules.py:190-230): gates GEMM + sigma/tanh + state update."""

@@ -290,8 +290,9 @@ typedef struct essb_tc_view {
  *   acc[n,oy,ox,co] = sum_t sum_seg sum_c  view[seg_view0[seg] + view[t]][n, oy+dy[t], ox+dx[t], c]
  *                                          * W[co][widx[t]*k_per_tap + seg_koff[seg] + c]
  * Epilogues: ESSB_EPI_LINEAR (bias, res_pre, act, res_post, strided placement, fp32 and/or bf16
- * hi/lo outputs) and ESSB_EPI_LSTM (as essb_conv; additionally writes the hidden state as bf16
- * planes so the next window's MMA can consume it without a conversion pass). */
+ * hi/lo outputs), ESSB_EPI_LSTM (as essb_conv; additionally writes the hidden state as bf16 planes so
+ * the next window's MMA can consume it without a conversion pass), ESSB_EPI_GRU_UR (update -> out,
+ * prev_state*reset -> out_hi/out_lo planes) and ESSB_EPI_GRU_OUT (new state -> out (+ planes)). */
 typedef struct essb_conv_tc {
   essb_tc_view views[8];
   const uint16_t* w_hi;  /* [w_rows][n_w_taps * k_per_tap] */
@@ -299,8 +300,9 @@ typedef struct essb_conv_tc {
   const float* bias;
   const float* res_pre;
   const float* res_post;
-  const float* aux0;     /* LSTM: previous cell or NULL */
-  float* out;            /* LINEAR: fp32 result or NULL; LSTM: hidden */
+  const float* aux0;     /* LSTM: previous cell or NULL; GRU_UR / GRU_OUT: previous state or NULL */
+  const float* aux1;     /* GRU_OUT: update gate */
+  float* out;            /* LINEAR: fp32 result or NULL; LSTM: hidden; GRU_UR: update; GRU_OUT: new state */
   float* out2;           /* LSTM: cell */
   uint16_t* out_hi;      /* optional bf16 planes of the result (LSTM: of the hidden state) */
   uint16_t* out_lo;
