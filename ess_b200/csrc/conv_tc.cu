@@ -20,6 +20,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -65,7 +67,217 @@ struct TcParams {
   float* out2;
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
+  // halo-reuse mode (conv_tc_halo_kernel): one A tile (output patch + halo) per (segment, chunk, view),
+  // shared by every tap that reads that view; separate A and B pipelines
+  int halo_w, halo_h, hx0, hy0;          // halo box extents (pixels) and the smallest tap offsets
+  int a_stages, b_stages, a_stage_bytes, b_stage_bytes, a_lo_off, b_lo_off;
+  int base_offset_mode;                  // 0: descriptor base_offset = 0; 1: (start address >> 7) & 7
+  int n_groups;                          // tap groups = views actually used; taps are sorted by group
+  int8_t grp_view[MAX_VIEWS], grp_first[MAX_VIEWS], grp_count[MAX_VIEWS];
 };
+
+// One accumulator tile: wait for the MMAs, TMEM -> registers -> fused epilogue -> global stores, then hand the
+// TMEM buffer back.  Shared by the classic and the halo-reuse kernels.  q = TMEM lane quarter (warp % 4),
+// half = which of the two warps of that quarter (interleaved 32-column chunks).
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                                                 uint64_t* tempty_bar, uint32_t (&tph)[2], int local, int item, int q,
+                                                 int half, int lane) {
+  const int BW = 1 << p.bw_log2, BH = TC_M >> p.bw_log2;
+    const int buf = local & 1;
+    const int nt = item % p.n_tiles;
+    int mt = item / p.n_tiles;
+    const int txi = mt % p.tiles_x; mt /= p.tiles_x;
+    const int tyi = mt % p.tiles_y;
+    const int n = mt / p.tiles_y;
+    const int m = q * 32 + lane;
+    const int oy = tyi * BH + (m >> p.bw_log2), ox = txi * BW + (m & (BW - 1));
+    const bool valid = oy < p.OH && ox < p.OW;
+    const int n0 = nt * p.BN;
+    const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
+    // LSTM: the previous cell state does not depend on the MMA -> fetch it BEFORE waiting for the
+    // accumulator so its latency hides under the main loop of this tile
+    float cp[4][8];
+    if constexpr (EPI == ESSB_EPI_LSTM) {
+      const int hidden = p.Cout >> 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c0 = half * 32 + j * 64;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cp[j][e] = 0.f;
+        if (valid && p.aux0 && c0 < p.BN) {
+          const float* src = p.aux0 + pix * hidden + ((n0 + c0) >> 2);
+          const float4 c0v = *reinterpret_cast<const float4*>(src);
+          const float4 c1v = *reinterpret_cast<const float4*>(src + 4);
+          cp[j][0] = c0v.x; cp[j][1] = c0v.y; cp[j][2] = c0v.z; cp[j][3] = c0v.w;
+          cp[j][4] = c1v.x; cp[j][5] = c1v.y; cp[j][6] = c1v.z; cp[j][7] = c1v.w;
+        }
+      }
+    }
+    mbar_wait(&tfull_bar[buf], tph[buf]);
+    tph[buf] ^= 1;
+    tc_fence_after();
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = half * 32 + j * 64;
+      if (c0 >= p.BN) break;  // warp-uniform
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(t_addr + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (!valid) {
+        // out-of-image rows of a partial tile: nothing to store
+      } else if constexpr (EPI == ESSB_EPI_LSTM) {
+        // columns co = 4*ch + {in, remember, out, cell}; 32 columns = 8 channels
+        const int hidden = p.Cout >> 2;
+        const int ch0 = (n0 + c0) >> 2;
+        float hv[8], cv[8];
+        bf16x8 hh, hl;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int co = n0 + c0 + e * 4;
+          float gi = __uint_as_float(r[e * 4 + 0]), gf = __uint_as_float(r[e * 4 + 1]);
+          float go = __uint_as_float(r[e * 4 + 2]), gc = __uint_as_float(r[e * 4 + 3]);
+          if (p.bias) {
+            const float4 b4 = *reinterpret_cast<const float4*>(p.bias + co);
+            gi += b4.x; gf += b4.y; go += b4.z; gc += b4.w;
+          }
+          const float cell = sigmoid_fast(gf) * cp[j][e] + sigmoid_fast(gi) * tanh_fast(gc);
+          cv[e] = cell;
+          hv[e] = sigmoid_fast(go) * tanh_fast(cell);
+          split_bf16(hv[e], hh.v[e], hl.v[e]);
+        }
+        float* ho = p.out + pix * hidden + ch0;
+        float* co_ = p.out2 + pix * hidden + ch0;
+        *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+        *reinterpret_cast<float4*>(co_) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        *reinterpret_cast<float4*>(co_ + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+        if (p.out_hi) {
+          *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0) = hh;
+          *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0) = hl;
+        }
+      } else if constexpr (EPI == ESSB_EPI_GRU_UR) {
+        // ConvGRU update / reset gates (submodules.py:267-268): columns co = 2*ch + {update, reset};
+        // 32 columns = 16 channels.  Writes update (fp32) and prev_state*reset as bf16 planes (the A
+        // operand of the out-gate convolution).
+        const int hidden = p.Cout >> 1;
+        const int ch0 = (n0 + c0) >> 1;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float uv[8];
+          bf16x8 hh, hl;
+          float hp[8];
+          if (p.aux0) {
+            const float4 a0 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0 + g * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0 + g * 8 + 4);
+            hp[0] = a0.x; hp[1] = a0.y; hp[2] = a0.z; hp[3] = a0.w; hp[4] = a1.x; hp[5] = a1.y; hp[6] = a1.z; hp[7] = a1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hp[e] = 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int col = g * 16 + e * 2;
+            float gu = __uint_as_float(r[col]), gr = __uint_as_float(r[col + 1]);
+            if (p.bias) { gu += p.bias[n0 + c0 + col]; gr += p.bias[n0 + c0 + col + 1]; }
+            uv[e] = sigmoid_fast(gu);
+            split_bf16(hp[e] * sigmoid_fast(gr), hh.v[e], hl.v[e]);
+          }
+          float* uo = p.out + pix * hidden + ch0 + g * 8;
+          *reinterpret_cast<float4*>(uo) = make_float4(uv[0], uv[1], uv[2], uv[3]);
+          *reinterpret_cast<float4*>(uo + 4) = make_float4(uv[4], uv[5], uv[6], uv[7]);
+          *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0 + g * 8) = hh;
+          *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0 + g * 8) = hl;
+        }
+      } else if constexpr (EPI == ESSB_EPI_GRU_OUT) {
+        // ConvGRU out gate + blend (submodules.py:269-271): h' = h*(1-u) + tanh(acc + b)*u
+        const int hidden = p.Cout;
+        const int ch0 = n0 + c0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int ch = ch0 + g * 8;
+          float hv[8], hp[8], uu[8];
+          const float4 u0 = *reinterpret_cast<const float4*>(p.aux1 + pix * hidden + ch);
+          const float4 u1 = *reinterpret_cast<const float4*>(p.aux1 + pix * hidden + ch + 4);
+          uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w; uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
+          if (p.aux0) {
+            const float4 a0 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch);
+            const float4 a1 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch + 4);
+            hp[0] = a0.x; hp[1] = a0.y; hp[2] = a0.z; hp[3] = a0.w; hp[4] = a1.x; hp[5] = a1.y; hp[6] = a1.z; hp[7] = a1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hp[e] = 0.f;
+          }
+          bf16x8 hh, hl;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float x = __uint_as_float(r[g * 8 + e]);
+            if (p.bias) x += p.bias[ch + e];
+            hv[e] = hp[e] * (1.f - uu[e]) + tanh_fast(x) * uu[e];
+            split_bf16(hv[e], hh.v[e], hl.v[e]);
+          }
+          float* ho = p.out + pix * hidden + ch;
+          *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+          if (p.out_hi) {
+            *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch) = hh;
+            *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch) = hl;
+          }
+        }
+      } else {
+        const size_t opix = ((size_t)n * p.OHf + (oy * p.osy + p.ooy)) * p.OWf + (ox * p.osx + p.oox);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {  // 8 channels per group
+          const int co = n0 + c0 + g * 8;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]);
+          if (p.bias) {
+            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co);
+            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (p.res_pre) {
+            const float4 a0 = *reinterpret_cast<const float4*>(p.res_pre + opix * p.ld_res + co);
+            const float4 a1 = *reinterpret_cast<const float4*>(p.res_pre + opix * p.ld_res + co + 4);
+            v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+            v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+          }
+          if (p.act == ESSB_ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+          } else if (p.act == ESSB_ACT_SIGMOID) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = essb_sigmoid(v[e]);
+          }
+          if (p.res_post) {
+            const float4 a0 = *reinterpret_cast<const float4*>(p.res_post + opix * p.ld_res + co);
+            const float4 a1 = *reinterpret_cast<const float4*>(p.res_post + opix * p.ld_res + co + 4);
+            v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+            v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+          }
+          if (p.out) {
+            float* o = p.out + opix * p.ldo + co;
+            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+          if (p.out_hi) {
+            bf16x8 hh, hl;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_bf16(v[e], hh.v[e], hl.v[e]);
+            *reinterpret_cast<bf16x8*>(p.out_hi + opix * p.ld_planes + co) = hh;
+            *reinterpret_cast<bf16x8*>(p.out_lo + opix * p.ld_planes + co) = hl;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+}
 
 // ------------------------------------------------------------------------------------ the kernel
 template <int EPI>
@@ -195,203 +407,183 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int half = (warp - 2) >> 2;
     uint32_t tph[2] = {0, 0};
     int local = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
-      const int buf = local & 1;
-      const int nt = item % p.n_tiles;
-      int mt = item / p.n_tiles;
-      const int txi = mt % p.tiles_x; mt /= p.tiles_x;
-      const int tyi = mt % p.tiles_y;
-      const int n = mt / p.tiles_y;
-      const int m = q * 32 + lane;
-      const int oy = tyi * BH + (m >> p.bw_log2), ox = txi * BW + (m & (BW - 1));
-      const bool valid = oy < p.OH && ox < p.OW;
-      const int n0 = nt * p.BN;
-      const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
-      // LSTM: the previous cell state does not depend on the MMA -> fetch it BEFORE waiting for the
-      // accumulator so its latency hides under the main loop of this tile
-      float cp[4][8];
-      if constexpr (EPI == ESSB_EPI_LSTM) {
-        const int hidden = p.Cout >> 2;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c0 = half * 32 + j * 64;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) cp[j][e] = 0.f;
-          if (valid && p.aux0 && c0 < p.BN) {
-            const float* src = p.aux0 + pix * hidden + ((n0 + c0) >> 2);
-            const float4 c0v = *reinterpret_cast<const float4*>(src);
-            const float4 c1v = *reinterpret_cast<const float4*>(src + 4);
-            cp[j][0] = c0v.x; cp[j][1] = c0v.y; cp[j][2] = c0v.z; cp[j][3] = c0v.w;
-            cp[j][4] = c1v.x; cp[j][5] = c1v.y; cp[j][6] = c1v.z; cp[j][7] = c1v.w;
-          }
-        }
-      }
-      mbar_wait(&tfull_bar[buf], tph[buf]);
-      tph[buf] ^= 1;
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c0 = half * 32 + j * 64;
-        if (c0 >= p.BN) break;  // warp-uniform
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld32(t_addr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (!valid) {
-          // out-of-image rows of a partial tile: nothing to store
-        } else if constexpr (EPI == ESSB_EPI_LSTM) {
-          // columns co = 4*ch + {in, remember, out, cell}; 32 columns = 8 channels
-          const int hidden = p.Cout >> 2;
-          const int ch0 = (n0 + c0) >> 2;
-          float hv[8], cv[8];
-          bf16x8 hh, hl;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int co = n0 + c0 + e * 4;
-            float gi = __uint_as_float(r[e * 4 + 0]), gf = __uint_as_float(r[e * 4 + 1]);
-            float go = __uint_as_float(r[e * 4 + 2]), gc = __uint_as_float(r[e * 4 + 3]);
-            if (p.bias) {
-              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + co);
-              gi += b4.x; gf += b4.y; go += b4.z; gc += b4.w;
-            }
-            const float cell = sigmoid_fast(gf) * cp[j][e] + sigmoid_fast(gi) * tanh_fast(gc);
-            cv[e] = cell;
-            hv[e] = sigmoid_fast(go) * tanh_fast(cell);
-            split_bf16(hv[e], hh.v[e], hl.v[e]);
-          }
-          float* ho = p.out + pix * hidden + ch0;
-          float* co_ = p.out2 + pix * hidden + ch0;
-          *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-          *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
-          *reinterpret_cast<float4*>(co_) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-          *reinterpret_cast<float4*>(co_ + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
-          if (p.out_hi) {
-            *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0) = hh;
-            *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0) = hl;
-          }
-        } else if constexpr (EPI == ESSB_EPI_GRU_UR) {
-          // ConvGRU update / reset gates (submodules.py:267-268): columns co = 2*ch + {update, reset};
-          // 32 columns = 16 channels.  Writes update (fp32) and prev_state*reset as bf16 planes (the A
-          // operand of the out-gate convolution).
-          const int hidden = p.Cout >> 1;
-          const int ch0 = (n0 + c0) >> 1;
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            float uv[8];
-            bf16x8 hh, hl;
-            float hp[8];
-            if (p.aux0) {
-              const float4 a0 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0 + g * 8);
-              const float4 a1 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0 + g * 8 + 4);
-              hp[0] = a0.x; hp[1] = a0.y; hp[2] = a0.z; hp[3] = a0.w; hp[4] = a1.x; hp[5] = a1.y; hp[6] = a1.z; hp[7] = a1.w;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) hp[e] = 0.f;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int col = g * 16 + e * 2;
-              float gu = __uint_as_float(r[col]), gr = __uint_as_float(r[col + 1]);
-              if (p.bias) { gu += p.bias[n0 + c0 + col]; gr += p.bias[n0 + c0 + col + 1]; }
-              uv[e] = sigmoid_fast(gu);
-              split_bf16(hp[e] * sigmoid_fast(gr), hh.v[e], hl.v[e]);
-            }
-            float* uo = p.out + pix * hidden + ch0 + g * 8;
-            *reinterpret_cast<float4*>(uo) = make_float4(uv[0], uv[1], uv[2], uv[3]);
-            *reinterpret_cast<float4*>(uo + 4) = make_float4(uv[4], uv[5], uv[6], uv[7]);
-            *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0 + g * 8) = hh;
-            *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0 + g * 8) = hl;
-          }
-        } else if constexpr (EPI == ESSB_EPI_GRU_OUT) {
-          // ConvGRU out gate + blend (submodules.py:269-271): h' = h*(1-u) + tanh(acc + b)*u
-          const int hidden = p.Cout;
-          const int ch0 = n0 + c0;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int ch = ch0 + g * 8;
-            float hv[8], hp[8], uu[8];
-            const float4 u0 = *reinterpret_cast<const float4*>(p.aux1 + pix * hidden + ch);
-            const float4 u1 = *reinterpret_cast<const float4*>(p.aux1 + pix * hidden + ch + 4);
-            uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w; uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
-            if (p.aux0) {
-              const float4 a0 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch);
-              const float4 a1 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch + 4);
-              hp[0] = a0.x; hp[1] = a0.y; hp[2] = a0.z; hp[3] = a0.w; hp[4] = a1.x; hp[5] = a1.y; hp[6] = a1.z; hp[7] = a1.w;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) hp[e] = 0.f;
-            }
-            bf16x8 hh, hl;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float x = __uint_as_float(r[g * 8 + e]);
-              if (p.bias) x += p.bias[ch + e];
-              hv[e] = hp[e] * (1.f - uu[e]) + tanh_fast(x) * uu[e];
-              split_bf16(hv[e], hh.v[e], hl.v[e]);
-            }
-            float* ho = p.out + pix * hidden + ch;
-            *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-            *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
-            if (p.out_hi) {
-              *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch) = hh;
-              *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch) = hl;
-            }
-          }
-        } else {
-          const size_t opix = ((size_t)n * p.OHf + (oy * p.osy + p.ooy)) * p.OWf + (ox * p.osx + p.oox);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {  // 8 channels per group
-            const int co = n0 + c0 + g * 8;
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]);
-            if (p.bias) {
-              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co);
-              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co + 4);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (p.res_pre) {
-              const float4 a0 = *reinterpret_cast<const float4*>(p.res_pre + opix * p.ld_res + co);
-              const float4 a1 = *reinterpret_cast<const float4*>(p.res_pre + opix * p.ld_res + co + 4);
-              v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-              v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-            }
-            if (p.act == ESSB_ACT_RELU) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-            } else if (p.act == ESSB_ACT_SIGMOID) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = essb_sigmoid(v[e]);
-            }
-            if (p.res_post) {
-              const float4 a0 = *reinterpret_cast<const float4*>(p.res_post + opix * p.ld_res + co);
-              const float4 a1 = *reinterpret_cast<const float4*>(p.res_post + opix * p.ld_res + co + 4);
-              v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-              v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-            }
-            if (p.out) {
-              float* o = p.out + opix * p.ldo + co;
-              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            if (p.out_hi) {
-              bf16x8 hh, hl;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) split_bf16(v[e], hh.v[e], hl.v[e]);
-              *reinterpret_cast<bf16x8*>(p.out_hi + opix * p.ld_planes + co) = hh;
-              *reinterpret_cast<bf16x8*>(p.out_lo + opix * p.ld_planes + co) = hl;
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-    }
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local)
+      tc_epilogue_item<EPI>(p, tmem_base, tfull_bar, tempty_bar, tph, local, item, q, half, lane);
   }
 
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------ halo-reuse kernel
+// Same GEMM as conv_tc_kernel, different operand traffic: for narrow layers (N <= 128) the A operand dominates
+// the TMA request stream because every tap re-fetches an almost identical 128-pixel box.  Here the output patch
+// is 16 rows x 8 pixels and ONE box of (16 + dy-range) x (8 + dx-range) pixels is loaded per (segment, 64-channel
+// chunk, view); tap (dy, dx) is then just a different START ADDRESS into that tile (whole 128-byte rows, so the
+// 128 B swizzle phase stays address-consistent) with the stride between 8-row groups = one halo row.
+// A and B have their own pipelines (A: 1-2 halo tiles, B: one [N x 64] tile per tap).
+constexpr int HALO_THREADS = 384;  // warp 0 A-TMA, 1 MMA, 2 B-TMA, 3 idle, 4..11 epilogue
+
+__device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t saddr, uint32_t sbo_bytes, int base_offset_mode) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_base = smem;
+  uint8_t* b_base = smem + (size_t)p.a_stages * p.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.b_stages * p.b_stage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + MAX_STAGES;
+  uint64_t* b_full = bars + 2 * MAX_STAGES;
+  uint64_t* b_empty = bars + 3 * MAX_STAGES;
+  uint64_t* tfull_bar = bars + 4 * MAX_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int BW = 8, BH = 16;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================================================ A (halo tile) producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = (uint32_t)(p.passes == 3 ? 2 : 1) * (uint32_t)(p.halo_w * p.halo_h * 128);
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        int mt = item / p.n_tiles;
+        const int txi = mt % p.tiles_x; mt /= p.tiles_x;
+        const int tyi = mt % p.tiles_y;
+        const int n = mt / p.tiles_y;
+        const int cx = txi * BW + p.hx0, cy = tyi * BH + p.hy0;
+        for (int seg = 0; seg < p.nseg; ++seg)
+          for (int c = 0; c < p.seg_chunks[seg]; ++c)
+            for (int g = 0; g < p.n_groups; ++g) {
+              const int v = p.seg_view0[seg] + p.grp_view[g];
+              mbar_wait(&a_empty[s], ph ^ 1);
+              uint8_t* st = a_base + (size_t)s * p.a_stage_bytes;
+              mbar_expect_tx(&a_full[s], tx);
+              tma_load_4d(st, &p.tmA_hi[v], &a_full[s], c * TC_KCH, cx, cy, n);
+              if (p.passes == 3) tma_load_4d(st + p.a_lo_off, &p.tmA_lo[v], &a_full[s], c * TC_KCH, cx, cy, n);
+              if (++s == p.a_stages) { s = 0; ph ^= 1; }
+            }
+      }
+    }
+  } else if (warp == 2) {
+    // ============================================================ B (weights) producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = (uint32_t)(p.passes == 3 ? 2 : 1) * (uint32_t)(p.BN * TC_KCH * 2);
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int nt = item % p.n_tiles;
+        for (int seg = 0; seg < p.nseg; ++seg)
+          for (int c = 0; c < p.seg_chunks[seg]; ++c)
+            for (int g = 0; g < p.n_groups; ++g)
+              for (int t = p.grp_first[g]; t < p.grp_first[g] + p.grp_count[g]; ++t) {
+                const int kcoord = p.widx[t] * p.k_per_tap + p.seg_koff[seg] + c * TC_KCH;
+                mbar_wait(&b_empty[s], ph ^ 1);
+                uint8_t* st = b_base + (size_t)s * p.b_stage_bytes;
+                mbar_expect_tx(&b_full[s], tx);
+                tma_load_2d(st, &p.tmB_hi, &b_full[s], kcoord, nt * p.BN);
+                if (p.passes == 3) tma_load_2d(st + p.b_lo_off, &p.tmB_lo, &b_full[s], kcoord, nt * p.BN);
+                if (++s == p.b_stages) { s = 0; ph ^= 1; }
+              }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TC_M, p.BN);
+      const uint32_t sbo = (uint32_t)p.halo_w * 128u;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      uint32_t tph[2] = {0, 0};
+      int local = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+        const int buf = local & 1;
+        mbar_wait(&tempty_bar[buf], tph[buf] ^ 1);
+        tph[buf] ^= 1;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+        uint32_t acc = 0;
+        for (int seg = 0; seg < p.nseg; ++seg)
+          for (int c = 0; c < p.seg_chunks[seg]; ++c)
+            for (int g = 0; g < p.n_groups; ++g) {
+              mbar_wait(&a_full[sa], pha);
+              tc_fence_after();
+              const uint32_t a_addr = smem_u32(a_base + (size_t)sa * p.a_stage_bytes);
+              for (int t = p.grp_first[g]; t < p.grp_first[g] + p.grp_count[g]; ++t) {
+                mbar_wait(&b_full[sb], phb);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(b_base + (size_t)sb * p.b_stage_bytes);
+                const uint32_t a_off = (uint32_t)((p.dy[t] - p.hy0) * p.halo_w + (p.dx[t] - p.hx0)) * 128u;
+                const uint64_t a_hi = make_smem_desc_sbo(a_addr + a_off, sbo, p.base_offset_mode);
+                const uint64_t b_hi = make_smem_desc(b_addr);
+                if (p.passes == 3) {
+                  const uint64_t a_lo = make_smem_desc_sbo(a_addr + p.a_lo_off + a_off, sbo, p.base_offset_mode);
+                  const uint64_t b_lo = make_smem_desc(b_addr + p.b_lo_off);
+#pragma unroll
+                  for (int k = 0; k < TC_KCH / 16; ++k) {
+                    const uint64_t ko = (uint64_t)(k * 2);
+                    umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, acc);
+                    umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                    umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+                    acc = 1u;
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < TC_KCH / 16; ++k) {
+                    umma_bf16(d_tmem, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, acc);
+                    acc = 1u;
+                  }
+                }
+                umma_commit(&b_empty[sb]);
+                if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+              }
+              umma_commit(&a_empty[sa]);  // every tap of this view has been issued: the halo tile can be refilled
+              if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+            }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    uint32_t tph[2] = {0, 0};
+    int local = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local)
+      tc_epilogue_item<EPI>(p, tmem_base, tfull_bar, tempty_bar, tph, local, item, q, half, lane);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -675,7 +867,37 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   }
 
   static thread_local TcParams p;  // 2.5 KB; filled per call, copied into the launch
-  const int BW = 1 << d->bw_log2, BH = TC_M >> d->bw_log2;
+  // ---- halo-reuse mode?  Narrow layers (N <= 128) with several taps: one halo tile per view feeds all its taps.
+  //      ESSB_TC_HALO=0 disables it; ESSB_TC_HALO_BASEOFF=1 sets the descriptor base_offset from the address.
+  static const int halo_env = [] { const char* e = getenv("ESSB_TC_HALO"); return e ? atoi(e) : 1; }();
+  static const int baseoff_env = [] { const char* e = getenv("ESSB_TC_HALO_BASEOFF"); return e ? atoi(e) : 0; }();
+  bool halo = halo_env != 0 && BN <= 128 && d->ntaps >= 2;
+  int hx0 = 0, hx1 = 0, hy0 = 0, hy1 = 0;
+  if (halo) {
+    hx0 = hx1 = d->dx[0]; hy0 = hy1 = d->dy[0];
+    for (int t = 1; t < d->ntaps; ++t) {
+      hx0 = d->dx[t] < hx0 ? d->dx[t] : hx0; hx1 = d->dx[t] > hx1 ? d->dx[t] : hx1;
+      hy0 = d->dy[t] < hy0 ? d->dy[t] : hy0; hy1 = d->dy[t] > hy1 ? d->dy[t] : hy1;
+    }
+    p.halo_w = 8 + (hx1 - hx0);
+    p.halo_h = 16 + (hy1 - hy0);
+    const int planes = d->passes == 3 ? 2 : 1;
+    const int a_plane = (p.halo_w * p.halo_h * 128 + 1023) & ~1023;
+    p.a_lo_off = a_plane;
+    p.a_stage_bytes = planes * a_plane;
+    const int b_plane = BN * TC_KCH * 2;
+    p.b_lo_off = b_plane;
+    p.b_stage_bytes = planes * b_plane;
+    const int budget = 200 * 1024;
+    p.a_stages = (2 * p.a_stage_bytes + 3 * p.b_stage_bytes <= budget) ? 2 : 1;
+    int nb = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
+    if (nb > MAX_STAGES) nb = MAX_STAGES;
+    p.b_stages = nb;
+    if (nb < 2 || p.halo_w > 64 || p.halo_h > 64) halo = false;
+  }
+  const int bw_log2 = halo ? 3 : d->bw_log2;
+  const int BW = 1 << bw_log2, BH = TC_M >> bw_log2;
+  const int boxW = halo ? p.halo_w : BW, boxH = halo ? p.halo_h : BH;
   int rc;
   for (int v = 0; v < d->n_views; ++v) {
     const essb_tc_view& vw = d->views[v];
@@ -684,8 +906,8 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
     ESSB_REQUIRE(vw.stride_x % 8 == 0 && vw.stride_y % 8 == 0 && vw.stride_n % 8 == 0 && essb_aligned16(vw.hi) &&
                      essb_aligned16(vw.lo),
                  "essb_conv_tc_run: view %d strides must be multiples of 8 elements and bases 16B aligned", v);
-    if ((rc = encode_a_map(&p.tmA_hi[v], vw.hi, vw, d->N, BW, BH)) != ESSB_OK) return rc;
-    if (d->passes == 3 && (rc = encode_a_map(&p.tmA_lo[v], vw.lo, vw, d->N, BW, BH)) != ESSB_OK) return rc;
+    if ((rc = encode_a_map(&p.tmA_hi[v], vw.hi, vw, d->N, boxW, boxH)) != ESSB_OK) return rc;
+    if (d->passes == 3 && (rc = encode_a_map(&p.tmA_lo[v], vw.lo, vw, d->N, boxW, boxH)) != ESSB_OK) return rc;
   }
   const long long ktot = (long long)d->n_w_taps * d->k_per_tap;
   if ((rc = encode_b_map(&p.tmB_hi, d->w_hi, ktot, d->w_rows, BN)) != ESSB_OK) return rc;
@@ -695,7 +917,7 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   p.tiles_y = (d->OH + BH - 1) / BH;
   p.n_tiles = Ngemm / BN;
   p.n_items = d->N * p.tiles_x * p.tiles_y * p.n_tiles;
-  p.bw_log2 = d->bw_log2;
+  p.bw_log2 = bw_log2;
   p.BN = BN;
   p.passes = d->passes;
   const int b_tile_bytes = BN * TC_KCH * 2;
@@ -714,7 +936,7 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   const int smem_budget = 200 * 1024;
   int stages = smem_budget / p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  ESSB_REQUIRE(stages >= 2, "essb_conv_tc_run: tile does not fit two pipeline stages");
+  ESSB_REQUIRE(halo || stages >= 2, "essb_conv_tc_run: tile does not fit two pipeline stages");
   p.stages = stages;
   p.ntaps = d->ntaps;
   p.nseg = d->nseg;
@@ -726,10 +948,34 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   }
   p.k_per_tap = d->k_per_tap;
   for (int t = 0; t < d->ntaps; ++t) {
-    p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.view[t] = d->view[t]; p.widx[t] = d->widx[t];
     ESSB_REQUIRE(d->widx[t] >= 0 && d->widx[t] < d->n_w_taps, "essb_conv_tc_run: widx out of range");
+    ESSB_REQUIRE(d->view[t] >= 0, "essb_conv_tc_run: negative view index");
     for (int s = 0; s < d->nseg; ++s)
       ESSB_REQUIRE(d->seg_view0[s] + d->view[t] < d->n_views, "essb_conv_tc_run: view index out of range");
+  }
+  if (!halo) {
+    for (int t = 0; t < d->ntaps; ++t) {
+      p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.view[t] = d->view[t]; p.widx[t] = d->widx[t];
+    }
+  } else {  // taps sorted by the view they read: one tap group per used view
+    p.hx0 = hx0; p.hy0 = hy0; p.base_offset_mode = baseoff_env;
+    int ng = 0, pos = 0;
+    bool used[MAX_VIEWS] = {false};
+    for (int t0 = 0; t0 < d->ntaps; ++t0) {
+      const int v = d->view[t0];
+      if (v >= MAX_VIEWS || used[v]) continue;
+      used[v] = true;
+      p.grp_view[ng] = (int8_t)v;
+      p.grp_first[ng] = (int8_t)pos;
+      for (int t = t0; t < d->ntaps; ++t)
+        if (d->view[t] == v) {
+          p.dy[pos] = d->dy[t]; p.dx[pos] = d->dx[t]; p.view[pos] = d->view[t]; p.widx[pos] = d->widx[t];
+          ++pos;
+        }
+      p.grp_count[ng] = (int8_t)(pos - p.grp_first[ng]);
+      ++ng;
+    }
+    p.n_groups = ng;
   }
   p.N = d->N; p.OH = d->OH; p.OW = d->OW; p.Cout = d->Cout;
   p.OHf = d->OHf; p.OWf = d->OWf; p.osy = d->osy; p.ooy = d->ooy; p.osx = d->osx; p.oox = d->oox;
@@ -740,10 +986,27 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   p.out_lo = reinterpret_cast<__nv_bfloat16*>(d->out_lo);
 
   size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  if (halo) smem_bytes = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + 512;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // one CTA per SM: each CTA allocates all 512 TMEM columns
   cudaStream_t st = (cudaStream_t)stream;
   int grid = p.n_items < num_sms() ? p.n_items : num_sms();
   cudaError_t e;
+  if (halo) {
+#define ESSB_LAUNCH_HALO(EPI)                                                                                       \
+  e = cudaFuncSetAttribute(conv_tc_halo_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); \
+  if (e == cudaSuccess) conv_tc_halo_kernel<EPI><<<grid, HALO_THREADS, smem_bytes, st>>>(p);
+    if (d->epilogue == ESSB_EPI_LSTM) { ESSB_LAUNCH_HALO(ESSB_EPI_LSTM) }
+    else if (d->epilogue == ESSB_EPI_GRU_UR) { ESSB_LAUNCH_HALO(ESSB_EPI_GRU_UR) }
+    else if (d->epilogue == ESSB_EPI_GRU_OUT) { ESSB_LAUNCH_HALO(ESSB_EPI_GRU_OUT) }
+    else { ESSB_LAUNCH_HALO(ESSB_EPI_LINEAR) }
+#undef ESSB_LAUNCH_HALO
+    if (e != cudaSuccess) {
+      essb_set_error("essb_conv_tc_run: cudaFuncSetAttribute (halo) failed: %s", cudaGetErrorString(e));
+      return ESSB_ERR_LAUNCH;
+    }
+    ESSB_LAUNCH_CHECK("essb_conv_tc_run (halo)");
+    return ESSB_OK;
+  }
   if (d->epilogue == ESSB_EPI_LSTM) {
     e = cudaFuncSetAttribute(conv_tc_kernel<ESSB_EPI_LSTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e == cudaSuccess) conv_tc_kernel<ESSB_EPI_LSTM><<<grid, TC_THREADS, smem_bytes, st>>>(p);
