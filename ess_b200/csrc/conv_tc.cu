@@ -868,9 +868,12 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
 
   static thread_local TcParams p;  // 2.5 KB; filled per call, copied into the launch
   // ---- halo-reuse mode?  Narrow layers (N <= 128) with several taps: one halo tile per view feeds all its taps.
-  //      ESSB_TC_HALO=0 disables it; ESSB_TC_HALO_BASEOFF=1 sets the descriptor base_offset from the address.
+  //      ESSB_TC_HALO=0 disables it (A/B comparison).  Measured on B200: the 128 B swizzle of both TMA writes and
+  //      UMMA reads is a pure function of the shared-memory ADDRESS bits, so a descriptor may start at any
+  //      128 B-aligned row of a TMA-written tile with base_offset = 0 (setting base_offset from the address
+  //      gives wrong results -- tried, tests/test_gpu_tc.py fails).
   static const int halo_env = [] { const char* e = getenv("ESSB_TC_HALO"); return e ? atoi(e) : 1; }();
-  static const int baseoff_env = [] { const char* e = getenv("ESSB_TC_HALO_BASEOFF"); return e ? atoi(e) : 0; }();
+  static const int baseoff_env = 0;
   bool halo = halo_env != 0 && BN <= 128 && d->ntaps >= 2;
   int hx0 = 0, hx1 = 0, hy0 = 0, hy1 = 0;
   if (halo) {
