@@ -71,6 +71,7 @@ struct TcParams {
   // shared by every tap that reads that view; separate A and B pipelines
   int halo_w, halo_h, hx0, hy0;          // halo box extents (pixels) and the smallest tap offsets
   int a_stages, b_stages, a_stage_bytes, b_stage_bytes, a_lo_off, b_lo_off;
+  int b_taps_per_stage, b_tap_bytes;     // a B stage holds up to G consecutive taps of one group behind ONE barrier
   int base_offset_mode;                  // 0: descriptor base_offset = 0; 1: (start address >> 7) & 7
   int n_groups;                          // tap groups = views actually used; taps are sorted by group
   int8_t grp_view[MAX_VIEWS], grp_first[MAX_VIEWS], grp_count[MAX_VIEWS];
@@ -508,16 +509,22 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
         const int nt = item % p.n_tiles;
         for (int seg = 0; seg < p.nseg; ++seg)
           for (int c = 0; c < p.seg_chunks[seg]; ++c)
-            for (int g = 0; g < p.n_groups; ++g)
-              for (int t = p.grp_first[g]; t < p.grp_first[g] + p.grp_count[g]; ++t) {
-                const int kcoord = p.widx[t] * p.k_per_tap + p.seg_koff[seg] + c * TC_KCH;
+            for (int g = 0; g < p.n_groups; ++g) {
+              const int t_end = p.grp_first[g] + p.grp_count[g];
+              for (int t0 = p.grp_first[g]; t0 < t_end; t0 += p.b_taps_per_stage) {
+                const int nt_taps = min(p.b_taps_per_stage, t_end - t0);
                 mbar_wait(&b_empty[s], ph ^ 1);
                 uint8_t* st = b_base + (size_t)s * p.b_stage_bytes;
-                mbar_expect_tx(&b_full[s], tx);
-                tma_load_2d(st, &p.tmB_hi, &b_full[s], kcoord, nt * p.BN);
-                if (p.passes == 3) tma_load_2d(st + p.b_lo_off, &p.tmB_lo, &b_full[s], kcoord, nt * p.BN);
+                mbar_expect_tx(&b_full[s], tx * (uint32_t)nt_taps);
+                for (int j = 0; j < nt_taps; ++j) {
+                  const int kcoord = p.widx[t0 + j] * p.k_per_tap + p.seg_koff[seg] + c * TC_KCH;
+                  tma_load_2d(st + j * p.b_tap_bytes, &p.tmB_hi, &b_full[s], kcoord, nt * p.BN);
+                  if (p.passes == 3)
+                    tma_load_2d(st + j * p.b_tap_bytes + p.b_lo_off, &p.tmB_lo, &b_full[s], kcoord, nt * p.BN);
+                }
                 if (++s == p.b_stages) { s = 0; ph ^= 1; }
               }
+            }
       }
     }
   } else if (warp == 1) {
@@ -542,10 +549,14 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
               mbar_wait(&a_full[sa], pha);
               tc_fence_after();
               const uint32_t a_addr = smem_u32(a_base + (size_t)sa * p.a_stage_bytes);
-              for (int t = p.grp_first[g]; t < p.grp_first[g] + p.grp_count[g]; ++t) {
-                mbar_wait(&b_full[sb], phb);
-                tc_fence_after();
-                const uint32_t b_addr = smem_u32(b_base + (size_t)sb * p.b_stage_bytes);
+              const int t_end = p.grp_first[g] + p.grp_count[g];
+              for (int t0 = p.grp_first[g]; t0 < t_end; t0 += p.b_taps_per_stage) {
+               const int nt_taps = min(p.b_taps_per_stage, t_end - t0);
+               mbar_wait(&b_full[sb], phb);
+               tc_fence_after();
+               for (int j = 0; j < nt_taps; ++j) {
+                const int t = t0 + j;
+                const uint32_t b_addr = smem_u32(b_base + (size_t)sb * p.b_stage_bytes) + (uint32_t)(j * p.b_tap_bytes);
                 const uint32_t a_off = (uint32_t)((p.dy[t] - p.hy0) * p.halo_w + (p.dx[t] - p.hx0)) * 128u;
                 const uint64_t a_hi = make_smem_desc_sbo(a_addr + a_off, sbo, p.base_offset_mode);
                 const uint64_t b_hi = make_smem_desc(b_addr);
@@ -567,8 +578,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
                     acc = 1u;
                   }
                 }
-                umma_commit(&b_empty[sb]);
-                if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+               }
+               umma_commit(&b_empty[sb]);
+               if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
               }
               umma_commit(&a_empty[sa]);  // every tap of this view has been issued: the halo tile can be refilled
               if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
@@ -890,9 +902,20 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
     p.a_stage_bytes = planes * a_plane;
     const int b_plane = BN * TC_KCH * 2;
     p.b_lo_off = b_plane;
-    p.b_stage_bytes = planes * b_plane;
+    p.b_tap_bytes = planes * b_plane;
     const int budget = 200 * 1024;
-    p.a_stages = (2 * p.a_stage_bytes + 3 * p.b_stage_bytes <= budget) ? 2 : 1;
+    p.a_stages = (2 * p.a_stage_bytes + 3 * p.b_tap_bytes <= budget) ? 2 : 1;
+    // Narrow tiles (N <= 64) are bound by the MMA thread's per-stage cost (barrier wait + fence + commit, ~200
+    // cycles) rather than by tensor work (12 MMAs x N/2 cycles per tap): put G taps behind one barrier.
+    int G = 1;
+    if (BN <= 64) {
+      G = (budget - p.a_stages * p.a_stage_bytes) / (2 * p.b_tap_bytes);
+      if (G > 8) G = 8;
+      if (G > d->ntaps) G = d->ntaps;
+      if (G < 1) G = 1;
+    }
+    p.b_taps_per_stage = G;
+    p.b_stage_bytes = G * p.b_tap_bytes;
     int nb = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
     if (nb > MAX_STAGES) nb = MAX_STAGES;
     p.b_stages = nb;
