@@ -179,11 +179,19 @@ class E2VIDRecurrent(nn.Module):
         if tc and cpad in (8, 16) and self.base_num_channels % 32 == 0 and self.base_num_channels <= 256:
             # per kernel row ky the head conv reads the 8-pixel x cpad-channel window starting at x-2 as one
             # contiguous K-chunk (ops.window_view): virtual weight [Cout][8*cpad][ky], zero for kx >= 5
-            wv = torch.zeros((self.base_num_channels, 8, cpad, 5), device=dev)
-            wv[:, :5, :self.num_bins] = u.head.conv2d.weight.detach().float().permute(0, 3, 1, 2)  # [co,kx,ci,ky]
-            wv = wv.reshape(self.base_num_channels, 8 * cpad, 5, 1).contiguous()
+            # `grp` adjacent output pixels share one window (output i uses window pixels i .. i+4) and are
+            # computed as grp*Cout accumulator columns: tcgen05.mma costs the same for N = 32 and N = 128,
+            # so widening N to 128 does 4 pixels per instruction.  [N,H,W,base] == [N,H,W/grp,grp*base].
+            base = self.base_num_channels
+            grp = 4 if 4 * base <= 256 else (2 if 2 * base <= 256 else 1)
+            wk = u.head.conv2d.weight.detach().float().permute(0, 3, 1, 2)  # [co,kx,ci,ky]
+            wv = torch.zeros((grp, base, 8, cpad, 5), device=dev)
+            for i in range(grp):
+                wv[i, :, i:i + 5, :self.num_bins] = wk
+            wv = wv.reshape(grp * base, 8 * cpad, 5, 1).contiguous()
             hi, lo, kinp = ops.pack_weight_tc(wv)
-            P['head_tc'] = dict(hi=hi, lo=lo, k_per_tap=kinp, cpad=cpad)
+            P['head_tc'] = dict(hi=hi, lo=lo, k_per_tap=kinp, cpad=cpad, grp=grp,
+                                bias=P['head'][1].repeat(grp).contiguous())
         for i, enc in enumerate(u.encoders):
             bn = getattr(enc.conv, 'norm_layer', None)
             scale, bias = _bn_fold(enc.conv.conv2d.bias, bn, None, dev)
@@ -309,13 +317,14 @@ class E2VIDRecurrent(nn.Module):
         """head conv5x5 + bias + ReLU (unet.py:131-132,153) on the tcgen05 kernel: 5 taps (kernel rows), each
         one 8*cpad-element K-chunk read through the overlapping-stride window view."""
         tcw = P['head_tc']
-        base = self.base_num_channels
+        grp = tcw['grp']
+        base, W = self.base_num_channels * grp, W // grp
         d = ConvTc()
-        ops.window_view(d.views[0], in_planes[0], in_planes[1], H, W)
+        ops.window_view(d.views[0], in_planes[0], in_planes[1], H, W * grp, grp)
         d.n_views, d.nseg = 1, 1
         d.seg_C[0], d.seg_view0[0], d.seg_koff[0] = 8 * tcw['cpad'], 0, 0
         d.k_per_tap, d.n_w_taps, d.w_rows = tcw['k_per_tap'], 5, tcw['hi'].shape[0]
-        d.w_hi, d.w_lo, d.bias = ops._p(tcw['hi']), ops._p(tcw['lo']), ops._p(P['head'][1])
+        d.w_hi, d.w_lo, d.bias = ops._p(tcw['hi']), ops._p(tcw['lo']), ops._p(tcw['bias'])
         d.out, d.ldo = ops._p(head), base
         d.out_hi, d.out_lo, d.ld_planes = ops._p(planes[0]), ops._p(planes[1]), base
         d.N, d.OH, d.OW, d.Cout = N, H, W, base

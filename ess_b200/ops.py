@@ -261,13 +261,14 @@ def event_prepare_planes(window, stats_row, normalize, Hp, Wp, pad_top, pad_left
     return planes
 
 
-def window_view(v: TcView, hi, lo, Hp, Wp):
+def window_view(v: TcView, hi, lo, Hp, Wp, group=1):
     """Overlapping-stride TMA view of a head_planes_alloc buffer: view pixel (x, y) is the 8-pixel x cpad
-    row window starting at padded pixel (x, y), i.e. image pixels (x-2 .. x+5, y-2) for tap row 0."""
+    row window starting at padded pixel (group*x, y), i.e. image pixels (group*x-2 .. group*x+5, y-2) for
+    tap row 0.  group > 1 makes one view pixel serve `group` adjacent output pixels."""
     N, Hb, Wb, cpad = hi.shape
     v.hi, v.lo = _p(hi), _p(lo)
-    v.stride_x, v.stride_y, v.stride_n = cpad, Wb * cpad, Hb * Wb * cpad
-    v.C, v.W, v.H = 8 * cpad, Wp, Hb
+    v.stride_x, v.stride_y, v.stride_n = group * cpad, Wb * cpad, Hb * Wb * cpad
+    v.C, v.W, v.H = 8 * cpad, Wp // group, Hb
 
 
 def nchw_to_nhwc(x, ld_out=None):
