@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint64_t* tempty_bar = tfull_bar + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the shuffle tells ptxas the warp index is warp-uniform, so the role branches below are uniform branches
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int cpt = p.seg_chunks[0] + (p.nseg > 1 ? p.seg_chunks[1] : 0);
   const int k_iters = p.ntaps * cpt;
   const int BW = 1 << p.bw_log2, BH = TC_M >> p.bw_log2;
@@ -358,8 +359,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer (one lane)
-    if (lane == 0) {
+    // ============================================================ MMA issuer (whole warp, convergent:
+    // umma_bf16 / umma_commit elect the issuing lane themselves, everything else stays in uniform registers)
+    {
       const uint32_t idesc = make_idesc(TC_M, p.BN);
       int s = 0;
       uint32_t ph = 0;
@@ -376,21 +378,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + (size_t)s * p.stage_bytes);
           if (p.passes == 3) {
-            const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + p.off_alo);
-            const uint64_t b_hi = make_smem_desc(sa + p.off_bhi);
-            const uint64_t b_lo = make_smem_desc(sa + p.off_blo);
+            const UDesc a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + p.off_alo);
+            const UDesc b_hi = make_smem_desc(sa + p.off_bhi);
+            const UDesc b_lo = make_smem_desc(sa + p.off_blo);
 #pragma unroll
             for (int k = 0; k < TC_KCH / 16; ++k) {
-              const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes (>>4) inside the 128 B swizzle row
+              const uint32_t ko = (uint32_t)(k * 2);  // +32 bytes (>>4) inside the 128 B swizzle row
               umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, (it | k) != 0);
               umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
               umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
             }
           } else {
-            const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + p.off_bhi);
+            const UDesc a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + p.off_bhi);
 #pragma unroll
             for (int k = 0; k < TC_KCH / 16; ++k) {
-              const uint64_t ko = (uint64_t)(k * 2);
+              const uint32_t ko = (uint32_t)(k * 2);
               umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, (it | k) != 0);
             }
           }
@@ -429,15 +431,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // A and B have their own pipelines (A: 1-2 halo tiles, B: one [N x 64] tile per tap).
 constexpr int HALO_THREADS = 384;  // warp 0 A-TMA, 1 MMA, 2 B-TMA, 3 idle, 4..11 epilogue
 
-__device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t saddr, uint32_t sbo_bytes, int base_offset_mode) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
-  d |= (uint64_t)2 << 61;
-  return d;
+// K-major SWIZZLE_128B descriptor whose 8-row groups are `sbo_bytes` apart (= one halo-tile pixel row).
+// The swizzle XOR is taken from the shared-memory address bits, so a start address on any whole 128 B row
+// of the 1024 B-aligned halo tile needs no base-offset field (measured: setting it breaks the results).
+__device__ __forceinline__ UDesc make_smem_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  return make_udesc(saddr, 1u, sbo_bytes);
 }
 
 template <int EPI>
@@ -454,7 +452,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
   uint64_t* tfull_bar = bars + 4 * MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the shuffle tells ptxas the warp index is warp-uniform, so the role branches below are uniform branches
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr int BW = 8, BH = 16;
 
   if (warp == 0 && lane == 0) {
@@ -528,8 +527,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer
-    if (lane == 0) {
+    // ============================================================ MMA issuer (whole warp, convergent)
+    {
       const uint32_t idesc = make_idesc(TC_M, p.BN);
       const uint32_t sbo = (uint32_t)p.halo_w * 128u;
       int sa = 0, sb = 0;
@@ -558,14 +557,14 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
                 const int t = t0 + j;
                 const uint32_t b_addr = smem_u32(b_base + (size_t)sb * p.b_stage_bytes) + (uint32_t)(j * p.b_tap_bytes);
                 const uint32_t a_off = (uint32_t)((p.dy[t] - p.hy0) * p.halo_w + (p.dx[t] - p.hx0)) * 128u;
-                const uint64_t a_hi = make_smem_desc_sbo(a_addr + a_off, sbo, p.base_offset_mode);
-                const uint64_t b_hi = make_smem_desc(b_addr);
+                const UDesc a_hi = make_smem_desc_sbo(a_addr + a_off, sbo);
+                const UDesc b_hi = make_smem_desc(b_addr);
                 if (p.passes == 3) {
-                  const uint64_t a_lo = make_smem_desc_sbo(a_addr + p.a_lo_off + a_off, sbo, p.base_offset_mode);
-                  const uint64_t b_lo = make_smem_desc(b_addr + p.b_lo_off);
+                  const UDesc a_lo = make_smem_desc_sbo(a_addr + p.a_lo_off + a_off, sbo);
+                  const UDesc b_lo = make_smem_desc(b_addr + p.b_lo_off);
 #pragma unroll
                   for (int k = 0; k < TC_KCH / 16; ++k) {
-                    const uint64_t ko = (uint64_t)(k * 2);
+                    const uint32_t ko = (uint32_t)(k * 2);
                     umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, acc);
                     umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
                     umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
@@ -574,7 +573,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
                 } else {
 #pragma unroll
                   for (int k = 0; k < TC_KCH / 16; ++k) {
-                    umma_bf16(d_tmem, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, acc);
+                    umma_bf16(d_tmem, a_hi + (uint32_t)(k * 2), b_hi + (uint32_t)(k * 2), idesc, acc);
                     acc = 1u;
                   }
                 }

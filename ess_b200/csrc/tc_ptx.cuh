@@ -58,32 +58,43 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B)
 //   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
+// The 64-bit descriptor is carried as two 32-bit halves: only the low half (start address, LBO) changes
+// between MMAs, so stepping along K is one 32-bit add and the high half stays a loop-invariant uniform
+// register (a 64-bit add would drag a carry chain and R2UR moves into the issue loop).
+struct UDesc {
+  uint32_t lo, hi;
+  __device__ __forceinline__ UDesc operator+(uint32_t k) const { return UDesc{lo + k, hi}; }
+};
+__device__ __forceinline__ UDesc make_udesc(uint32_t saddr, uint32_t lbo_enc, uint32_t sbo_bytes) {
+  return UDesc{((saddr & 0x3FFFFu) >> 4) | (lbo_enc << 16), ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29)};
 }
+__device__ __forceinline__ UDesc make_smem_desc(uint32_t saddr) { return make_udesc(saddr, 1u, 1024u); }
 // kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B,
 // N>>3 at [17,23), M>>4 at [24,29).
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
+// tcgen05.mma / tcgen05.commit are issued by ONE lane, but the issuing warp stays convergent: the leader is
+// elected inside the asm (elect.sync is deterministic for a fixed member mask, so the commit tracks the MMAs
+// of the same lane).  Keeping all 32 lanes on the loop lets ptxas hold descriptors, TMEM addresses and
+// barrier addresses in uniform registers; a `if (lane == 0)` region instead costs an ELECT + R2UR.BROADCAST
+// chain per operand (~60 issue cycles per MMA, measured with ncu on the N <= 128 layers).
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, UDesc a, UDesc b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a.lo), "r"(a.hi), "r"(b.lo), "r"(b.hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -37,14 +37,8 @@ struct WgTcParams {
 
 // MN-major SWIZZLE_128B descriptor: [0,14) start>>4, [16,30) LBO>>4 (stride between 64-element blocks
 // along M/N), [32,46) SBO>>4 (stride between 8-row groups along K), version 1, layout SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(WG_BOX_BYTES >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
+__device__ __forceinline__ UDesc make_smem_desc_mn(uint32_t saddr) {
+  return make_udesc(saddr, (uint32_t)(WG_BOX_BYTES >> 4), 1024u);
 }
 __device__ __forceinline__ uint32_t make_idesc_mn(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
@@ -60,7 +54,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   uint64_t* tfull_bar = bars + 2 * WG_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the shuffle tells ptxas the warp index is warp-uniform, so the role branches below are uniform branches
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int BW = 1 << p.bw_log2, BH = WG_PIX >> p.bw_log2;
   const int BN = 64 * p.nb;
 
@@ -123,7 +118,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp, convergent: umma_bf16 / umma_commit elect the issuing lane themselves
       const uint32_t idesc = make_idesc_mn(128, BN);
       int s = 0;
       uint32_t ph = 0;
@@ -142,11 +137,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
-          const uint64_t a_hi = make_smem_desc_mn(sa), g_hi = make_smem_desc_mn(sa + p.off_ghi);
-          const uint64_t a_lo = make_smem_desc_mn(sa + p.off_alo), g_lo = make_smem_desc_mn(sa + p.off_glo);
+          const UDesc a_hi = make_smem_desc_mn(sa), g_hi = make_smem_desc_mn(sa + p.off_ghi);
+          const UDesc a_lo = make_smem_desc_mn(sa + p.off_alo), g_lo = make_smem_desc_mn(sa + p.off_glo);
 #pragma unroll
           for (int k = 0; k < WG_PIX / 16; ++k) {
-            const uint64_t ko = (uint64_t)(k * (16 * 128 >> 4));  // 16 pixel rows of 128 B
+            const uint32_t ko = (uint32_t)(k * (16 * 128 >> 4));  // 16 pixel rows of 128 B
             const uint32_t first = (pp != p0 || k != 0) ? 1u : 0u;
             if (p.passes == 3) {
               umma_bf16(d_tmem, a_lo + ko, g_hi + ko, idesc, first);
