@@ -72,10 +72,35 @@ struct TcParams {
   int halo_w, halo_h, hx0, hy0;          // halo box extents (pixels) and the smallest tap offsets
   int a_stages, b_stages, a_stage_bytes, b_stage_bytes, a_lo_off, b_lo_off;
   int b_taps_per_stage, b_tap_bytes;     // a B stage holds up to G consecutive taps of one group behind ONE barrier
-  int base_offset_mode;                  // 0: descriptor base_offset = 0; 1: (start address >> 7) & 7
+  int base_offset_mode;                  // unused (kept for layout stability): base_offset is always 0
+  int wide;                              // TC_WIDE_* bits (256-bit epilogue accesses)
   int n_groups;                          // tap groups = views actually used; taps are sorted by group
   int8_t grp_view[MAX_VIEWS], grp_first[MAX_VIEWS], grp_count[MAX_VIEWS];
 };
+
+// TcParams::wide bits: which epilogue streams are 32 B-aligned and may use 256-bit accesses
+constexpr int TC_WIDE_OUT = 1, TC_WIDE_PLANES = 2, TC_WIDE_RES = 4, TC_WIDE_AUX = 8;
+constexpr int TC_BIAS_SMEM_FLOATS = 1024;  // the bias vector is staged in shared memory once per CTA
+
+// v[0..15] += 16 consecutive floats of a residual stream
+__device__ __forceinline__ void tc_add_res(const TcParams& p, const float* src, float (&v)[2][8]) {
+  if (p.wide & TC_WIDE_RES) {
+    float a[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      ld_global_256(src + h * 8, a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[h][e] += a[e];
+    }
+  } else {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float4 a = *reinterpret_cast<const float4*>(src + h * 4);
+      float* vv = &v[h >> 1][(h & 1) * 4];
+      vv[0] += a.x; vv[1] += a.y; vv[2] += a.z; vv[3] += a.w;
+    }
+  }
+}
 
 // One accumulator tile: wait for the MMAs, TMEM -> registers -> fused epilogue -> global stores, then hand the
 // TMEM buffer back.  Shared by the classic and the halo-reuse kernels.  q = TMEM lane quarter (warp % 4),
@@ -83,7 +108,7 @@ struct TcParams {
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                                  uint64_t* tempty_bar, uint32_t (&tph)[2], int local, int item, int q,
-                                                 int half, int lane) {
+                                                 int half, int lane, const float* __restrict__ s_bias) {
   const int BW = 1 << p.bw_log2, BH = TC_M >> p.bw_log2;
     const int buf = local & 1;
     const int nt = item % p.n_tiles;
@@ -108,10 +133,14 @@ __device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tme
         for (int e = 0; e < 8; ++e) cp[j][e] = 0.f;
         if (valid && p.aux0 && c0 < p.BN) {
           const float* src = p.aux0 + pix * hidden + ((n0 + c0) >> 2);
-          const float4 c0v = *reinterpret_cast<const float4*>(src);
-          const float4 c1v = *reinterpret_cast<const float4*>(src + 4);
-          cp[j][0] = c0v.x; cp[j][1] = c0v.y; cp[j][2] = c0v.z; cp[j][3] = c0v.w;
-          cp[j][4] = c1v.x; cp[j][5] = c1v.y; cp[j][6] = c1v.z; cp[j][7] = c1v.w;
+          if (p.wide & TC_WIDE_AUX) {
+            ld_global_256(src, cp[j]);
+          } else {
+            const float4 c0v = *reinterpret_cast<const float4*>(src);
+            const float4 c1v = *reinterpret_cast<const float4*>(src + 4);
+            cp[j][0] = c0v.x; cp[j][1] = c0v.y; cp[j][2] = c0v.z; cp[j][3] = c0v.w;
+            cp[j][4] = c1v.x; cp[j][5] = c1v.y; cp[j][6] = c1v.z; cp[j][7] = c1v.w;
+          }
         }
       }
     }
@@ -140,8 +169,8 @@ __device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tme
           const int co = n0 + c0 + e * 4;
           float gi = __uint_as_float(r[e * 4 + 0]), gf = __uint_as_float(r[e * 4 + 1]);
           float go = __uint_as_float(r[e * 4 + 2]), gc = __uint_as_float(r[e * 4 + 3]);
-          if (p.bias) {
-            const float4 b4 = *reinterpret_cast<const float4*>(p.bias + co);
+          if (s_bias) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + co);
             gi += b4.x; gf += b4.y; go += b4.z; gc += b4.w;
           }
           const float cell = sigmoid_fast(gf) * cp[j][e] + sigmoid_fast(gi) * tanh_fast(gc);
@@ -151,10 +180,15 @@ __device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tme
         }
         float* ho = p.out + pix * hidden + ch0;
         float* co_ = p.out2 + pix * hidden + ch0;
-        *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-        *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
-        *reinterpret_cast<float4*>(co_) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-        *reinterpret_cast<float4*>(co_ + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+        if (p.wide & TC_WIDE_OUT) {
+          st_global_256(ho, hv);
+          st_global_256(co_, cv);
+        } else {
+          *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+          *reinterpret_cast<float4*>(co_) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+          *reinterpret_cast<float4*>(co_ + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+        }
         if (p.out_hi) {
           *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0) = hh;
           *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0) = hl;
@@ -182,7 +216,7 @@ __device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tme
           for (int e = 0; e < 8; ++e) {
             const int col = g * 16 + e * 2;
             float gu = __uint_as_float(r[col]), gr = __uint_as_float(r[col + 1]);
-            if (p.bias) { gu += p.bias[n0 + c0 + col]; gr += p.bias[n0 + c0 + col + 1]; }
+            if (s_bias) { gu += s_bias[n0 + c0 + col]; gr += s_bias[n0 + c0 + col + 1]; }
             uv[e] = sigmoid_fast(gu);
             split_bf16(hp[e] * sigmoid_fast(gr), hh.v[e], hl.v[e]);
           }
@@ -215,7 +249,7 @@ __device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tme
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             float x = __uint_as_float(r[g * 8 + e]);
-            if (p.bias) x += p.bias[ch + e];
+            if (s_bias) x += s_bias[ch + e];
             hv[e] = hp[e] * (1.f - uu[e]) + tanh_fast(x) * uu[e];
             split_bf16(hv[e], hh.v[e], hl.v[e]);
           }
@@ -230,47 +264,62 @@ __device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tme
       } else {
         const size_t opix = ((size_t)n * p.OHf + (oy * p.osy + p.ooy)) * p.OWf + (ox * p.osx + p.oox);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {  // 8 channels per group
-          const int co = n0 + c0 + g * 8;
-          float v[8];
+        for (int g = 0; g < 2; ++g) {  // 16 channels per group: 2 x 32 B of fp32, 32 B per bf16 plane
+          const int co = n0 + c0 + g * 16;
+          float v[2][8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]);
-          if (p.bias) {
-            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co);
-            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co + 4);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          for (int e = 0; e < 16; ++e) v[e >> 3][e & 7] = __uint_as_float(r[g * 16 + e]);
+          if (s_bias) {
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + co + e4 * 4);
+              float* vv = &v[e4 >> 1][(e4 & 1) * 4];
+              vv[0] += b4.x; vv[1] += b4.y; vv[2] += b4.z; vv[3] += b4.w;
+            }
           }
-          if (p.res_pre) {
-            const float4 a0 = *reinterpret_cast<const float4*>(p.res_pre + opix * p.ld_res + co);
-            const float4 a1 = *reinterpret_cast<const float4*>(p.res_pre + opix * p.ld_res + co + 4);
-            v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-            v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-          }
+          if (p.res_pre) tc_add_res(p, p.res_pre + opix * p.ld_res + co, v);
           if (p.act == ESSB_ACT_RELU) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            for (int e = 0; e < 16; ++e) v[e >> 3][e & 7] = fmaxf(v[e >> 3][e & 7], 0.f);
           } else if (p.act == ESSB_ACT_SIGMOID) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = essb_sigmoid(v[e]);
+            for (int e = 0; e < 16; ++e) v[e >> 3][e & 7] = essb_sigmoid(v[e >> 3][e & 7]);
           }
-          if (p.res_post) {
-            const float4 a0 = *reinterpret_cast<const float4*>(p.res_post + opix * p.ld_res + co);
-            const float4 a1 = *reinterpret_cast<const float4*>(p.res_post + opix * p.ld_res + co + 4);
-            v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-            v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-          }
+          if (p.res_post) tc_add_res(p, p.res_post + opix * p.ld_res + co, v);
           if (p.out) {
             float* o = p.out + opix * p.ldo + co;
-            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            if (p.wide & TC_WIDE_OUT) {
+              st_global_256(o, v[0]);
+              st_global_256(o + 8, v[1]);
+            } else {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                *reinterpret_cast<float4*>(o + h * 8) = make_float4(v[h][0], v[h][1], v[h][2], v[h][3]);
+                *reinterpret_cast<float4*>(o + h * 8 + 4) = make_float4(v[h][4], v[h][5], v[h][6], v[h][7]);
+              }
+            }
           }
           if (p.out_hi) {
-            bf16x8 hh, hl;
+            uint32_t ph[8], pl[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) split_bf16(v[e], hh.v[e], hl.v[e]);
-            *reinterpret_cast<bf16x8*>(p.out_hi + opix * p.ld_planes + co) = hh;
-            *reinterpret_cast<bf16x8*>(p.out_lo + opix * p.ld_planes + co) = hl;
+            for (int e = 0; e < 8; ++e) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(v[e >> 2][(e & 3) * 2], h0, l0);
+              split_bf16(v[e >> 2][(e & 3) * 2 + 1], h1, l1);
+              ph[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              pl[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            __nv_bfloat16* oh = p.out_hi + opix * p.ld_planes + co;
+            __nv_bfloat16* ol = p.out_lo + opix * p.ld_planes + co;
+            if (p.wide & TC_WIDE_PLANES) {
+              st_global_256(oh, ph);
+              st_global_256(ol, pl);
+            } else {
+              *reinterpret_cast<uint4*>(oh) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+              *reinterpret_cast<uint4*>(oh + 8) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+              *reinterpret_cast<uint4*>(ol) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+              *reinterpret_cast<uint4*>(ol + 8) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+            }
           }
         }
       }
@@ -319,6 +368,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // bias vector -> shared memory (read by every epilogue warp for every tile)
+  float* s_bias_buf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  if (p.bias)
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias_buf[i] = p.bias[i];
+  const float* s_bias = p.bias ? s_bias_buf : nullptr;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -411,7 +465,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint32_t tph[2] = {0, 0};
     int local = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local)
-      tc_epilogue_item<EPI>(p, tmem_base, tfull_bar, tempty_bar, tph, local, item, q, half, lane);
+      tc_epilogue_item<EPI>(p, tmem_base, tfull_bar, tempty_bar, tph, local, item, q, half, lane, s_bias);
   }
 
   tc_fence_before();
@@ -468,6 +522,11 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // bias vector -> shared memory (read by every epilogue warp for every tile)
+  float* s_bias_buf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  if (p.bias)
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias_buf[i] = p.bias[i];
+  const float* s_bias = p.bias ? s_bias_buf : nullptr;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -593,7 +652,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
     uint32_t tph[2] = {0, 0};
     int local = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local)
-      tc_epilogue_item<EPI>(p, tmem_base, tfull_bar, tempty_bar, tph, local, item, q, half, lane);
+      tc_epilogue_item<EPI>(p, tmem_base, tfull_bar, tempty_bar, tph, local, item, q, half, lane, s_bias);
   }
   tc_fence_before();
   __syncthreads();
@@ -1009,9 +1068,26 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   p.out = d->out; p.out2 = d->out2;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(d->out_hi);
   p.out_lo = reinterpret_cast<__nv_bfloat16*>(d->out_lo);
+  ESSB_REQUIRE(!d->bias || d->Cout <= TC_BIAS_SMEM_FLOATS, "essb_conv_tc_run: Cout=%d > %d with a bias", d->Cout,
+               TC_BIAS_SMEM_FLOATS);
+  {
+    auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
+    int wide = 0;
+    if (d->epilogue == ESSB_EPI_LINEAR) {
+      if (!d->out || (al32(d->out) && d->ldo % 8 == 0)) wide |= TC_WIDE_OUT;
+      if (!d->out_hi || (al32(d->out_hi) && al32(d->out_lo) && d->ld_planes % 16 == 0)) wide |= TC_WIDE_PLANES;
+      if (al32(d->res_pre) && al32(d->res_post) && d->ld_res % 8 == 0) wide |= TC_WIDE_RES;
+    } else if (d->epilogue == ESSB_EPI_LSTM) {
+      const int hidden = d->Cout / 4;
+      if (al32(d->out) && al32(d->out2) && hidden % 8 == 0) wide |= TC_WIDE_OUT;
+      if (al32(d->aux0) && hidden % 8 == 0) wide |= TC_WIDE_AUX;
+    }
+    p.wide = wide;
+  }
 
-  size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  if (halo) smem_bytes = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + 512;
+  const size_t tail = 1024 /*align slack*/ + 512 /*barriers*/ + TC_BIAS_SMEM_FLOATS * sizeof(float);
+  size_t smem_bytes = (size_t)stages * p.stage_bytes + tail;
+  if (halo) smem_bytes = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + tail;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // one CTA per SM: each CTA allocates all 512 TMEM columns
   cudaStream_t st = (cudaStream_t)stream;
   int grid = p.n_items < num_sms() ? p.n_items : num_sms();
