@@ -98,6 +98,10 @@ SIGNATURES = {
     'essb_in_bwd_pass2': (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _L, _I, _P]),
     'essb_partial_reduce': (_I, [_P, _I, _I, _I, _P, _P]),
     'essb_colsum': (_I, [_P, _I, _L, _I, _P, _P, _L, _P]),
+    'essb_pw_conv_fwd': (_I, [C.POINTER(Src), _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'essb_pw_conv_dgrad': (_I, [_P, _I, _P, _P, _I, _L, _I, _I, _P]),
+    'essb_pw_conv_wgrad_workspace_bytes': (_L, [_I, _I, _I, _I]),
+    'essb_pw_conv_wgrad': (_I, [C.POINTER(Src), _P, _I, _I, _I, _I, _I, _P, _P, _P, _L, _P]),
     'essb_upsample2_bwd': (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     'essb_event_stats': (_I, [_P, _L, _I, _I, _L, _P, _P]),
     'essb_event_prepare': (_I, [_P, _L, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
@@ -120,7 +124,7 @@ SIGNATURES = {
     'essb_voxel_grid_ddd17': (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
     'essb_radam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P]),
     'essb_event_prepare_planes': (_I, [_P, _L, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
-    'essb_split_bf16': (_I, [C.POINTER(Src), _I, _I, _I, _P, _P, _I, _I, _P]),
+    'essb_split_bf16': (_I, [C.POINTER(Src), _I, _I, _I, _P, _P, _I, _I, _I, _P]),
     'essb_pack_weight_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'essb_conv_tc_run': (_I, [C.POINTER(ConvTc), _P]),
     'essb_wgrad_tc_workspace_bytes': (_L, [C.POINTER(WgradTc)]),
@@ -153,7 +157,7 @@ def check(rc, what=''):
 
 
 # kernels launched per successful API call (for bench.py's `gpu_launches` claim)
-_LAUNCHES = {'essb_wgrad_fp32': 4, 'essb_colsum': 2, 'essb_wgrad_tc_run': 2}
+_LAUNCHES = {'essb_wgrad_fp32': 4, 'essb_colsum': 2, 'essb_wgrad_tc_run': 2, 'essb_pw_conv_wgrad': 2}
 launch_count = 0
 PROFILE = None   # when a list: (tag, algorithmic_flops, start_event, end_event) per profiled launch
 

@@ -664,12 +664,17 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
 
 // --------------------------------------------------------------------------- fp32 -> bf16 hi/lo
 __global__ void split_bf16_kernel(essb_src s, int N, int H, int W, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, int ld_out, int c_off, long long total) {
+                                  __nv_bfloat16* __restrict__ lo, int ld_out, int c_off, int c_write, long long total) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int CQ = s.C >> 2;
+  const int CQ = c_write >> 2;
   const int c = (int)(idx % CQ) * 4;
   const long long pix = idx / CQ;
+  if (c >= s.C) {  // zero channel padding [C, c_write) (K padding of the tensor-core operand)
+    *reinterpret_cast<uint2*>(hi + pix * ld_out + c_off + c) = make_uint2(0u, 0u);
+    *reinterpret_cast<uint2*>(lo + pix * ld_out + c_off + c) = make_uint2(0u, 0u);
+    return;
+  }
   const long long P = (long long)H * W;
   const int n = (int)(pix / P);
   const long long pp = pix - (long long)n * P;
@@ -706,13 +711,11 @@ __global__ void event_prepare_planes_kernel(const float* __restrict__ x, long lo
                                             const double* __restrict__ stats, int normalize,
                                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int C, int H,
                                             int W, int Hp, int Wp, int pad_top, int pad_left, int Hb, int Wb, int off_y,
-                                            int off_x, long long total) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int ox = (int)(idx % Wp);
-  const long long r = idx / Wp;
-  const int oy = (int)(r % Hp);
-  const int n = (int)(r / Hp);
+                                            int off_x) {
+  // grid (ceil(Wp / blockDim.x), Hp, B): no index division
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ox >= Wp) return;
+  const int oy = blockIdx.y, n = blockIdx.z;
   const int iy = reflect_idx_tc(oy - pad_top, H), ix = reflect_idx_tc(ox - pad_left, W);
   float mean = 0.f, stdv = 1.f;
   bool do_norm = false;
@@ -855,14 +858,17 @@ int num_sms() {
 }  // namespace
 
 extern "C" int essb_split_bf16(const essb_src* src, int N, int H, int W, uint16_t* hi, uint16_t* lo, int ld_out,
-                               int c_off, void* stream) {
+                               int c_off, int c_pad, void* stream) {
   ESSB_REQUIRE(src && src->ptr && hi && lo && N > 0 && H > 0 && W > 0, "essb_split_bf16: bad arguments");
   ESSB_REQUIRE(src->C % 4 == 0 && src->ld % 4 == 0 && essb_aligned16(src->ptr) && ld_out % 4 == 0 && c_off % 4 == 0,
                "essb_split_bf16: C, ld, ld_out, c_off must be multiples of 4 and pointers 16B aligned");
   ESSB_REQUIRE((src->mean == nullptr) == (src->rstd == nullptr), "essb_split_bf16: mean/rstd must come together");
-  const long long total = (long long)N * H * W * (src->C / 4);
+  const int c_write = c_pad > src->C ? c_pad : src->C;
+  ESSB_REQUIRE(c_write % 4 == 0 && c_off + c_write <= ld_out, "essb_split_bf16: c_off + max(C, c_pad) exceeds ld_out");
+  const long long total = (long long)N * H * W * (c_write / 4);
   split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      *src, N, H, W, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), ld_out, c_off, total);
+      *src, N, H, W, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), ld_out, c_off, c_write,
+      total);
   ESSB_LAUNCH_CHECK("essb_split_bf16");
   return ESSB_OK;
 }
@@ -877,16 +883,17 @@ extern "C" int essb_event_prepare_planes(const float* x, int64_t bstride, const 
   ESSB_REQUIRE(pad_top < H && Hp - H - pad_top < H && pad_left < W && Wp - W - pad_left < W,
                "essb_event_prepare_planes: reflection padding must be smaller than the image");
   ESSB_REQUIRE(essb_aligned16(hi) && essb_aligned16(lo), "essb_event_prepare_planes: planes must be 16B aligned");
-  const long long total = (long long)B * Hp * Wp;
-  const unsigned blocks = (unsigned)((total + 255) / 256);
+  ESSB_REQUIRE(B <= 65535 && Hp <= 65535, "essb_event_prepare_planes: B and Hp must fit a grid dimension");
+  const int threads = Wp >= 512 ? 128 : 64;
+  const dim3 grid((unsigned)((Wp + threads - 1) / threads), (unsigned)Hp, (unsigned)B);
   __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(hi);
   __nv_bfloat16* l = reinterpret_cast<__nv_bfloat16*>(lo);
   if (cpad == 8)
-    event_prepare_planes_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, bstride, stats, normalize, h, l, C, H, W, Hp,
-                                                                          Wp, pad_top, pad_left, Hb, Wb, off_y, off_x, total);
+    event_prepare_planes_kernel<8><<<grid, threads, 0, (cudaStream_t)stream>>>(x, bstride, stats, normalize, h, l, C, H, W, Hp,
+                                                                           Wp, pad_top, pad_left, Hb, Wb, off_y, off_x);
   else
-    event_prepare_planes_kernel<16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, bstride, stats, normalize, h, l, C, H, W, Hp,
-                                                                           Wp, pad_top, pad_left, Hb, Wb, off_y, off_x, total);
+    event_prepare_planes_kernel<16><<<grid, threads, 0, (cudaStream_t)stream>>>(x, bstride, stats, normalize, h, l, C, H, W, Hp,
+                                                                            Wp, pad_top, pad_left, Hb, Wb, off_y, off_x);
   ESSB_LAUNCH_CHECK("essb_event_prepare_planes");
   return ESSB_OK;
 }

@@ -327,27 +327,45 @@ __global__ void colsum_stage2(const float* __restrict__ part, int nblocks, int C
 
 // ------------------------------------------------------------------------- event pre-processing
 // stats[w][3] += (sum, sumsq, nnz) of window w; x is [B][T][count] with batch stride bstride.
-__global__ void event_stats_kernel(const float* __restrict__ x, long long bstride, int B, long long count,
-                                   double* __restrict__ stats) {
-  __shared__ double red[3][8];
+// grid (chunks, T, B): one block reduces ES_CHUNK consecutive floats of the (b, w) slab -- no index division,
+// 128-bit loads when the slab is 16 B aligned; <= 64 values per thread are summed in fp32, everything above in double.
+constexpr int ES_THREADS = 256;
+constexpr int ES_CHUNK = ES_THREADS * 4 * 16;
+__global__ void __launch_bounds__(ES_THREADS) event_stats_kernel(const float* __restrict__ x, long long bstride,
+                                                                 long long count, double* __restrict__ stats) {
+  __shared__ double red[3][ES_THREADS / 32];
   const int w = blockIdx.y;
-  const long long total = (long long)B * count;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / count, r = i - b * count;
-    const float v = x[b * bstride + (long long)w * count + r];
-    s0 += (double)v;
-    s1 += (double)v * (double)v;
-    s2 += (v != 0.f) ? 1.0 : 0.0;
+  const float* base = x + (long long)blockIdx.z * bstride + (long long)w * count;
+  const long long i0 = (long long)blockIdx.x * ES_CHUNK;
+  long long i1 = i0 + ES_CHUNK;
+  if (i1 > count) i1 = count;
+  float f0 = 0.f, f1 = 0.f;
+  int nz = 0;
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0 && ((i1 - i0) & 3) == 0) {
+    const float4* b4 = reinterpret_cast<const float4*>(base + i0);
+    const int n4 = (int)((i1 - i0) >> 2);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += ES_THREADS) {
+      const float4 v = b4[i];
+      f0 += (v.x + v.y) + (v.z + v.w);
+      f1 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      nz += (v.x != 0.f) + (v.y != 0.f) + (v.z != 0.f) + (v.w != 0.f);
+    }
+  } else {
+    for (long long i = i0 + threadIdx.x; i < i1; i += ES_THREADS) {
+      const float v = base[i];
+      f0 += v;
+      f1 += v * v;
+      nz += (v != 0.f);
+    }
   }
-  s0 = warp_sum_d(s0); s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+  double s0 = warp_sum_d((double)f0), s1 = warp_sum_d((double)f1), s2 = warp_sum_d((double)nz);
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   if (lane == 0) { red[0][wy] = s0; red[1][wy] = s1; red[2][wy] = s2; }
   __syncthreads();
   if (threadIdx.x < 3) {
     double t = 0.0;
-    for (int k = 0; k < 8; ++k) t += red[threadIdx.x][k];
+    for (int k = 0; k < ES_THREADS / 32; ++k) t += red[threadIdx.x][k];
     atomicAdd(&stats[w * 3 + threadIdx.x], t);
   }
 }
@@ -626,11 +644,9 @@ extern "C" int essb_event_stats(const float* x, int64_t bstride, int B, int T, i
     essb_set_error("essb_event_stats: memset failed: %s", cudaGetErrorString(e));
     return ESSB_ERR_LAUNCH;
   }
-  long long blocks = ((long long)B * count + 256 * 16 - 1) / (256 * 16);
-  if (blocks > 592) blocks = 592;
-  if (blocks < 1) blocks = 1;
-  dim3 grid((unsigned)blocks, T, 1);
-  event_stats_kernel<<<grid, 256, 0, st>>>(x, bstride, B, count, stats);
+  ESSB_REQUIRE(B <= 65535 && T <= 65535, "essb_event_stats: B and T must fit a grid dimension");
+  dim3 grid((unsigned)((count + ES_CHUNK - 1) / ES_CHUNK), T, B);
+  event_stats_kernel<<<grid, ES_THREADS, 0, st>>>(x, bstride, count, stats);
   ESSB_LAUNCH_CHECK("essb_event_stats");
   return ESSB_OK;
 }

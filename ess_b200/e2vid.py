@@ -252,6 +252,10 @@ class E2VIDRecurrent(nn.Module):
                     P['dec%d_tc' % i] = ops.pack_weight_tc(dec.transposed_conv2d.weight, scale, transposed_layout=True)
         scale, bias = _bn_fold(u.pred.conv2d.bias, getattr(u.pred, 'norm_layer', None), None, dev)
         P['pred'] = (ops.pack_weight(u.pred.conv2d.weight, scale), bias)
+        wp = u.pred.conv2d.weight.detach().float().reshape(1, -1)
+        if scale is not None:
+            wp = wp * scale.view(1, 1)
+        P['pred_pw'] = wp.contiguous() if wp.shape[1] in (32, 64) else None    # streaming 1x1 kernel (pw_conv.cu)
         self._packed, self._packed_key = P, key
         return P
 
@@ -304,9 +308,13 @@ class E2VIDRecurrent(nn.Module):
             self._in_planes = {key: buf}
         return buf
 
-    def forward_planes(self, in_planes, H, W, prev_states, with_image=True):
-        """forward() for an input already in the head conv's operand format (essb_event_prepare_planes)."""
-        return self._forward_impl(None, in_planes, in_planes[0].shape[0], H, W, prev_states, with_image)
+    def forward_planes(self, in_planes, H, W, prev_states, with_image=True, want_head=True):
+        """forward() for an input already in the head conv's operand format (essb_event_prepare_planes).
+        want_head=False (only with with_image=False): the fp32 head activation -- latent[1], needed by nobody
+        between the windows of an unroll -- is not written (latent[1] is None); the head conv then only emits
+        the bf16 operand planes of the first encoder."""
+        return self._forward_impl(None, in_planes, in_planes[0].shape[0], H, W, prev_states, with_image,
+                                  want_head=want_head or with_image)
 
     def forward_nhwc(self, x, prev_states, with_image=True):
         """Same as forward() for an already pixel-major input [N, H, W, ceil8(num_bins)] (zero-padded
@@ -335,7 +343,7 @@ class E2VIDRecurrent(nn.Module):
             d.dy[ky], d.dx[ky], d.view[ky], d.widx[ky] = ky, 0, 0, ky
         ops.conv_tc(d, tag='head_tc')
 
-    def _forward_impl(self, x, in_planes, N, H, W, prev_states, with_image):
+    def _forward_impl(self, x, in_planes, N, H, W, prev_states, with_image, want_head=True):
         P = self._pack()
         u = self.unetrecurrent
         ne = self.num_encoders
@@ -355,7 +363,7 @@ class E2VIDRecurrent(nn.Module):
             planes = (torch.empty((N, H, W, base), device=dev, dtype=torch.bfloat16),
                       torch.empty((N, H, W, base), device=dev, dtype=torch.bfloat16))
         if in_planes is not None:
-            head = torch.empty((N, H, W, base), device=dev, dtype=torch.float32)
+            head = torch.empty((N, H, W, base), device=dev, dtype=torch.float32) if (want_head or not want_planes) else None
             self._head_tc(P, in_planes, N, H, W, head, planes, passes)
         else:
             head, _, _, _ = ops.conv([Seg(x, C=cpad)], wh, bh, N, H, W, H, W, base, ops.taps_conv(5, 2), act=ACT_RELU,
@@ -424,7 +432,7 @@ class E2VIDRecurrent(nn.Module):
             h_in, w_in = oh, ow
         self._planes = new_planes
 
-        latent = {1: ops.as_nchw(head), 2: ops.as_nchw(blocks[0]), 4: ops.as_nchw(blocks[1]),
+        latent = {1: ops.as_nchw(head) if head is not None else None, 2: ops.as_nchw(blocks[0]), 4: ops.as_nchw(blocks[1]),
                   8: ops.as_nchw(blocks[2])}                                       # unet.py:172
         if not with_image:
             return None, states, latent
@@ -477,6 +485,8 @@ class E2VIDRecurrent(nn.Module):
             x, xp = out, op
             h, w = 2 * h, 2 * w
         wp, bp = P['pred']
+        if P['pred_pw'] is not None and x.shape[-1] == P['pred_pw'].shape[1]:
+            return ops.pw_conv_fwd(Seg(x), P['pred_pw'], bp, N, h, w, 1, act=ACT_SIGMOID)                  # unet.py:179
         img, _, _, _ = ops.conv([Seg(x)], wp, bp, N, h, w, h, w, 1, ops.taps_conv(1, 0), act=ACT_SIGMOID)  # unet.py:179
         return img
 

@@ -335,15 +335,16 @@ def confusion_logits(logits, target, K, ignore_index, conf=None):
 
 
 # --------------------------------------------------------------------------- tensor-core path helpers
-def split_bf16(seg: Seg, N, H, W, hi=None, lo=None, c_off=0, ld_out=None):
-    """fp32 (optionally normalised / ReLU'd / upsampled) -> bf16 hi/lo planes [N, H, W, ld_out]."""
+def split_bf16(seg: Seg, N, H, W, hi=None, lo=None, c_off=0, ld_out=None, c_pad=0):
+    """fp32 (optionally normalised / ReLU'd / upsampled) -> bf16 hi/lo planes [N, H, W, ld_out]; channels
+    [C, c_pad) of the output are zero-filled by the same kernel (K padding of a tensor-core operand)."""
     s = Src()
     c = seg.fill(s)
     if hi is None:
-        ld_out = ld_out or c
+        ld_out = ld_out or max(c, c_pad)
         hi = torch.empty((N, H, W, ld_out), device=seg.t.device, dtype=torch.bfloat16)
         lo = torch.empty_like(hi)
-    call('essb_split_bf16', C.byref(s), N, H, W, _p(hi), _p(lo), hi.shape[-1], c_off, _stream())
+    call('essb_split_bf16', C.byref(s), N, H, W, _p(hi), _p(lo), hi.shape[-1], c_off, c_pad, _stream())
     return hi, lo
 
 
@@ -540,6 +541,40 @@ def jsdiv(predict, target, K, want_sum=True, gscale=None, want_grad=False):
     call('essb_jsdiv', _p(predict), predict.shape[-1], _p(target), target.shape[-1], rows, K, _p(sums), _p(gscale),
          _p(dp), K, _stream())
     return sums, dp
+
+
+def pw_conv_fwd(seg: Seg, w, bias, N, H, W, Cout, act=ACT_NONE):
+    """essb_pw_conv_fwd: 1x1 conv (Cin 32/64 -> Cout <= 16) with the source's IN/ReLU applied on the fly.
+    w [Cout, Cin] fp32 contiguous (reference layout)."""
+    s = Src()
+    seg.fill(s)
+    out = torch.empty((N, H, W, Cout), device=seg.t.device, dtype=torch.float32)
+    call('essb_pw_conv_fwd', C.byref(s), _p(w), _p(bias), _p(out), Cout, N, H, W, Cout, act, _stream())
+    return out
+
+
+def pw_conv_dgrad(dy, w, Cin):
+    """essb_pw_conv_dgrad: dy [N, H, W, Cout], w [Cout, Cin] -> gradient w.r.t. the conv input [N, H, W, Cin]."""
+    N, H, W, Cout = dy.shape
+    dx = torch.empty((N, H, W, Cin), device=dy.device, dtype=torch.float32)
+    call('essb_pw_conv_dgrad', _p(dy), Cout, _p(w), _p(dx), Cin, N * H * W, Cin, Cout, _stream())
+    return dx
+
+
+def pw_conv_wgrad(seg: Seg, dy, want_w=True, want_b=True):
+    """essb_pw_conv_wgrad -> (dW [Cout, Cin], dbias [Cout]) (None where not wanted)."""
+    N, H, W, Cout = dy.shape
+    s = Src()
+    cin = seg.fill(s)
+    dev = dy.device
+    dw = torch.empty((Cout, cin), device=dev, dtype=torch.float32) if want_w else None
+    db = torch.empty((Cout,), device=dev, dtype=torch.float32) if want_b else None
+    nbytes = _lib.lib().essb_pw_conv_wgrad_workspace_bytes(N, H, W, cin)
+    if nbytes < 0:
+        raise RuntimeError('essb_pw_conv_wgrad: unsupported shape')
+    ws = torch.empty((int(nbytes) // 4,), device=dev, dtype=torch.float32)
+    call('essb_pw_conv_wgrad', C.byref(s), _p(dy), Cout, N, H, W, Cout, _p(dw), _p(db), _p(ws), ws.numel() * 4, _stream())
+    return dw, db
 
 
 def colsum(x, Cc=None):

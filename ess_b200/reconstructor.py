@@ -44,7 +44,7 @@ class ImageReconstructor:
         self.last_states_for_each_channel = {'grayscale': None}
         self.stats_reduce_fn = None
 
-    def _step(self, window, stats_row, states, with_image):
+    def _step(self, window, stats_row, states, with_image, want_head=True):
         """normalise + reflect-pad + layout/precision conversion (one kernel) -> model."""
         B, C, H, W = window.shape
         left, right, top, bottom = crop_padding(H, W, self.model.num_encoders)
@@ -52,7 +52,7 @@ class ImageReconstructor:
         buf = self.model.head_planes_buffer(B, Hp, Wp, window.device)
         if buf is not None:      # tensor-core head conv: write its bf16 hi/lo operand planes directly
             ops.event_prepare_planes(window, stats_row, not self.no_normalize, Hp, Wp, top, left, buf)
-            return self.model.forward_planes(buf, Hp, Wp, states, with_image=with_image)
+            return self.model.forward_planes(buf, Hp, Wp, states, with_image=with_image, want_head=want_head)
         x = ops.event_prepare(window, stats_row, not self.no_normalize, Hp, Wp, top, left, (C + 7) // 8 * 8)
         return self.model.forward_nhwc(x, states, with_image=with_image)
 
@@ -100,7 +100,8 @@ class ImageReconstructor:
             for i in range(num_windows):
                 win = data[:, i * channels:(i + 1) * channels]
                 need_img = (i == num_windows - 1) or not image_on_last_only
-                img, states, latent = self._step(win, stats[i] if stats is not None else None, states, need_img)
+                img, states, latent = self._step(win, stats[i] if stats is not None else None, states, need_img,
+                                                 want_head=(i == num_windows - 1))
                 if self.no_recurrent:
                     states = None
             self.last_states_for_each_channel['grayscale'] = states

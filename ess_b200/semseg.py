@@ -181,6 +181,23 @@ def _taps(k):
     return ops.taps_conv(k, k // 2)
 
 
+def _bias_grad(nd, gy):
+    """Bias gradient of a conv node.  A bias that feeds an InstanceNorm (every conv of the IN blocks,
+    style_networks.py:162-163,174-183) is cancelled by the mean subtraction: the incoming gradient gy is the
+    output of the InstanceNorm backward, whose per-(n, c) sum over pixels is identically zero (the reference
+    produces ~1e-10 rounding noise there).  Those gradients are returned as exact zeros instead of being
+    summed over all pixels; only a conv whose output is not normalised has a real bias gradient."""
+    if nd.stats:
+        return torch.zeros((nd.cout,), device=gy.device, dtype=torch.float32)
+    return ops.colsum(gy, nd.cout)
+
+
+def _pw_ok(nd, segs, cin_total):
+    """1x1 conv with one non-upsampled 32/64-channel source and <= 16 outputs -> pw_conv.cu kernels."""
+    return nd.k == 1 and not nd.stats and len(segs) == 1 and segs[0].ups == 0 and cin_total in (32, 64) and \
+        nd.cout <= 16 and segs[0].t.shape[-1] == cin_total
+
+
 class _DecoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, names, x8, x4, x2, *params):
@@ -221,6 +238,10 @@ class _DecoderFn(torch.autograd.Function):
                     T[nd.out] = y
                     if nd.stats:
                         S[nd.out] = ops.in_stats(y)
+                elif _pw_ok(nd, segs, cin_total):
+                    # 1x1 classifier (style_networks.py:34,88): HBM-bound, dedicated streaming kernel
+                    T[nd.out] = ops.pw_conv_fwd(segs[0], w.detach().float().reshape(nd.cout, cin_total), bias, N, H, W,
+                                                nd.cout)
                 else:
                     wp = ops.pack_weight(w)
                     y, _, st, _ = ops.conv(segs, wp, bias, N, H, W, H, W, nd.cout, _taps(nd.k), epilogue=EPI_LINEAR,
@@ -234,6 +255,7 @@ class _DecoderFn(torch.autograd.Function):
                                              res=T[nd.res] if nd.res is not None else None)
         ctx.module, ctx.names = module, names
         ctx.T, ctx.S = T, S
+        ctx.set_materialize_grads(False)     # unused outputs (out[4], out[2] in the supervised step) stay None
         ctx.save_for_backward(*params)
         outs = tuple(ops.as_nchw(T[o]) for o in module._outs)
         return outs
@@ -301,10 +323,9 @@ class _DecoderFn(torch.autograd.Function):
             def dy_planes():
                 """bf16 hi/lo planes of dY (channel-padded to a multiple of 64 with zeros), built once per node"""
                 kinp = (nd.cout + 63) // 64 * 64
-                alloc = torch.zeros if kinp != nd.cout else torch.empty
-                pl = (alloc((N, H, W, kinp), device=gy.device, dtype=torch.bfloat16),
-                      alloc((N, H, W, kinp), device=gy.device, dtype=torch.bfloat16))
-                ops.split_bf16(Seg(gy), N, H, W, pl[0], pl[1], 0)
+                pl = (torch.empty((N, H, W, kinp), device=gy.device, dtype=torch.bfloat16),
+                      torch.empty((N, H, W, kinp), device=gy.device, dtype=torch.bfloat16))
+                ops.split_bf16(Seg(gy), N, H, W, pl[0], pl[1], 0, c_pad=kinp)
                 return pl
 
             if need_p[nd.w] or need_p[nd.b]:
@@ -315,7 +336,13 @@ class _DecoderFn(torch.autograd.Function):
                     else:
                         segs.append(Seg(T[sid], ups=ups))
                 cin_total = w.shape[1]
-                if tc and cin_total % 64 == 0 and nd.cout <= 256:
+                if _pw_ok(nd, segs, cin_total):
+                    dw, db = ops.pw_conv_wgrad(segs[0], gy, want_w=need_p[nd.w], want_b=need_p[nd.b])
+                    if need_p[nd.w]:
+                        grads[nd.w] = dw.view(w.shape)
+                    if need_p[nd.b]:
+                        grads[nd.b] = db
+                elif tc and cin_total % 64 == 0 and nd.cout <= 256:
                     # tensor-core wgrad: re-create the conv's operand planes (cheaper than keeping them alive)
                     hi = torch.empty((N, H, W, cin_total), device=gy.device, dtype=torch.bfloat16)
                     lo = torch.empty_like(hi)
@@ -328,7 +355,7 @@ class _DecoderFn(torch.autograd.Function):
                         grads[nd.w] = ops.wgrad_tc((hi, lo), gplanes, cin_total, nd.cout, taps, N, H, W, passes).view(w.shape)
                     del hi, lo
                     if need_p[nd.b]:
-                        grads[nd.b] = ops.colsum(gy, nd.cout)
+                        grads[nd.b] = _bias_grad(nd, gy)
                 else:
                     dw, db = ops.wgrad(segs, gy, N, H, W, H, W, nd.cout, taps, want_bias=need_p[nd.b])
                     if need_p[nd.w]:
@@ -342,7 +369,9 @@ class _DecoderFn(torch.autograd.Function):
                 cs = src.shape[-1]
                 if need[sid]:
                     wseg = w.detach()[:, c_off:c_off + cs].contiguous()
-                    if tc and cs in (64, 128, 256):
+                    if nd.k == 1 and len(nd.srcs) == 1 and cs in (32, 64) and nd.cout <= 16 and not ups:
+                        dA = ops.pw_conv_dgrad(gy, wseg.float().reshape(nd.cout, cs), cs)
+                    elif tc and cs in (64, 128, 256):
                         kinp = (nd.cout + 63) // 64 * 64
                         if gplanes is None:
                             gplanes = dy_planes()

@@ -173,6 +173,24 @@ int essb_colsum(const float* x, int ld, int64_t rows, int C, float* out, float* 
 int essb_upsample2_bwd(const float* in, int ld_in, float* out, int ld_out, int N, int H, int W, int C,
                        int accumulate, void* stream);
 
+/* ---- 1x1 convolutions with few output channels (HBM-bound; pw_conv.cu) ---------------------------
+ * Replaces nn.Conv2d(32, K, 1) of SemSegE2VID.decoder_scale_5 (models/style_networks.py:34,88: forward, and
+ * its autograd input / weight / bias gradients) and the E2VID prediction layer conv1x1 + BatchNorm(eval) +
+ * sigmoid (e2vid/model/unet.py:65-67,179; BN folded into w / bias by the caller).
+ * src: fp32 NHWC with C = 32 or 64 channels, no upsampling; its optional (mean, rstd, relu) apply the
+ * preceding InstanceNorm + ReLU on the fly.  w is the reference layout [Cout][Cin] (fp32), 1 <= Cout <= 16.
+ *   fwd  : out[p][k] = act(sum_c f(x[p][c]) * w[k][c] + bias[k])          (out pitch ldo >= Cout)
+ *   dgrad: dx[p][c]  = sum_k dy[p][k] * w[k][c]                           (gradient w.r.t. f(x))
+ *   wgrad: dw[k][c]  = sum_p dy[p][k] * f(x[p][c]),  dbias[k] = sum_p dy[p][k]   (either may be NULL);
+ *          two-stage fixed-order reduction (deterministic) through `workspace`. */
+int essb_pw_conv_fwd(const essb_src* src, const float* w, const float* bias, float* out, int ldo, int N,
+                     int H, int W, int Cout, int act, void* stream);
+int essb_pw_conv_dgrad(const float* dy, int ld_dy, const float* w, float* dx, int ld_dx, int64_t rows,
+                       int Cin, int Cout, void* stream);
+int64_t essb_pw_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin);
+int essb_pw_conv_wgrad(const essb_src* src, const float* dy, int ld_dy, int N, int H, int W, int Cout,
+                       float* dw, float* dbias, float* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- event pre-processing (e2vid/utils/inference_utils.py:84-109, 311-338) --------------- */
 /* stats[w][3] = (sum x, sum x^2, count of non-zeros) of window w for ALL T windows in one launch;
  * x is [B][T][count] with batch stride `bstride` floats (count = C*H*W of one window).  One launch
@@ -257,7 +275,8 @@ int essb_radam_step(float* p, const float* g, float* m, float* v, int64_t n, flo
 /* Split an fp32 tensor into bf16 hi/lo planes: hi = bf16(x), lo = bf16(x - hi)  (x ~= hi + lo to
  * 2^-17 relative).  Optionally applies the same normalise/ReLU/upsample transform as essb_src. */
 int essb_split_bf16(const essb_src* src, int N, int H, int W, uint16_t* hi, uint16_t* lo, int ld_out,
-                    int c_off, void* stream);
+                    int c_off, int c_pad /* channels [C, c_pad) are written as zeros (K padding); 0 = none */,
+                    void* stream);
 /* Event pre-processing (same arithmetic as essb_event_prepare) written directly in the head
  * convolution's tensor-core operand format: bf16 hi/lo planes with `cpad` (8 or 16) channels per
  * pixel, stored at (off_y, off_x) inside a caller-zeroed bordered buffer [B][Hb][Wb][cpad].  With a

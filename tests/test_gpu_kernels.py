@@ -287,3 +287,76 @@ def test_voxel_grids():
     ev2 = ev.clone()
     ev2[:, 2] = 7.0
     assert float((generate_voxel_grid(ev2.cuda(), (H, W), C).cpu() - O.voxel_grid_ddd17(ev2.numpy(), (H, W), C)).abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------ 1x1 streaming kernels
+@pytest.mark.parametrize('N,H,W,Cin,K,norm', [
+    (2, 9, 7, 32, 11, True),          # classifier shape, ragged block (126 rows)
+    (1, 40, 56, 32, 6, True),         # DDD17 class count, several blocks
+    (3, 17, 33, 64, 16, False),       # Cin = 64, Cout = 16, rows cross sample boundaries inside a warp
+    (2, 16, 24, 32, 1, False),        # E2VID prediction layer (Cout = 1)
+])
+def test_pw_conv_fwd_dgrad_wgrad(N, H, W, Cin, K, norm):
+    """essb_pw_conv_{fwd,dgrad,wgrad} vs autograd of conv1x1(relu(instance_norm(y))) (style_networks.py:34,88)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    y = (torch.randn(N, Cin, H, W, generator=g) * 1.5 + 0.3).double()
+    w = (torch.randn(K, Cin, 1, 1, generator=g) * 0.2).double().requires_grad_(True)
+    b = torch.randn(K, generator=g).double().requires_grad_(True)
+    gy = torch.randn(N, K, H, W, generator=g).double()
+    a = (torch.relu(F.instance_norm(y, eps=1e-5)) if norm else y).detach().requires_grad_(True)
+    out = F.conv2d(a, w, b)
+    out.backward(gy)
+    yd = nhwc(y.float())
+    mean = rstd = None
+    if norm:
+        mean, rstd = ops.in_stats(yd)
+    seg = ops.Seg(yd, mean=mean, rstd=rstd, relu=norm)
+    wd = w.detach().float().reshape(K, Cin).cuda().contiguous()
+    o = ops.pw_conv_fwd(seg, wd, b.detach().float().cuda(), N, H, W, K)
+    assert rel_err(nchw(o), out) < TIGHT
+    gyd = nhwc(gy.float())
+    dx = ops.pw_conv_dgrad(gyd, wd, Cin)
+    assert rel_err(nchw(dx), a.grad) < TIGHT
+    dw, db = ops.pw_conv_wgrad(seg, gyd)
+    assert rel_err(dw.cpu(), w.grad.reshape(K, Cin)) < TIGHT
+    assert rel_err(db.cpu(), b.grad) < TIGHT
+
+
+def test_pw_conv_sigmoid_matches_pred_layer():
+    ops = _ops()
+    from ess_b200._lib import ACT_SIGMOID
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 32, 24, 40, generator=g)
+    w = torch.randn(1, 32, 1, 1, generator=g) * 0.3
+    b = torch.randn(1, generator=g)
+    ref = torch.sigmoid(F.conv2d(x, w, b))
+    o = ops.pw_conv_fwd(ops.Seg(nhwc(x)), w.reshape(1, 32).cuda().contiguous(), b.cuda(), 2, 24, 40, 1, act=ACT_SIGMOID)
+    assert rel_err(nchw(o), ref) < TIGHT
+
+
+@pytest.mark.parametrize('B,T,count', [(2, 3, 5 * 16 * 24), (3, 2, 1001), (1, 4, 70000)])
+def test_event_stats_vectorised(B, T, count):
+    """essb_event_stats (128-bit path, scalar tail path, multi-chunk slabs) vs torch sums."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, T, count, generator=g) * (torch.rand(B, T, count, generator=g) < 0.3)
+    xd = x.cuda()
+    from ess_b200.ops import _p, _stream, call
+    stats = torch.empty((T, 3), device='cuda', dtype=torch.float64)
+    call('essb_event_stats', _p(xd), xd.stride(0), B, T, count, _p(stats), _stream())
+    xd64 = x.double()
+    ref = torch.stack([xd64.sum((0, 2)), (xd64 * xd64).sum((0, 2)), (x != 0).double().sum((0, 2))], 1)
+    assert rel_err(stats.cpu(), ref) < 1e-6
+    assert torch.equal(stats[:, 2].cpu(), ref[:, 2])
+
+
+def test_split_bf16_zero_pads_channels():
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 6, 10, 32, generator=g).cuda()
+    hi = torch.full((2, 6, 10, 64), 7.0, device='cuda', dtype=torch.bfloat16)
+    lo = torch.full_like(hi, 7.0)
+    ops.split_bf16(ops.Seg(x), 2, 6, 10, hi, lo, 0, c_pad=64)
+    assert float(hi[..., 32:].abs().max()) == 0.0 and float(lo[..., 32:].abs().max()) == 0.0
+    assert rel_err(hi[..., :32].float() + lo[..., :32].float(), x) < 1e-4
