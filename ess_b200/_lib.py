@@ -56,6 +56,8 @@ class ConvTc(C.Structure):
                 ('w_hi', C.c_void_p), ('w_lo', C.c_void_p), ('bias', C.c_void_p), ('res_pre', C.c_void_p),
                 ('res_post', C.c_void_p), ('aux0', C.c_void_p), ('aux1', C.c_void_p), ('out', C.c_void_p),
                 ('out2', C.c_void_p), ('out_hi', C.c_void_p), ('out_lo', C.c_void_p),
+                ('sched', C.c_void_p), ('splitk_ws', C.c_void_p), ('splitk_cnt', C.c_void_p),
+                ('splitk_ws_bytes', C.c_int64),
                 ('n_views', C.c_int32), ('nseg', C.c_int32),
                 ('seg_C', C.c_int32 * 2), ('seg_view0', C.c_int32 * 2), ('seg_koff', C.c_int32 * 2),
                 ('k_per_tap', C.c_int32), ('n_w_taps', C.c_int32), ('w_rows', C.c_int32),
@@ -95,7 +97,7 @@ SIGNATURES = {
     'essb_in_bwd_blocks': (_I, [_L]),
     'essb_in_stats': (_I, [_P, _I, _P, _I, _L, _I, _P]),
     'essb_in_bwd_pass1': (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
-    'essb_in_bwd_pass2': (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _L, _I, _P]),
+    'essb_in_bwd_pass2': (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P]),
     'essb_partial_reduce': (_I, [_P, _I, _I, _I, _P, _P]),
     'essb_colsum': (_I, [_P, _I, _L, _I, _P, _P, _L, _P]),
     'essb_pw_conv_fwd': (_I, [C.POINTER(Src), _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

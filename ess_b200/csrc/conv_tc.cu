@@ -76,7 +76,63 @@ struct TcParams {
   int wide;                              // TC_WIDE_* bits (256-bit epilogue accesses)
   int n_groups;                          // tap groups = views actually used; taps are sorted by group
   int8_t grp_view[MAX_VIEWS], grp_first[MAX_VIEWS], grp_count[MAX_VIEWS];
+  // dynamic tile scheduler + split-K tail (see TcUnit)
+  int* sched;                            // [0] next unit, [1] CTAs done; zero before the launch, reset by the last CTA
+  int n_units, n_whole, split;           // units [0, n_whole) are whole tiles; the rest are 1/split K-slices of the tail tiles
+  float* splitk_ws;                      // [tail tile][part][32-col chunk][128 rows][32] fp32 partial accumulators
+  int* splitk_cnt;                       // [tail tile][8 epilogue warps] arrival counters (zero; the last arriver resets)
 };
+
+// Work unit handed out by the scheduler.  The persistent CTAs pull units from a global counter (warp 0 fetches,
+// an mbarrier-guarded ring in shared memory broadcasts the unit to the MMA and epilogue warps), so a CTA that
+// runs slow simply takes fewer tiles.  The tiles of the last, partially filled wave are cut into `split`
+// K-slices: each slice leaves its fp32 partial accumulator in splitk_ws, and the epilogue warp that arrives
+// last on the tile's counter sums the slices in slice order (deterministic) and runs the fused epilogue.
+struct TcUnit {
+  int item, k0, k1, part, slot;          // slot < 0: whole tile
+};
+__device__ __forceinline__ TcUnit tc_decode_unit(const TcParams& p, int u, int k_iters) {
+  TcUnit t;
+  if (u < p.n_whole) {
+    t.item = u; t.k0 = 0; t.k1 = k_iters; t.part = 0; t.slot = -1;
+  } else {
+    const int v = u - p.n_whole;
+    t.slot = v / p.split;
+    t.part = v - t.slot * p.split;
+    t.item = p.n_whole + t.slot;
+    t.k0 = (t.part * k_iters) / p.split;
+    t.k1 = ((t.part + 1) * k_iters) / p.split;
+  }
+  return t;
+}
+constexpr int SCHED_DEPTH = 4;
+// producer side: fetch the next unit (or -1) and publish it in ring slot local % SCHED_DEPTH
+__device__ __forceinline__ int tc_sched_fetch(const TcParams& p, int local, int* ring, uint64_t* s_full, uint64_t* s_empty) {
+  const int slot = local % SCHED_DEPTH;
+  mbar_wait(&s_empty[slot], ((uint32_t)(local / SCHED_DEPTH) & 1u) ^ 1u);
+  int u = atomicAdd(p.sched, 1);
+  if (u >= p.n_units) u = -1;
+  ring[slot] = u;
+  mbar_arrive(&s_full[slot]);
+  return u;
+}
+// consumer side (whole warp): read the unit published for iteration `local`
+__device__ __forceinline__ int tc_sched_read(int local, int lane, const int* ring, uint64_t* s_full, uint64_t* s_empty) {
+  const int slot = local % SCHED_DEPTH;
+  mbar_wait(&s_full[slot], (uint32_t)(local / SCHED_DEPTH) & 1u);
+  const int u = *reinterpret_cast<const volatile int*>(&ring[slot]);
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&s_empty[slot]);
+  return u;
+}
+// last CTA out resets the scheduler counters for the next launch that uses this slot
+__device__ __forceinline__ void tc_sched_finish(const TcParams& p) {
+  const int old = atomicAdd(p.sched + 1, 1);
+  if (old == (int)gridDim.x - 1) {
+    p.sched[0] = 0;
+    p.sched[1] = 0;
+  }
+}
 
 // TcParams::wide bits: which epilogue streams are 32 B-aligned and may use 256-bit accesses
 constexpr int TC_WIDE_OUT = 1, TC_WIDE_PLANES = 2, TC_WIDE_RES = 4, TC_WIDE_AUX = 8;
@@ -102,52 +158,239 @@ __device__ __forceinline__ void tc_add_res(const TcParams& p, const float* src, 
   }
 }
 
-// One accumulator tile: wait for the MMAs, TMEM -> registers -> fused epilogue -> global stores, then hand the
-// TMEM buffer back.  Shared by the classic and the halo-reuse kernels.  q = TMEM lane quarter (warp % 4),
-// half = which of the two warps of that quarter (interleaved 32-column chunks).
+// Fused epilogue of one 32-column chunk of an accumulator row (r = the fp32 accumulators of row `pix`, columns
+// n0 + c0 .. + 31): bias / gates / activation / residuals -> global stores.  cpj = previous cell state (LSTM).
 template <int EPI>
-__device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
-                                                 uint64_t* tempty_bar, uint32_t (&tph)[2], int local, int item, int q,
-                                                 int half, int lane, const float* __restrict__ s_bias) {
-  const int BW = 1 << p.bw_log2, BH = TC_M >> p.bw_log2;
-    const int buf = local & 1;
-    const int nt = item % p.n_tiles;
-    int mt = item / p.n_tiles;
-    const int txi = mt % p.tiles_x; mt /= p.tiles_x;
-    const int tyi = mt % p.tiles_y;
-    const int n = mt / p.tiles_y;
-    const int m = q * 32 + lane;
-    const int oy = tyi * BH + (m >> p.bw_log2), ox = txi * BW + (m & (BW - 1));
-    const bool valid = oy < p.OH && ox < p.OW;
-    const int n0 = nt * p.BN;
-    const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
-    // LSTM: the previous cell state does not depend on the MMA -> fetch it BEFORE waiting for the
-    // accumulator so its latency hides under the main loop of this tile
-    float cp[4][8];
-    if constexpr (EPI == ESSB_EPI_LSTM) {
-      const int hidden = p.Cout >> 2;
+__device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint32_t (&r)[32], int n0, int c0, size_t pix,
+                                                  int n, int oy, int ox, const float (&cpj)[8],
+                                                  const float* __restrict__ s_bias) {
+  if constexpr (EPI == ESSB_EPI_LSTM) {
+    // columns co = 4*ch + {in, remember, out, cell}; 32 columns = 8 channels
+    const int hidden = p.Cout >> 2;
+    const int ch0 = (n0 + c0) >> 2;
+    float hv[8], cv[8];
+    bf16x8 hh, hl;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c0 = half * 32 + j * 64;
+    for (int e = 0; e < 8; ++e) {
+      const int co = n0 + c0 + e * 4;
+      float gi = __uint_as_float(r[e * 4 + 0]), gf = __uint_as_float(r[e * 4 + 1]);
+      float go = __uint_as_float(r[e * 4 + 2]), gc = __uint_as_float(r[e * 4 + 3]);
+      if (s_bias) {
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + co);
+        gi += b4.x; gf += b4.y; go += b4.z; gc += b4.w;
+      }
+      const float cell = sigmoid_fast(gf) * cpj[e] + sigmoid_fast(gi) * tanh_fast(gc);
+      cv[e] = cell;
+      hv[e] = sigmoid_fast(go) * tanh_fast(cell);
+      split_bf16(hv[e], hh.v[e], hl.v[e]);
+    }
+    float* ho = p.out + pix * hidden + ch0;
+    float* co_ = p.out2 + pix * hidden + ch0;
+    if (p.wide & TC_WIDE_OUT) {
+      st_global_256(ho, hv);
+      st_global_256(co_, cv);
+    } else {
+      *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+      *reinterpret_cast<float4*>(co_) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+      *reinterpret_cast<float4*>(co_ + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+    }
+    if (p.out_hi) {
+      *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0) = hh;
+      *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0) = hl;
+    }
+  } else if constexpr (EPI == ESSB_EPI_GRU_UR) {
+    // ConvGRU update / reset gates (submodules.py:267-268): columns co = 2*ch + {update, reset};
+    // 32 columns = 16 channels.  Writes update (fp32) and prev_state*reset as bf16 planes (the A
+    // operand of the out-gate convolution).
+    const int hidden = p.Cout >> 1;
+    const int ch0 = (n0 + c0) >> 1;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) cp[j][e] = 0.f;
-        if (valid && p.aux0 && c0 < p.BN) {
-          const float* src = p.aux0 + pix * hidden + ((n0 + c0) >> 2);
-          if (p.wide & TC_WIDE_AUX) {
-            ld_global_256(src, cp[j]);
-          } else {
-            const float4 c0v = *reinterpret_cast<const float4*>(src);
-            const float4 c1v = *reinterpret_cast<const float4*>(src + 4);
-            cp[j][0] = c0v.x; cp[j][1] = c0v.y; cp[j][2] = c0v.z; cp[j][3] = c0v.w;
-            cp[j][4] = c1v.x; cp[j][5] = c1v.y; cp[j][6] = c1v.z; cp[j][7] = c1v.w;
+    for (int g = 0; g < 2; ++g) {
+      float uv[8];
+      bf16x8 hh, hl;
+      float hp[8];
+      if (p.aux0) {
+        const float4 a0 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0 + g * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0 + g * 8 + 4);
+        hp[0] = a0.x; hp[1] = a0.y; hp[2] = a0.z; hp[3] = a0.w; hp[4] = a1.x; hp[5] = a1.y; hp[6] = a1.z; hp[7] = a1.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) hp[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int col = g * 16 + e * 2;
+        float gu = __uint_as_float(r[col]), gr = __uint_as_float(r[col + 1]);
+        if (s_bias) { gu += s_bias[n0 + c0 + col]; gr += s_bias[n0 + c0 + col + 1]; }
+        uv[e] = sigmoid_fast(gu);
+        split_bf16(hp[e] * sigmoid_fast(gr), hh.v[e], hl.v[e]);
+      }
+      float* uo = p.out + pix * hidden + ch0 + g * 8;
+      *reinterpret_cast<float4*>(uo) = make_float4(uv[0], uv[1], uv[2], uv[3]);
+      *reinterpret_cast<float4*>(uo + 4) = make_float4(uv[4], uv[5], uv[6], uv[7]);
+      *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0 + g * 8) = hh;
+      *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0 + g * 8) = hl;
+    }
+  } else if constexpr (EPI == ESSB_EPI_GRU_OUT) {
+    // ConvGRU out gate + blend (submodules.py:269-271): h' = h*(1-u) + tanh(acc + b)*u
+    const int hidden = p.Cout;
+    const int ch0 = n0 + c0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int ch = ch0 + g * 8;
+      float hv[8], hp[8], uu[8];
+      const float4 u0 = *reinterpret_cast<const float4*>(p.aux1 + pix * hidden + ch);
+      const float4 u1 = *reinterpret_cast<const float4*>(p.aux1 + pix * hidden + ch + 4);
+      uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w; uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
+      if (p.aux0) {
+        const float4 a0 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch);
+        const float4 a1 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch + 4);
+        hp[0] = a0.x; hp[1] = a0.y; hp[2] = a0.z; hp[3] = a0.w; hp[4] = a1.x; hp[5] = a1.y; hp[6] = a1.z; hp[7] = a1.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) hp[e] = 0.f;
+      }
+      bf16x8 hh, hl;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float x = __uint_as_float(r[g * 8 + e]);
+        if (s_bias) x += s_bias[ch + e];
+        hv[e] = hp[e] * (1.f - uu[e]) + tanh_fast(x) * uu[e];
+        split_bf16(hv[e], hh.v[e], hl.v[e]);
+      }
+      float* ho = p.out + pix * hidden + ch;
+      *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+      if (p.out_hi) {
+        *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch) = hh;
+        *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch) = hl;
+      }
+    }
+  } else {
+    const size_t opix = ((size_t)n * p.OHf + (oy * p.osy + p.ooy)) * p.OWf + (ox * p.osx + p.oox);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {  // 16 channels per group: 2 x 32 B of fp32, 32 B per bf16 plane
+      const int co = n0 + c0 + g * 16;
+      float v[2][8];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e >> 3][e & 7] = __uint_as_float(r[g * 16 + e]);
+      if (s_bias) {
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + co + e4 * 4);
+          float* vv = &v[e4 >> 1][(e4 & 1) * 4];
+          vv[0] += b4.x; vv[1] += b4.y; vv[2] += b4.z; vv[3] += b4.w;
+        }
+      }
+      if (p.res_pre) tc_add_res(p, p.res_pre + opix * p.ld_res + co, v);
+      if (p.act == ESSB_ACT_RELU) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e >> 3][e & 7] = fmaxf(v[e >> 3][e & 7], 0.f);
+      } else if (p.act == ESSB_ACT_SIGMOID) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e >> 3][e & 7] = essb_sigmoid(v[e >> 3][e & 7]);
+      }
+      if (p.res_post) tc_add_res(p, p.res_post + opix * p.ld_res + co, v);
+      if (p.out) {
+        float* o = p.out + opix * p.ldo + co;
+        if (p.wide & TC_WIDE_OUT) {
+          st_global_256(o, v[0]);
+          st_global_256(o + 8, v[1]);
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            *reinterpret_cast<float4*>(o + h * 8) = make_float4(v[h][0], v[h][1], v[h][2], v[h][3]);
+            *reinterpret_cast<float4*>(o + h * 8 + 4) = make_float4(v[h][4], v[h][5], v[h][6], v[h][7]);
           }
         }
       }
+      if (p.out_hi) {
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(v[e >> 2][(e & 3) * 2], h0, l0);
+          split_bf16(v[e >> 2][(e & 3) * 2 + 1], h1, l1);
+          ph[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          pl[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        __nv_bfloat16* oh = p.out_hi + opix * p.ld_planes + co;
+        __nv_bfloat16* ol = p.out_lo + opix * p.ld_planes + co;
+        if (p.wide & TC_WIDE_PLANES) {
+          st_global_256(oh, ph);
+          st_global_256(ol, pl);
+        } else {
+          *reinterpret_cast<uint4*>(oh) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          *reinterpret_cast<uint4*>(oh + 8) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+          *reinterpret_cast<uint4*>(ol) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          *reinterpret_cast<uint4*>(ol + 8) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+        }
+      }
+    }
+  }
+}
+
+// 256-bit L2-only load (split-K partials written by another SM: must not be served from this SM's L1)
+__device__ __forceinline__ void ld_global_cg_256(const float* ptr, float (&v)[8]) {
+  asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(ptr)
+               : "memory");
+}
+
+// LSTM: previous cell state of this thread's row for column chunk c0 (8 channels)
+__device__ __forceinline__ void tc_load_cprev(const TcParams& p, bool valid, size_t pix, int n0, int c0, float (&cpj)[8]) {
+  const int hidden = p.Cout >> 2;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) cpj[e] = 0.f;
+  if (valid && p.aux0 && c0 < p.BN) {
+    const float* src = p.aux0 + pix * hidden + ((n0 + c0) >> 2);
+    if (p.wide & TC_WIDE_AUX) {
+      ld_global_256(src, cpj);
+    } else {
+      const float4 c0v = *reinterpret_cast<const float4*>(src);
+      const float4 c1v = *reinterpret_cast<const float4*>(src + 4);
+      cpj[0] = c0v.x; cpj[1] = c0v.y; cpj[2] = c0v.z; cpj[3] = c0v.w;
+      cpj[4] = c1v.x; cpj[5] = c1v.y; cpj[6] = c1v.z; cpj[7] = c1v.w;
+    }
+  }
+}
+
+// One work unit: wait for the MMAs, TMEM -> registers -> fused epilogue -> global stores, then hand the TMEM
+// buffer back.  Shared by the classic and the halo-reuse kernels.  q = TMEM lane quarter (warp % 4), half =
+// which of the two warps of that quarter (interleaved 32-column chunks).  A split-K unit (un.slot >= 0) parks
+// its partial accumulator in splitk_ws instead; the warp that arrives last on the tile's counter sums all
+// slices in slice order and runs the epilogue.
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                                                 uint64_t* tempty_bar, uint32_t (&tph)[2], int local, const TcUnit& un,
+                                                 int q, int half, int lane, const float* __restrict__ s_bias) {
+  const int BW = 1 << p.bw_log2, BH = TC_M >> p.bw_log2;
+  const int buf = local & 1;
+  const int item = un.item;
+  const int nt = item % p.n_tiles;
+  int mt = item / p.n_tiles;
+  const int txi = mt % p.tiles_x; mt /= p.tiles_x;
+  const int tyi = mt % p.tiles_y;
+  const int n = mt / p.tiles_y;
+  const int m = q * 32 + lane;
+  const int oy = tyi * BH + (m >> p.bw_log2), ox = txi * BW + (m & (BW - 1));
+  const bool valid = oy < p.OH && ox < p.OW;
+  const int n0 = nt * p.BN;
+  const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
+  const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
+  float cp[4][8];
+  if (un.slot < 0) {
+    // LSTM: the previous cell state does not depend on the MMA -> fetch it BEFORE waiting for the
+    // accumulator so its latency hides under the main loop of this tile
+    if constexpr (EPI == ESSB_EPI_LSTM) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tc_load_cprev(p, valid, pix, n0, half * 32 + j * 64, cp[j]);
     }
     mbar_wait(&tfull_bar[buf], tph[buf]);
     tph[buf] ^= 1;
     tc_fence_after();
-    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c0 = half * 32 + j * 64;
@@ -156,177 +399,76 @@ __device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tme
       __syncwarp();
       tmem_ld32(t_addr + (uint32_t)c0, r);
       tmem_ld_wait();
-      if (!valid) {
-        // out-of-image rows of a partial tile: nothing to store
-      } else if constexpr (EPI == ESSB_EPI_LSTM) {
-        // columns co = 4*ch + {in, remember, out, cell}; 32 columns = 8 channels
-        const int hidden = p.Cout >> 2;
-        const int ch0 = (n0 + c0) >> 2;
-        float hv[8], cv[8];
-        bf16x8 hh, hl;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int co = n0 + c0 + e * 4;
-          float gi = __uint_as_float(r[e * 4 + 0]), gf = __uint_as_float(r[e * 4 + 1]);
-          float go = __uint_as_float(r[e * 4 + 2]), gc = __uint_as_float(r[e * 4 + 3]);
-          if (s_bias) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + co);
-            gi += b4.x; gf += b4.y; go += b4.z; gc += b4.w;
-          }
-          const float cell = sigmoid_fast(gf) * cp[j][e] + sigmoid_fast(gi) * tanh_fast(gc);
-          cv[e] = cell;
-          hv[e] = sigmoid_fast(go) * tanh_fast(cell);
-          split_bf16(hv[e], hh.v[e], hl.v[e]);
-        }
-        float* ho = p.out + pix * hidden + ch0;
-        float* co_ = p.out2 + pix * hidden + ch0;
-        if (p.wide & TC_WIDE_OUT) {
-          st_global_256(ho, hv);
-          st_global_256(co_, cv);
-        } else {
-          *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-          *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
-          *reinterpret_cast<float4*>(co_) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-          *reinterpret_cast<float4*>(co_ + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
-        }
-        if (p.out_hi) {
-          *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0) = hh;
-          *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0) = hl;
-        }
-      } else if constexpr (EPI == ESSB_EPI_GRU_UR) {
-        // ConvGRU update / reset gates (submodules.py:267-268): columns co = 2*ch + {update, reset};
-        // 32 columns = 16 channels.  Writes update (fp32) and prev_state*reset as bf16 planes (the A
-        // operand of the out-gate convolution).
-        const int hidden = p.Cout >> 1;
-        const int ch0 = (n0 + c0) >> 1;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float uv[8];
-          bf16x8 hh, hl;
-          float hp[8];
-          if (p.aux0) {
-            const float4 a0 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0 + g * 8);
-            const float4 a1 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0 + g * 8 + 4);
-            hp[0] = a0.x; hp[1] = a0.y; hp[2] = a0.z; hp[3] = a0.w; hp[4] = a1.x; hp[5] = a1.y; hp[6] = a1.z; hp[7] = a1.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) hp[e] = 0.f;
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int col = g * 16 + e * 2;
-            float gu = __uint_as_float(r[col]), gr = __uint_as_float(r[col + 1]);
-            if (s_bias) { gu += s_bias[n0 + c0 + col]; gr += s_bias[n0 + c0 + col + 1]; }
-            uv[e] = sigmoid_fast(gu);
-            split_bf16(hp[e] * sigmoid_fast(gr), hh.v[e], hl.v[e]);
-          }
-          float* uo = p.out + pix * hidden + ch0 + g * 8;
-          *reinterpret_cast<float4*>(uo) = make_float4(uv[0], uv[1], uv[2], uv[3]);
-          *reinterpret_cast<float4*>(uo + 4) = make_float4(uv[4], uv[5], uv[6], uv[7]);
-          *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0 + g * 8) = hh;
-          *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0 + g * 8) = hl;
-        }
-      } else if constexpr (EPI == ESSB_EPI_GRU_OUT) {
-        // ConvGRU out gate + blend (submodules.py:269-271): h' = h*(1-u) + tanh(acc + b)*u
-        const int hidden = p.Cout;
-        const int ch0 = n0 + c0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int ch = ch0 + g * 8;
-          float hv[8], hp[8], uu[8];
-          const float4 u0 = *reinterpret_cast<const float4*>(p.aux1 + pix * hidden + ch);
-          const float4 u1 = *reinterpret_cast<const float4*>(p.aux1 + pix * hidden + ch + 4);
-          uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w; uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
-          if (p.aux0) {
-            const float4 a0 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch);
-            const float4 a1 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch + 4);
-            hp[0] = a0.x; hp[1] = a0.y; hp[2] = a0.z; hp[3] = a0.w; hp[4] = a1.x; hp[5] = a1.y; hp[6] = a1.z; hp[7] = a1.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) hp[e] = 0.f;
-          }
-          bf16x8 hh, hl;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float x = __uint_as_float(r[g * 8 + e]);
-            if (s_bias) x += s_bias[ch + e];
-            hv[e] = hp[e] * (1.f - uu[e]) + tanh_fast(x) * uu[e];
-            split_bf16(hv[e], hh.v[e], hl.v[e]);
-          }
-          float* ho = p.out + pix * hidden + ch;
-          *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-          *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
-          if (p.out_hi) {
-            *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch) = hh;
-            *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch) = hl;
-          }
-        }
-      } else {
-        const size_t opix = ((size_t)n * p.OHf + (oy * p.osy + p.ooy)) * p.OWf + (ox * p.osx + p.oox);
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {  // 16 channels per group: 2 x 32 B of fp32, 32 B per bf16 plane
-          const int co = n0 + c0 + g * 16;
-          float v[2][8];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e >> 3][e & 7] = __uint_as_float(r[g * 16 + e]);
-          if (s_bias) {
-#pragma unroll
-            for (int e4 = 0; e4 < 4; ++e4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + co + e4 * 4);
-              float* vv = &v[e4 >> 1][(e4 & 1) * 4];
-              vv[0] += b4.x; vv[1] += b4.y; vv[2] += b4.z; vv[3] += b4.w;
-            }
-          }
-          if (p.res_pre) tc_add_res(p, p.res_pre + opix * p.ld_res + co, v);
-          if (p.act == ESSB_ACT_RELU) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e >> 3][e & 7] = fmaxf(v[e >> 3][e & 7], 0.f);
-          } else if (p.act == ESSB_ACT_SIGMOID) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e >> 3][e & 7] = essb_sigmoid(v[e >> 3][e & 7]);
-          }
-          if (p.res_post) tc_add_res(p, p.res_post + opix * p.ld_res + co, v);
-          if (p.out) {
-            float* o = p.out + opix * p.ldo + co;
-            if (p.wide & TC_WIDE_OUT) {
-              st_global_256(o, v[0]);
-              st_global_256(o + 8, v[1]);
-            } else {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                *reinterpret_cast<float4*>(o + h * 8) = make_float4(v[h][0], v[h][1], v[h][2], v[h][3]);
-                *reinterpret_cast<float4*>(o + h * 8 + 4) = make_float4(v[h][4], v[h][5], v[h][6], v[h][7]);
-              }
-            }
-          }
-          if (p.out_hi) {
-            uint32_t ph[8], pl[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(v[e >> 2][(e & 3) * 2], h0, l0);
-              split_bf16(v[e >> 2][(e & 3) * 2 + 1], h1, l1);
-              ph[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-              pl[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-            }
-            __nv_bfloat16* oh = p.out_hi + opix * p.ld_planes + co;
-            __nv_bfloat16* ol = p.out_lo + opix * p.ld_planes + co;
-            if (p.wide & TC_WIDE_PLANES) {
-              st_global_256(oh, ph);
-              st_global_256(ol, pl);
-            } else {
-              *reinterpret_cast<uint4*>(oh) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-              *reinterpret_cast<uint4*>(oh + 8) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-              *reinterpret_cast<uint4*>(ol) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-              *reinterpret_cast<uint4*>(ol + 8) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
-            }
-          }
-        }
-      }
+      if (valid) tc_epilogue_chunk<EPI>(p, r, n0, c0, pix, n, oy, ox, cp[j], s_bias);
     }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    return;
+  }
+  // ---- split-K slice
+  mbar_wait(&tfull_bar[buf], tph[buf]);
+  tph[buf] ^= 1;
+  tc_fence_after();
+  const int nchunks = p.BN >> 5;
+  float* ws_tile = p.splitk_ws + (size_t)un.slot * p.split * nchunks * (TC_M * 32);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c0 = half * 32 + j * 64;
+    if (c0 >= p.BN) break;
+    uint32_t r[32];
+    __syncwarp();
+    tmem_ld32(t_addr + (uint32_t)c0, r);
+    tmem_ld_wait();
+    float* dst = ws_tile + ((size_t)(un.part * nchunks + (c0 >> 5)) * TC_M + m) * 32;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t v8[8] = {r[e * 8], r[e * 8 + 1], r[e * 8 + 2], r[e * 8 + 3],
+                              r[e * 8 + 4], r[e * 8 + 5], r[e * 8 + 6], r[e * 8 + 7]};
+      st_global_256(dst + e * 8, v8);
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+  if (half * 32 >= p.BN) return;                       // this warp owns no columns of a narrow tile
+  __threadfence();                                     // partials visible device-wide before the arrival
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    int* cnt = p.splitk_cnt + un.slot * 8 + half * 4 + q;
+    last = atomicAdd(cnt, 1) == p.split - 1;
+    if (last) *cnt = 0;                                // ready for the next launch
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence();
+  if constexpr (EPI == ESSB_EPI_LSTM) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tc_load_cprev(p, valid, pix, n0, half * 32 + j * 64, cp[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c0 = half * 32 + j * 64;
+    if (c0 >= p.BN) break;
+    float acc[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+    for (int part = 0; part < p.split; ++part) {
+      const float* src = ws_tile + ((size_t)(part * nchunks + (c0 >> 5)) * TC_M + m) * 32;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v[8];
+        ld_global_cg_256(src + e * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[e * 8 + i] += v[i];
+      }
+    }
+    uint32_t r[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(acc[e]);
+    if (valid) tc_epilogue_chunk<EPI>(p, r, n0, c0, pix, n, oy, ox, cp[j], s_bias);
+  }
 }
 
 // ------------------------------------------------------------------------------------ the kernel
@@ -341,7 +483,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint64_t* empty_bar = bars + MAX_STAGES;      // [stages]
   uint64_t* tfull_bar = bars + 2 * MAX_STAGES;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* sfull_bar = tempty_bar + 2;         // [SCHED_DEPTH] scheduler ring: unit published
+  uint64_t* sempty_bar = sfull_bar + SCHED_DEPTH;  // [SCHED_DEPTH] unit read by the MMA warp + 8 epilogue warps
+  int* sched_ring = reinterpret_cast<int*>(sempty_bar + SCHED_DEPTH);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_ring + SCHED_DEPTH);
 
   // the shuffle tells ptxas the warp index is warp-uniform, so the role branches below are uniform branches
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -357,6 +502,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], 8);  // one arrive per epilogue warp
+    }
+    for (int i = 0; i < SCHED_DEPTH; ++i) {
+      mbar_init(&sfull_bar[i], 1);
+      mbar_init(&sempty_bar[i], 9);
     }
     fence_barrier_init();
     tma_prefetch_desc(&p.tmB_hi);
@@ -384,14 +533,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx_bytes = (uint32_t)p.tx_bytes;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int nt = item % p.n_tiles;
-        int mt = item / p.n_tiles;
+      for (int local = 0;; ++local) {
+        const int u = tc_sched_fetch(p, local, sched_ring, sfull_bar, sempty_bar);
+        if (u < 0) break;
+        const TcUnit un = tc_decode_unit(p, u, k_iters);
+        const int nt = un.item % p.n_tiles;
+        int mt = un.item / p.n_tiles;
         const int txi = mt % p.tiles_x; mt /= p.tiles_x;
         const int tyi = mt % p.tiles_y;
         const int n = mt / p.tiles_y;
         const int x0 = txi * BW, y0 = tyi * BH;
-        for (int it = 0; it < k_iters; ++it) {
+        for (int it = un.k0; it < un.k1; ++it) {
           const int tap = it / cpt;
           const int r = it - tap * cpt;
           const int seg = (r >= p.seg_chunks[0]) ? 1 : 0;
@@ -411,6 +563,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
+      tc_sched_finish(p);
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer (whole warp, convergent:
@@ -420,14 +573,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       int s = 0;
       uint32_t ph = 0;
       uint32_t tph[2] = {0, 0};
-      int local = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+      for (int local = 0;; ++local) {
+        const int u = tc_sched_read(local, lane, sched_ring, sfull_bar, sempty_bar);
+        if (u < 0) break;
+        const TcUnit un = tc_decode_unit(p, u, k_iters);
         const int buf = local & 1;
         mbar_wait(&tempty_bar[buf], tph[buf] ^ 1);  // epilogue has drained this accumulator
         tph[buf] ^= 1;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
-        for (int it = 0; it < k_iters; ++it) {
+        for (int it = un.k0; it < un.k1; ++it) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + (size_t)s * p.stage_bytes);
@@ -438,7 +593,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
             for (int k = 0; k < TC_KCH / 16; ++k) {
               const uint32_t ko = (uint32_t)(k * 2);  // +32 bytes (>>4) inside the 128 B swizzle row
-              umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, (it | k) != 0);
+              umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, ((it - un.k0) | k) != 0);
               umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
               umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
             }
@@ -447,7 +602,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
             for (int k = 0; k < TC_KCH / 16; ++k) {
               const uint32_t ko = (uint32_t)(k * 2);
-              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, (it | k) != 0);
+              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, ((it - un.k0) | k) != 0);
             }
           }
           umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
@@ -463,9 +618,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     uint32_t tph[2] = {0, 0};
-    int local = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local)
-      tc_epilogue_item<EPI>(p, tmem_base, tfull_bar, tempty_bar, tph, local, item, q, half, lane, s_bias);
+    for (int local = 0;; ++local) {
+      const int u = tc_sched_read(local, lane, sched_ring, sfull_bar, sempty_bar);
+      if (u < 0) break;
+      const TcUnit un = tc_decode_unit(p, u, k_iters);
+      tc_epilogue_item<EPI>(p, tmem_base, tfull_bar, tempty_bar, tph, local, un, q, half, lane, s_bias);
+    }
   }
 
   tc_fence_before();
@@ -505,7 +663,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
   uint64_t* b_empty = bars + 3 * MAX_STAGES;
   uint64_t* tfull_bar = bars + 4 * MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* sfull_bar = tempty_bar + 2;            // scheduler ring (see tc_sched_fetch / tc_sched_read)
+  uint64_t* sempty_bar = sfull_bar + SCHED_DEPTH;  // readers: B producer, MMA warp, 8 epilogue warps
+  int* sched_ring = reinterpret_cast<int*>(sempty_bar + SCHED_DEPTH);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_ring + SCHED_DEPTH);
   // the shuffle tells ptxas the warp index is warp-uniform, so the role branches below are uniform branches
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr int BW = 8, BH = 16;
@@ -514,6 +675,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }
+    for (int i = 0; i < SCHED_DEPTH; ++i) { mbar_init(&sfull_bar[i], 1); mbar_init(&sempty_bar[i], 10); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -538,7 +700,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx = (uint32_t)(p.passes == 3 ? 2 : 1) * (uint32_t)(p.halo_w * p.halo_h * 128);
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int local = 0;; ++local) {
+        const int item = tc_sched_fetch(p, local, sched_ring, sfull_bar, sempty_bar);   // whole tiles only
+        if (item < 0) break;
         int mt = item / p.n_tiles;
         const int txi = mt % p.tiles_x; mt /= p.tiles_x;
         const int tyi = mt % p.tiles_y;
@@ -556,14 +720,18 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
               if (++s == p.a_stages) { s = 0; ph ^= 1; }
             }
       }
+      tc_sched_finish(p);
     }
   } else if (warp == 2) {
     // ============================================================ B (weights) producer
-    if (lane == 0) {
+    {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx = (uint32_t)(p.passes == 3 ? 2 : 1) * (uint32_t)(p.BN * TC_KCH * 2);
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int local = 0;; ++local) {
+        const int item = tc_sched_read(local, lane, sched_ring, sfull_bar, sempty_bar);
+        if (item < 0) break;
+        if (lane != 0) continue;
         const int nt = item % p.n_tiles;
         for (int seg = 0; seg < p.nseg; ++seg)
           for (int c = 0; c < p.seg_chunks[seg]; ++c)
@@ -593,8 +761,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       uint32_t tph[2] = {0, 0};
-      int local = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+      for (int local = 0;; ++local) {
+        const int item = tc_sched_read(local, lane, sched_ring, sfull_bar, sempty_bar);
+        if (item < 0) break;
         const int buf = local & 1;
         mbar_wait(&tempty_bar[buf], tph[buf] ^ 1);
         tph[buf] ^= 1;
@@ -650,9 +819,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     uint32_t tph[2] = {0, 0};
-    int local = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local)
-      tc_epilogue_item<EPI>(p, tmem_base, tfull_bar, tempty_bar, tph, local, item, q, half, lane, s_bias);
+    for (int local = 0;; ++local) {
+      const int item = tc_sched_read(local, lane, sched_ring, sfull_bar, sempty_bar);
+      if (item < 0) break;
+      const TcUnit un = {item, 0, 0, 0, -1};
+      tc_epilogue_item<EPI>(p, tmem_base, tfull_bar, tempty_bar, tph, local, un, q, half, lane, s_bias);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1098,6 +1270,32 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // one CTA per SM: each CTA allocates all 512 TMEM columns
   cudaStream_t st = (cudaStream_t)stream;
   int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+  // ---- scheduler: whole tiles first, then the tiles of the partially filled last wave cut into K-slices
+  ESSB_REQUIRE(d->sched != nullptr, "essb_conv_tc_run: sched (2 zeroed int32) is required");
+  p.sched = d->sched;
+  p.n_whole = p.n_items;
+  p.split = 1;
+  p.splitk_ws = d->splitk_ws;
+  p.splitk_cnt = d->splitk_cnt;
+  if (!halo && d->splitk_ws && d->splitk_cnt) {
+    const int k_iters = d->ntaps * (p.seg_chunks[0] + p.seg_chunks[1]);
+    const int rounds = p.n_items / grid, rem = p.n_items % grid;
+    if (rounds >= 1 && rem > 0 && rem * 8 <= 148 * 8) {
+      const long long tile_bytes = (long long)TC_M * BN * (long long)sizeof(float);
+      int best = 1;
+      double best_cost = 1.0 - 0.08;   // a split must shorten the tail wave by at least 8 %
+      for (int S = 2; S <= 8 && S * 4 <= k_iters; ++S) {
+        if ((long long)rem * S * tile_bytes > d->splitk_ws_bytes) break;
+        const double cost = (double)((rem * S + grid - 1) / grid) / S;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = S; }
+      }
+      if (best > 1) {
+        p.n_whole = p.n_items - rem;
+        p.split = best;
+      }
+    }
+  }
+  p.n_units = p.n_whole + (p.n_items - p.n_whole) * p.split;
   cudaError_t e;
   if (halo) {
 #define ESSB_LAUNCH_HALO(EPI)                                                                                       \

@@ -1,6 +1,8 @@
 // Memory-bound helpers around the convolutions: weight packing, instance-norm statistics and
 // backward, event pre-processing, layout conversion.  All HBM-bound; coalesced float4 access,
 // grids sized from the element count.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -240,12 +242,18 @@ __global__ void __launch_bounds__(256) in_stats_kernel(const float* __restrict__
 __global__ void in_bwd_pass2_kernel(const float* __restrict__ g, const float* __restrict__ y, int ld_y,
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ gsum, float* __restrict__ dy, long long P, int C,
-                                    float inv_p, long long total) {
+                                    float inv_p, long long total, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int ld_planes, int c_write) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int CQ = C >> 2;
+  const int CQ = c_write >> 2;
   const int c = (int)(idx % CQ) * 4;
   const long long pix = idx / CQ;
+  if (c >= C) {  // zero channel padding of the bf16 planes (K padding of the tensor-core operand)
+    *reinterpret_cast<uint2*>(hi + pix * ld_planes + c) = make_uint2(0u, 0u);
+    *reinterpret_cast<uint2*>(lo + pix * ld_planes + c) = make_uint2(0u, 0u);
+    return;
+  }
   const int n = (int)(pix / P);
   const float4 gv = *reinterpret_cast<const float4*>(g + pix * C + c);
   const float4 yv = *reinterpret_cast<const float4*>(y + pix * ld_y + c);
@@ -262,7 +270,17 @@ __global__ void in_bwd_pass2_kernel(const float* __restrict__ g, const float* __
     const float xh = (ya[e] - ma[e]) * ra[e];
     o[e] = ra[e] * (ga[e] - gs[e * 2] * inv_p - xh * (gs[e * 2 + 1] * inv_p));
   }
-  *reinterpret_cast<float4*>(dy + pix * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+  if (dy) *reinterpret_cast<float4*>(dy + pix * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+  if (hi) {  // the gradient goes straight into the tcgen05 operand format (dgrad / wgrad of the producing conv)
+    __align__(8) __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      h[e] = __float2bfloat16_rn(o[e]);
+      l[e] = __float2bfloat16_rn(o[e] - __bfloat162float(h[e]));
+    }
+    *reinterpret_cast<uint2*>(hi + pix * ld_planes + c) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + pix * ld_planes + c) = *reinterpret_cast<const uint2*>(l);
+  }
 }
 
 // out[n,y,x,c] (+)= sum of the 2x2 children of in
@@ -589,15 +607,22 @@ extern "C" int essb_in_bwd_pass1(const float* dA, int ld_dA, int ups, const floa
 }
 
 extern "C" int essb_in_bwd_pass2(const float* g, const float* y, int ld_y, const float* mean, const float* rstd,
-                                 const float* gsum, float* dy, int N, int64_t P, int C, void* stream) {
-  ESSB_REQUIRE(g && y && mean && rstd && gsum && dy && N > 0 && P > 0 && C % 4 == 0, "essb_in_bwd_pass2: bad arguments");
+                                 const float* gsum, float* dy, uint16_t* dy_hi, uint16_t* dy_lo, int ld_planes, int N,
+                                 int64_t P, int C, void* stream) {
+  ESSB_REQUIRE(g && y && mean && rstd && gsum && (dy || dy_hi) && N > 0 && P > 0 && C % 4 == 0,
+               "essb_in_bwd_pass2: bad arguments");
+  ESSB_REQUIRE(!dy_hi || (dy_lo && ld_planes >= C && ld_planes % 4 == 0 && (reinterpret_cast<uintptr_t>(dy_hi) & 7u) == 0 &&
+                          (reinterpret_cast<uintptr_t>(dy_lo) & 7u) == 0),
+               "essb_in_bwd_pass2: bad planes");
   int rc;
   if ((rc = check_vec4(y, ld_y, "essb_in_bwd_pass2")) || (rc = check_vec4(g, 4, "essb_in_bwd_pass2")) ||
-      (rc = check_vec4(dy, 4, "essb_in_bwd_pass2")))
+      (dy && (rc = check_vec4(dy, 4, "essb_in_bwd_pass2"))))
     return rc;
-  const long long total = (long long)N * P * (C / 4);
-  in_bwd_pass2_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(g, y, ld_y, mean, rstd, gsum, dy, P,
-                                                                                C, 1.0f / (float)P, total);
+  const int c_write = dy_hi ? ld_planes : C;   // planes are written across their whole pitch (zeros beyond C)
+  const long long total = (long long)N * P * (c_write / 4);
+  in_bwd_pass2_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      g, y, ld_y, mean, rstd, gsum, dy, P, C, 1.0f / (float)P, total, reinterpret_cast<__nv_bfloat16*>(dy_hi),
+      reinterpret_cast<__nv_bfloat16*>(dy_lo), ld_planes, c_write);
   ESSB_LAUNCH_CHECK("essb_in_bwd_pass2");
   return ESSB_OK;
 }

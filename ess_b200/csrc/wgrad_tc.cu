@@ -30,6 +30,7 @@ struct WgTcParams {
   int nb;                // 64-channel boxes of dY (N = 64*nb)
   int stages, passes, stage_bytes;
   int off_alo, off_ghi, off_glo;
+  int pair;              // Cin <= 64: the two 64-row halves of the M tile are two TAPS (tap 2*i, 2*i+1) of the same channels
   int cin, cout;
   float* partial;
   int8_t dy[ESSB_MAX_TAPS], dx[ESSB_MAX_TAPS];
@@ -80,7 +81,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int per_split = p.ntaps * p.m_tiles;
+  const int tap_items = p.pair ? (p.ntaps + 1) / 2 : p.ntaps;   // tap (or tap-pair) items per split
+  const int per_split = tap_items * p.m_tiles;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -101,12 +103,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = smem + (size_t)s * p.stage_bytes;
           mbar_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
-          const int ax = x0 + p.dx[tap], ay = y0 + p.dy[tap];
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            tma_load_4d(st + j * WG_BOX_BYTES, &p.tmA_hi, &full_bar[s], mt * 128 + j * 64, ax, ay, n);
+            // pair mode: `tap` counts tap pairs; half j of the M tile is tap 2*tap + j (the odd tap out re-reads
+            // the last tap, its rows are dropped by the epilogue)
+            const int tj = p.pair ? min(2 * tap + j, p.ntaps - 1) : tap;
+            const int cj = p.pair ? 0 : mt * 128 + j * 64;
+            const int ax = x0 + p.dx[tj], ay = y0 + p.dy[tj];
+            tma_load_4d(st + j * WG_BOX_BYTES, &p.tmA_hi, &full_bar[s], cj, ax, ay, n);
             if (p.passes == 3)
-              tma_load_4d(st + p.off_alo + j * WG_BOX_BYTES, &p.tmA_lo, &full_bar[s], mt * 128 + j * 64, ax, ay, n);
+              tma_load_4d(st + p.off_alo + j * WG_BOX_BYTES, &p.tmA_lo, &full_bar[s], cj, ax, ay, n);
           }
           for (int j = 0; j < p.nb; ++j) {
             tma_load_4d(st + p.off_ghi + j * WG_BOX_BYTES, &p.tmG_hi, &full_bar[s], j * 64, x0, y0, n);
@@ -167,12 +173,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const int r = item - split * per_split;
       const int tap = r / p.m_tiles, mt = r - tap * p.m_tiles;
       const int buf = local & 1;
-      const int ci = mt * 128 + q * 32 + lane;
+      const int row = q * 32 + lane;
+      const int ci = p.pair ? (row & 63) : mt * 128 + row;
+      const int otap = p.pair ? 2 * tap + (row >> 6) : tap;
       mbar_wait(&tfull_bar[buf], tph[buf]);
       tph[buf] ^= 1;
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
-      float* dst = p.partial + (((size_t)split * p.ntaps + tap) * p.cin + ci) * p.cout;
+      float* dst = p.partial + (((size_t)split * p.ntaps + min(otap, p.ntaps - 1)) * p.cin + ci) * p.cout;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c0 = half * 32 + j * 64;
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         __syncwarp();
         tmem_ld32(t_addr + (uint32_t)c0, rr);
         tmem_ld_wait();
-        if (ci < p.cin && c0 < p.cout) {   // cout is a multiple of 32
+        if (ci < p.cin && otap < p.ntaps && c0 < p.cout) {   // cout is a multiple of 32
 #pragma unroll
           for (int e = 0; e < 32; e += 4)
             *reinterpret_cast<float4*>(dst + c0 + e) =
@@ -256,12 +264,13 @@ int wg_encode(CUtensorMap* tm, const void* base, int C, int ld, int N, int H, in
 }
 
 struct WgPlan {
-  int m_tiles, splits, patches_total, patches_per_split, tiles_x, tiles_y, bw_log2, nb;
+  int m_tiles, splits, patches_total, patches_per_split, tiles_x, tiles_y, bw_log2, nb, pair;
 };
 
 int wg_plan(const essb_wgrad_tc& d, WgPlan* pl) {
   if (d.Cin <= 0 || d.Cout <= 0 || d.Cout % 32 != 0 || d.Cout > 256 || d.g_ld % 64 != 0 || d.g_ld < d.Cout) return -1;
   pl->m_tiles = (d.Cin + 127) / 128;
+  pl->pair = (d.Cin <= 64 && d.ntaps >= 2) ? 1 : 0;
   pl->nb = (d.Cout + 63) / 64;
   int best = 4;
   double best_waste = 1e30;
@@ -275,7 +284,7 @@ int wg_plan(const essb_wgrad_tc& d, WgPlan* pl) {
   pl->tiles_x = (d.W + BW - 1) / BW;
   pl->tiles_y = (d.H + BH - 1) / BH;
   pl->patches_total = d.N * pl->tiles_x * pl->tiles_y;
-  const int per_split = d.ntaps * pl->m_tiles;
+  const int per_split = (pl->pair ? (d.ntaps + 1) / 2 : d.ntaps) * pl->m_tiles;
   int splits = (2 * 148 + per_split - 1) / per_split;
   const int max_splits = (pl->patches_total + 3) / 4;
   if (splits > max_splits) splits = max_splits;
@@ -319,7 +328,8 @@ extern "C" int essb_wgrad_tc_run(const essb_wgrad_tc* d, void* stream) {
     if ((rc = wg_encode(&p.tmG_lo, d->g_lo, d->g_ld, d->g_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK) return rc;
   }
   p.m_tiles = pl.m_tiles; p.splits = pl.splits; p.ntaps = d->ntaps;
-  p.n_items = pl.splits * d->ntaps * pl.m_tiles;
+  p.pair = pl.pair;
+  p.n_items = pl.splits * (pl.pair ? (d->ntaps + 1) / 2 : d->ntaps) * pl.m_tiles;
   p.patches_total = pl.patches_total; p.patches_per_split = pl.patches_per_split;
   p.tiles_x = pl.tiles_x; p.tiles_y = pl.tiles_y; p.bw_log2 = pl.bw_log2; p.nb = pl.nb;
   p.passes = d->passes;

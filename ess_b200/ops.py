@@ -5,6 +5,7 @@ only to own device memory and streams; every arithmetic op on the hot path is a 
 library.  Nothing here falls back to torch ops: a missing library or a failing call raises.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -165,9 +166,11 @@ def norm_act_add(y, mean=None, rstd=None, relu=False, res=None, out=None, c_off=
     return out
 
 
-def in_backward(dA, y, mean, rstd, relu, ups=0, c_off=0, extra=None):
+def in_backward(dA, y, mean, rstd, relu, ups=0, c_off=0, extra=None, planes_ld=0, want_fp32=True):
     """Gradient w.r.t. y of  A = [upsample2]( relu?( (y-mean)*rstd ) )  given dA (channel slice
-    [c_off, c_off+C) of dA's last dim).  y: [N, H, W, C]."""
+    [c_off, c_off+C) of dA's last dim).  y: [N, H, W, C].  planes_ld > 0: the second pass also (or, with
+    want_fp32=False, only) writes the gradient as bf16 hi/lo planes of pitch planes_ld (zero padded) and a
+    (dy | None, (hi, lo)) pair is returned."""
     N, H, W, Cc = y.shape
     dev = y.device
     blocks = _lib.lib().essb_in_bwd_blocks(H * W)
@@ -177,9 +180,14 @@ def in_backward(dA, y, mean, rstd, relu, ups=0, c_off=0, extra=None):
          _p(y), Cc, _p(mean), _p(rstd), int(relu), _p(g), _p(partial), N, H, W, Cc, _stream())
     totals = torch.empty((N, Cc, 2), device=dev, dtype=torch.float32)
     call('essb_partial_reduce', _p(partial), N, blocks, Cc, _p(totals), _stream())
-    dy = torch.empty_like(g)
-    call('essb_in_bwd_pass2', _p(g), _p(y), Cc, _p(mean), _p(rstd), _p(totals), _p(dy), N, H * W, Cc, _stream())
-    return dy
+    dy = torch.empty_like(g) if (want_fp32 or not planes_ld) else None
+    planes = None
+    if planes_ld:
+        planes = (torch.empty((N, H, W, planes_ld), device=dev, dtype=torch.bfloat16),
+                  torch.empty((N, H, W, planes_ld), device=dev, dtype=torch.bfloat16))
+    call('essb_in_bwd_pass2', _p(g), _p(y), Cc, _p(mean), _p(rstd), _p(totals), _p(dy),
+         _p(planes[0]) if planes else None, _p(planes[1]) if planes else None, planes_ld, N, H * W, Cc, _stream())
+    return (dy, planes) if planes_ld else dy
 
 
 def upsample2_bwd(dA, H, W, Cc, c_off=0, out=None, accumulate=False):
@@ -618,9 +626,39 @@ def conv_tc_s2(planes, w_hi, w_lo, k_per_tap, k, pad, N, H, W, Cout, passes, bia
     return out
 
 
+_TC_POOL = {}
+TC_SCHED_SLOTS = 256
+TC_SPLITK_WS_BYTES = 80 << 20      # covers 7 K-slices of the 84 tail tiles of the 1/8-scale ConvLSTM at B=8 (75 MB)
+# Split-K of the tail wave is OFF by default: measured on B200 (profiles/r01_bench_g_splitk.json) the fused
+# ConvLSTM kernel is power-bound, not tail-bound (SM clock drops to ~1.54 GHz under the 1 kW cap while the idle SMs
+# of the last wave give their power budget to the busy ones), so the extra partial-accumulator traffic costs
+# more (+7.7 % kernel time) than the recovered wave quantisation.  ESSB_TC_SPLITK=1 turns it on.
+SPLITK = os.environ.get('ESSB_TC_SPLITK', '0') == '1'
+
+
+def _tc_workspace(device):
+    """Per (device, stream) scratch of the tcgen05 launches: rotating scheduler slots (2 zeroed int32 each,
+    left zero by every launch), split-K arrival counters and the split-K partial-accumulator buffer.
+    Launches on one stream are ordered, so they can share the buffers."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ent = _TC_POOL.get(key)
+    if ent is None:
+        ent = {'sched': torch.zeros((TC_SCHED_SLOTS, 2), device=device, dtype=torch.int32), 'next': 0,
+               'cnt': torch.zeros((148 * 8,), device=device, dtype=torch.int32),
+               'ws': torch.empty((TC_SPLITK_WS_BYTES // 4,), device=device, dtype=torch.float32)}
+        _TC_POOL[key] = ent
+    return ent
+
+
 def conv_tc(d: ConvTc, tag=None):
     """essb_conv_tc_run; when _lib.PROFILE is a list, brackets the launch with CUDA events on the
     launching stream and records (tag, algorithmic FLOPs, start, end)."""
+    ent = _tc_workspace(torch.device('cuda', torch.cuda.current_device()))
+    slot = ent['next']
+    ent['next'] = (slot + 1) % TC_SCHED_SLOTS
+    d.sched = _p(ent['sched'], 2 * slot)
+    if SPLITK:
+        d.splitk_ws, d.splitk_cnt, d.splitk_ws_bytes = _p(ent['ws']), _p(ent['cnt']), TC_SPLITK_WS_BYTES
     prof = _lib.PROFILE
     if prof is None:
         call('essb_conv_tc_run', C.byref(d), _stream())

@@ -181,14 +181,14 @@ def _taps(k):
     return ops.taps_conv(k, k // 2)
 
 
-def _bias_grad(nd, gy):
+def _bias_grad(nd, gy, dev):
     """Bias gradient of a conv node.  A bias that feeds an InstanceNorm (every conv of the IN blocks,
     style_networks.py:162-163,174-183) is cancelled by the mean subtraction: the incoming gradient gy is the
     output of the InstanceNorm backward, whose per-(n, c) sum over pixels is identically zero (the reference
     produces ~1e-10 rounding noise there).  Those gradients are returned as exact zeros instead of being
     summed over all pixels; only a conv whose output is not normalised has a real bias gradient."""
     if nd.stats:
-        return torch.zeros((nd.cout,), device=gy.device, dtype=torch.float32)
+        return torch.zeros((nd.cout,), device=dev, dtype=torch.float32)
     return ops.colsum(gy, nd.cout)
 
 
@@ -208,6 +208,10 @@ class _DecoderFn(torch.autograd.Function):
         tc = module.mode != 'fp32'
         passes = 3 if module.mode == 'bf16x3' else 1
         ctx.mode = module.mode
+        # operand planes of every tensor-core conv are kept for its weight gradient (same bytes as the fp32
+        # activation; ~1.7 GB at B=8 DSEC) instead of being re-created in the backward pass
+        keep_planes = any(ctx.needs_input_grad[5:])
+        ctx.planes = {}
         for nd in nodes:
             if isinstance(nd, _Conv):
                 first = T[nd.srcs[0][0]]
@@ -234,6 +238,8 @@ class _DecoderFn(torch.autograd.Function):
                     w_hi, w_lo, kinp = ops.pack_weight_tc(w)
                     y = ops.conv_tc_dense((hi, lo), w_hi, w_lo, kinp, _taps(nd.k), N, H, W, nd.cout, passes, bias=bias,
                                           tag='seg_fwd')
+                    if keep_planes:
+                        ctx.planes[nd.out] = (hi, lo)
                     del hi, lo
                     T[nd.out] = y
                     if nd.stats:
@@ -279,19 +285,44 @@ class _DecoderFn(torch.autograd.Function):
             else:
                 need[nd.out] = need[nd.src] or (nd.res is not None and need[nd.res])
 
-        G = {}   # tensor id -> [grad NHWC tensor, owned]
+        G = {}   # tensor id -> [grad NHWC fp32 tensor | None, owned, bf16 (hi, lo) planes | None]
+        conv_of = {nd.out: nd for nd in nodes if isinstance(nd, _Conv)}
 
-        def add_grad(tid, g, owned):
+        def planes_spec(tid):
+            """How the InstanceNorm backward should emit the gradient of conv output `tid`: (pitch of the bf16
+            hi/lo planes or 0, fp32 copy still needed).  When the producing conv runs its dgrad and wgrad on the
+            tcgen05 kernels the gradient is written ONLY in their operand format (no fp32 round trip)."""
+            nd = conv_of.get(tid)
+            if nd is None or ctx.mode == 'fp32' or nd.k != 3 or nd.cout % 32:
+                return 0, True
+            ok = True
+            if need_p[nd.w] or need_p[nd.b]:
+                ok = P[nd.w].shape[1] % 64 == 0 and nd.cout <= 256 and (nd.stats or not need_p[nd.b])
+            for (sid, _, _) in nd.srcs:
+                if need[sid] and T[sid].shape[-1] not in (64, 128, 256):
+                    ok = False
+            return (nd.cout + 63) // 64 * 64, not ok
+
+        def add_grad(tid, g, owned, planes=None):
             if not need.get(tid, False):
                 return
             if tid not in G:
-                G[tid] = [g, owned]
+                G[tid] = [g, owned, planes]
             else:
                 cur = G[tid]
+                if cur[0] is None or g is None:
+                    raise RuntimeError('internal: plane-only gradient of a tensor with two consumers')
                 if not cur[1]:
                     cur[0] = cur[0].clone()
                     cur[1] = True
+                cur[2] = None
                 ops.norm_act_add(cur[0], res=g, out=cur[0])
+
+        def in_bwd(tid, dA, y, mean, rstd, relu, ups=0):
+            ld, want32 = planes_spec(tid)
+            if not ld:
+                return ops.in_backward(dA, y, mean, rstd, relu=relu, ups=ups), None
+            return ops.in_backward(dA, y, mean, rstd, relu=relu, ups=ups, planes_ld=ld, want_fp32=want32)
 
         for o, g in zip(module._outs, gouts):
             if g is not None:
@@ -301,12 +332,13 @@ class _DecoderFn(torch.autograd.Function):
         for nd in reversed(nodes):
             if nd.out not in G:
                 continue
-            gy = G.pop(nd.out)[0]
+            gy, _, gy_planes = G.pop(nd.out)
             if isinstance(nd, _Mat):
                 y = T[nd.src]
                 mean, rstd = S[nd.src]
                 if need[nd.src]:
-                    add_grad(nd.src, ops.in_backward(gy, y, mean, rstd, relu=nd.relu), True)
+                    g32, gpl = in_bwd(nd.src, gy, y, mean, rstd, nd.relu)
+                    add_grad(nd.src, g32, True, gpl)
                 if nd.res is not None:
                     add_grad(nd.res, gy, False)   # ownership not transferred: gy may alias a caller tensor
                 continue
@@ -318,7 +350,7 @@ class _DecoderFn(torch.autograd.Function):
             taps = _taps(nd.k)
             tc = ctx.mode != 'fp32' and nd.k == 3 and nd.cout % 32 == 0
             passes = 3 if ctx.mode == 'bf16x3' else 1
-            gplanes = None
+            gplanes = gy_planes
 
             def dy_planes():
                 """bf16 hi/lo planes of dY (channel-padded to a multiple of 64 with zeros), built once per node"""
@@ -343,19 +375,25 @@ class _DecoderFn(torch.autograd.Function):
                     if need_p[nd.b]:
                         grads[nd.b] = db
                 elif tc and cin_total % 64 == 0 and nd.cout <= 256:
-                    # tensor-core wgrad: re-create the conv's operand planes (cheaper than keeping them alive)
-                    hi = torch.empty((N, H, W, cin_total), device=gy.device, dtype=torch.bfloat16)
-                    lo = torch.empty_like(hi)
-                    co = 0
-                    for sg in segs:
-                        ops.split_bf16(sg, N, H, W, hi, lo, co)
-                        co += sg.C if sg.C is not None else sg.t.shape[-1]
-                    gplanes = dy_planes()
+                    # tensor-core wgrad: the conv's operand planes kept by the forward pass (re-created if absent)
+                    kept = ctx.planes.pop(nd.out, None)
+                    if kept is not None:
+                        hi, lo = kept
+                    else:
+                        hi = torch.empty((N, H, W, cin_total), device=w.device, dtype=torch.bfloat16)
+                        lo = torch.empty_like(hi)
+                        co = 0
+                        for sg in segs:
+                            ops.split_bf16(sg, N, H, W, hi, lo, co)
+                            co += sg.C if sg.C is not None else sg.t.shape[-1]
+                    del kept
+                    if gplanes is None:
+                        gplanes = dy_planes()
                     if need_p[nd.w]:
                         grads[nd.w] = ops.wgrad_tc((hi, lo), gplanes, cin_total, nd.cout, taps, N, H, W, passes).view(w.shape)
                     del hi, lo
                     if need_p[nd.b]:
-                        grads[nd.b] = _bias_grad(nd, gy)
+                        grads[nd.b] = _bias_grad(nd, gy, w.device)
                 else:
                     dw, db = ops.wgrad(segs, gy, N, H, W, H, W, nd.cout, taps, want_bias=need_p[nd.b])
                     if need_p[nd.w]:
@@ -381,7 +419,8 @@ class _DecoderFn(torch.autograd.Function):
                         wp = ops.pack_weight(wseg, swap_io=True)
                         dA, _, _, _ = ops.conv([Seg(gy)], wp, None, N, H, W, H, W, cs, dtaps)
                     if xf == 'nr':
-                        add_grad(sid, ops.in_backward(dA, src, S[sid][0], S[sid][1], relu=True, ups=ups), True)
+                        g32, gpl = in_bwd(sid, dA, src, S[sid][0], S[sid][1], True, ups=ups)
+                        add_grad(sid, g32, True, gpl)
                     elif ups:
                         add_grad(sid, ops.upsample2_bwd(dA, H >> 1, W >> 1, cs), True)
                     else:

@@ -161,9 +161,11 @@ int essb_in_stats(const float* y, int ld_y, float* partial, int N, int64_t P, in
 int essb_in_bwd_pass1(const float* dA, int ld_dA, int ups, const float* extra, int ld_extra,
                       const float* y, int ld_y, const float* mean, const float* rstd, int relu,
                       float* g, float* partial, int N, int H, int W, int C, void* stream);
+/* dy (fp32, pitch C) and/or its bf16 hi/lo planes (pitch ld_planes >= C, channels [C, ld_planes) zeroed:
+ * the operand format of the producing conv's tcgen05 dgrad / wgrad) -- either output may be NULL. */
 int essb_in_bwd_pass2(const float* g, const float* y, int ld_y, const float* mean, const float* rstd,
-                      const float* gsum /* [N][C][2] totals */, float* dy, int N, int64_t P, int C,
-                      void* stream);
+                      const float* gsum /* [N][C][2] totals */, float* dy, uint16_t* dy_hi, uint16_t* dy_lo,
+                      int ld_planes, int N, int64_t P, int C, void* stream);
 /* totals[N][C][2] = sum over blocks of partial (fixed order => deterministic) */
 int essb_partial_reduce(const float* partial, int N, int blocks, int C, float* totals, void* stream);
 /* out[c] = sum over rows of x[rows][ld] (bias gradients) */
@@ -325,6 +327,16 @@ typedef struct essb_conv_tc {
   float* out2;           /* LSTM: cell */
   uint16_t* out_hi;      /* optional bf16 planes of the result (LSTM: of the hidden state) */
   uint16_t* out_lo;
+  /* Dynamic tile scheduler (required): 2 int32 that are ZERO when the launch starts; the kernel leaves them
+   * zero again (last CTA resets), so a slot can be reused by the next launch on the same stream.  Launches
+   * that may overlap (different streams) need different slots. */
+  int32_t* sched;
+  /* Split-K of the last, partially filled wave of tiles (optional, NULL = off): fp32 partial-accumulator
+   * workspace and >= 148*8 zero-initialised int32 arrival counters (left zero by the kernel).  The library
+   * splits only as far as splitk_ws_bytes allows; the reduction order is fixed (deterministic). */
+  float* splitk_ws;
+  int32_t* splitk_cnt;
+  int64_t splitk_ws_bytes;
   int32_t n_views, nseg;
   int32_t seg_C[2];      /* channels consumed per segment (multiples of 64) */
   int32_t seg_view0[2];

@@ -25,6 +25,16 @@ def planes_of(x_nchw):
     return ops.split_bf16(ops.Seg(t), N, H, W)
 
 
+@pytest.fixture(autouse=True)
+def _splitk_on():
+    """The split-K tail of the tile scheduler is opt-in (ESSB_TC_SPLITK=1); these kernel tests keep it covered."""
+    from ess_b200 import ops
+    old = ops.SPLITK
+    ops.SPLITK = True
+    yield
+    ops.SPLITK = old
+
+
 def test_split_bf16_roundtrip():
     g = torch.Generator().manual_seed(0)
     x = torch.randn(2, 64, 5, 7, generator=g) * 3
@@ -35,7 +45,11 @@ def test_split_bf16_roundtrip():
 
 @pytest.mark.parametrize('passes,tol', [(3, 1e-3), (1, 3e-2)])
 @pytest.mark.parametrize('N,H,W,C,with_state', [(1, 8, 16, 64, True), (2, 13, 20, 64, False), (1, 7, 10, 128, True),
-                                                (1, 55, 80, 64, True)])
+                                                (1, 55, 80, 64, True),
+                                                # 168 tiles on 148 SMs: a full wave + 20 tail tiles cut into 4 K-slices
+                                                # (split-K path of the scheduler); 2 x 168 n-tiles, 40 tail tiles
+                                                (1, 112, 192, 64, True), (1, 112, 192, 128, True),
+                                                (2, 55, 80, 256, False)])
 def test_convlstm_tc(passes, tol, N, H, W, C, with_state):
     import ess_b200
     from ess_b200.e2vid import _interleave
@@ -110,3 +124,36 @@ def test_wgrad_tc(passes, tol, N, H, W, Cin, Cout):
     torch.cuda.synchronize()
     err = rel_err(dw.view(Cout, Cin, 3, 3).cpu(), gw)
     assert err < tol, err
+
+
+def test_convlstm_tc_splitk_is_deterministic_and_leaves_scratch_clean():
+    """The split-K tail (fixed slice order) must give bit-identical results run to run and equal the
+    whole-tile schedule to accumulation-order noise; the scheduler slots and arrival counters must be left zero."""
+    import ess_b200
+    from ess_b200.e2vid import _interleave
+    from ess_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    N, H, W, C = 1, 112, 192, 64
+    x = torch.randn(N, C, H, W, generator=g)
+    w = torch.randn(4 * C, 2 * C, 3, 3, generator=g) * 0.03
+    b = torch.randn(4 * C, generator=g) * 0.1
+    prev = (torch.randn(N, C, H, W, generator=g), torch.randn(N, C, H, W, generator=g))
+    m = ess_b200.E2VIDRecurrent.__new__(ess_b200.E2VIDRecurrent)
+    hi, lo, kinp = ops.pack_weight_tc(w.cuda(), interleave=4)
+    e = dict(lstm_tc=dict(hi=hi, lo=lo, k_per_tap=kinp), lstm_b=_interleave(b.cuda(), 4))
+    xp, hp, cp = planes_of(x), planes_of(prev[0]), nhwc(prev[1])
+    run = lambda: ess_b200.E2VIDRecurrent._lstm_tc(m, e, xp, hp, cp, N, H, W, C, 3)
+    assert ops.SPLITK
+    h1, c1, _, _ = run()
+    h2, c2, _, _ = run()
+    torch.cuda.synchronize()
+    assert torch.equal(h1, h2) and torch.equal(c1, c2)
+    ent = ops._tc_workspace(torch.device('cuda', torch.cuda.current_device()))
+    assert int(ent['sched'].abs().sum()) == 0 and int(ent['cnt'].abs().sum()) == 0
+    ops.SPLITK = False
+    try:
+        h3, c3, _, _ = run()
+    finally:
+        ops.SPLITK = True
+    torch.cuda.synchronize()
+    assert rel_err(h1, h3) < 1e-5 and rel_err(c1, c3) < 1e-5
