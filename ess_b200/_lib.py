@@ -162,6 +162,8 @@ def check(rc, what=''):
 _LAUNCHES = {'essb_wgrad_fp32': 4, 'essb_colsum': 2, 'essb_wgrad_tc_run': 2, 'essb_pw_conv_wgrad': 2}
 launch_count = 0
 PROFILE = None   # when a list: (tag, algorithmic_flops, start_event, end_event) per profiled launch
+PROFILE_TAGS = None   # optional set of tags to bracket with events (None = all); every event pair costs a few us of
+                      # stream time, so bench.py brackets only the dominant kernel inside its timed region
 
 
 def call(name, *args):

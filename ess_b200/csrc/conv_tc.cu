@@ -77,6 +77,7 @@ struct TcParams {
   int n_groups;                          // tap groups = views actually used; taps are sorted by group
   int8_t grp_view[MAX_VIEWS], grp_first[MAX_VIEWS], grp_count[MAX_VIEWS];
   // dynamic tile scheduler + split-K tail (see TcUnit)
+  int tmem_cols, tmem_buf_stride;        // TMEM columns allocated per CTA (power of two) / column offset of accumulator buffer 1
   int* sched;                            // [0] next unit, [1] CTAs done; zero before the launch, reset by the last CTA
   int n_units, n_whole, split;           // units [0, n_whole) are whole tiles; the rest are 1/split K-slices of the tail tiles
   float* splitk_ws;                      // [tail tile][part][32-col chunk][128 rows][32] fp32 partial accumulators
@@ -379,7 +380,7 @@ __device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tme
   const bool valid = oy < p.OH && ox < p.OW;
   const int n0 = nt * p.BN;
   const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
-  const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
+  const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.tmem_buf_stride);
   float cp[4][8];
   if (un.slot < 0) {
     // LSTM: the previous cell state does not depend on the MMA -> fetch it BEFORE waiting for the
@@ -651,7 +652,7 @@ __device__ __forceinline__ UDesc make_smem_desc_sbo(uint32_t saddr, uint32_t sbo
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_base = smem;
@@ -680,7 +681,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(512u)
+                 "r"((uint32_t)p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -768,7 +769,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
         mbar_wait(&tempty_bar[buf], tph[buf] ^ 1);
         tph[buf] ^= 1;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.tmem_buf_stride);
         uint32_t acc = 0;
         for (int seg = 0; seg < p.nseg; ++seg)
           for (int c = 0; c < p.seg_chunks[seg]; ++c)
@@ -830,7 +831,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -1124,6 +1125,7 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   static const int halo_env = [] { const char* e = getenv("ESSB_TC_HALO"); return e ? atoi(e) : 1; }();
   static const int baseoff_env = 0;
   bool halo = halo_env != 0 && BN <= 128 && d->ntaps >= 2;
+  int halo_occ = 1;
   int hx0 = 0, hx1 = 0, hy0 = 0, hy1 = 0;
   if (halo) {
     hx0 = hx1 = d->dx[0]; hy0 = hy1 = d->dy[0];
@@ -1140,7 +1142,18 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
     const int b_plane = BN * TC_KCH * 2;
     p.b_lo_off = b_plane;
     p.b_tap_bytes = planes * b_plane;
-    const int budget = 200 * 1024;
+    // Two CTAs per SM (ESSB_TC_OCC=2, default) when the pipeline fits half an SM's shared memory: the narrow-N
+    // layers are latency-bound (42 % tensor-pipe utilisation for the first encoder at one CTA/SM, ncu), so a
+    // second resident CTA with its own TMEM accumulators fills the stalls; each CTA then allocates only the
+    // TMEM columns it needs (2 x BN) instead of all 512.
+    static const int occ_env = [] { const char* e = getenv("ESSB_TC_OCC"); return e ? atoi(e) : 2; }();
+    const int tail_bytes = 1024 + 512 + TC_BIAS_SMEM_FLOATS * (int)sizeof(float);
+    int budget = 200 * 1024;
+    halo_occ = 1;
+    if (occ_env >= 2 && 2 * BN <= 256) {
+      const int half = 112 * 1024 - tail_bytes;
+      if (p.a_stage_bytes + 2 * p.b_tap_bytes <= half) { budget = half; halo_occ = 2; }
+    }
     p.a_stages = (2 * p.a_stage_bytes + 3 * p.b_tap_bytes <= budget) ? 2 : 1;
     // Narrow tiles (N <= 64) are bound by the MMA thread's per-stage cost (barrier wait + fence + commit, ~200
     // cycles) rather than by tensor work (12 MMAs x N/2 cycles per tap): put G taps behind one barrier.
@@ -1267,9 +1280,20 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   const size_t tail = 1024 /*align slack*/ + 512 /*barriers*/ + TC_BIAS_SMEM_FLOATS * sizeof(float);
   size_t smem_bytes = (size_t)stages * p.stage_bytes + tail;
   if (halo) smem_bytes = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + tail;
-  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // one CTA per SM: each CTA allocates all 512 TMEM columns
+  p.tmem_cols = 512;
+  p.tmem_buf_stride = 256;
+  if (halo && halo_occ == 2) {
+    int cols = 32;
+    while (cols < 2 * BN) cols <<= 1;
+    p.tmem_cols = cols;
+    p.tmem_buf_stride = BN;
+    if (smem_bytes < 80 * 1024) smem_bytes = 80 * 1024;  // at most two CTAs per SM (2 x tmem_cols <= 512)
+  } else if (smem_bytes < 120 * 1024) {
+    smem_bytes = 120 * 1024;  // one CTA per SM: each CTA allocates all 512 TMEM columns
+  }
   cudaStream_t st = (cudaStream_t)stream;
-  int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+  const int max_ctas = num_sms() * ((halo && halo_occ == 2) ? 2 : 1);
+  int grid = p.n_items < max_ctas ? p.n_items : max_ctas;
   // ---- scheduler: whole tiles first, then the tiles of the partially filled last wave cut into K-slices
   ESSB_REQUIRE(d->sched != nullptr, "essb_conv_tc_run: sched (2 zeroed int32) is required");
   p.sched = d->sched;

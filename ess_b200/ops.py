@@ -471,7 +471,7 @@ def wgrad_tc(a_planes, g_planes, Cin, Cout, taps, N, H, W, passes, tag='seg_wgra
     ws = torch.empty((int(nbytes) // 4 + 4,), device=dev, dtype=torch.float32)
     d.dw, d.workspace, d.workspace_bytes = _p(dw), _p(ws), ws.numel() * 4
     prof = _lib.PROFILE
-    if prof is None:
+    if prof is None or (_lib.PROFILE_TAGS is not None and tag not in _lib.PROFILE_TAGS):
         call('essb_wgrad_tc_run', C.byref(d), _stream())
     else:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -660,7 +660,7 @@ def conv_tc(d: ConvTc, tag=None):
     if SPLITK:
         d.splitk_ws, d.splitk_cnt, d.splitk_ws_bytes = _p(ent['ws']), _p(ent['cnt']), TC_SPLITK_WS_BYTES
     prof = _lib.PROFILE
-    if prof is None:
+    if prof is None or (_lib.PROFILE_TAGS is not None and tag not in _lib.PROFILE_TAGS):
         call('essb_conv_tc_run', C.byref(d), _stream())
         return
     k = sum(d.seg_C[s] for s in range(d.nseg)) * d.ntaps
