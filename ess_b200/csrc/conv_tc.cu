@@ -78,6 +78,7 @@ struct TcParams {
   int8_t grp_view[MAX_VIEWS], grp_first[MAX_VIEWS], grp_count[MAX_VIEWS];
   // dynamic tile scheduler + split-K tail (see TcUnit)
   int tmem_cols, tmem_buf_stride;        // TMEM columns allocated per CTA (power of two) / column offset of accumulator buffer 1
+  int fuse_b;                            // bf16x3 with 2*BN <= 256: A_hi x [B_hi; B_lo] is ONE MMA of N = 2*BN (see below)
   int* sched;                            // [0] next unit, [1] CTAs done; zero before the launch, reset by the last CTA
   int n_units, n_whole, split;           // units [0, n_whole) are whole tiles; the rest are 1/split K-slices of the tail tiles
   float* splitk_ws;                      // [tail tile][part][32-col chunk][128 rows][32] fp32 partial accumulators
@@ -399,7 +400,15 @@ __device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tme
       uint32_t r[32];
       __syncwarp();
       tmem_ld32(t_addr + (uint32_t)c0, r);
-      tmem_ld_wait();
+      if (p.fuse_b) {  // columns [BN, 2*BN) hold the A_hi x B_lo products of the same outputs
+        uint32_t r2[32];
+        tmem_ld32(t_addr + (uint32_t)(p.BN + c0), r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+      } else {
+        tmem_ld_wait();
+      }
       if (valid) tc_epilogue_chunk<EPI>(p, r, n0, c0, pix, n, oy, ox, cp[j], s_bias);
     }
     tc_fence_before();
@@ -758,6 +767,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __g
     // ============================================================ MMA issuer (whole warp, convergent)
     {
       const uint32_t idesc = make_idesc(TC_M, p.BN);
+      const uint32_t idesc2 = make_idesc(TC_M, 2 * p.BN);
       const uint32_t sbo = (uint32_t)p.halo_w * 128u;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
@@ -788,7 +798,20 @@ __global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __g
                 const uint32_t a_off = (uint32_t)((p.dy[t] - p.hy0) * p.halo_w + (p.dx[t] - p.hx0)) * 128u;
                 const UDesc a_hi = make_smem_desc_sbo(a_addr + a_off, sbo);
                 const UDesc b_hi = make_smem_desc(b_addr);
-                if (p.passes == 3) {
+                if (p.passes == 3 && p.fuse_b) {
+                  // B_hi and B_lo tiles are adjacent K-major tiles, i.e. ONE tile of 2*BN rows: A_hi x [B_hi; B_lo]
+                  // is a single MMA of N = 2*BN whose upper BN accumulator columns collect the hi*lo products
+                  // (added back by the epilogue).  Two MMAs and two A reads per K-step instead of three: the
+                  // narrow layers are bound by the shared-memory operand feed, not by tensor math.
+                  const UDesc a_lo = make_smem_desc_sbo(a_addr + p.a_lo_off + a_off, sbo);
+#pragma unroll
+                  for (int k = 0; k < TC_KCH / 16; ++k) {
+                    const uint32_t ko = (uint32_t)(k * 2);
+                    umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc2, acc);
+                    umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
+                    acc = 1u;
+                  }
+                } else if (p.passes == 3) {
                   const UDesc a_lo = make_smem_desc_sbo(a_addr + p.a_lo_off + a_off, sbo);
                   const UDesc b_lo = make_smem_desc(b_addr + p.b_lo_off);
 #pragma unroll
@@ -1126,6 +1149,7 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   static const int baseoff_env = 0;
   bool halo = halo_env != 0 && BN <= 128 && d->ntaps >= 2;
   int halo_occ = 1;
+  bool halo_fuse = false;
   int hx0 = 0, hx1 = 0, hy0 = 0, hy1 = 0;
   if (halo) {
     hx0 = hx1 = d->dx[0]; hy0 = hy1 = d->dy[0];
@@ -1150,7 +1174,10 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
     const int tail_bytes = 1024 + 512 + TC_BIAS_SMEM_FLOATS * (int)sizeof(float);
     int budget = 200 * 1024;
     halo_occ = 1;
-    if (occ_env >= 2 && 2 * BN <= 256) {
+    static const int fuse_env = [] { const char* e = getenv("ESSB_TC_FUSEB"); return e ? atoi(e) : 1; }();
+    halo_fuse = fuse_env != 0 && d->passes == 3 && 2 * BN <= 256;
+    // TMEM per CTA: two accumulator buffers of BN (or 2*BN when fused) columns; two CTAs/SM need <= 256 each
+    if (occ_env >= 2 && 2 * BN * (halo_fuse ? 2 : 1) <= 256) {
       const int half = 112 * 1024 - tail_bytes;
       if (p.a_stage_bytes + 2 * p.b_tap_bytes <= half) { budget = half; halo_occ = 2; }
     }
@@ -1282,11 +1309,13 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   if (halo) smem_bytes = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + tail;
   p.tmem_cols = 512;
   p.tmem_buf_stride = 256;
+  p.fuse_b = (halo && halo_fuse) ? 1 : 0;
   if (halo && halo_occ == 2) {
+    const int stride = BN * (halo_fuse ? 2 : 1);
     int cols = 32;
-    while (cols < 2 * BN) cols <<= 1;
+    while (cols < 2 * stride) cols <<= 1;
     p.tmem_cols = cols;
-    p.tmem_buf_stride = BN;
+    p.tmem_buf_stride = stride;
     if (smem_bytes < 80 * 1024) smem_bytes = 80 * 1024;  // at most two CTAs per SM (2 x tmem_cols <= 512)
   } else if (smem_bytes < 120 * 1024) {
     smem_bytes = 120 * 1024;  // one CTA per SM: each CTA allocates all 512 TMEM columns

@@ -14,30 +14,58 @@ namespace {
 constexpr int PW_THREADS = 256;
 constexpr int PW_MAX_COUT = 16;
 
+// 16-byte global -> shared copy that needs no register staging (all of a thread's copies are in flight at once)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Pixels per block: the block's [TPIX][CIN] fp32 slab is staged through shared memory (row pitch CIN + 4 floats:
+// 128-bit row reads by consecutive threads are bank-conflict free), so every global access is a fully
+// coalesced 128-bit one even though a thread owns a whole pixel row.
+template <int CIN>
+struct PwTile {
+  static constexpr int TPIX = CIN == 32 ? 256 : 128;
+  static constexpr int PITCH = CIN + 4;
+};
+
 // out[p][k] = act( sum_c f(x[p][c]) * w[k][c] + bias[k] ),  f = optional (x - mean) * rstd, ReLU
 template <int CIN>
 __global__ void __launch_bounds__(PW_THREADS) pw_conv_fwd_kernel(essb_src s, const float* __restrict__ w,
                                                                  const float* __restrict__ bias,
                                                                  float* __restrict__ out, int ldo, long long rows,
                                                                  long long P, int Cout, int act) {
+  constexpr int TPIX = PwTile<CIN>::TPIX, PITCH = PwTile<CIN>::PITCH, C4 = CIN / 4;
   __shared__ __align__(16) float w_s[PW_MAX_COUT * CIN];
   __shared__ float b_s[PW_MAX_COUT];
-  __shared__ float o_s[PW_THREADS * PW_MAX_COUT];
+  __shared__ __align__(16) float x_s[TPIX * PITCH];     // input slab, later the [TPIX][Cout] output slab
   for (int i = threadIdx.x; i < Cout * CIN; i += PW_THREADS) w_s[i] = w[i];
   if (threadIdx.x < Cout) b_s[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  const long long row0 = (long long)blockIdx.x * TPIX;
+  const long long left = rows - row0;
+  const int rows_here = left < TPIX ? (int)left : TPIX;
+  for (int i = threadIdx.x; i < rows_here * C4; i += PW_THREADS) {
+    const int r = i / C4, c4 = i - r * C4;
+    cp_async16(x_s + r * PITCH + c4 * 4, s.ptr + (row0 + r) * s.ld + c4 * 4);
+  }
+  cp_async_wait_all();
   __syncthreads();
-  const long long row0 = (long long)blockIdx.x * PW_THREADS;
-  const long long row = row0 + threadIdx.x;
-  if (row < rows) {
+  float ov[PW_MAX_COUT];
+  const bool active = threadIdx.x < rows_here;
+  if (active) {
     float xv[CIN];
-    const float* src = s.ptr + row * s.ld;
 #pragma unroll
     for (int c = 0; c < CIN; c += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(src + c);
+      const float4 v = *reinterpret_cast<const float4*>(x_s + threadIdx.x * PITCH + c);
       xv[c] = v.x; xv[c + 1] = v.y; xv[c + 2] = v.z; xv[c + 3] = v.w;
     }
     if (s.mean) {
-      const long long n = row / P;
+      const long long n = (row0 + threadIdx.x) / P;
       const float* mp = s.mean + n * CIN;
       const float* rp = s.rstd + n * CIN;
 #pragma unroll
@@ -52,32 +80,40 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_fwd_kernel(essb_src s, con
 #pragma unroll
       for (int c = 0; c < CIN; ++c) xv[c] = fmaxf(xv[c], 0.f);
     }
-    for (int k = 0; k < Cout; ++k) {
-      float a0 = b_s[k], a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      const float* wk = w_s + k * CIN;
 #pragma unroll
-      for (int c = 0; c < CIN; c += 4) {
-        const float4 ww = *reinterpret_cast<const float4*>(wk + c);
-        a0 = fmaf(xv[c], ww.x, a0); a1 = fmaf(xv[c + 1], ww.y, a1);
-        a2 = fmaf(xv[c + 2], ww.z, a2); a3 = fmaf(xv[c + 3], ww.w, a3);
+    for (int k = 0; k < PW_MAX_COUT; ++k) {
+      ov[k] = 0.f;
+      if (k < Cout) {
+        float a0 = b_s[k], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float* wk = w_s + k * CIN;
+#pragma unroll
+        for (int c = 0; c < CIN; c += 4) {
+          const float4 ww = *reinterpret_cast<const float4*>(wk + c);
+          a0 = fmaf(xv[c], ww.x, a0); a1 = fmaf(xv[c + 1], ww.y, a1);
+          a2 = fmaf(xv[c + 2], ww.z, a2); a3 = fmaf(xv[c + 3], ww.w, a3);
+        }
+        float v = (a0 + a1) + (a2 + a3);
+        if (act == ESSB_ACT_RELU) v = fmaxf(v, 0.f);
+        else if (act == ESSB_ACT_SIGMOID) v = essb_sigmoid(v);
+        ov[k] = v;
       }
-      float v = (a0 + a1) + (a2 + a3);
-      if (act == ESSB_ACT_RELU) v = fmaxf(v, 0.f);
-      else if (act == ESSB_ACT_SIGMOID) v = essb_sigmoid(v);
-      o_s[threadIdx.x * Cout + k] = v;
     }
+  }
+  __syncthreads();                                      // every row has been read: reuse x_s for the outputs
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < PW_MAX_COUT; ++k)
+      if (k < Cout) x_s[threadIdx.x * Cout + k] = ov[k];
   }
   __syncthreads();
   // coalesced write-back of the block's [rows_here][Cout] slab
-  const long long left = rows - row0;
-  const int rows_here = left < PW_THREADS ? (int)left : PW_THREADS;
   if (ldo == Cout) {
     float* dst = out + row0 * Cout;
-    for (int i = threadIdx.x; i < rows_here * Cout; i += PW_THREADS) dst[i] = o_s[i];
+    for (int i = threadIdx.x; i < rows_here * Cout; i += PW_THREADS) dst[i] = x_s[i];
   } else {
     for (int i = threadIdx.x; i < rows_here * Cout; i += PW_THREADS) {
       const int r = i / Cout, k = i - r * Cout;
-      out[(row0 + r) * ldo + k] = o_s[i];
+      out[(row0 + r) * ldo + k] = x_s[i];
     }
   }
 }
@@ -88,134 +124,155 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_dgrad_kernel(const float* 
                                                                    const float* __restrict__ w,
                                                                    float* __restrict__ dx, int ld_dx, long long rows,
                                                                    int Cout) {
+  constexpr int TPIX = PwTile<CIN>::TPIX, PITCH = PwTile<CIN>::PITCH, C4 = CIN / 4;
   __shared__ __align__(16) float w_s[PW_MAX_COUT * CIN];
-  __shared__ float g_s[PW_THREADS * PW_MAX_COUT];
+  __shared__ __align__(16) float t_s[TPIX * PITCH];     // dy slab [TPIX][Cout], later the dx slab [TPIX][PITCH]
   for (int i = threadIdx.x; i < Cout * CIN; i += PW_THREADS) w_s[i] = w[i];
-  const long long row0 = (long long)blockIdx.x * PW_THREADS;
+  const long long row0 = (long long)blockIdx.x * TPIX;
   const long long left = rows - row0;
-  const int rows_here = left < PW_THREADS ? (int)left : PW_THREADS;
+  const int rows_here = left < TPIX ? (int)left : TPIX;
   if (ld_dy == Cout) {
     const float* src = dy + row0 * Cout;
-    for (int i = threadIdx.x; i < rows_here * Cout; i += PW_THREADS) g_s[i] = src[i];
+    for (int i = threadIdx.x; i < rows_here * Cout; i += PW_THREADS) cp_async4(t_s + i, src + i);
   } else {
     for (int i = threadIdx.x; i < rows_here * Cout; i += PW_THREADS) {
       const int r = i / Cout, k = i - r * Cout;
-      g_s[i] = dy[(row0 + r) * ld_dy + k];
+      cp_async4(t_s + i, dy + (row0 + r) * ld_dy + k);
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const bool active = threadIdx.x < rows_here;
+  float g[PW_MAX_COUT];
+#pragma unroll
+  for (int k = 0; k < PW_MAX_COUT; ++k) g[k] = (active && k < Cout) ? t_s[threadIdx.x * Cout + k] : 0.f;
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < CIN; c += 4) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < PW_MAX_COUT; ++k) {
+        if (k < Cout) {
+          const float4 ww = *reinterpret_cast<const float4*>(w_s + k * CIN + c);
+          a.x = fmaf(g[k], ww.x, a.x); a.y = fmaf(g[k], ww.y, a.y);
+          a.z = fmaf(g[k], ww.z, a.z); a.w = fmaf(g[k], ww.w, a.w);
+        }
+      }
+      *reinterpret_cast<float4*>(t_s + threadIdx.x * PITCH + c) = a;
     }
   }
   __syncthreads();
-  if (threadIdx.x >= rows_here) return;
-  float g[PW_MAX_COUT];
-#pragma unroll
-  for (int k = 0; k < PW_MAX_COUT; ++k) g[k] = k < Cout ? g_s[threadIdx.x * Cout + k] : 0.f;
-  float* dst = dx + (row0 + threadIdx.x) * ld_dx;
-#pragma unroll
-  for (int c = 0; c < CIN; c += 4) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < PW_MAX_COUT; ++k) {
-      if (k < Cout) {
-        const float4 ww = *reinterpret_cast<const float4*>(w_s + k * CIN + c);
-        a.x = fmaf(g[k], ww.x, a.x); a.y = fmaf(g[k], ww.y, a.y);
-        a.z = fmaf(g[k], ww.z, a.z); a.w = fmaf(g[k], ww.w, a.w);
-      }
-    }
-    *reinterpret_cast<float4*>(dst + c) = a;
+  for (int i = threadIdx.x; i < rows_here * C4; i += PW_THREADS) {
+    const int r = i / C4, c4 = i - r * C4;
+    *reinterpret_cast<float4*>(dx + (row0 + r) * ld_dx + c4 * 4) = *reinterpret_cast<const float4*>(t_s + r * PITCH + c4 * 4);
   }
 }
 
-// part[block][k][c] = sum over the block's rows of dy[p][k] * f(x[p][c]);  part[block][Cout][k] = sum dy[p][k]
-// lane = input channel (CPL channels per lane: lane, lane + 32), one pixel row per warp iteration.
-template <int CPL>
+// part[block][k][c] = sum over the block's rows of dy[p][k] * f(x[p][c]);  part[block][16][k] = sum dy[p][k].
+// A warp instruction loads RPW = 128 / CIN consecutive pixel rows as float4 per lane (fully coalesced); lane =
+// (row within the group, 4-channel group).  Each lane keeps 4 x 16 accumulators; row groups are folded with
+// shuffles once at the end.
+template <int CIN>
 __global__ void __launch_bounds__(PW_THREADS) pw_conv_wgrad_kernel(essb_src s, const float* __restrict__ dy, int ld_dy,
                                                                    long long rows, long long P, int Cout,
                                                                    long long rows_per_block, float* __restrict__ part) {
-  constexpr int CIN = 32 * CPL;
-  constexpr int GP = PW_MAX_COUT;                      // padded dy row in shared memory
-  __shared__ __align__(16) float g_s[PW_THREADS * GP];
+  constexpr int C4 = CIN / 4;                          // lanes per pixel row
+  constexpr int RPW = 32 / C4;                         // pixel rows per warp load (4 or 2)
+  constexpr int GP = PW_MAX_COUT + 4;                  // dy row pitch in shared memory (conflict-free 128-bit reads)
+  constexpr int TROWS = PW_THREADS;                    // rows per staged dy tile
+  __shared__ __align__(16) float g_s[TROWS * GP];
   __shared__ float red[PW_MAX_COUT + 1][CIN];          // cross-warp reduction ([PW_MAX_COUT] row = bias partials)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = lane % C4, rg = lane / C4;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
-  float acc[CPL][PW_MAX_COUT];
-  float accb = 0.f;
+  float acc[4][PW_MAX_COUT];
+  float accb[PW_MAX_COUT];
 #pragma unroll
-  for (int j = 0; j < CPL; ++j)
+  for (int k = 0; k < PW_MAX_COUT; ++k) {
+    accb[k] = 0.f;
 #pragma unroll
-    for (int k = 0; k < PW_MAX_COUT; ++k) acc[j][k] = 0.f;
-
-  for (long long t0 = r0; t0 < r1; t0 += PW_THREADS) {
+    for (int j = 0; j < 4; ++j) acc[j][k] = 0.f;
+  }
+  for (long long t0 = r0; t0 < r1; t0 += TROWS) {
     const long long left = r1 - t0;
-    const int rows_here = left < PW_THREADS ? (int)left : PW_THREADS;
+    const int rows_here = left < TROWS ? (int)left : TROWS;
     __syncthreads();
     // stage the dy tile [rows_here][Cout] -> g_s[row][GP] (zero padded)
-    for (int i = threadIdx.x; i < PW_THREADS * GP; i += PW_THREADS) {
-      const int r = i / GP, k = i - r * GP;
-      g_s[i] = (r < rows_here && k < Cout) ? dy[(t0 + r) * ld_dy + k] : 0.f;
+    for (int i = threadIdx.x; i < TROWS * PW_MAX_COUT; i += PW_THREADS) {
+      const int r = i / PW_MAX_COUT, k = i - r * PW_MAX_COUT;
+      g_s[r * GP + k] = (r < rows_here && k < Cout) ? dy[(t0 + r) * ld_dy + k] : 0.f;
     }
     __syncthreads();
-    const int wr0 = warp * 32;
+    const int wr0 = warp * 32;                          // this warp's 32 rows of the tile
     if (wr0 >= rows_here) continue;
     const int wrows = min(32, rows_here - wr0);
     const long long p0 = t0 + wr0;
-    long long n = p0 / P;
-    long long next_n = (n + 1) * P;                     // first row of the next sample
-    float mean[CPL], rstd[CPL];
-#pragma unroll
-    for (int j = 0; j < CPL; ++j) {
-      mean[j] = s.mean ? s.mean[n * CIN + lane + 32 * j] : 0.f;
-      rstd[j] = s.mean ? s.rstd[n * CIN + lane + 32 * j] : 1.f;
+    const long long n_first = p0 / P, n_last = (p0 + wrows - 1) / P;
+    float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), rstd = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (s.mean) {
+      mean = *reinterpret_cast<const float4*>(s.mean + n_first * CIN + cg * 4);
+      rstd = *reinterpret_cast<const float4*>(s.rstd + n_first * CIN + cg * 4);
     }
 #pragma unroll 4
-    for (int i = 0; i < wrows; ++i) {
-      const long long p = p0 + i;
-      if (p >= next_n) {                                // warp-uniform
-        n = p / P;
-        next_n = (n + 1) * P;
+    for (int i = 0; i < 32; i += RPW) {
+      const int r = i + rg;
+      if (r < wrows) {
+        const long long p = p0 + r;
+        float4 v = *reinterpret_cast<const float4*>(s.ptr + p * s.ld + cg * 4);
+        if (s.mean) {
+          float4 m = mean, q = rstd;
+          if (n_first != n_last && p / P != n_first) {    // the warp's rows straddle two samples (rare)
+            m = *reinterpret_cast<const float4*>(s.mean + n_last * CIN + cg * 4);
+            q = *reinterpret_cast<const float4*>(s.rstd + n_last * CIN + cg * 4);
+          }
+          v.x = (v.x - m.x) * q.x; v.y = (v.y - m.y) * q.y; v.z = (v.z - m.z) * q.z; v.w = (v.w - m.w) * q.w;
+        }
+        if (s.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        const float4* gr = reinterpret_cast<const float4*>(g_s + (wr0 + r) * GP);
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          mean[j] = s.mean ? s.mean[n * CIN + lane + 32 * j] : 0.f;
-          rstd[j] = s.mean ? s.rstd[n * CIN + lane + 32 * j] : 1.f;
+        for (int k4 = 0; k4 < PW_MAX_COUT / 4; ++k4) {
+          const float4 g = gr[k4];
+          const float gk[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = k4 * 4 + e;
+            acc[0][k] = fmaf(v.x, gk[e], acc[0][k]);
+            acc[1][k] = fmaf(v.y, gk[e], acc[1][k]);
+            acc[2][k] = fmaf(v.z, gk[e], acc[2][k]);
+            acc[3][k] = fmaf(v.w, gk[e], acc[3][k]);
+            if (cg == 0) accb[k] += gk[e];
+          }
         }
       }
-      float a[CPL];
-#pragma unroll
-      for (int j = 0; j < CPL; ++j) {
-        float v = s.ptr[p * s.ld + lane + 32 * j];
-        v = (v - mean[j]) * rstd[j];
-        if (s.relu) v = fmaxf(v, 0.f);
-        a[j] = v;
-      }
-      const float4* gr = reinterpret_cast<const float4*>(g_s + (wr0 + i) * GP);
-#pragma unroll
-      for (int k4 = 0; k4 < PW_MAX_COUT / 4; ++k4) {
-        const float4 g = gr[k4];                        // broadcast read
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          acc[j][k4 * 4 + 0] = fmaf(a[j], g.x, acc[j][k4 * 4 + 0]);
-          acc[j][k4 * 4 + 1] = fmaf(a[j], g.y, acc[j][k4 * 4 + 1]);
-          acc[j][k4 * 4 + 2] = fmaf(a[j], g.z, acc[j][k4 * 4 + 2]);
-          acc[j][k4 * 4 + 3] = fmaf(a[j], g.w, acc[j][k4 * 4 + 3]);
-        }
-      }
-      if (lane < PW_MAX_COUT) accb += g_s[(wr0 + i) * GP + lane];
     }
   }
-  // warps add their partials into `red` one after the other (fixed order => deterministic)
+  // fold the row groups of the warp (lanes with equal cg), then the warps one after the other (deterministic)
+#pragma unroll
+  for (int k = 0; k < PW_MAX_COUT; ++k) {
+#pragma unroll
+    for (int o = C4; o < 32; o <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j][k] += __shfl_xor_sync(0xffffffffu, acc[j][k], o);
+      accb[k] += __shfl_xor_sync(0xffffffffu, accb[k], o);
+    }
+  }
   for (int wv = 0; wv < PW_THREADS / 32; ++wv) {
     __syncthreads();
-    if (warp == wv) {
+    if (warp == wv && rg == 0) {
 #pragma unroll
-      for (int k = 0; k < PW_MAX_COUT; ++k)
+      for (int k = 0; k < PW_MAX_COUT; ++k) {
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          float* r = &red[k][lane + 32 * j];
+        for (int j = 0; j < 4; ++j) {
+          float* r = &red[k][cg * 4 + j];
           *r = (wv == 0 ? 0.f : *r) + acc[j][k];
         }
-      if (lane < PW_MAX_COUT) {
-        float* r = &red[PW_MAX_COUT][lane];
-        *r = (wv == 0 ? 0.f : *r) + accb;
+        if (cg == 0) {
+          float* r = &red[PW_MAX_COUT][k];
+          *r = (wv == 0 ? 0.f : *r) + accb[k];
+        }
       }
     }
   }
@@ -227,23 +284,22 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_wgrad_kernel(essb_src s, c
   }
 }
 
-// dw[k][c] = sum_blocks part[b][k][c] (double, fixed order => deterministic); dbias[k] = sum_blocks part[b][16][k]
+// dw[k][c] = sum_blocks part[b][k][c], dbias[k] = sum_blocks part[b][16][k]: one warp per output, lanes stride over
+// the blocks in double precision, fixed shuffle tree => deterministic
 __global__ void pw_conv_wgrad_reduce_kernel(const float* __restrict__ part, int nblocks, int Cin, int Cout,
                                             float* __restrict__ dw, float* __restrict__ dbias) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int slab = (PW_MAX_COUT + 1) * Cin;
-  if (i < Cout * Cin) {
-    if (!dw) return;
-    const int k = i / Cin, c = i - k * Cin;
-    double t = 0.0;
-    for (int b = 0; b < nblocks; ++b) t += (double)part[(size_t)b * slab + k * Cin + c];
-    dw[i] = (float)t;
-  } else if (i < Cout * Cin + Cout) {
-    if (!dbias) return;
-    const int k = i - Cout * Cin;
-    double t = 0.0;
-    for (int b = 0; b < nblocks; ++b) t += (double)part[(size_t)b * slab + PW_MAX_COUT * Cin + k];
-    dbias[k] = (float)t;
+  if (i >= Cout * Cin + Cout) return;
+  const bool is_w = i < Cout * Cin;
+  if ((is_w && !dw) || (!is_w && !dbias)) return;
+  const int off = is_w ? i : PW_MAX_COUT * Cin + (i - Cout * Cin);
+  double t = 0.0;
+  for (int b = lane; b < nblocks; b += 32) t += (double)part[(size_t)b * slab + off];
+  t = warp_sum_d(t);
+  if (lane == 0) {
+    if (is_w) dw[i] = (float)t;
+    else dbias[i - Cout * Cin] = (float)t;
   }
 }
 
@@ -267,7 +323,8 @@ extern "C" int essb_pw_conv_fwd(const essb_src* src, const float* w, const float
   ESSB_REQUIRE(w && out && N > 0 && H > 0 && W > 0 && Cout >= 1 && Cout <= PW_MAX_COUT && ldo >= Cout,
                "essb_pw_conv_fwd: bad arguments (1 <= Cout <= %d)", PW_MAX_COUT);
   const long long P = (long long)H * W, rows = P * N;
-  const unsigned blocks = (unsigned)((rows + PW_THREADS - 1) / PW_THREADS);
+  const int tpix = src->C == 32 ? PwTile<32>::TPIX : PwTile<64>::TPIX;
+  const unsigned blocks = (unsigned)((rows + tpix - 1) / tpix);
   cudaStream_t st = (cudaStream_t)stream;
   if (src->C == 32)
     pw_conv_fwd_kernel<32><<<blocks, PW_THREADS, 0, st>>>(*src, w, bias, out, ldo, rows, P, Cout, act);
@@ -282,7 +339,8 @@ extern "C" int essb_pw_conv_dgrad(const float* dy, int ld_dy, const float* w, fl
   ESSB_REQUIRE(dy && w && dx && rows > 0 && (Cin == 32 || Cin == 64) && Cout >= 1 && Cout <= PW_MAX_COUT &&
                    ld_dy >= Cout && ld_dx >= Cin && ld_dx % 4 == 0 && essb_aligned16(dx),
                "essb_pw_conv_dgrad: bad arguments (Cin 32 or 64, 1 <= Cout <= %d)", PW_MAX_COUT);
-  const unsigned blocks = (unsigned)((rows + PW_THREADS - 1) / PW_THREADS);
+  const int tpix = Cin == 32 ? PwTile<32>::TPIX : PwTile<64>::TPIX;
+  const unsigned blocks = (unsigned)((rows + tpix - 1) / tpix);
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 32)
     pw_conv_dgrad_kernel<32><<<blocks, PW_THREADS, 0, st>>>(dy, ld_dy, w, dx, ld_dx, rows, Cout);
@@ -304,6 +362,7 @@ extern "C" int essb_pw_conv_wgrad(const essb_src* src, const float* dy, int ld_d
                    ld_dy >= Cout,
                "essb_pw_conv_wgrad: bad arguments (1 <= Cout <= %d)", PW_MAX_COUT);
   const long long P = (long long)H * W, rows = P * N;
+  ESSB_REQUIRE(P >= 32, "essb_pw_conv_wgrad: H*W must be >= 32 (a warp's 32 rows may straddle at most two samples)");
   const int nb = pw_wgrad_blocks(rows);
   const int64_t need = essb_pw_conv_wgrad_workspace_bytes(N, H, W, src->C);
   if (workspace_bytes < need) {
@@ -313,12 +372,12 @@ extern "C" int essb_pw_conv_wgrad(const essb_src* src, const float* dy, int ld_d
   const long long rpb = (rows + nb - 1) / nb;
   cudaStream_t st = (cudaStream_t)stream;
   if (src->C == 32)
-    pw_conv_wgrad_kernel<1><<<nb, PW_THREADS, 0, st>>>(*src, dy, ld_dy, rows, P, Cout, rpb, workspace);
+    pw_conv_wgrad_kernel<32><<<nb, PW_THREADS, 0, st>>>(*src, dy, ld_dy, rows, P, Cout, rpb, workspace);
   else
-    pw_conv_wgrad_kernel<2><<<nb, PW_THREADS, 0, st>>>(*src, dy, ld_dy, rows, P, Cout, rpb, workspace);
+    pw_conv_wgrad_kernel<64><<<nb, PW_THREADS, 0, st>>>(*src, dy, ld_dy, rows, P, Cout, rpb, workspace);
   ESSB_LAUNCH_CHECK("essb_pw_conv_wgrad");
   const int total = Cout * src->C + Cout;
-  pw_conv_wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(workspace, nb, src->C, Cout, dw, dbias);
+  pw_conv_wgrad_reduce_kernel<<<(total * 32 + 255) / 256, 256, 0, st>>>(workspace, nb, src->C, Cout, dw, dbias);
   ESSB_LAUNCH_CHECK("essb_pw_conv_wgrad reduce");
   return ESSB_OK;
 }

@@ -10,6 +10,7 @@
 // workspace [split][tap][ci][co] and are reduced in fixed order (deterministic).
 // bf16x3: D += A_lo*G_hi + A_hi*G_lo + A_hi*G_hi, fp32 accumulation in TMEM.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -30,6 +31,7 @@ struct WgTcParams {
   int nb;                // 64-channel boxes of dY (N = 64*nb)
   int stages, passes, stage_bytes;
   int off_alo, off_ghi, off_glo;
+  int fuse_g;            // bf16x3 and 2*BN <= 256: A_hi x [G_hi | G_lo] is one MMA of N = 2*BN (upper half added by the epilogue)
   int pair;              // Cin <= 64: the two 64-row halves of the M tile are two TAPS (tap 2*i, 2*i+1) of the same channels
   int cin, cout;
   float* partial;
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   } else if (warp == 1) {
     {  // whole warp, convergent: umma_bf16 / umma_commit elect the issuing lane themselves
       const uint32_t idesc = make_idesc_mn(128, BN);
+      const uint32_t idesc2 = make_idesc_mn(128, 2 * BN);
       int s = 0;
       uint32_t ph = 0;
       uint32_t tph[2] = {0, 0};
@@ -149,7 +152,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           for (int k = 0; k < WG_PIX / 16; ++k) {
             const uint32_t ko = (uint32_t)(k * (16 * 128 >> 4));  // 16 pixel rows of 128 B
             const uint32_t first = (pp != p0 || k != 0) ? 1u : 0u;
-            if (p.passes == 3) {
+            if (p.passes == 3 && p.fuse_g) {
+              // G_lo's 64-channel boxes follow G_hi's in the stage, i.e. [G_hi | G_lo] is one MN-major operand of
+              // 2*BN columns: two MMAs and two A reads per K-step instead of three (same trick as conv_tc.cu)
+              umma_bf16(d_tmem, a_hi + ko, g_hi + ko, idesc2, first);
+              umma_bf16(d_tmem, a_lo + ko, g_hi + ko, idesc, 1u);
+            } else if (p.passes == 3) {
               umma_bf16(d_tmem, a_lo + ko, g_hi + ko, idesc, first);
               umma_bf16(d_tmem, a_hi + ko, g_lo + ko, idesc, 1u);
               umma_bf16(d_tmem, a_hi + ko, g_hi + ko, idesc, 1u);
@@ -188,7 +196,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         uint32_t rr[32];
         __syncwarp();
         tmem_ld32(t_addr + (uint32_t)c0, rr);
-        tmem_ld_wait();
+        if (p.fuse_g) {
+          uint32_t r2[32];
+          tmem_ld32(t_addr + (uint32_t)(BN + c0), r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) rr[e] = __float_as_uint(__uint_as_float(rr[e]) + __uint_as_float(r2[e]));
+        } else {
+          tmem_ld_wait();
+        }
         if (ci < p.cin && otap < p.ntaps && c0 < p.cout) {   // cout is a multiple of 32
 #pragma unroll
           for (int e = 0; e < 32; e += 4)
@@ -328,6 +344,8 @@ extern "C" int essb_wgrad_tc_run(const essb_wgrad_tc* d, void* stream) {
     if ((rc = wg_encode(&p.tmG_lo, d->g_lo, d->g_ld, d->g_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK) return rc;
   }
   p.m_tiles = pl.m_tiles; p.splits = pl.splits; p.ntaps = d->ntaps;
+  static const int fuse_env = [] { const char* e = getenv("ESSB_TC_FUSEB"); return e ? atoi(e) : 1; }();
+  p.fuse_g = (fuse_env != 0 && d->passes == 3 && 2 * 64 * pl.nb <= 256) ? 1 : 0;
   p.pair = pl.pair;
   p.n_items = pl.splits * (pl.pair ? (d->ntaps + 1) / 2 : d->ntaps) * pl.m_tiles;
   p.patches_total = pl.patches_total; p.patches_per_split = pl.patches_per_split;
