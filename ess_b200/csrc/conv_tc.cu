@@ -1148,6 +1148,8 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   static const int halo_env = [] { const char* e = getenv("ESSB_TC_HALO"); return e ? atoi(e) : 1; }();
   static const int baseoff_env = 0;
   bool halo = halo_env != 0 && BN <= 128 && d->ntaps >= 2;
+  // shared-memory bias staging area: as small as the layer allows (it competes with pipeline stages at 2 CTAs/SM)
+  const int bias_floats = d->bias ? ((d->Cout + 255) / 256) * 256 : 0;
   int halo_occ = 1;
   bool halo_fuse = false;
   int hx0 = 0, hx1 = 0, hy0 = 0, hy1 = 0;
@@ -1171,22 +1173,24 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
     // second resident CTA with its own TMEM accumulators fills the stalls; each CTA then allocates only the
     // TMEM columns it needs (2 x BN) instead of all 512.
     static const int occ_env = [] { const char* e = getenv("ESSB_TC_OCC"); return e ? atoi(e) : 2; }();
-    const int tail_bytes = 1024 + 512 + TC_BIAS_SMEM_FLOATS * (int)sizeof(float);
+    const int tail_bytes = 1024 + 512 + bias_floats * (int)sizeof(float);
     int budget = 200 * 1024;
     halo_occ = 1;
     static const int fuse_env = [] { const char* e = getenv("ESSB_TC_FUSEB"); return e ? atoi(e) : 1; }();
     halo_fuse = fuse_env != 0 && d->passes == 3 && 2 * BN <= 256;
     // TMEM per CTA: two accumulator buffers of BN (or 2*BN when fused) columns; two CTAs/SM need <= 256 each
     if (occ_env >= 2 && 2 * BN * (halo_fuse ? 2 : 1) <= 256) {
-      const int half = 112 * 1024 - tail_bytes;
+      const int half = 113 * 1024 - tail_bytes;   // 2 x (113 KB + 1 KB reserved per CTA) = the SM's 228 KB
       if (p.a_stage_bytes + 2 * p.b_tap_bytes <= half) { budget = half; halo_occ = 2; }
     }
     p.a_stages = (2 * p.a_stage_bytes + 3 * p.b_tap_bytes <= budget) ? 2 : 1;
     // Narrow tiles (N <= 64) are bound by the MMA thread's per-stage cost (barrier wait + fence + commit, ~200
     // cycles) rather than by tensor work (12 MMAs x N/2 cycles per tap): put G taps behind one barrier.
+    static const int g_env = [] { const char* e = getenv("ESSB_TC_HALO_G"); return e ? atoi(e) : 0; }();
     int G = 1;
     if (BN <= 64) {
       G = (budget - p.a_stages * p.a_stage_bytes) / (2 * p.b_tap_bytes);
+      if (g_env > 0) G = g_env;
       if (G > 8) G = 8;
       if (G > d->ntaps) G = d->ntaps;
       if (G < 1) G = 1;
@@ -1304,7 +1308,7 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
     p.wide = wide;
   }
 
-  const size_t tail = 1024 /*align slack*/ + 512 /*barriers*/ + TC_BIAS_SMEM_FLOATS * sizeof(float);
+  const size_t tail = 1024 /*align slack*/ + 512 /*barriers*/ + (size_t)bias_floats * sizeof(float);
   size_t smem_bytes = (size_t)stages * p.stage_bytes + tail;
   if (halo) smem_bytes = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + tail;
   p.tmem_cols = 512;
