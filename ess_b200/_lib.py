@@ -106,7 +106,8 @@ SIGNATURES = {
     'essb_pw_conv_wgrad': (_I, [C.POINTER(Src), _P, _I, _I, _I, _I, _I, _P, _P, _P, _L, _P]),
     'essb_upsample2_bwd': (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     'essb_event_stats': (_I, [_P, _L, _I, _I, _L, _P, _P]),
-    'essb_event_prepare': (_I, [_P, _L, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'essb_event_prepare': (_I, [_P, _L, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'essb_zero_pixels': (_I, [_P, _L, _I, _I, _I, _I, _P, _I, _P]),
     'essb_nchw_to_nhwc': (_I, [_P, _P, _I, _I, _I, _L, _P]),
     'essb_nhwc_to_nchw': (_I, [_P, _I, _P, _I, _I, _L, _P]),
     'essb_bilinear_up2': (_I, [_P, _P, _I, _I, _I, _I, _P]),
@@ -125,7 +126,7 @@ SIGNATURES = {
     'essb_voxel_grid_dsec': (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P, _P]),
     'essb_voxel_grid_ddd17': (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
     'essb_radam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P]),
-    'essb_event_prepare_planes': (_I, [_P, _L, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'essb_event_prepare_planes': (_I, [_P, _L, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'essb_split_bf16': (_I, [C.POINTER(Src), _I, _I, _I, _P, _P, _I, _I, _I, _P]),
     'essb_pack_weight_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'essb_conv_tc_run': (_I, [C.POINTER(ConvTc), _P]),

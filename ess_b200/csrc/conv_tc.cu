@@ -907,12 +907,13 @@ __global__ void event_prepare_planes_kernel(const float* __restrict__ x, long lo
                                             const double* __restrict__ stats, int normalize,
                                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int C, int H,
                                             int W, int Hp, int Wp, int pad_top, int pad_left, int Hb, int Wb, int off_y,
-                                            int off_x) {
+                                            int off_x, int flip) {
   // grid (ceil(Wp / blockDim.x), Hp, B): no index division
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   if (ox >= Wp) return;
   const int oy = blockIdx.y, n = blockIdx.z;
-  const int iy = reflect_idx_tc(oy - pad_top, H), ix = reflect_idx_tc(ox - pad_left, W);
+  int iy = reflect_idx_tc(oy - pad_top, H), ix = reflect_idx_tc(ox - pad_left, W);
+  if (flip) { iy = H - 1 - iy; ix = W - 1 - ix; }   // torch.flip(events, dims=[2, 3]) precedes the padding
   float mean = 0.f, stdv = 1.f;
   bool do_norm = false;
   if (normalize) {
@@ -1071,7 +1072,8 @@ extern "C" int essb_split_bf16(const essb_src* src, int N, int H, int W, uint16_
 
 extern "C" int essb_event_prepare_planes(const float* x, int64_t bstride, const double* stats, int normalize,
                                          uint16_t* hi, uint16_t* lo, int cpad, int B, int C, int H, int W, int Hp, int Wp,
-                                         int pad_top, int pad_left, int Hb, int Wb, int off_y, int off_x, void* stream) {
+                                         int pad_top, int pad_left, int Hb, int Wb, int off_y, int off_x, int flip,
+                                         void* stream) {
   ESSB_REQUIRE(x && hi && lo && B > 0 && C > 0 && H > 0 && W > 0 && Hp >= H && Wp >= W, "essb_event_prepare_planes: bad arguments");
   ESSB_REQUIRE((cpad == 8 || cpad == 16) && C <= cpad, "essb_event_prepare_planes: cpad must be 8 or 16 and >= C");
   ESSB_REQUIRE(!normalize || stats, "essb_event_prepare_planes: stats required when normalising");
@@ -1086,10 +1088,10 @@ extern "C" int essb_event_prepare_planes(const float* x, int64_t bstride, const 
   __nv_bfloat16* l = reinterpret_cast<__nv_bfloat16*>(lo);
   if (cpad == 8)
     event_prepare_planes_kernel<8><<<grid, threads, 0, (cudaStream_t)stream>>>(x, bstride, stats, normalize, h, l, C, H, W, Hp,
-                                                                           Wp, pad_top, pad_left, Hb, Wb, off_y, off_x);
+                                                                           Wp, pad_top, pad_left, Hb, Wb, off_y, off_x, flip);
   else
     event_prepare_planes_kernel<16><<<grid, threads, 0, (cudaStream_t)stream>>>(x, bstride, stats, normalize, h, l, C, H, W, Hp,
-                                                                            Wp, pad_top, pad_left, Hb, Wb, off_y, off_x);
+                                                                            Wp, pad_top, pad_left, Hb, Wb, off_y, off_x, flip);
   ESSB_LAUNCH_CHECK("essb_event_prepare_planes");
   return ESSB_OK;
 }

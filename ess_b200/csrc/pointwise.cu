@@ -396,14 +396,15 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 
 __global__ void event_prepare_kernel(const float* __restrict__ x, long long bstride, const double* __restrict__ stats,
                                      int normalize, float* __restrict__ out, int ld_out, int C, int H, int W,
-                                     int Hp, int Wp, int pad_top, int pad_left, long long total) {
+                                     int Hp, int Wp, int pad_top, int pad_left, int flip, long long total) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int ox = (int)(idx % Wp);
   const long long r = idx / Wp;
   const int oy = (int)(r % Hp);
   const int n = (int)(r / Hp);
-  const int iy = reflect_idx(oy - pad_top, H), ix = reflect_idx(ox - pad_left, W);
+  int iy = reflect_idx(oy - pad_top, H), ix = reflect_idx(ox - pad_left, W);
+  if (flip) { iy = H - 1 - iy; ix = W - 1 - ix; }   // torch.flip(events, dims=[2, 3]) precedes the padding
   float mean = 0.f, inv_std = 1.f;
   bool do_norm = false;
   if (normalize) {
@@ -660,6 +661,30 @@ extern "C" int essb_colsum(const float* x, int ld, int64_t rows, int C, float* o
   return ESSB_OK;
 }
 
+// x[b][c][y][x] = 0 for every listed pixel (hot-pixel removal, inference_utils.py:88-89); in place, as the reference
+__global__ void zero_pixels_kernel(float* __restrict__ x, long long bstride, int B, int C, int H, int W,
+                                   const int* __restrict__ xy, int n) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n * B * C;
+  if (idx >= total) return;
+  const int i = (int)(idx % n);
+  const long long r = idx / n;
+  const int c = (int)(r % C), b = (int)(r / C);
+  const int px = xy[2 * i], py = xy[2 * i + 1];
+  if (px < 0 || px >= W || py < 0 || py >= H) return;
+  x[(long long)b * bstride + ((long long)c * H + py) * W + px] = 0.f;
+}
+
+extern "C" int essb_zero_pixels(float* x, int64_t bstride, int B, int C, int H, int W, const int32_t* xy, int n,
+                                void* stream) {
+  ESSB_REQUIRE(x && B > 0 && C > 0 && H > 0 && W > 0 && n >= 0 && (n == 0 || xy), "essb_zero_pixels: bad arguments");
+  if (n == 0) return ESSB_OK;
+  const long long total = (long long)n * B * C;
+  zero_pixels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, bstride, B, C, H, W, xy, n);
+  ESSB_LAUNCH_CHECK("essb_zero_pixels");
+  return ESSB_OK;
+}
+
 extern "C" int essb_event_stats(const float* x, int64_t bstride, int B, int T, int64_t count, double* stats,
                                 void* stream) {
   ESSB_REQUIRE(x && stats && B > 0 && T > 0 && count > 0, "essb_event_stats: bad arguments");
@@ -678,7 +703,7 @@ extern "C" int essb_event_stats(const float* x, int64_t bstride, int B, int T, i
 
 extern "C" int essb_event_prepare(const float* x, int64_t bstride, const double* stats, int normalize, float* out,
                                   int ld_out, int B, int C, int H, int W, int Hp, int Wp, int pad_top, int pad_left,
-                                  void* stream) {
+                                  int flip, void* stream) {
   ESSB_REQUIRE(x && out && B > 0 && C > 0 && H > 0 && W > 0 && Hp >= H && Wp >= W && ld_out >= C,
                "essb_event_prepare: bad arguments");
   ESSB_REQUIRE(!normalize || stats, "essb_event_prepare: stats required when normalising");
@@ -686,7 +711,7 @@ extern "C" int essb_event_prepare(const float* x, int64_t bstride, const double*
                "essb_event_prepare: reflection padding must be smaller than the image");
   const long long total = (long long)B * Hp * Wp;
   event_prepare_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      x, bstride, stats, normalize, out, ld_out, C, H, W, Hp, Wp, pad_top, pad_left, total);
+      x, bstride, stats, normalize, out, ld_out, C, H, W, Hp, Wp, pad_top, pad_left, flip, total);
   ESSB_LAUNCH_CHECK("essb_event_prepare");
   return ESSB_OK;
 }

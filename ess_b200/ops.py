@@ -236,7 +236,16 @@ def event_stats(data, T, Cw):
     return stats
 
 
-def event_prepare(window, stats_row, normalize, Hp, Wp, pad_top, pad_left, ld_out, out=None):
+def zero_pixels(data, xy):
+    """Hot-pixel removal in place: data [B, C, H, W] (per-sample contiguous), xy int32 [n, 2] (x, y) on the device."""
+    B, Cc, H, W = data.shape
+    if data.stride(1) != H * W or data.stride(2) != W or data.stride(3) != 1:
+        raise RuntimeError('event tensor must be contiguous within each sample')
+    call('essb_zero_pixels', _p(data), data.stride(0), B, Cc, H, W, _p(xy), xy.shape[0], _stream())
+    return data
+
+
+def event_prepare(window, stats_row, normalize, Hp, Wp, pad_top, pad_left, ld_out, out=None, flip=False):
     """window: [B, C, H, W] view (per-sample contiguous) -> NHWC [B, Hp, Wp, ld_out] normalised+padded."""
     B, Cw, H, W = window.shape
     if window.stride(1) != H * W or window.stride(2) != W or window.stride(3) != 1:
@@ -244,7 +253,7 @@ def event_prepare(window, stats_row, normalize, Hp, Wp, pad_top, pad_left, ld_ou
     if out is None:
         out = torch.empty((B, Hp, Wp, ld_out), device=window.device, dtype=torch.float32)
     call('essb_event_prepare', _p(window), window.stride(0), _p(stats_row), int(normalize), _p(out), ld_out, B, Cw, H,
-         W, Hp, Wp, pad_top, pad_left, _stream())
+         W, Hp, Wp, pad_top, pad_left, int(flip), _stream())
     return out
 
 
@@ -257,7 +266,7 @@ def head_planes_alloc(B, Hp, Wp, cpad, device):
     return (torch.zeros(shape, device=device, dtype=torch.bfloat16), torch.zeros(shape, device=device, dtype=torch.bfloat16))
 
 
-def event_prepare_planes(window, stats_row, normalize, Hp, Wp, pad_top, pad_left, planes):
+def event_prepare_planes(window, stats_row, normalize, Hp, Wp, pad_top, pad_left, planes, flip=False):
     """Like event_prepare but writes bf16 hi/lo planes into the interior of a head_planes_alloc buffer."""
     B, Cw, H, W = window.shape
     if window.stride(1) != H * W or window.stride(2) != W or window.stride(3) != 1:
@@ -265,7 +274,7 @@ def event_prepare_planes(window, stats_row, normalize, Hp, Wp, pad_top, pad_left
     hi, lo = planes
     call('essb_event_prepare_planes', _p(window), window.stride(0), _p(stats_row), int(normalize), _p(hi), _p(lo),
          hi.shape[3], B, Cw, H, W, Hp, Wp, pad_top, pad_left, hi.shape[1], hi.shape[2], HEAD_PAD_BEFORE,
-         HEAD_PAD_BEFORE, _stream())
+         HEAD_PAD_BEFORE, int(flip), _stream())
     return planes
 
 

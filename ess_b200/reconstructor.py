@@ -38,11 +38,25 @@ class ImageReconstructor:
         self.standardization = standardization
         self.no_recurrent = bool(getattr(options, 'no_recurrent', False))
         self.no_normalize = bool(getattr(options, 'no_normalize', False))
-        if getattr(options, 'flip', False) or getattr(options, 'hot_pixels_file', None) or \
-                getattr(options, 'color', False):
-            raise NotImplementedError('flip / hot_pixels_file / color options are not built')
+        if getattr(options, 'color', False):
+            raise NotImplementedError('color reconstruction (per-Bayer-channel states) is not built')
+        # EventPreprocessor options (e2vid/utils/inference_utils.py:73-93)
+        self.flip = bool(getattr(options, 'flip', False))
+        self.hot_pixels = None          # int32 [n, 2] (x, y) on the device, or None
+        hp_file = getattr(options, 'hot_pixels_file', None)
+        if hp_file:
+            import numpy as np
+            try:
+                self.set_hot_pixels(np.loadtxt(hp_file, delimiter=',').astype(np.int64).reshape(-1, 2))
+            except IOError:
+                print('WARNING: could not load hot pixels file: {}'.format(hp_file))   # as the reference
         self.last_states_for_each_channel = {'grayscale': None}
         self.stats_reduce_fn = None
+
+    def set_hot_pixels(self, xy):
+        """(x, y) pixel locations zeroed in every event tensor before normalisation (inference_utils.py:88-89)."""
+        xy = torch.as_tensor(xy, dtype=torch.int32).reshape(-1, 2)
+        self.hot_pixels = xy.to(self.device if self.device is not None else 'cuda').contiguous() if xy.numel() else None
 
     def _step(self, window, stats_row, states, with_image, want_head=True):
         """normalise + reflect-pad + layout/precision conversion (one kernel) -> model."""
@@ -51,9 +65,9 @@ class ImageReconstructor:
         Hp, Wp = H + top + bottom, W + left + right
         buf = self.model.head_planes_buffer(B, Hp, Wp, window.device)
         if buf is not None:      # tensor-core head conv: write its bf16 hi/lo operand planes directly
-            ops.event_prepare_planes(window, stats_row, not self.no_normalize, Hp, Wp, top, left, buf)
+            ops.event_prepare_planes(window, stats_row, not self.no_normalize, Hp, Wp, top, left, buf, flip=self.flip)
             return self.model.forward_planes(buf, Hp, Wp, states, with_image=with_image, want_head=want_head)
-        x = ops.event_prepare(window, stats_row, not self.no_normalize, Hp, Wp, top, left, (C + 7) // 8 * 8)
+        x = ops.event_prepare(window, stats_row, not self.no_normalize, Hp, Wp, top, left, (C + 7) // 8 * 8, flip=self.flip)
         return self.model.forward_nhwc(x, states, with_image=with_image)
 
     @staticmethod
@@ -69,6 +83,8 @@ class ImageReconstructor:
             ops.require_cuda(ev)
             ev = self._per_sample_contiguous(ev.float())
             B, C, H, W = ev.shape
+            if self.hot_pixels is not None:
+                ops.zero_pixels(ev, self.hot_pixels)       # in place, like the reference
             stats = None
             if not self.no_normalize:
                 stats = ops.event_stats(ev, 1, C)
@@ -90,6 +106,8 @@ class ImageReconstructor:
             ops.require_cuda(data)
             data = self._per_sample_contiguous(data.float())
             self.last_states_for_each_channel = {'grayscale': None}
+            if self.hot_pixels is not None:
+                ops.zero_pixels(data, self.hot_pixels)     # all T*C channels at once
             stats = None
             if not self.no_normalize:
                 stats = ops.event_stats(data, num_windows, channels)

@@ -197,6 +197,10 @@ int essb_pw_conv_wgrad(const essb_src* src, const float* dy, int ld_dy, int N, i
 /* stats[w][3] = (sum x, sum x^2, count of non-zeros) of window w for ALL T windows in one launch;
  * x is [B][T][count] with batch stride `bstride` floats (count = C*H*W of one window).  One launch
  * before the unroll removes the reference's per-window blocking `if num_nonzeros > 0` D2H sync. */
+/* Hot-pixel removal (EventPreprocessor.__call__, inference_utils.py:88-89): x[:, :, y, x] = 0 for the n listed
+ * (x, y) pairs, in place like the reference; runs before essb_event_stats so the statistics exclude them. */
+int essb_zero_pixels(float* x, int64_t bstride, int B, int C, int H, int W, const int32_t* xy, int n,
+                     void* stream);
 int essb_event_stats(const float* x, int64_t bstride, int B, int T, int64_t count, double* stats,
                      void* stream);
 /* Normalise non-zeros to mean 0 / std 1 using stats (no-op scale if nnz == 0), reflect-pad to
@@ -204,7 +208,7 @@ int essb_event_stats(const float* x, int64_t bstride, int B, int T, int64_t coun
  * channels zero-filled).  x is a [B, C, H, W] slice with batch stride `bstride` floats. */
 int essb_event_prepare(const float* x, int64_t bstride, const double* stats, int normalize,
                        float* out, int ld_out, int B, int C, int H, int W, int Hp, int Wp,
-                       int pad_top, int pad_left, void* stream);
+                       int pad_top, int pad_left, int flip /* torch.flip(dims=[2,3]) before padding (inference_utils.py:92-93) */, void* stream);
 
 /* ---- layout plumbing ---------------------------------------------------------------------- */
 int essb_nchw_to_nhwc(const float* in, float* out, int ld_out, int N, int C, int64_t P, void* stream);
@@ -288,7 +292,7 @@ int essb_split_bf16(const essb_src* src, int N, int H, int W, uint16_t* hi, uint
 int essb_event_prepare_planes(const float* x, int64_t bstride, const double* stats, int normalize,
                               uint16_t* hi, uint16_t* lo, int cpad, int B, int C, int H, int W, int Hp,
                               int Wp, int pad_top, int pad_left, int Hb, int Wb, int off_y, int off_x,
-                              void* stream);
+                              int flip, void* stream);
 /* Pack conv weights for the tensor-core path: K-major [NoutP][T*KinP] bf16 hi and lo planes
  * (same transposed_layout / swap_io / flip / interleave / scale semantics as essb_pack_weight;
  * KinP = input channels padded to a multiple of 64, rows beyond Nout are zero). */

@@ -27,11 +27,16 @@ IN_EPS = 1e-5   # torch.nn.InstanceNorm2d default, models/style_networks.py:163
 # ------------------------------------------------------------------------------------------------
 # a1 / a2: event pre-processing (e2vid/utils/inference_utils.py:84-109, 311-338)
 # ------------------------------------------------------------------------------------------------
-def event_normalize(events):
-    """EventPreprocessor.__call__ with default options (no hot pixels, no flip, normalise on).
+def event_normalize(events, hot_pixels=(), flip=False):
+    """EventPreprocessor.__call__ (default options: no hot pixels, no flip, normalise on).
 
-    inference_utils.py:96-107: mean/std over the non-zero entries of the WHOLE [B,C,H,W] tensor,
-    zeros stay zero.  If there is no non-zero entry the tensor is returned unchanged."""
+    inference_utils.py:88-93: hot pixels (x, y) are zeroed IN PLACE in the caller's tensor, then the tensor is
+    flipped over H and W.  inference_utils.py:96-107: mean/std over the non-zero entries of the WHOLE
+    [B,C,H,W] tensor, zeros stay zero.  If there is no non-zero entry the tensor is returned unchanged."""
+    for x, y in hot_pixels:
+        events[:, :, y, x] = 0
+    if flip:
+        events = torch.flip(events, dims=[2, 3])
     nonzero = events != 0
     nnz = nonzero.sum()
     if nnz > 0:
@@ -195,11 +200,11 @@ def e2vid_recurrent_forward(sd, config, x, prev_states, with_image=True):
     return img, states, latent
 
 
-def reconstructor_step(sd, config, event_tensor, last_states, with_image=True):
+def reconstructor_step(sd, config, event_tensor, last_states, with_image=True, hot_pixels=(), flip=False):
     """ImageReconstructor.update_reconstruction (e2vid/image_reconstructor.py:82-163), default
     options: normalise -> reflect pad -> model -> carry states.  All under no_grad (:83)."""
     with torch.no_grad():
-        ev = event_normalize(event_tensor)
+        ev = event_normalize(event_tensor, hot_pixels, flip)
         ev = reflect_pad(ev, e2vid_config_defaults(config)['num_encoders'])
         return e2vid_recurrent_forward(sd, config, ev, last_states, with_image)
 

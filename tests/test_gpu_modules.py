@@ -368,3 +368,38 @@ def test_convgru_in_tensor_core_mode():
     assert rel_err(img, img_r) < TOL
     for k in (1, 2, 4, 8):
         assert rel_err(lat[k], lat_r[k]) < TOL, k
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16x3'])
+def test_reconstructor_flip_and_hot_pixels(mode, tmp_path):
+    """ImageReconstructor with the EventPreprocessor options of e2vid/utils/inference_utils.py:73-93 (hot-pixel
+    file, flip) on a width that needs reflect padding (30 -> 32), per-window and fused-unroll forms."""
+    import types
+    import ess_b200
+    B, T, C, H, W = 2, 2, 5, 24, 30
+    hot = [(3, 5), (29, 0), (10, 23)]
+    f = tmp_path / 'hot.txt'
+    f.write_text('\n'.join('%d,%d' % xy for xy in hot))
+    m = make_e2vid(mode=mode)
+    sd = sd_cpu(m)
+    data = make_events(B, T, C, H, W)
+    for x, y in hot:
+        data[:, :, y, x] = 7.0
+    ref_in = data.clone()
+    states = None
+    for i in range(T):
+        win = ref_in[:, i * C:(i + 1) * C]
+        img_r, states, lat_r = O.reconstructor_step(sd, E2VID_CFG, win, states, hot_pixels=hot, flip=True)
+    opts = types.SimpleNamespace(flip=True, hot_pixels_file=str(f), no_normalize=False, no_recurrent=False, color=False)
+    rec = ess_b200.ImageReconstructor(m.cuda(), H, W, C, 'cuda', opts)
+    d = data.clone().cuda()
+    for i in range(T):
+        img, st, lat = rec.update_reconstruction(d[:, i * C:(i + 1) * C].contiguous())
+    tol = TOL if mode != 'fp32' else 2e-5
+    assert rel_err(img, img_r) < tol
+    for k in (1, 2, 4, 8):
+        assert rel_err(lat[k], lat_r[k]) < tol
+    d2 = data.clone().cuda()
+    img_u, _, lat_u = rec.unroll(d2, T, C)
+    assert float(d2[0, 0, 5, 3]) == 0.0                       # zeroed in place, all T*C channels
+    assert rel_err(lat_u[8], lat_r[8]) < tol and rel_err(img_u, img_r) < tol

@@ -201,3 +201,31 @@ def test_oracle_voxel_grid_dsec_vs_live_reference():
     t = torch.sort(torch.rand(n, generator=g))[0] * 1e3
     ref = VoxelGrid(C, H, W, normalize=False).convert(x, y, pol, t)
     assert torch.allclose(O.voxel_grid_dsec(x, y, pol, t, C, H, W), ref, rtol=0, atol=1e-5)
+
+
+@needs_ref
+def test_oracle_flip_and_hot_pixels_vs_live_reference(tmp_path):
+    """EventPreprocessor options (inference_utils.py:73-93): hot-pixel removal (in place) and the H/W flip."""
+    import numpy as np
+    ref_shim.install()
+    from e2vid.image_reconstructor import ImageReconstructor
+    if not hasattr(np, 'int'):
+        np.int = int          # the reference predates numpy 1.24 (inference_utils.py:76 uses np.int)
+    cfg = dict(ref_shim.E2VID_LIGHTWEIGHT_CFG, base_num_channels=8, num_bins=3)
+    m = ref_shim.make_reference_e2vid(cfg)
+    B, C, H, W = 2, 3, 24, 30            # W = 30 -> reflect pad to 32: the flip must precede the padding
+    hot = [(3, 5), (29, 0), (10, 23)]
+    f = tmp_path / 'hot.txt'
+    f.write_text('\n'.join('%d,%d' % xy for xy in hot))
+    torch.manual_seed(1)
+    data = torch.randn(B, C, H, W) * (torch.rand(B, C, H, W) < 0.3)
+    for x, y in hot:
+        data[:, :, y, x] = 7.0           # make sure the hot pixels matter
+    rec = ImageReconstructor(m, H, W, C, 'cpu', ref_shim.e2vid_options(flip=True, hot_pixels_file=str(f)))
+    d1, d2 = data.clone(), data.clone()
+    img, st, lat = rec.update_reconstruction(d1)
+    img2, st2, lat2 = O.reconstructor_step(m.state_dict(), cfg, d2, None, hot_pixels=hot, flip=True)
+    assert torch.equal(d1, d2) and float(d2[0, 0, 5, 3]) == 0.0     # both zero the caller's tensor in place
+    assert rel_err(img2, img) < 1e-6
+    for k in lat:
+        assert rel_err(lat2[k], lat[k]) < 1e-6
