@@ -76,6 +76,7 @@ class WgradTc(C.Structure):
                 ('dw', C.c_void_p), ('workspace', C.c_void_p), ('workspace_bytes', C.c_int64),
                 ('a_ld', C.c_int32), ('Cin', C.c_int32), ('g_ld', C.c_int32), ('Cout', C.c_int32),
                 ('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('passes', C.c_int32), ('ntaps', C.c_int32),
+                ('a_stride', C.c_int32),
                 ('dy', C.c_int8 * MAX_TAPS), ('dx', C.c_int8 * MAX_TAPS)]
 
 
@@ -104,6 +105,10 @@ SIGNATURES = {
     'essb_pw_conv_dgrad': (_I, [_P, _I, _P, _P, _I, _L, _I, _I, _P]),
     'essb_pw_conv_wgrad_workspace_bytes': (_L, [_I, _I, _I, _I]),
     'essb_pw_conv_wgrad': (_I, [C.POINTER(Src), _P, _I, _I, _I, _I, _I, _P, _P, _P, _L, _P]),
+    'essb_stem_conv_supported': (_I, [_I, _I, _I]),
+    'essb_stem_conv_fwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'essb_stem_conv_wgrad_workspace_bytes': (_L, [_I, _I]),
+    'essb_stem_conv_wgrad': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
     'essb_upsample2_bwd': (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     'essb_event_stats': (_I, [_P, _L, _I, _I, _L, _P, _P]),
     'essb_event_prepare': (_I, [_P, _L, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
@@ -160,7 +165,7 @@ def check(rc, what=''):
 
 
 # kernels launched per successful API call (for bench.py's `gpu_launches` claim)
-_LAUNCHES = {'essb_wgrad_fp32': 4, 'essb_colsum': 2, 'essb_wgrad_tc_run': 2, 'essb_pw_conv_wgrad': 2}
+_LAUNCHES = {'essb_wgrad_fp32': 4, 'essb_colsum': 2, 'essb_wgrad_tc_run': 2, 'essb_pw_conv_wgrad': 2, 'essb_stem_conv_wgrad': 2}
 launch_count = 0
 PROFILE = None   # when a list: (tag, algorithmic_flops, start_event, end_event) per profiled launch
 PROFILE_TAGS = None   # optional set of tags to bracket with events (None = all); every event pair costs a few us of

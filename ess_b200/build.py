@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libess_b200.so')
-SOURCES = ['api.cu', 'conv_fp32.cu', 'conv_tc.cu', 'wgrad_tc.cu', 'pointwise.cu', 'loss.cu', 'bn.cu', 'voxel.cu', 'pw_conv.cu']
+SOURCES = ['api.cu', 'conv_fp32.cu', 'conv_tc.cu', 'wgrad_tc.cu', 'pointwise.cu', 'loss.cu', 'bn.cu', 'voxel.cu', 'pw_conv.cu', 'stem_conv.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-I' + os.path.join(ROOT, 'include')]
 

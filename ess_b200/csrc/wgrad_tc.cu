@@ -24,7 +24,7 @@ constexpr int WG_BOX_BYTES = WG_PIX * 128; // one [64 px][64 ch] bf16 box = 8 KB
 constexpr int WG_MAX_STAGES = 8;
 
 struct WgTcParams {
-  CUtensorMap tmA_hi, tmA_lo, tmG_hi, tmG_lo;
+  CUtensorMap tmA_hi[4], tmA_lo[4], tmG_hi, tmG_lo;   // A: one map per input parity plane (stride 2) or map 0 only
   int n_items, m_tiles, splits, ntaps;
   int patches_total, patches_per_split, tiles_x, tiles_y;
   int bw_log2;           // patch = BW x (64/BW) pixels
@@ -35,7 +35,7 @@ struct WgTcParams {
   int pair;              // Cin <= 64: the two 64-row halves of the M tile are two TAPS (tap 2*i, 2*i+1) of the same channels
   int cin, cout;
   float* partial;
-  int8_t dy[ESSB_MAX_TAPS], dx[ESSB_MAX_TAPS];
+  int8_t dy[ESSB_MAX_TAPS], dx[ESSB_MAX_TAPS], view[ESSB_MAX_TAPS];   // per tap: shift inside its A view, view index
 };
 
 // MN-major SWIZZLE_128B descriptor: [0,14) start>>4, [16,30) LBO>>4 (stride between 64-element blocks
@@ -112,9 +112,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             const int tj = p.pair ? min(2 * tap + j, p.ntaps - 1) : tap;
             const int cj = p.pair ? 0 : mt * 128 + j * 64;
             const int ax = x0 + p.dx[tj], ay = y0 + p.dy[tj];
-            tma_load_4d(st + j * WG_BOX_BYTES, &p.tmA_hi, &full_bar[s], cj, ax, ay, n);
+            tma_load_4d(st + j * WG_BOX_BYTES, &p.tmA_hi[p.view[tj]], &full_bar[s], cj, ax, ay, n);
             if (p.passes == 3)
-              tma_load_4d(st + p.off_alo + j * WG_BOX_BYTES, &p.tmA_lo, &full_bar[s], cj, ax, ay, n);
+              tma_load_4d(st + p.off_alo + j * WG_BOX_BYTES, &p.tmA_lo[p.view[tj]], &full_bar[s], cj, ax, ay, n);
           }
           for (int j = 0; j < p.nb; ++j) {
             tma_load_4d(st + p.off_ghi + j * WG_BOX_BYTES, &p.tmG_hi, &full_bar[s], j * 64, x0, y0, n);
@@ -259,6 +259,27 @@ PFN_encodeTiled wg_get_encode() {
   return fn;
 }
 
+int wg_encode_view(CUtensorMap* tm, const void* base, int C, long long sx, long long sy, long long sn, int N, int H,
+                   int W, int BW, int BH) {
+  PFN_encodeTiled enc = wg_get_encode();
+  if (!enc) {
+    essb_set_error("wgrad_tc: cuTensorMapEncodeTiled unavailable");
+    return ESSB_ERR_DRIVER;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sn * 2};
+  cuuint32_t box[4] = {64u, (cuuint32_t)BW, (cuuint32_t)BH, 1u};
+  cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    essb_set_error("wgrad_tc: cuTensorMapEncodeTiled (view) failed with %d", (int)r);
+    return ESSB_ERR_DRIVER;
+  }
+  return ESSB_OK;
+}
+
 int wg_encode(CUtensorMap* tm, const void* base, int C, int ld, int N, int H, int W, int BW, int BH) {
   PFN_encodeTiled enc = wg_get_encode();
   if (!enc) {
@@ -337,12 +358,28 @@ extern "C" int essb_wgrad_tc_run(const essb_wgrad_tc* d, void* stream) {
   static thread_local WgTcParams p;
   const int BW = 1 << pl.bw_log2, BH = WG_PIX >> pl.bw_log2;
   int rc;
-  if ((rc = wg_encode(&p.tmA_hi, d->a_hi, d->Cin, d->a_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK) return rc;
-  if ((rc = wg_encode(&p.tmG_hi, d->g_hi, d->g_ld, d->g_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK) return rc;
-  if (d->passes == 3) {
-    if ((rc = wg_encode(&p.tmA_lo, d->a_lo, d->Cin, d->a_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK) return rc;
-    if ((rc = wg_encode(&p.tmG_lo, d->g_lo, d->g_ld, d->g_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK) return rc;
+  const int astride = d->a_stride == 2 ? 2 : 1;
+  ESSB_REQUIRE(d->a_stride == 0 || d->a_stride == 1 || d->a_stride == 2, "essb_wgrad_tc_run: a_stride must be 1 or 2");
+  if (astride == 1) {
+    if ((rc = wg_encode(&p.tmA_hi[0], d->a_hi, d->Cin, d->a_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK) return rc;
+    if (d->passes == 3 && (rc = wg_encode(&p.tmA_lo[0], d->a_lo, d->Cin, d->a_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK)
+      return rc;
+  } else {
+    // stride-2 convolution: the input [N, 2H, 2W, a_ld] is read through its four parity planes (view = 2*py + px;
+    // base shifted by (py*2W + px)*a_ld, pixel strides doubled), exactly like the forward kernel's parity views
+    const long long ld = d->a_ld, Wi = 2LL * d->W, Hi = 2LL * d->H;
+    for (int v = 0; v < 4; ++v) {
+      const long long off = ((long long)(v >> 1) * Wi + (v & 1)) * ld;
+      if ((rc = wg_encode_view(&p.tmA_hi[v], d->a_hi + off, d->Cin, 2 * ld, 2 * Wi * ld, Hi * Wi * ld, d->N, d->H, d->W, BW,
+                               BH)) != ESSB_OK)
+        return rc;
+      if (d->passes == 3 && (rc = wg_encode_view(&p.tmA_lo[v], d->a_lo + off, d->Cin, 2 * ld, 2 * Wi * ld, Hi * Wi * ld,
+                                                 d->N, d->H, d->W, BW, BH)) != ESSB_OK)
+        return rc;
+    }
   }
+  if ((rc = wg_encode(&p.tmG_hi, d->g_hi, d->g_ld, d->g_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK) return rc;
+  if (d->passes == 3 && (rc = wg_encode(&p.tmG_lo, d->g_lo, d->g_ld, d->g_ld, d->N, d->H, d->W, BW, BH)) != ESSB_OK) return rc;
   p.m_tiles = pl.m_tiles; p.splits = pl.splits; p.ntaps = d->ntaps;
   static const int fuse_env = [] { const char* e = getenv("ESSB_TC_FUSEB"); return e ? atoi(e) : 1; }();
   p.fuse_g = (fuse_env != 0 && d->passes == 3 && 2 * 64 * pl.nb <= 256) ? 1 : 0;
@@ -364,7 +401,15 @@ extern "C" int essb_wgrad_tc_run(const essb_wgrad_tc* d, void* stream) {
   ESSB_REQUIRE(stages >= 2, "essb_wgrad_tc_run: tile does not fit two stages");
   p.stages = stages;
   p.cin = d->Cin; p.cout = d->Cout; p.partial = d->workspace;
-  for (int t = 0; t < d->ntaps; ++t) { p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; }
+  for (int t = 0; t < d->ntaps; ++t) {
+    if (astride == 1) {
+      p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.view[t] = 0;
+    } else {  // input offset o = 2a + parity (floor division): view = parity plane, shift a inside it
+      const int oy = d->dy[t], ox = d->dx[t];
+      const int py = oy & 1, px = ox & 1;
+      p.dy[t] = (int8_t)((oy - py) / 2); p.dx[t] = (int8_t)((ox - px) / 2); p.view[t] = (int8_t)(py * 2 + px);
+    }
+  }
   size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024 + 256;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
   cudaStream_t st = (cudaStream_t)stream;

@@ -463,9 +463,11 @@ def conv_tc_dense(planes, w_hi, w_lo, k_per_tap, taps, N, H, W, Cout, passes, bi
     return out
 
 
-def wgrad_tc(a_planes, g_planes, Cin, Cout, taps, N, H, W, passes, tag='seg_wgrad'):
-    """essb_wgrad_tc_run: dW [Cout, Cin, ntaps] from the bf16 planes of the conv input and of dY."""
+def wgrad_tc(a_planes, g_planes, Cin, Cout, taps, N, H, W, passes, tag='seg_wgrad', stride=1):
+    """essb_wgrad_tc_run: dW [Cout, Cin, ntaps] from the bf16 planes of the conv input and of dY.  N, H, W are
+    dY's dims; stride=2: the input planes are [N, 2H, 2W, Cin] and the taps' (dy, dx) are input-pixel offsets."""
     d = _lib.WgradTc()
+    d.a_stride = stride
     d.a_hi, d.a_lo, d.g_hi, d.g_lo = _p(a_planes[0]), _p(a_planes[1]), _p(g_planes[0]), _p(g_planes[1])
     d.a_ld, d.Cin, d.g_ld, d.Cout = a_planes[0].shape[-1], Cin, g_planes[0].shape[-1], Cout
     d.N, d.H, d.W, d.passes = N, H, W, passes
@@ -592,6 +594,32 @@ def pw_conv_wgrad(seg: Seg, dy, want_w=True, want_b=True):
     ws = torch.empty((int(nbytes) // 4,), device=dev, dtype=torch.float32)
     call('essb_pw_conv_wgrad', C.byref(s), _p(dy), Cout, N, H, W, Cout, _p(dw), _p(db), _p(ws), ws.numel() * 4, _stream())
     return dw, db
+
+
+def stem_conv_supported(cin, cout, k, stride):
+    return cin == 1 and bool(_lib.lib().essb_stem_conv_supported(cout, k, stride))
+
+
+def stem_conv_fwd(x, w, stride, pad):
+    """essb_stem_conv_fwd: x [N, H, W, 1] fp32, w [Cout, 1, k, k] -> [N, OH, OW, Cout]."""
+    N, H, W, _ = x.shape
+    Cout, _, k, _ = w.shape
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    out = torch.empty((N, OH, OW, Cout), device=x.device, dtype=torch.float32)
+    call('essb_stem_conv_fwd', _p(x), _p(w), _p(out), N, H, W, Cout, k, stride, pad, _stream())
+    return out
+
+
+def stem_conv_wgrad(x, dy, Cout, k, stride, pad):
+    """essb_stem_conv_wgrad -> dW [Cout, 1, k, k]."""
+    N, H, W, _ = x.shape
+    dw = torch.empty((Cout, 1, k, k), device=x.device, dtype=torch.float32)
+    nbytes = _lib.lib().essb_stem_conv_wgrad_workspace_bytes(Cout, k)
+    if nbytes < 0:
+        raise RuntimeError('essb_stem_conv_wgrad: unsupported shape')
+    ws = torch.empty((int(nbytes) // 4,), device=x.device, dtype=torch.float32)
+    call('essb_stem_conv_wgrad', _p(x), _p(dy), _p(dw), N, H, W, Cout, k, stride, pad, _p(ws), ws.numel() * 4, _stream())
+    return dw
 
 
 def colsum(x, Cc=None):

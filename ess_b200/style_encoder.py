@@ -13,8 +13,8 @@ Execution: two small autograd Functions on pixel-major fp32 tensors -- a bias-fr
 and train-mode BatchNorm fused with the BasicBlock residual add and ReLU (batch statistics in one
 memory pass, apply in one pass; backward in two passes).  In the tensor-core modes every 3x3 / 1x1 convolution
 runs on the tcgen05 kernels (stride 2 through parity views; input gradients of strided convs as per-phase
-gathers with strided stores); the 1-channel 7x7 stem and the stride-2 weight gradients stay on the exact-fp32
-CUDA-core kernels.
+gathers with strided stores); the 1-channel 7x7 stem has its own HBM-bound kernels (stem_conv.cu); the stride-2
+weight gradients read the input through parity planes on the tcgen05 wgrad kernel.
 """
 import torch
 import torch.nn as nn
@@ -50,6 +50,8 @@ class _ConvFn(torch.autograd.Function):
                 y = ops.conv_tc_dense(planes, w_hi, w_lo, kinp, ops.taps_conv(k, pad), N, H, W, Cout, passes, tag='uda_fwd')
             else:
                 y = ops.conv_tc_s2(planes, w_hi, w_lo, kinp, k, pad, N, H, W, Cout, passes, tag='uda_fwd')
+        elif ops.stem_conv_supported(Cin, Cout, k, stride) and x.is_contiguous():
+            y = ops.stem_conv_fwd(x, w.detach().float().contiguous(), stride, pad)      # 1-channel 7x7 stem (HBM-bound)
         else:
             wp = ops.pack_weight(w)
             y, _, _, _ = ops.conv([Seg(x)], wp, None, N, H, W, OH, OW, Cout, ops.taps_conv(k, pad), stride=stride,
@@ -71,10 +73,12 @@ class _ConvFn(torch.autograd.Function):
         gplanes = ops.split_bf16(Seg(gy), N, OH, OW) if tc else None          # Cout is a multiple of 64
         gx = gw = None
         if ctx.needs_input_grad[1]:
-            if tc and stride == 1:
+            if tc and (stride == 1 or (stride == 2 and H == 2 * OH and W == 2 * OW)):
                 planes = ops.split_bf16(Seg(x), N, H, W)
-                gw = ops.wgrad_tc(planes, gplanes, Cin, Cout, ops.taps_conv(k, pad), N, H, W, passes,
-                                  tag='uda_wgrad').view(w.shape)
+                gw = ops.wgrad_tc(planes, gplanes, Cin, Cout, ops.taps_conv(k, pad), N, OH, OW, passes,
+                                  tag='uda_wgrad', stride=stride).view(w.shape)
+            elif ops.stem_conv_supported(Cin, Cout, k, stride) and x.is_contiguous():
+                gw = ops.stem_conv_wgrad(x, gy, Cout, k, stride, pad).view(w.shape)
             else:
                 dw, _ = ops.wgrad([Seg(x)], gy, N, H, W, OH, OW, Cout, ops.taps_conv(k, pad), stride=stride,
                                   want_bias=False)

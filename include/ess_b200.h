@@ -193,6 +193,19 @@ int64_t essb_pw_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin);
 int essb_pw_conv_wgrad(const essb_src* src, const float* dy, int ld_dy, int N, int H, int W, int Cout,
                        float* dw, float* dbias, float* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- single-input-channel stem convolution (stem_conv.cu) ------------------------------------------
+ * Replaces resnet18.conv1 = nn.Conv2d(1, 64, 7, stride 2, padding 3, bias=False) of StyleEncoderE2VID
+ * (models/style_networks.py:117-121) forward and its autograd weight gradient (UDA step,
+ * training/ess_trainer.py:159-162,282).  x: [N][H][W] fp32 (one channel), w / dw: [Cout][k*k] (reference
+ * layout), out / dy: pixel-major [N][OH][OW][Cout].  Only (Cout, k, stride) = (64, 7, 2) is built
+ * (essb_stem_conv_supported); HBM-bound, deterministic two-stage wgrad reduction through `workspace`. */
+int essb_stem_conv_supported(int Cout, int k, int stride);
+int essb_stem_conv_fwd(const float* x, const float* w, float* out, int N, int H, int W, int Cout, int k,
+                       int stride, int pad, void* stream);
+int64_t essb_stem_conv_wgrad_workspace_bytes(int Cout, int k);
+int essb_stem_conv_wgrad(const float* x, const float* dy, float* dw, int N, int H, int W, int Cout, int k,
+                         int stride, int pad, float* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- event pre-processing (e2vid/utils/inference_utils.py:84-109, 311-338) --------------- */
 /* stats[w][3] = (sum x, sum x^2, count of non-zeros) of window w for ALL T windows in one launch;
  * x is [B][T][count] with batch stride `bstride` floats (count = C*H*W of one window).  One launch
@@ -376,6 +389,8 @@ typedef struct essb_wgrad_tc {
   int32_t N, H, W;
   int32_t passes;
   int32_t ntaps;
+  int32_t a_stride;      /* 0/1: stride-1 conv, A is [N,H,W,a_ld]; 2: stride-2 conv, A is [N,2H,2W,a_ld] (read through
+                            its parity planes) and dy/dx are INPUT-pixel offsets (ky - pad) of dY's pixel (2y, 2x) */
   int8_t dy[ESSB_MAX_TAPS];
   int8_t dx[ESSB_MAX_TAPS];
 } essb_wgrad_tc;

@@ -360,3 +360,22 @@ def test_split_bf16_zero_pads_channels():
     ops.split_bf16(ops.Seg(x), 2, 6, 10, hi, lo, 0, c_pad=64)
     assert float(hi[..., 32:].abs().max()) == 0.0 and float(lo[..., 32:].abs().max()) == 0.0
     assert rel_err(hi[..., :32].float() + lo[..., :32].float(), x) < 1e-4
+
+
+@pytest.mark.parametrize('N,H,W', [(2, 32, 64), (1, 46, 70), (3, 16, 24)])
+def test_stem_conv_fwd_wgrad(N, H, W):
+    """essb_stem_conv_{fwd,wgrad} (ResNet-18 conv1: 1 -> 64, 7x7, stride 2, pad 3; style_networks.py:117-121) vs
+    autograd, incl. ragged tiles (OW = 35 not a multiple of the 32-pixel tile, OH = 23 not a multiple of 8)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(N, 1, H, W, generator=g).double()
+    w = (torch.randn(64, 1, 7, 7, generator=g) * 0.1).double().requires_grad_(True)
+    y = F.conv2d(x, w, stride=2, padding=3)
+    gy = torch.randn(y.shape, generator=g).double()
+    y.backward(gy)
+    assert ops.stem_conv_supported(1, 64, 7, 2)
+    xd = nhwc(x.float())
+    out = ops.stem_conv_fwd(xd, w.detach().float().cuda().contiguous(), 2, 3)
+    assert rel_err(nchw(out), y) < TIGHT
+    dw = ops.stem_conv_wgrad(xd, nhwc(gy.float()), 64, 7, 2, 3)
+    assert rel_err(dw.cpu(), w.grad) < TIGHT

@@ -157,3 +157,24 @@ def test_convlstm_tc_splitk_is_deterministic_and_leaves_scratch_clean():
         ops.SPLITK = True
     torch.cuda.synchronize()
     assert rel_err(h1, h3) < 1e-5 and rel_err(c1, c3) < 1e-5
+
+
+@pytest.mark.parametrize('Cin,Cout,k', [(64, 128, 3), (128, 256, 3), (64, 128, 1)])
+def test_wgrad_tc_stride2(Cin, Cout, k):
+    """Weight gradient of a stride-2 conv (ResNet layer2/3 conv1 and the 1x1 downsample, style_networks.py:117-121)
+    on the tcgen05 wgrad kernel: the input is read through its four parity planes."""
+    from ess_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    N, H, W = 2, 20, 28
+    pad = k // 2
+    x = torch.randn(N, Cin, H, W, generator=g).double()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) * 0.05).double().requires_grad_(True)
+    y = torch.nn.functional.conv2d(x, w, stride=2, padding=pad)
+    gy = torch.randn(y.shape, generator=g).double()
+    y.backward(gy)
+    OH, OW = y.shape[2:]
+    assert (OH, OW) == (H // 2, W // 2)
+    xp, gp = planes_of(x.float()), planes_of(gy.float())
+    dw = ops.wgrad_tc(xp, gp, Cin, Cout, ops.taps_conv(k, pad), N, OH, OW, 3, stride=2)
+    torch.cuda.synchronize()
+    assert rel_err(dw.view(Cout, Cin, k, k).cpu(), w.grad) < 1e-3

@@ -80,3 +80,23 @@ out = dict(config='DSEC UDA: B=%d images + B=%d event stacks, 440x640, T=%d, C=5
 print(json.dumps(out))
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'uda_probe.json'), 'w'))
+
+if os.environ.get('PROBE_TRACE'):
+    # kernel-level trace of one UDA iteration (CUPTI): where the ~80 ms outside the encoder unroll go
+    import collections
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    tot = collections.OrderedDict()
+    for e in ev:
+        name = e.name.replace('(anonymous namespace)::', '').replace('void ', '').split('(')[0][:52]
+        a = tot.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += (e.time_range.end - e.time_range.start) / 1e3
+    total = sum(v[1] for v in tot.values())
+    print('UDA iteration: %d kernels, kernel time %.2f ms' % (len(ev), total))
+    for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1])[:32]:
+        print('%-54s %4d %8.3f ms %5.1f%%' % (k, v[0], v[1], 100 * v[1] / total))
+    for pat in ('wgrad_fp32_kernel', 'conv_fp32_kernel', 'wgrad_tc_kernel'):
+        print(pat, ' '.join('%.3f' % ((e.time_range.end - e.time_range.start) / 1e3) for e in ev if pat in e.name))
