@@ -681,9 +681,10 @@ def _tc_workspace(device):
     ent = _TC_POOL.get(key)
     if ent is None:
         ent = {'sched': torch.zeros((TC_SCHED_SLOTS, 2), device=device, dtype=torch.int32), 'next': 0,
-               'cnt': torch.zeros((148 * 8,), device=device, dtype=torch.int32),
-               'ws': torch.empty((TC_SPLITK_WS_BYTES // 4,), device=device, dtype=torch.float32)}
+               'cnt': torch.zeros((148 * 8,), device=device, dtype=torch.int32), 'ws': None}
         _TC_POOL[key] = ent
+    if SPLITK and ent['ws'] is None:     # the 80 MB partial-accumulator buffer exists only when split-K is switched on
+        ent['ws'] = torch.empty((TC_SPLITK_WS_BYTES // 4,), device=device, dtype=torch.float32)
     return ent
 
 

@@ -62,4 +62,7 @@ class RAdam(Optimizer):
                 rectified, step_size = rectification(st['step'], float(beta1), float(beta2))
                 call('essb_radam_step', ops._p(p), ops._p(g), ops._p(st['exp_avg']), ops._p(st['exp_avg_sq']), p.numel(),
                      beta1, beta2, step_size * lr, eps, wd * lr, int(rectified), stream)
+                # the kernel wrote p through its raw pointer: tell autograd / the packed-weight caches (keyed on
+                # Parameter._version) that the tensor changed in place
+                torch._C._increment_version([p])
         return loss

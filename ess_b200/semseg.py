@@ -181,6 +181,18 @@ def _taps(k):
     return ops.taps_conv(k, k // 2)
 
 
+def _packed_tc(module, w, **kw):
+    """pack_weight_tc(w, **kw) cached on the module per (parameter storage, version, options): the UDA iteration
+    runs the decoder five times forward and three times backward between two optimizer steps."""
+    cache = module.__dict__.setdefault('_wcache', {})
+    key = (w.data_ptr(), tuple(sorted(kw.items())))
+    ent = cache.get(key)
+    if ent is None or ent[0] != w._version or ent[1] != tuple(w.shape):
+        ent = (w._version, tuple(w.shape), ops.pack_weight_tc(w, **kw))
+        cache[key] = ent
+    return ent[2]
+
+
 def _bias_grad(nd, gy, dev):
     """Bias gradient of a conv node.  A bias that feeds an InstanceNorm (every conv of the IN blocks,
     style_networks.py:162-163,174-183) is cancelled by the mean subtraction: the incoming gradient gy is the
@@ -235,7 +247,7 @@ class _DecoderFn(torch.autograd.Function):
                     for sg in segs:
                         ops.split_bf16(sg, N, H, W, hi, lo, c_off)
                         c_off += sg.C if sg.C is not None else sg.t.shape[-1]
-                    w_hi, w_lo, kinp = ops.pack_weight_tc(w)
+                    w_hi, w_lo, kinp = _packed_tc(module, w)
                     y = ops.conv_tc_dense((hi, lo), w_hi, w_lo, kinp, _taps(nd.k), N, H, W, nd.cout, passes, bias=bias,
                                           tag='seg_fwd')
                     if keep_planes:
@@ -413,7 +425,13 @@ class _DecoderFn(torch.autograd.Function):
                         kinp = (nd.cout + 63) // 64 * 64
                         if gplanes is None:
                             gplanes = dy_planes()
-                        w_hi, w_lo, _ = ops.pack_weight_tc(wseg, swap_io=True, kin_pad=kinp)
+                        cache = module.__dict__.setdefault('_wcache', {})
+                        key = (w.data_ptr(), 'dgrad', c_off, cs, kinp)
+                        ent = cache.get(key)
+                        if ent is None or ent[0] != w._version:
+                            ent = (w._version, ops.pack_weight_tc(wseg, swap_io=True, kin_pad=kinp))
+                            cache[key] = ent
+                        w_hi, w_lo, _ = ent[1]
                         dA = ops.conv_tc_dense(gplanes, w_hi, w_lo, kinp, dtaps, N, H, W, cs, passes, tag='seg_dgrad')
                     else:
                         wp = ops.pack_weight(wseg, swap_io=True)
