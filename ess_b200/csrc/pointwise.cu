@@ -105,13 +105,17 @@ __global__ void norm_act_add_kernel(const float* __restrict__ y, int ld_y, const
   *reinterpret_cast<float4*>(out + pix * ld_out + c) = v;
 }
 
-constexpr int BWD_PIX_PER_BLOCK = 256;
+// Pixels reduced by one block of the InstanceNorm statistics / backward kernels.  Small images get small blocks
+// so that even a 55x80 layer launches >= 4 blocks per SM (ncu: 288 blocks of 256 pixels left the 1/8-scale
+// layers at 23 % resident warps and 34 % of DRAM bandwidth); the per-block partials are reduced by one warp per
+// (n, c) in a fixed order, so the result does not depend on the block size.
+static inline int in_pix_per_block(long long P) { return P >= 65536 ? 256 : (P >= 16384 ? 128 : 64); }
 
 // pass 1 of the IN(+ReLU)(+upsample) backward.  grid = (blocks_per_sample, N, channel groups of 128)
 __global__ void __launch_bounds__(256) in_bwd_pass1_kernel(
     const float* __restrict__ dA, int ld_dA, int ups, const float* __restrict__ extra, int ld_extra,
     const float* __restrict__ y, int ld_y, const float* __restrict__ mean, const float* __restrict__ rstd,
-    int relu, float* __restrict__ g, float* __restrict__ partial, int H, int W, int C) {
+    int relu, float* __restrict__ g, float* __restrict__ partial, int H, int W, int C, int ppb) {
   __shared__ float red[8][32][8];
   const int n = blockIdx.y, blk = blockIdx.x;
   const int CQ = C >> 2;
@@ -132,8 +136,8 @@ __global__ void __launch_bounds__(256) in_bwd_pass1_kernel(
     r4 = *reinterpret_cast<const float4*>(rstd + (size_t)n * C + c);
   }
   float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
-  const long long p_begin = (long long)blk * BWD_PIX_PER_BLOCK;
-  for (int i = warp * ppw + sub; i < BWD_PIX_PER_BLOCK; i += 8 * ppw) {
+  const long long p_begin = (long long)blk * ppb;
+  for (int i = warp * ppw + sub; i < ppb; i += 8 * ppw) {
     const long long pp = p_begin + i;
     if (pp >= P || !cq_ok) continue;
     const long long pix = (long long)n * P + pp;
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(256) in_bwd_pass1_kernel(
 
 // per-block (sum, sumsq) of y over pixels: partial [N][blocks][C][2].  Same thread mapping as pass 1.
 __global__ void __launch_bounds__(256) in_stats_kernel(const float* __restrict__ y, int ld_y,
-                                                       float* __restrict__ partial, long long P, int C) {
+                                                       float* __restrict__ partial, long long P, int C, int ppb) {
   __shared__ float red[8][32][8];
   const int n = blockIdx.y, blk = blockIdx.x;
   const int CQ = C >> 2;
@@ -208,8 +212,8 @@ __global__ void __launch_bounds__(256) in_stats_kernel(const float* __restrict__
   const bool cq_ok = q < cq_left;
   const int c = (cq_base + q) * 4;
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-  const long long p_begin = (long long)blk * BWD_PIX_PER_BLOCK;
-  for (int i = warp * ppw + sub; i < BWD_PIX_PER_BLOCK; i += 8 * ppw) {
+  const long long p_begin = (long long)blk * ppb;
+  for (int i = warp * ppw + sub; i < ppb; i += 8 * ppw) {
     const long long pp = p_begin + i;
     if (pp >= P || !cq_ok) continue;
     const float4 v = *reinterpret_cast<const float4*>(y + ((long long)n * P + pp) * ld_y + c);
@@ -580,14 +584,17 @@ extern "C" int essb_in_stats(const float* y, int ld_y, float* partial, int N, in
   ESSB_REQUIRE(y && partial && N > 0 && P > 0 && C > 0 && C % 4 == 0, "essb_in_stats: bad arguments (C %% 4 == 0)");
   int rc;
   if ((rc = check_vec4(y, ld_y, "essb_in_stats"))) return rc;
-  const int blocks = (int)((P + BWD_PIX_PER_BLOCK - 1) / BWD_PIX_PER_BLOCK);
+  const int blocks = essb_in_bwd_blocks(P);
   dim3 grid(blocks, N, (C / 4 + 31) / 32);
-  in_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, ld_y, partial, P, C);
+  in_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, ld_y, partial, P, C, in_pix_per_block(P));
   ESSB_LAUNCH_CHECK("essb_in_stats");
   return ESSB_OK;
 }
 
-extern "C" int essb_in_bwd_blocks(int64_t P) { return (int)((P + BWD_PIX_PER_BLOCK - 1) / BWD_PIX_PER_BLOCK); }
+extern "C" int essb_in_bwd_blocks(int64_t P) {
+  const int ppb = in_pix_per_block(P);
+  return (int)((P + ppb - 1) / ppb);
+}
 
 extern "C" int essb_in_bwd_pass1(const float* dA, int ld_dA, int ups, const float* extra, int ld_extra,
                                  const float* y, int ld_y, const float* mean, const float* rstd, int relu, float* g,
@@ -602,7 +609,8 @@ extern "C" int essb_in_bwd_pass1(const float* dA, int ld_dA, int ups, const floa
   const int blocks = essb_in_bwd_blocks((int64_t)H * W);
   dim3 grid(blocks, N, (C / 4 + 31) / 32);
   in_bwd_pass1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dA, ld_dA, ups, extra, ld_extra, y, ld_y, mean, rstd,
-                                                              relu, g, partial, H, W, C);
+                                                              relu, g, partial, H, W, C,
+                                                              in_pix_per_block((long long)H * W));
   ESSB_LAUNCH_CHECK("essb_in_bwd_pass1");
   return ESSB_OK;
 }
