@@ -908,39 +908,51 @@ __global__ void event_prepare_planes_kernel(const float* __restrict__ x, long lo
                                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int C, int H,
                                             int W, int Hp, int Wp, int pad_top, int pad_left, int Hb, int Wb, int off_y,
                                             int off_x, int flip) {
-  // grid (ceil(Wp / blockDim.x), Hp, B): no index division
+  // grid (ceil(Wp / blockDim.x), ceil(Hp / 2), B): no index division; a thread converts the pixels (oy, ox) and
+  // (oy + 1, ox) and issues the loads of both before any arithmetic (the kernel is latency-bound otherwise)
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   if (ox >= Wp) return;
-  const int oy = blockIdx.y, n = blockIdx.z;
-  int iy = reflect_idx_tc(oy - pad_top, H), ix = reflect_idx_tc(ox - pad_left, W);
-  if (flip) { iy = H - 1 - iy; ix = W - 1 - ix; }   // torch.flip(events, dims=[2, 3]) precedes the padding
-  float mean = 0.f, stdv = 1.f;
+  const int oy0 = blockIdx.y * 2, n = blockIdx.z;
+  float mean = 0.f, inv_std = 1.f;
   bool do_norm = false;
   if (normalize) {
     const double nnz = stats[2];
     if (nnz > 0.0) {
       const float fm = (float)stats[0] / (float)nnz;
-      stdv = sqrtf((float)stats[1] / (float)nnz - fm * fm);
+      inv_std = 1.f / sqrtf((float)stats[1] / (float)nnz - fm * fm);
       mean = fm;
       do_norm = true;
     }
   }
-  const float* src = x + (long long)n * bstride + (long long)iy * W + ix;
-  __align__(16) __nv_bfloat16 h[CPAD], l[CPAD];
+  int ix = reflect_idx_tc(ox - pad_left, W);
+  if (flip) ix = W - 1 - ix;                            // torch.flip(events, dims=[2, 3]) precedes the padding
+  float v[2][CPAD];
 #pragma unroll
-  for (int c = 0; c < CPAD; ++c) {
-    float v = 0.f;
-    if (c < C) {
-      v = src[(long long)c * H * W];
-      if (do_norm) v = (v != 0.f) ? (v - mean) / stdv : 0.f;
-    }
-    split_bf16(v, h[c], l[c]);
+  for (int r = 0; r < 2; ++r) {
+    const int oy = min(oy0 + r, Hp - 1);
+    int iy = reflect_idx_tc(oy - pad_top, H);
+    if (flip) iy = H - 1 - iy;
+    const float* src = x + (long long)n * bstride + (long long)iy * W + ix;
+#pragma unroll
+    for (int c = 0; c < CPAD; ++c) v[r][c] = (c < C) ? src[(long long)c * H * W] : 0.f;
   }
-  const size_t dst = (((size_t)n * Hb + oy + off_y) * Wb + ox + off_x) * CPAD;
 #pragma unroll
-  for (int c = 0; c < CPAD; c += 8) {
-    *reinterpret_cast<uint4*>(hi + dst + c) = *reinterpret_cast<const uint4*>(h + c);
-    *reinterpret_cast<uint4*>(lo + dst + c) = *reinterpret_cast<const uint4*>(l + c);
+  for (int r = 0; r < 2; ++r) {
+    const int oy = oy0 + r;
+    if (oy >= Hp) break;
+    __align__(16) __nv_bfloat16 h[CPAD], l[CPAD];
+#pragma unroll
+    for (int c = 0; c < CPAD; ++c) {
+      float t = v[r][c];
+      if (do_norm) t = (t != 0.f) ? (t - mean) * inv_std : 0.f;
+      split_bf16(t, h[c], l[c]);
+    }
+    const size_t dst = (((size_t)n * Hb + oy + off_y) * Wb + ox + off_x) * CPAD;
+#pragma unroll
+    for (int c = 0; c < CPAD; c += 8) {
+      *reinterpret_cast<uint4*>(hi + dst + c) = *reinterpret_cast<const uint4*>(h + c);
+      *reinterpret_cast<uint4*>(lo + dst + c) = *reinterpret_cast<const uint4*>(l + c);
+    }
   }
 }
 
@@ -1083,7 +1095,7 @@ extern "C" int essb_event_prepare_planes(const float* x, int64_t bstride, const 
   ESSB_REQUIRE(essb_aligned16(hi) && essb_aligned16(lo), "essb_event_prepare_planes: planes must be 16B aligned");
   ESSB_REQUIRE(B <= 65535 && Hp <= 65535, "essb_event_prepare_planes: B and Hp must fit a grid dimension");
   const int threads = Wp >= 512 ? 128 : 64;
-  const dim3 grid((unsigned)((Wp + threads - 1) / threads), (unsigned)Hp, (unsigned)B);
+  const dim3 grid((unsigned)((Wp + threads - 1) / threads), (unsigned)((Hp + 1) / 2), (unsigned)B);
   __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(hi);
   __nv_bfloat16* l = reinterpret_cast<__nv_bfloat16*>(lo);
   if (cpad == 8)

@@ -12,7 +12,7 @@ imports it.
 
 PINNING: the reference ships no tests, golden vectors or fixtures, so upstream
 parity is unpinned.  This oracle is pinned instead against the *imported reference modules run in the
-build container* (`tests/test_oracle_vs_reference.py`, skipped where /root/reference is absent) and
+build container* (`tests/test_oracle.py`, skipped where /root/reference is absent) and
 against committed golden tensors generated from the reference by `tests/golden/make_golden.py`.
 """
 import math
