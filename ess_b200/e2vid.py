@@ -341,7 +341,7 @@ class E2VIDRecurrent(nn.Module):
         d.ntaps = 5
         for ky in range(5):
             d.dy[ky], d.dx[ky], d.view[ky], d.widx[ky] = ky, 0, 0, ky
-        ops.conv_tc(d, tag='head_tc')
+        ops.conv_tc(d, tag='head_tc', device=head.device if head is not None else planes[0].device)
 
     def _forward_impl(self, x, in_planes, N, H, W, prev_states, with_image, want_head=True):
         P = self._pack()
@@ -564,7 +564,7 @@ class E2VIDRecurrent(nn.Module):
         d.ntaps = len(taps)
         for t, (dy, dx, v, wi) in enumerate(taps):
             d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, v, wi
-        ops.conv_tc(d, tag='enc_tc')
+        ops.conv_tc(d, tag='enc_tc', device=out_hi.device)
 
     def _gru_tc(self, e, x_planes, h_prev, h_planes, N, oh, ow, C, passes):
         """ConvGRU cell (submodules.py:255-273) as two tcgen05 launches: [update, reset] gates (epilogue writes
@@ -599,7 +599,7 @@ class E2VIDRecurrent(nn.Module):
         d.w_hi, d.w_lo, d.w_rows, d.bias = ops._p(tcw['ur_hi']), ops._p(tcw['ur_lo']), tcw['ur_hi'].shape[0], ops._p(e['gru_ur_b'])
         d.aux0, d.out, d.out_hi, d.out_lo = ops._p(h_prev), ops._p(upd), ops._p(hr[0]), ops._p(hr[1])
         d.Cout, d.epilogue = 2 * C, EPI_GRU_UR
-        ops.conv_tc(d, tag='gru_tc')
+        ops.conv_tc(d, tag='gru_tc', device=dev)
         h = torch.empty((N, oh, ow, C), device=dev, dtype=torch.float32)
         hh = torch.empty((N, oh, ow, C), device=dev, dtype=torch.bfloat16)
         hl = torch.empty_like(hh)
@@ -608,7 +608,7 @@ class E2VIDRecurrent(nn.Module):
         d.w_hi, d.w_lo, d.w_rows, d.bias = ops._p(tcw['o_hi']), ops._p(tcw['o_lo']), tcw['o_hi'].shape[0], ops._p(e['gru_o_b'])
         d.aux0, d.aux1, d.out, d.out_hi, d.out_lo = ops._p(h_prev), ops._p(upd), ops._p(h), ops._p(hh), ops._p(hl)
         d.Cout, d.epilogue = C, EPI_GRU_OUT
-        ops.conv_tc(d, tag='gru_tc')
+        ops.conv_tc(d, tag='gru_tc', device=dev)
         return h, hh, hl
 
     def _lstm_tc(self, e, x_planes, h_planes, c_prev, N, oh, ow, C, passes):
@@ -639,5 +639,5 @@ class E2VIDRecurrent(nn.Module):
         d.ntaps = len(taps)
         for t, (dy, dx, wi) in enumerate(taps):
             d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, 0, wi
-        ops.conv_tc(d, tag='lstm_tc')
+        ops.conv_tc(d, tag='lstm_tc', device=dev)
         return h, c, hh, hl

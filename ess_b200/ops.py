@@ -459,7 +459,7 @@ def conv_tc_dense(planes, w_hi, w_lo, k_per_tap, taps, N, H, W, Cout, passes, bi
     d.ntaps = len(taps)
     for t, (dy, dx, wi) in enumerate(taps):
         d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, 0, wi
-    conv_tc(d, tag=tag)
+    conv_tc(d, tag=tag, device=hi.device)
     return out
 
 
@@ -659,7 +659,7 @@ def conv_tc_s2(planes, w_hi, w_lo, k_per_tap, k, pad, N, H, W, Cout, passes, bia
             d.dy[t], d.dx[t], d.view[t], d.widx[t] = (oy - py) // 2, (ox - px) // 2, py * 2 + px, ky * k + kx
             t += 1
     d.ntaps = t
-    conv_tc(d, tag=tag)
+    conv_tc(d, tag=tag, device=hi.device)
     return out
 
 
@@ -688,10 +688,13 @@ def _tc_workspace(device):
     return ent
 
 
-def conv_tc(d: ConvTc, tag=None):
+def conv_tc(d: ConvTc, tag=None, device=None):
     """essb_conv_tc_run; when _lib.PROFILE is a list, brackets the launch with CUDA events on the
-    launching stream and records (tag, algorithmic FLOPs, start, end)."""
-    ent = _tc_workspace(torch.device('cuda', torch.cuda.current_device()))
+    launching stream and records (tag, algorithmic FLOPs, start, end).  `device`: the device the operands live
+    on (scheduler slots / split-K scratch are allocated there; default = the current device)."""
+    if device is None or device.index is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    ent = _tc_workspace(device)
     slot = ent['next']
     ent['next'] = (slot + 1) % TC_SCHED_SLOTS
     d.sched = _p(ent['sched'], 2 * slot)
