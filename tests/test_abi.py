@@ -63,3 +63,46 @@ def test_product_does_not_import_oracle():
     for fn in os.listdir(pkg):
         if fn.endswith('.py'):
             assert 'oracle' not in open(os.path.join(pkg, fn)).read(), fn
+
+
+def _prototypes():
+    """name -> list of C parameter type strings, parsed from the header's function declarations."""
+    src = open(os.path.join(ROOT, 'include', 'ess_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r'\b(?:int|int64_t|const char\s*\*)\s+(essb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', src, flags=re.S):
+        args = [a.strip() for a in m.group(2).replace('\n', ' ').split(',')]
+        protos[m.group(1)] = [] if args in ([''], ['void']) else args
+    return protos
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """Every ctypes signature has the header's parameter count and the same kind per parameter (pointer /
+    32-bit int / 64-bit int / float): a drifted hand-written mirror would corrupt the call frame silently."""
+    import ctypes as C
+    from ess_b200 import _lib
+    protos = _prototypes()
+    assert set(protos) == set(_lib.SIGNATURES), set(protos) ^ set(_lib.SIGNATURES)
+
+    def kind_c(t):
+        t = re.sub(r'\b[a-zA-Z_][a-zA-Z0-9_]*\s*$', '', t).strip() if not t.endswith('*') else t   # drop the name
+        if '*' in t:
+            return 'ptr'
+        if 'int64_t' in t or 'long long' in t:
+            return 'i64'
+        if 'float' in t:
+            return 'f32'
+        if 'double' in t:
+            return 'f64'
+        return 'i32'
+
+    def kind_py(t):
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return 'ptr'
+        return {C.c_int: 'i32', C.c_int32: 'i32', C.c_int64: 'i64', C.c_float: 'f32', C.c_double: 'f64'}[t]
+
+    for name, (res, args) in _lib.SIGNATURES.items():
+        cargs = protos[name]
+        assert len(cargs) == len(args), '%s: header has %d parameters, ctypes mirror %d' % (name, len(cargs), len(args))
+        for i, (ca, pa) in enumerate(zip(cargs, args)):
+            assert kind_c(ca) == kind_py(pa), '%s: parameter %d is `%s` in the header but %s in _lib.py' % (name, i, ca, pa)
