@@ -226,6 +226,152 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------- all-taps (halo) variant
+// For Cin = 64, Cout <= 64 (the high-resolution decoder layers) the kernel above is bound by operand traffic: every
+// tap pair re-loads a shifted A box and the same dY box (48 KB per 384 MMA cycles).  Here a CTA owns a contiguous
+// range of 8x8-pixel patches and, per patch, loads ONE A tile (patch + halo, e.g. 10x10 pixels) and ONE dY tile and
+// issues the MMAs of ALL taps from them: tap (dy, dx) is a different start row inside the halo tile (rows are whole
+// 128-byte pixels, so the address-based 128 B swizzle stays consistent, as in conv_tc_halo_kernel), an 8-pixel
+// K atom is one patch row, and the stride between K atoms (SBO) is one halo row.  The two 64-row halves of the
+// M = 128 tile are two taps (LBO = distance between their start rows).  All (ntaps + 1) / 2 accumulators stay in
+// TMEM for the CTA's whole pixel range; one epilogue per CTA writes the split-K partials.
+struct WgHaloParams {
+  CUtensorMap tmA_hi, tmA_lo, tmG_hi, tmG_lo;
+  int splits, patches_total, patches_per_split, tiles_x, tiles_y;
+  int ntaps, npairs, passes, stages, stage_bytes, a_plane_bytes, a_tx_bytes;
+  int halo_w, hx0, hy0;
+  int cin, cout;
+  float* partial;
+  int off[ESSB_MAX_TAPS];   // byte offset of tap t's first pixel row inside the halo tile
+};
+
+__device__ __forceinline__ UDesc make_smem_desc_mn_halo(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_udesc(saddr, lbo_bytes >> 4, sbo_bytes);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_halo_kernel(const __grid_constant__ WgHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + WG_MAX_STAGES;
+  uint64_t* tfull_bar = bars + 2 * WG_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int off_alo = p.a_plane_bytes, off_ghi = 2 * p.a_plane_bytes, off_glo = 2 * p.a_plane_bytes + WG_BOX_BYTES;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int split = blockIdx.x;
+  const int p0 = split * p.patches_per_split;
+  const int p1 = min(p0 + p.patches_per_split, p.patches_total);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = (uint32_t)(p.passes == 3 ? 2 : 1) * (uint32_t)(p.a_tx_bytes + WG_BOX_BYTES);
+      for (int pp = p0; pp < p1; ++pp) {
+        int q = pp;
+        const int txi = q % p.tiles_x; q /= p.tiles_x;
+        const int tyi = q % p.tiles_y;
+        const int n = q / p.tiles_y;
+        const int x0 = txi * 8, y0 = tyi * 8;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * p.stage_bytes;
+        mbar_expect_tx(&full_bar[s], tx);
+        tma_load_4d(st, &p.tmA_hi, &full_bar[s], 0, x0 + p.hx0, y0 + p.hy0, n);
+        tma_load_4d(st + off_ghi, &p.tmG_hi, &full_bar[s], 0, x0, y0, n);
+        if (p.passes == 3) {
+          tma_load_4d(st + off_alo, &p.tmA_lo, &full_bar[s], 0, x0 + p.hx0, y0 + p.hy0, n);
+          tma_load_4d(st + off_glo, &p.tmG_lo, &full_bar[s], 0, x0, y0, n);
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_mn(128, 64);
+    const uint32_t sbo = (uint32_t)p.halo_w * 128u;          // next 8-pixel K atom = next patch row = one halo row
+    const uint32_t kstep = (2u * sbo) >> 4;                   // a K step of 16 pixels = two patch rows
+    int s = 0;
+    uint32_t ph = 0;
+    for (int pp = p0; pp < p1; ++pp) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
+      const UDesc g_hi = make_smem_desc_mn(sa + off_ghi), g_lo = make_smem_desc_mn(sa + off_glo);
+      for (int tp = 0; tp < p.npairs; ++tp) {
+        const int t0 = 2 * tp, t1 = min(2 * tp + 1, p.ntaps - 1);
+        const uint32_t lbo = (uint32_t)(p.off[t1] - p.off[t0]);
+        const UDesc a_hi = make_smem_desc_mn_halo(sa + (uint32_t)p.off[t0], lbo, sbo);
+        const UDesc a_lo = make_smem_desc_mn_halo(sa + off_alo + (uint32_t)p.off[t0], lbo, sbo);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(tp * 64);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t ka = (uint32_t)k * kstep;
+          const uint32_t kg = (uint32_t)(k * (16 * 128 >> 4));
+          const uint32_t first = (pp != p0 || k != 0) ? 1u : 0u;
+          if (p.passes == 3) {
+            umma_bf16(d_tmem, a_lo + ka, g_hi + kg, idesc, first);
+            umma_bf16(d_tmem, a_hi + ka, g_lo + kg, idesc, 1u);
+            umma_bf16(d_tmem, a_hi + ka, g_hi + kg, idesc, 1u);
+          } else {
+            umma_bf16(d_tmem, a_hi + ka, g_hi + kg, idesc, first);
+          }
+        }
+      }
+      umma_commit(&empty_bar[s]);
+      if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
+    umma_commit(tfull_bar);
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    if (p1 > p0) {
+      for (int tp = 0; tp < p.npairs; ++tp) {
+        const int tap = 2 * tp + (row >> 6), ci = row & 63;
+        uint32_t rr[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * 64 + half * 32), rr);
+        tmem_ld_wait();
+        const int c0 = half * 32;
+        if (tap < p.ntaps && ci < p.cin && c0 < p.cout) {
+          float* dst = p.partial + (((size_t)split * p.ntaps + tap) * p.cin + ci) * p.cout + c0;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(dst + e) = make_float4(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]),
+                                                              __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // dw[co][ci][tap] = sum_split partial[split][tap][ci][co]
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int splits, int ntaps,
                                        int cin, int cout) {
@@ -333,10 +479,40 @@ int wg_plan(const essb_wgrad_tc& d, WgPlan* pl) {
 
 }  // namespace
 
+// all-taps variant: which layers, and how the patches are split over the CTAs
+static bool wg_halo_ok(const essb_wgrad_tc& d) {
+  static const int env = [] { const char* e = getenv("ESSB_WGRAD_HALO"); return e ? atoi(e) : 1; }();
+  if (!env || d.a_stride == 2 || d.Cin != 64 || d.Cout > 64 || d.Cout % 32 != 0 || d.g_ld != 64 || d.ntaps < 2 ||
+      d.ntaps > 10)
+    return false;
+  int x0 = d.dx[0], x1 = d.dx[0], y0 = d.dy[0], y1 = d.dy[0];
+  for (int t = 1; t < d.ntaps; ++t) {
+    x0 = d.dx[t] < x0 ? d.dx[t] : x0; x1 = d.dx[t] > x1 ? d.dx[t] : x1;
+    y0 = d.dy[t] < y0 ? d.dy[t] : y0; y1 = d.dy[t] > y1 ? d.dy[t] : y1;
+    // tap pairs (2i, 2i+1) need non-decreasing start rows inside the halo tile (LBO is unsigned)
+    if ((t & 1) && (d.dy[t] < d.dy[t - 1] || (d.dy[t] == d.dy[t - 1] && d.dx[t] < d.dx[t - 1]))) return false;
+  }
+  return (x1 - x0) <= 8 && (y1 - y0) <= 8;
+}
+static void wg_halo_split(const essb_wgrad_tc& d, int* splits, int* per_split, int* total, int* tiles_x, int* tiles_y) {
+  *tiles_x = (d.W + 7) / 8;
+  *tiles_y = (d.H + 7) / 8;
+  *total = d.N * *tiles_x * *tiles_y;
+  int sp = *total < 148 ? *total : 148;
+  *per_split = (*total + sp - 1) / sp;
+  *splits = (*total + *per_split - 1) / *per_split;
+}
+
 extern "C" int64_t essb_wgrad_tc_workspace_bytes(const essb_wgrad_tc* d) {
   WgPlan pl;
   if (!d || wg_plan(*d, &pl) != 0) return -1;
-  return (int64_t)pl.splits * d->ntaps * d->Cin * d->Cout * (int64_t)sizeof(float);
+  int64_t splits = pl.splits;
+  if (wg_halo_ok(*d)) {
+    int sp, per, total, tx, ty;
+    wg_halo_split(*d, &sp, &per, &total, &tx, &ty);
+    if (sp > splits) splits = sp;
+  }
+  return splits * d->ntaps * d->Cin * d->Cout * (int64_t)sizeof(float);
 }
 
 extern "C" int essb_wgrad_tc_run(const essb_wgrad_tc* d, void* stream) {
@@ -354,6 +530,54 @@ extern "C" int essb_wgrad_tc_run(const essb_wgrad_tc* d, void* stream) {
   if (d->workspace_bytes < need) {
     essb_set_error("essb_wgrad_tc_run: workspace %lld < %lld bytes", (long long)d->workspace_bytes, (long long)need);
     return ESSB_ERR_WORKSPACE;
+  }
+  if (wg_halo_ok(*d)) {
+    static thread_local WgHaloParams h;
+    int hx0 = d->dx[0], hx1 = d->dx[0], hy0 = d->dy[0], hy1 = d->dy[0];
+    for (int t = 1; t < d->ntaps; ++t) {
+      hx0 = d->dx[t] < hx0 ? d->dx[t] : hx0; hx1 = d->dx[t] > hx1 ? d->dx[t] : hx1;
+      hy0 = d->dy[t] < hy0 ? d->dy[t] : hy0; hy1 = d->dy[t] > hy1 ? d->dy[t] : hy1;
+    }
+    const int halo_w = 8 + (hx1 - hx0), halo_h = 8 + (hy1 - hy0);
+    int rc2;
+    if ((rc2 = wg_encode(&h.tmA_hi, d->a_hi, d->Cin, d->a_ld, d->N, d->H, d->W, halo_w, halo_h)) != ESSB_OK) return rc2;
+    if ((rc2 = wg_encode(&h.tmG_hi, d->g_hi, d->g_ld, d->g_ld, d->N, d->H, d->W, 8, 8)) != ESSB_OK) return rc2;
+    if (d->passes == 3) {
+      if ((rc2 = wg_encode(&h.tmA_lo, d->a_lo, d->Cin, d->a_ld, d->N, d->H, d->W, halo_w, halo_h)) != ESSB_OK) return rc2;
+      if ((rc2 = wg_encode(&h.tmG_lo, d->g_lo, d->g_ld, d->g_ld, d->N, d->H, d->W, 8, 8)) != ESSB_OK) return rc2;
+    }
+    wg_halo_split(*d, &h.splits, &h.patches_per_split, &h.patches_total, &h.tiles_x, &h.tiles_y);
+    h.ntaps = d->ntaps; h.npairs = (d->ntaps + 1) / 2; h.passes = d->passes;
+    h.halo_w = halo_w; h.hx0 = hx0; h.hy0 = hy0;
+    h.a_tx_bytes = halo_w * halo_h * 128;
+    h.a_plane_bytes = (h.a_tx_bytes + 1023) & ~1023;
+    h.stage_bytes = 2 * h.a_plane_bytes + 2 * WG_BOX_BYTES;   // [A_hi | A_lo | G_hi | G_lo] (lo halves unused in 1-pass mode)
+    int stages = (200 * 1024) / h.stage_bytes;
+    if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
+    ESSB_REQUIRE(stages >= 2, "essb_wgrad_tc_run: halo tile does not fit two stages");
+    h.stages = stages;
+    h.cin = d->Cin; h.cout = d->Cout; h.partial = d->workspace;
+    for (int t = 0; t < d->ntaps; ++t) h.off[t] = ((d->dy[t] - hy0) * halo_w + (d->dx[t] - hx0)) * 128;
+    const int64_t need_h = (int64_t)h.splits * d->ntaps * d->Cin * d->Cout * (int64_t)sizeof(float);
+    if (d->workspace_bytes < need_h) {
+      essb_set_error("essb_wgrad_tc_run: workspace %lld < %lld bytes", (long long)d->workspace_bytes, (long long)need_h);
+      return ESSB_ERR_WORKSPACE;
+    }
+    size_t smem_h = (size_t)stages * h.stage_bytes + 1024 + 256;
+    if (smem_h < 120 * 1024) smem_h = 120 * 1024;
+    cudaStream_t sth = (cudaStream_t)stream;
+    cudaError_t eh = cudaFuncSetAttribute(wgrad_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h);
+    if (eh != cudaSuccess) {
+      essb_set_error("essb_wgrad_tc_run: cudaFuncSetAttribute (halo) failed: %s", cudaGetErrorString(eh));
+      return ESSB_ERR_LAUNCH;
+    }
+    wgrad_tc_halo_kernel<<<h.splits, WG_THREADS, smem_h, sth>>>(h);
+    ESSB_LAUNCH_CHECK("essb_wgrad_tc_run (halo)");
+    const long long total_h = (long long)d->ntaps * d->Cin * d->Cout;
+    wgrad_tc_reduce_kernel<<<(unsigned)((total_h + 255) / 256), 256, 0, sth>>>(d->workspace, d->dw, h.splits, d->ntaps,
+                                                                             d->Cin, d->Cout);
+    ESSB_LAUNCH_CHECK("essb_wgrad_tc_reduce");
+    return ESSB_OK;
   }
   static thread_local WgTcParams p;
   const int BW = 1 << pl.bw_log2, BH = WG_PIX >> pl.bw_log2;
