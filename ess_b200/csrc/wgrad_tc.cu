@@ -239,6 +239,9 @@ struct WgHaloParams {
   CUtensorMap tmA_hi, tmA_lo, tmG_hi, tmG_lo;
   int splits, patches_total, patches_per_split, tiles_x, tiles_y;
   int ntaps, npairs, passes, stages, stage_bytes, a_plane_bytes, a_tx_bytes;
+  int a_blocks;          // 64-channel blocks of A per stage: 1 = Cin 64 (M halves = two taps), 2 = Cin 128 (M halves = the
+                         // two channel blocks of ONE tap; npairs then counts taps and tap0 is the first tap of this launch)
+  int tap0;
   int halo_w, hx0, hy0;
   int cin, cout;
   float* partial;
@@ -258,7 +261,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_halo_kernel(const __gr
   uint64_t* tfull_bar = bars + 2 * WG_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int off_alo = p.a_plane_bytes, off_ghi = 2 * p.a_plane_bytes, off_glo = 2 * p.a_plane_bytes + WG_BOX_BYTES;
+  const int off_alo = p.a_blocks * p.a_plane_bytes, off_ghi = 2 * p.a_blocks * p.a_plane_bytes;
+  const int off_glo = off_ghi + WG_BOX_BYTES;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_halo_kernel(const __gr
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t tx = (uint32_t)(p.passes == 3 ? 2 : 1) * (uint32_t)(p.a_tx_bytes + WG_BOX_BYTES);
+      const uint32_t tx = (uint32_t)(p.passes == 3 ? 2 : 1) * (uint32_t)(p.a_blocks * p.a_tx_bytes + WG_BOX_BYTES);
       for (int pp = p0; pp < p1; ++pp) {
         int q = pp;
         const int txi = q % p.tiles_x; q /= p.tiles_x;
@@ -296,10 +300,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_halo_kernel(const __gr
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + (size_t)s * p.stage_bytes;
         mbar_expect_tx(&full_bar[s], tx);
-        tma_load_4d(st, &p.tmA_hi, &full_bar[s], 0, x0 + p.hx0, y0 + p.hy0, n);
+        for (int b = 0; b < p.a_blocks; ++b)
+          tma_load_4d(st + b * p.a_plane_bytes, &p.tmA_hi, &full_bar[s], b * 64, x0 + p.hx0, y0 + p.hy0, n);
         tma_load_4d(st + off_ghi, &p.tmG_hi, &full_bar[s], 0, x0, y0, n);
         if (p.passes == 3) {
-          tma_load_4d(st + off_alo, &p.tmA_lo, &full_bar[s], 0, x0 + p.hx0, y0 + p.hy0, n);
+          for (int b = 0; b < p.a_blocks; ++b)
+            tma_load_4d(st + off_alo + b * p.a_plane_bytes, &p.tmA_lo, &full_bar[s], b * 64, x0 + p.hx0, y0 + p.hy0, n);
           tma_load_4d(st + off_glo, &p.tmG_lo, &full_bar[s], 0, x0, y0, n);
         }
         if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -317,8 +323,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_halo_kernel(const __gr
       const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
       const UDesc g_hi = make_smem_desc_mn(sa + off_ghi), g_lo = make_smem_desc_mn(sa + off_glo);
       for (int tp = 0; tp < p.npairs; ++tp) {
-        const int t0 = 2 * tp, t1 = min(2 * tp + 1, p.ntaps - 1);
-        const uint32_t lbo = (uint32_t)(p.off[t1] - p.off[t0]);
+        // pair mode: M halves = taps 2tp, 2tp+1 (LBO = distance of their start rows); full mode: M halves = the two
+        // channel blocks of tap tap0 + tp (LBO = distance of the two block tiles)
+        const int t0 = p.a_blocks == 1 ? 2 * tp : p.tap0 + tp;
+        const int t1 = p.a_blocks == 1 ? min(2 * tp + 1, p.ntaps - 1) : t0;
+        const uint32_t lbo = p.a_blocks == 1 ? (uint32_t)(p.off[t1] - p.off[t0]) : (uint32_t)p.a_plane_bytes;
         const UDesc a_hi = make_smem_desc_mn_halo(sa + (uint32_t)p.off[t0], lbo, sbo);
         const UDesc a_lo = make_smem_desc_mn_halo(sa + off_alo + (uint32_t)p.off[t0], lbo, sbo);
         const uint32_t d_tmem = tmem_base + (uint32_t)(tp * 64);
@@ -348,7 +357,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_halo_kernel(const __gr
     tc_fence_after();
     if (p1 > p0) {
       for (int tp = 0; tp < p.npairs; ++tp) {
-        const int tap = 2 * tp + (row >> 6), ci = row & 63;
+        const int tap = p.a_blocks == 1 ? 2 * tp + (row >> 6) : p.tap0 + tp;
+        const int ci = p.a_blocks == 1 ? (row & 63) : row;
         uint32_t rr[32];
         __syncwarp();
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * 64 + half * 32), rr);
@@ -482,8 +492,10 @@ int wg_plan(const essb_wgrad_tc& d, WgPlan* pl) {
 // all-taps variant: which layers, and how the patches are split over the CTAs
 static bool wg_halo_ok(const essb_wgrad_tc& d) {
   static const int env = [] { const char* e = getenv("ESSB_WGRAD_HALO"); return e ? atoi(e) : 1; }();
-  if (!env || d.a_stride == 2 || d.Cin != 64 || d.Cout > 64 || d.Cout % 32 != 0 || d.g_ld != 64 || d.ntaps < 2 ||
-      d.ntaps > 10)
+  static const int env128 = [] { const char* e = getenv("ESSB_WGRAD_HALO_128"); return e ? atoi(e) : 1; }();
+  const bool cin_ok = d.Cin == 64 || (d.Cin == 128 && env128 != 0);
+  if (!env || d.a_stride == 2 || !cin_ok || d.Cout > 64 || d.Cout % 32 != 0 || d.g_ld != 64 || d.ntaps < 2 ||
+      d.ntaps > (d.Cin == 64 ? 10 : 16))
     return false;
   int x0 = d.dx[0], x1 = d.dx[0], y0 = d.dy[0], y1 = d.dy[0];
   for (int t = 1; t < d.ntaps; ++t) {
@@ -547,12 +559,14 @@ extern "C" int essb_wgrad_tc_run(const essb_wgrad_tc* d, void* stream) {
       if ((rc2 = wg_encode(&h.tmG_lo, d->g_lo, d->g_ld, d->g_ld, d->N, d->H, d->W, 8, 8)) != ESSB_OK) return rc2;
     }
     wg_halo_split(*d, &h.splits, &h.patches_per_split, &h.patches_total, &h.tiles_x, &h.tiles_y);
-    h.ntaps = d->ntaps; h.npairs = (d->ntaps + 1) / 2; h.passes = d->passes;
+    h.a_blocks = d->Cin == 64 ? 1 : 2;
+    h.ntaps = d->ntaps; h.passes = d->passes;
     h.halo_w = halo_w; h.hx0 = hx0; h.hy0 = hy0;
     h.a_tx_bytes = halo_w * halo_h * 128;
     h.a_plane_bytes = (h.a_tx_bytes + 1023) & ~1023;
-    h.stage_bytes = 2 * h.a_plane_bytes + 2 * WG_BOX_BYTES;   // [A_hi | A_lo | G_hi | G_lo] (lo halves unused in 1-pass mode)
-    int stages = (200 * 1024) / h.stage_bytes;
+    // stage = [A_hi blocks | A_lo blocks | G_hi | G_lo] (lo halves unused in 1-pass mode)
+    h.stage_bytes = 2 * h.a_blocks * h.a_plane_bytes + 2 * WG_BOX_BYTES;
+    int stages = (216 * 1024) / h.stage_bytes;
     if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
     ESSB_REQUIRE(stages >= 2, "essb_wgrad_tc_run: halo tile does not fit two stages");
     h.stages = stages;
@@ -571,8 +585,20 @@ extern "C" int essb_wgrad_tc_run(const essb_wgrad_tc* d, void* stream) {
       essb_set_error("essb_wgrad_tc_run: cudaFuncSetAttribute (halo) failed: %s", cudaGetErrorString(eh));
       return ESSB_ERR_LAUNCH;
     }
-    wgrad_tc_halo_kernel<<<h.splits, WG_THREADS, smem_h, sth>>>(h);
-    ESSB_LAUNCH_CHECK("essb_wgrad_tc_run (halo)");
+    if (h.a_blocks == 1) {      // Cin = 64: all taps in one launch, two taps per accumulator
+      h.tap0 = 0;
+      h.npairs = (d->ntaps + 1) / 2;
+      wgrad_tc_halo_kernel<<<h.splits, WG_THREADS, smem_h, sth>>>(h);
+      ESSB_LAUNCH_CHECK("essb_wgrad_tc_run (halo)");
+    } else {                    // Cin = 128: one tap per accumulator, 8 accumulators (512 TMEM columns) per launch
+      const int ngroups = (d->ntaps + 7) / 8, gsize = (d->ntaps + ngroups - 1) / ngroups;   // 9 taps -> 5 + 4
+      for (int t0 = 0; t0 < d->ntaps; t0 += gsize) {
+        h.tap0 = t0;
+        h.npairs = d->ntaps - t0 < gsize ? d->ntaps - t0 : gsize;
+        wgrad_tc_halo_kernel<<<h.splits, WG_THREADS, smem_h, sth>>>(h);
+        ESSB_LAUNCH_CHECK("essb_wgrad_tc_run (halo)");
+      }
+    }
     const long long total_h = (long long)d->ntaps * d->Cin * d->Cout;
     wgrad_tc_reduce_kernel<<<(unsigned)((total_h + 255) / 256), 256, 0, sth>>>(d->workspace, d->dw, h.splits, d->ntaps,
                                                                              d->Cin, d->Cout);

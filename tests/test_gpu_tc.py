@@ -108,7 +108,9 @@ def test_encoder_conv_tc(passes, tol, Cin, Cout, H, W):
 @pytest.mark.parametrize('N,H,W,Cin,Cout', [(2, 12, 20, 64, 64), (1, 55, 80, 256, 128), (2, 9, 14, 192, 256),
                                             (1, 40, 64, 64, 32), (2, 16, 16, 128, 96),
                                             # all-taps (halo) variant with several patches per CTA and ragged 8x8 patches
-                                            (2, 88, 124, 64, 32), (3, 50, 76, 64, 64)])
+                                            (2, 88, 124, 64, 32), (3, 50, 76, 64, 64),
+                                            # Cin = 128: one tap per accumulator, taps in two launches (5 + 4)
+                                            (2, 24, 40, 128, 64), (1, 70, 94, 128, 32)])
 def test_wgrad_tc(passes, tol, N, H, W, Cin, Cout):
     """tcgen05 weight gradient (MN-major operands, split-K over pixels) vs autograd of F.conv2d."""
     from ess_b200 import ops
