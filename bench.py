@@ -83,6 +83,25 @@ def load_peaks():
     return dict(bf16=1400.0, bf16_burst=1590.0, hbm=6650.0, source='fallback')
 
 
+def bind_to_gpu_numa_node(index):
+    """Restrict this process to the CPUs NVML reports as local to GPU `index` (no-op when NVML or the affinity
+    call is unavailable).  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return '%d of %d cpus' % (len(cpus), ncpu)
+    except Exception as ex:      # diagnostics only; never take the measurement down
+        return 'unavailable (%s)' % type(ex).__name__
+    return 'unavailable'
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -257,6 +276,11 @@ def main():
 
     # two distinct device-resident batches (901 MB each >> 126 MB L2) alternate between timed steps
     host = [synth_inputs(B, T, C, H, W, K, 1234 + 17 * rank + i) for i in range(2)]
+    # Pinned staging memory is allocated from threads bound to the GPU's own NUMA node (what `numactl
+    # --cpunodebind` does for a DataLoader process): on a two-socket host a far-node buffer halves the H2D rate,
+    # and at 70 ms per step the 919 MB of inputs need > 13 GB/s to stay hidden behind the compute.
+    affinity_all = os.sched_getaffinity(0) if hasattr(os, 'sched_getaffinity') else None
+    numa = bind_to_gpu_numa_node(local)
     host = [(d.pin_memory(), l.pin_memory()) for d, l in host]
     devb = [(d.to(dev), l.to(dev)) for d, l in host]
     stage_d = torch.empty_like(devb[0][0])
@@ -352,6 +376,14 @@ def main():
             losses.append(float(loss.item()))               # D2H read of the step's result
         return losses
 
+    # plain H2D rate of the staging copy (diagnostic: explains an e2e value that falls below `value`)
+    torch.cuda.synchronize()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    stage_d.copy_(host[0][0], non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = stage_d.numel() * 4 / (h0.elapsed_time(h1) / 1e3) / 1e9
     e2e_run(2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -417,10 +449,16 @@ def main():
                             gflop_per_sample=flops_per_sample(T, C, H, W, K) / 1e9),
                 tflops=value * flops_per_sample(T, C, H, W, K) / 1e12,
                 e2e=dict(value=e2e_value, unit='samples/s', ms_per_step=ms_e2e / args.steps,
-                         h2d_bytes_per_step=stage_d.numel() * 4 + stage_l.numel() * 8, d2h_bytes_per_step=4),
+                         h2d_bytes_per_step=stage_d.numel() * 4 + stage_l.numel() * 8, d2h_bytes_per_step=4,
+                         h2d_gb_per_s=h2d_gbs, host_numa_binding=numa),
                 gpu_launches=launches, clocks=dict(sm_mhz=clk['sm_mhz'], sm_max_mhz=clk['sm_max_mhz'],
                                                    reasons=clk['reasons'], samples=clk['samples']),
                 roofline=roof)
+    if affinity_all is not None:
+        try:
+            os.sched_setaffinity(0, affinity_all)       # the CPU baseline gets every host core back
+        except Exception:
+            pass
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cores = os.cpu_count() or 1
