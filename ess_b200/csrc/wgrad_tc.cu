@@ -478,7 +478,9 @@ int wg_plan(const essb_wgrad_tc& d, WgPlan* pl) {
   pl->tiles_y = (d.H + BH - 1) / BH;
   pl->patches_total = d.N * pl->tiles_x * pl->tiles_y;
   const int per_split = (pl->pair ? (d.ntaps + 1) / 2 : d.ntaps) * pl->m_tiles;
-  int splits = (2 * 148 + per_split - 1) / per_split;
+  // two full waves of work items on the 148 SMs, never a third, mostly empty one: items = splits * per_split must
+  // not exceed 2 * 148 (rounding UP here gave 306 items = 3 waves at 69 % occupancy for the 256 -> 256 layers)
+  int splits = (2 * 148) / per_split;
   const int max_splits = (pl->patches_total + 3) / 4;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
