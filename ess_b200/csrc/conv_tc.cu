@@ -11,9 +11,14 @@
 // MMA: tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, fp32 accumulators in TMEM.  In the
 //   3-pass mode each K-step issues hi*hi + lo*hi + hi*lo (drops only lo*lo ~ 2^-16 relative), which
 //   restores fp32-level accuracy (logits 1.1e-4 vs 4.7e-2 for single-pass bf16).
+//   Narrow tiles (2*BN <= 256) fuse the two B planes: [B_hi; B_lo] are adjacent K-major tiles, so A_hi x [B_hi; B_lo]
+//   is ONE MMA of N = 2*BN and the epilogue adds the upper BN accumulator columns back (2 MMAs / 2 A reads per K-step).
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 //   warps 2..9 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter split the columns).  Two TMEM accumulator buffers let the
-//   epilogue of tile i overlap the main loop of tile i+1.  Persistent CTAs, one per SM.
+//   epilogue of tile i overlap the main loop of tile i+1.
+// Scheduling: persistent CTAs (one per SM; two per SM for the halo variant when its pipeline fits half an SM) pull
+//   tiles from a global atomic counter; the producer thread publishes each tile to the other warps through an
+//   mbarrier-guarded ring in shared memory (TcUnit / tc_sched_*).  Optional split-K of the tail wave (off by default).
 // Epilogues: LINEAR (bias / residual / ReLU / sigmoid / strided placement / bf16 planes out) and
 //   LSTM (sigma/tanh gates + cell/hidden update in registers: the 4C-channel `gates` tensor of
 //   e2vid/model/submodules.py:213 never reaches HBM).

@@ -8,7 +8,10 @@
 // The tap shift of A is, as in conv_tc.cu, just a shifted TMA box with hardware zero fill.
 // Work item = (split-K range of 64-pixel patches, tap, 128-wide ci tile); partial results go to a
 // workspace [split][tap][ci][co] and are reduced in fixed order (deterministic).
-// bf16x3: D += A_lo*G_hi + A_hi*G_lo + A_hi*G_hi, fp32 accumulation in TMEM.
+// bf16x3: D += A_lo*G_hi + A_hi*G_lo + A_hi*G_hi, fp32 accumulation in TMEM (for N <= 128 the G planes are fused:
+// A_hi x [G_hi | G_lo] is one MMA of 2N columns).  Cin <= 64: the two 64-row halves of the M tile are two TAPS.
+// Stride-2 convolutions read A through its four parity planes.  wgrad_tc_halo_kernel (below) is the all-taps
+// variant for the high-resolution Cin = 64 / 128, Cout <= 64 layers.
 #include <cuda.h>
 #include <stdlib.h>
 #include <cuda_bf16.h>
