@@ -152,10 +152,17 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_sample(windows=2, threads=None):
-    """Times the oracle (CPU restatement of the reference path) on a bounded sample of the workload:
-    B=1, `windows` of the 20 event windows (image decoder on the last one) + the full decoder
-    forward/backward, then extrapolates linearly in T to one full sample.  Returns samples/s."""
+CPU_SAMPLE_B = 2     # samples of the bounded CPU run (full T = 20 windows each, no extrapolation)
+CPU_SAMPLE_NOTE = ('B=%d samples of the workload, all T=20 event windows (image decoder on the last one) + SemSeg decoder '
+                   'forward/backward + loss at 440x640 through oracle/ess_oracle.py (the reference\'s own PyTorch CPU ops), '
+                   'all host threads' % CPU_SAMPLE_B)
+
+
+def cpu_reference_sample(threads=None, batch=CPU_SAMPLE_B):
+    """Times the oracle (CPU restatement of the reference path: the same PyTorch/MKL-DNN operators the reference
+    calls) on a bounded sample of the workload: `batch` samples through one complete supervised iteration -- the
+    T-window unroll, image decoder on the last window, decoder forward, Dice+CE, backward.  No extrapolation.
+    Returns (samples/s, parts)."""
     from oracle import ess_oracle as O
     w = WORK
     if threads:
@@ -167,33 +174,18 @@ def cpu_reference_sample(windows=2, threads=None):
     dec = ess_b200.SemSegE2VID(256, w['K'], skip_connect=True, skip_type='concat')
     e_sd = {k: v.detach() for k, v in m.state_dict().items()}
     d_sd = {k: v.detach() for k, v in dec.state_dict().items()}
-    data, labels = synth_inputs(1, windows, w['C'], w['H'], w['W'], w['K'], 1234)
-    states = None
-    t_win = []
+    data, labels = synth_inputs(batch, w['T'], w['C'], w['H'], w['W'], w['K'], 1234)
+    t0 = time.perf_counter()
     with torch.no_grad():
-        for i in range(windows):
-            t0 = time.perf_counter()
-            ev = data[:, i * w['C']:(i + 1) * w['C']]
-            _, states, latent = O.reconstructor_step(e_sd, E2VID_CFG, ev, states, with_image=False)
-            t_win.append(time.perf_counter() - t0)
-        # image decoder = (window with image) - (same window, same states, without image)
-        ev = data[:, (windows - 1) * w['C']:windows * w['C']]
-        t0 = time.perf_counter()
-        O.reconstructor_step(e_sd, E2VID_CFG, ev, states, with_image=False)
-        t_plain = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        O.reconstructor_step(e_sd, E2VID_CFG, ev, states, with_image=True)
-        t_img = max(time.perf_counter() - t0 - t_plain, 0.0)
-        t_win.append(t_plain)
+        _, _, latent = O.encoder_unroll(e_sd, E2VID_CFG, data, w['T'], w['C'], with_image_last=True)
+    t_enc = time.perf_counter() - t0
     t0 = time.perf_counter()
     params = {k: v.clone().requires_grad_(True) for k, v in d_sd.items()}
     pred = O.semseg_forward(params, {k: v.detach() for k, v in latent.items()})
     loss = O.task_loss(pred[1], labels, w['K'])
     torch.autograd.grad(loss, list(params.values()))
     t_dec = time.perf_counter() - t0
-    t_window = min(t_win[1:]) if len(t_win) > 1 else t_win[0]     # first window has no recurrent input
-    t_sample = w['T'] * t_window + t_img + t_dec
-    return 1.0 / t_sample, dict(t_window_s=t_window, t_image_decoder_s=t_img, t_decoder_fwd_bwd_s=t_dec)
+    return batch / (t_enc + t_dec), dict(batch=batch, t_unroll_s=t_enc, t_decoder_fwd_bwd_s=t_dec)
 
 
 def run_reference(args):
@@ -204,12 +196,11 @@ def run_reference(args):
     torch.set_num_threads(cores)
     vals = []
     for i in range(args.warmup + args.steps):
-        v, parts = cpu_reference_sample(windows=2)
+        v, parts = cpu_reference_sample()
         if i >= args.warmup:
             vals.append(v)
     value = sum(vals) / len(vals)
-    sample = 'B=1: 2 of T=20 event windows + image decoder once + full SemSeg decoder fwd/bwd at 440x640, ' \
-             'extrapolated linearly in T to one sample; all host threads'
+    sample = CPU_SAMPLE_NOTE
     line = dict(impl='reference', metric=METRIC, value=value, unit='samples/s', n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1000.0 / value, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f32', data='synthetic',
@@ -462,10 +453,9 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cores = os.cpu_count() or 1
-            v, parts = cpu_reference_sample(windows=2, threads=cores)
+            v, parts = cpu_reference_sample(threads=cores)
             line['cpu_baseline'] = dict(value=v, unit='samples/s', cores=torch.get_num_threads(), kind='port',
-                                        sample='B=1: 2 of T=20 windows + image decoder once + SemSeg decoder fwd/bwd at '
-                                               '440x640 through oracle/ess_oracle.py, extrapolated linearly in T',
+                                        sample=CPU_SAMPLE_NOTE,
                                         parts=parts)
         except Exception as ex:   # the baseline must never take the measurement down
             line['cpu_baseline'] = dict(value=None, error=repr(ex))
