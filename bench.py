@@ -213,6 +213,125 @@ def run_reference(args):
     return 0
 
 
+# ----------------------------------------------------------------------- optional workload: UDA iteration
+def run_uda(args):
+    """`--workload uda`: BASELINE.json configs[3] -- one `ESSModel.train_step` (training/ess_trainer.py:103-148, DSEC
+    branch: image-encoder task step, T-window event unroll, cycle + task-consistency losses, two backward passes
+    with the decoder frozen for the first, two RAdam steps) assembled from the drop-in modules, B images + B event
+    stacks per step.  Single GPU; NOT the headline metric (bench.py's default workload is the supervised step) --
+    unit is (image, event-stack) pairs per second.  Same timing rules: device time over K steps after W warm-ups,
+    inputs alternate between two resident batches (> L2); e2e = inputs from pinned host memory + loss read back."""
+    import ess_b200
+    from ess_b200 import _lib
+    from ess_b200.optim import RAdam
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product arm')
+    if int(os.environ.get('WORLD_SIZE', '1')) != 1:
+        raise RuntimeError('--workload uda is a single-GPU line')
+    dev = torch.device('cuda', 0)
+    _lib.check(_lib.lib().essb_device_check(), 'device check')
+    w = dict(WORK, B=args.batch, T=args.windows)
+    B, T, C, H, W, K = w['B'], w['T'], w['C'], w['H'], w['W'], w['K']
+    torch.manual_seed(6)
+    e2vid = ess_b200.E2VIDRecurrent(dict(E2VID_CFG), mode=args.mode)
+    randomize_bn_(e2vid)
+    e2vid = e2vid.to(dev).eval()
+    for p in e2vid.parameters():
+        p.requires_grad = False
+    torch.manual_seed(3)
+    enc = ess_b200.StyleEncoderE2VID(1, skip_connect=True).to(dev).train()
+    dec = ess_b200.SemSegE2VID(256, K, skip_connect=True, skip_type='concat').to(dev)
+    rec = ess_b200.ImageReconstructor(e2vid, H, W, C, dev)
+    task = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255)
+    l1, js = ess_b200.L1Loss(), ess_b200.symJSDivLoss()
+    opt_f = RAdam(enc.parameters(), lr=5e-4, betas=(0., 0.999))
+    opt_b = RAdam(dec.parameters(), lr=5e-4, betas=(0., 0.999))
+
+    def make(seed):
+        g = torch.Generator().manual_seed(seed)
+        img = torch.rand(B, 1, H, W, generator=g)
+        data, labels = synth_inputs(B, T, C, H, W, K, seed)
+        return img.pin_memory(), labels.pin_memory(), data.pin_memory()
+
+    host = [make(1234 + i) for i in range(2)]
+    devb = [tuple(t.to(dev) for t in h) for h in host]
+
+    def step(img_a, labels_a, data_b):
+        opt_f.zero_grad()
+        opt_b.zero_grad()
+        lat_fake = enc(img_a)                                                      # ess_trainer.py:150-180
+        t_img = task(dec({k: v.detach() for k, v in lat_fake.items()})[1], labels_a)
+        t_img.backward()
+        img_fake, _, lat_real = rec.unroll(data_b, T, C)                           # :277-280
+        lat_real = {k: v.detach() for k, v in lat_real.items()}
+        lat_fake = enc(img_fake.detach())                                          # :282
+        e_loss = l1(lat_fake[2], lat_real[2]) + l1(lat_fake[4], lat_real[4]) + l1(lat_fake[8], lat_real[8])
+        pred_second = dec(lat_fake)                                                # :211-255
+        with torch.no_grad():
+            pred_first_ng = dec(lat_real)
+        e_loss = e_loss + js(pred_second[1], pred_first_ng[1]) + l1(pred_second[2], pred_first_ng[2]) + \
+            l1(pred_second[4], pred_first_ng[4])
+        pred_first = dec(lat_real)                                                 # :303-330
+        with torch.no_grad():
+            pred_second_ng = dec({k: v.detach() for k, v in lat_fake.items()})
+        t_loss = js(pred_first[1], pred_second_ng[1]) + l1(pred_first[2], pred_second_ng[2]) + \
+            l1(pred_first[4], pred_second_ng[4])
+        for p in dec.parameters():                                                 # :133-137
+            p.requires_grad = False
+        e_loss.backward()
+        for p in dec.parameters():
+            p.requires_grad = True
+        t_loss.backward()                                                          # :138
+        opt_f.step()
+        opt_b.step()
+        return t_img.detach() + e_loss.detach() + t_loss.detach()
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    for i in range(max(args.warmup, 3)):
+        step(*devb[i & 1])
+    clocks = ClockSampler(0)
+    clocks.start()
+    l0 = _lib.launch_count
+    ms_dev = timed(lambda i: step(*devb[i & 1]), args.steps)
+    launches = _lib.launch_count - l0
+
+    def e2e_step(i):
+        h = host[i & 1]
+        loss = step(*(t.to(dev, non_blocking=True) for t in h))                    # H2D of the step's inputs
+        return float(loss.item())                                                  # D2H of its result
+
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+    clk = clocks.stop()
+    value = args.steps * B / (ms_dev / 1e3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    line = dict(metric='(image, event-stack) pairs/sec of one UDA iteration, 640x440x5bin voxel grids', value=value,
+                unit='pairs/s', n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_dev / args.steps,
+                higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype={'bf16x3': 'bf16x3-split (f32 accumulate, f32 epilogues)', 'bf16': 'bf16 (f32 accumulate)',
+                       'fp32': 'f32'}[args.mode],
+                data='synthetic',
+                config=dict(workload='DSEC 440x640 UDA (ESSModel.train_step, DSEC branch): %d images + %d event stacks, '
+                                     'C=5 bins, T=%d windows, K=11' % (B, B, T), batch_per_gpu=B, mode=args.mode,
+                            l2_policy='two alternating input batches (larger than the 126 MB L2)'),
+                e2e=dict(value=args.steps * B / (ms_e2e / 1e3), unit='pairs/s', ms_per_step=ms_e2e / args.steps,
+                         h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
+                gpu_launches=launches,
+                clocks=dict(sm_mhz=clk['sm_mhz'], sm_max_mhz=clk['sm_max_mhz'], reasons=clk['reasons'], samples=clk['samples']),
+                roofline=None, cpu_baseline=None)
+    emit(line)
+    return 0
+
+
 # --------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -227,11 +346,15 @@ def main():
     ap.add_argument('--no-optimizer', action='store_true')
     ap.add_argument('--profile-all', action='store_true',
                     help='bracket every tcgen05 launch (not only the ConvLSTM cell) with CUDA events inside the timed region')
+    ap.add_argument('--workload', default='supervised', choices=['supervised', 'uda'],
+                    help="'supervised' (default, the BASELINE.json metric) or 'uda' (configs[3]: one ESSModel.train_step; single GPU)")
     ap.add_argument('--torch-gpu-baseline', action='store_true',
                     help='also time the oracle (the reference op stream as plain PyTorch/cuDNN ops, TF32 default) on this GPU')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.workload == 'uda':
+        return run_uda(args)
     if args.warmup < 3:
         args.warmup = 3
 
