@@ -519,8 +519,8 @@ def voxel_grid_dsec(x, y, pol, time, channels, height, width):
 
 def voxel_grid_ddd17(events, shape, nr_temporal_bins, separate_pol=True):
     """generate_voxel_grid (datasets/data_util.py:54-126) restated with numpy; `events` = [N,4] float64 rows
-    [x, y, t, polarity].  (The reference function itself uses `np.int`, removed in numpy >= 1.24, so it cannot
-    run in this image: this restatement is unpinned against live reference output.)"""
+    [x, y, t, polarity].  (The reference function uses `np.int`, removed in numpy >= 1.24; tests/test_oracle.py
+    restores that alias and pins this restatement against the live reference function.)"""
     import numpy as np
     events = np.array(events, dtype=np.float64)
     height, width = shape

@@ -229,3 +229,26 @@ def test_oracle_flip_and_hot_pixels_vs_live_reference(tmp_path):
     assert rel_err(img2, img) < 1e-6
     for k in lat:
         assert rel_err(lat2[k], lat[k]) < 1e-6
+
+
+@needs_ref
+@pytest.mark.parametrize('separate_pol', [True, False])
+def test_oracle_voxel_grid_ddd17_vs_live_reference(separate_pol):
+    """generate_voxel_grid (datasets/data_util.py:54-126, bilinear in time) run from the unmodified reference (with
+    the `np.int` alias numpy >= 1.24 dropped) vs the oracle restatement, incl. out-of-range pixels and polarity 0."""
+    import numpy as np
+    ref_shim.install()
+    if not hasattr(np, 'int'):
+        np.int = int
+    from datasets.data_util import generate_voxel_grid
+    rng = np.random.RandomState(0)
+    n, C, H, W = 4000, 5, 20, 28
+    ev = np.zeros((n, 4), np.float64)
+    ev[:, 0] = rng.randint(-2, W + 2, n)                      # x, some outside the image
+    ev[:, 1] = rng.randint(-2, H + 2, n)                      # y
+    ev[:, 2] = np.sort(rng.rand(n)) * 1e4 + 17.0              # t, increasing
+    ev[:, 3] = rng.randint(0, 2, n)                           # polarity in {0, 1}
+    ref = generate_voxel_grid(ev.copy(), (H, W), C, separate_pol=separate_pol)
+    out = O.voxel_grid_ddd17(ev.copy(), (H, W), C, separate_pol=separate_pol)
+    assert out.shape == ref.shape
+    assert np.allclose(out.numpy(), ref, rtol=0, atol=1e-5)
