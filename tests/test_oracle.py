@@ -133,7 +133,17 @@ def test_reference_trainer_runs_with_shim():
         torch.manual_seed(0)
         data = torch.randn(2, 2, 64, 64) * (torch.rand(2, 2, 64, 64) < 0.2)
         labels = torch.randint(0, 11, (2, 64, 64))
-        losses = [float(t.train_step([data, labels])[2]) for _ in range(3)]
+        labels[:, :3] = 255
+        # oracle.supervised_step (the checker of __graft_entry__.smoke) vs the trainer's own first iteration:
+        # same loss and the same gradient on every decoder parameter (ess_supervised_trainer.py:92-152)
+        e2vid_sd = {k: v.detach().clone() for k, v in t.front_end_sensor_b.state_dict().items()}
+        dec_sd = {k: v.detach().clone() for k, v in t.task_backend.state_dict().items()}
+        first = float(t.train_step([data, labels])[2])
+        loss_o, _, grads_o = O.supervised_step(e2vid_sd, cfg, dec_sd, data, labels, 2, 1, 11)
+        assert abs(first - float(loss_o)) < 1e-5 * max(1.0, abs(first))
+        for n, p_ in t.task_backend.named_parameters():
+            assert (p_.grad - grads_o[n]).abs().max() <= 1e-4 * grads_o[n].abs().max() + 5e-6, n
+        losses = [first] + [float(t.train_step([data, labels])[2]) for _ in range(2)]
         assert all(torch.isfinite(torch.tensor(losses)))
     finally:
         os.remove(path)
