@@ -2,17 +2,24 @@
 """bench.py -- headline benchmark of the ESS hot path on B200 (contract: see the task statement).
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--mode bf16x3|bf16|fp32]
+                    [--workload dsec|ddd17|uda] [--bins C] [--contract A|B] [--global-batch G]
 
-Metric (BASELINE.json): samples/s of one supervised training iteration -- frozen E2VID encoder unrolled
-over T event windows (forward) + SemSegE2VID decoder forward + Dice/CE loss + backward (+ RAdam step)
--- on synthetic [B, T*C, H, W] voxel grids.  Workload at every N: BASELINE.json configs[2] "DSEC shape
-640x440, 5 bins, 11 classes, batch=8, ess_supervised" per GPU (weak scaling: 8 samples per GPU; for
-N > 1 the minibatch is sharded by sample with global-batch semantics, ess_b200/dp.py).
+Metric (BASELINE.json): samples/s of one supervised training iteration -- frozen E2VID encoder unrolled over T
+event windows (forward) + SemSegE2VID decoder forward + Dice/CE loss + backward + RAdam step -- on synthetic
+[B, T*C, H, W] voxel grids.  Default workload at every N: BASELINE.json configs[2] "DSEC shape 640x440, 5 bins, 11
+classes, batch=8, ess_supervised" per GPU (weak scaling: 8 samples per GPU; for N > 1 the minibatch is sharded by
+sample with global-batch semantics, ess_b200/dp.py).  The other BASELINE.json configs are selectable:
+  configs[1]  --workload ddd17                  (200x346 reflect-padded to 200x352, K=6)
+  configs[3]  --workload uda                    (one ESSModel.train_step; unit = (image, event-stack) pairs/s)
+  configs[4]  --bins 10 --global-batch 64       (under torchrun at N = 2/4/8: strong scaling, 64/N samples per GPU)
+  --contract A  times the call sequence of the UNMODIFIED trainer (training/ess_supervised_trainer.py:126-130:
+                update_reconstruction per window, E2VID image decoder on every window) instead of the fused unroll.
 
-One JSON line on rank 0.  `value` = device-resident inputs; `e2e` = the same step through the public
-module API with HOST (pinned) inputs: H2D copy of the events + labels and D2H read of the loss inside
-the timed region.  `--impl reference` times the CPU restatement of the reference (oracle/, "port":
-the reference is pure Python/PyTorch and cannot travel to the GPU box) on the host cores.
+One JSON line on rank 0.  `value` = device-resident inputs; `e2e` = the same step through the public module API
+with HOST (pinned) inputs: H2D copy of the events + labels and D2H read of the loss inside the timed region.
+`cpu_baseline` / `--impl reference`: the CPU restatement of the reference (oracle/, "port": the reference is pure
+Python/PyTorch and cannot travel to the GPU box) on the host cores; `torch_gpu_baseline`: the same restatement's op
+stream through PyTorch/ATen/cuDNN on this GPU, TF32 on and off ("the existing Blackwell kernel to beat").
 """
 import argparse
 import json
@@ -30,7 +37,10 @@ sys.path.insert(0, ROOT)
 E2VID_CFG = dict(num_bins=5, skip_type='sum', recurrent_block_type='convlstm', num_encoders=3, base_num_channels=32,
                  num_residual_blocks=2, norm='BN', use_upsample_conv=False)
 WORK = dict(B=8, T=20, C=5, H=440, W=640, K=11)
+SHAPES = {'dsec': dict(H=440, W=640, K=11, name='DSEC 440x640'),
+          'ddd17': dict(H=200, W=346, K=6, name='DDD17 200x346 (reflect-padded to 200x352)')}
 METRIC = 'samples/sec fwd+bwd 640x440x5bin voxel grids'
+DTYPES = {'bf16x3': 'bf16x3-split (f32 accumulate, f32 epilogues)', 'bf16': 'bf16 (f32 accumulate)', 'fp32': 'f32'}
 
 
 # stdout must carry exactly ONE JSON line (the driver parses it): keep a private handle on the real stdout
@@ -44,9 +54,15 @@ def emit(line):
     _REAL_STDOUT.flush()
 
 
+def padded_hw(H, W, num_encoders=3):
+    f = 2 ** num_encoders
+    return (H + f - 1) // f * f, (W + f - 1) // f * f
+
+
 def flops_per_sample(T, C, H, W, K, contract='B'):
-    """Algorithmic FLOPs (2*MAC) of one sample, SURVEY.md s8d / BASELINE.md s3."""
-    P = H * W
+    """Algorithmic FLOPs (2*MAC) of one sample, SURVEY.md s8d / BASELINE.md s3 (P = padded pixels)."""
+    Hp, Wp = padded_hw(H, W)
+    P = Hp * Wp
     f_enc = (1600 * C + 519168) * P
     f_img = 150592 * P
     f_seg = (331776 + 64 * K) * P
@@ -55,10 +71,26 @@ def flops_per_sample(T, C, H, W, K, contract='B'):
     return T * f_enc + f_img + 3 * f_seg
 
 
+def workload_string(w, contract, kind='ess_supervised'):
+    """ONE string for both arms (the driver compares the arms' `config`)."""
+    sh = SHAPES[w['shape']]
+    c = 'contract A: update_reconstruction per window, E2VID image decoder on every window' if contract == 'A' else \
+        'contract B: E2VID image decoder on the last window only'
+    return '%s, C=%d bins, T=%d windows, K=%d, %s (%s)' % (sh['name'], w['C'], w['T'], w['K'], kind, c)
+
+
+def bench_config(w, contract, world, kind='ess_supervised'):
+    """The workload-defining part of the JSON line, byte-identical in the product and the reference arm."""
+    return dict(workload=workload_string(w, contract, kind), batch_per_gpu=w['B'], global_batch=w['B'] * world,
+                gflop_per_sample=flops_per_sample(w['T'], w['C'], w['H'], w['W'], w['K'], contract) / 1e9)
+
+
 def synth_inputs(B, T, C, H, W, K, seed):
+    """events N(0,1)*Bernoulli(0.2) at the RAW size; labels at the padded size (the logits stay padded)."""
     g = torch.Generator().manual_seed(seed)
     data = torch.randn(B, T * C, H, W, generator=g) * (torch.rand(B, T * C, H, W, generator=g) < 0.2)
-    labels = torch.randint(0, K, (B, H, W), generator=g)
+    Hp, Wp = padded_hw(H, W)
+    labels = torch.randint(0, K, (B, Hp, Wp), generator=g)
     labels[:, :5] = 255
     return data, labels
 
@@ -78,28 +110,51 @@ def load_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
         p = json.load(open(path))
-        return dict(bf16=p.get('bf16_tflops_sustained', 1401.6), bf16_burst=p.get('bf16_tflops', 1645.8),
-                    hbm=p.get('hbm_gbs', 6549.8), source='measured')
+        return dict(bf16=p.get('bf16_tflops_sustained', 1396.6), bf16_burst=p.get('bf16_tflops', 1652.0),
+                    hbm=p.get('hbm_gbs', 6449.1), source='measured')
     return dict(bf16=1400.0, bf16_burst=1590.0, hbm=6650.0, source='fallback')
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        if '-' in part:
+            lo, hi = part.split('-')
+            cpus.update(range(int(lo), int(hi) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
 def bind_to_gpu_numa_node(index):
-    """Restrict this process to the CPUs NVML reports as local to GPU `index` (no-op when NVML or the affinity
-    call is unavailable).  Returns a short description for the JSON line."""
+    """Restrict this process to the CPUs of the NUMA node the GPU hangs off: the PCI device's sysfs `local_cpulist`
+    (meaningful even when NVML calls every CPU 'ideal', as on the round-1 SCALE box: "32 of 32 cpus"), else NVML's
+    affinity mask.  No-op when neither narrows the set.  Returns a description for the JSON line."""
+    ncpu = os.cpu_count() or 1
     try:
         import pynvml
+        allowed = os.sched_getaffinity(0)
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        ncpu = os.cpu_count() or 1
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
-        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return '%d of %d cpus' % (len(cpus), ncpu)
+        cand, src = None, None
+        pci = pynvml.nvmlDeviceGetPciInfo(h).busId
+        pci = pci.decode() if isinstance(pci, bytes) else str(pci)
+        path = '/sys/bus/pci/devices/%s/local_cpulist' % pci[-12:].lower()
+        if os.path.exists(path):
+            c = _parse_cpulist(open(path).read()) & allowed
+            if c and len(c) < len(allowed):
+                cand, src = c, 'sysfs local_cpulist'
+        if cand is None:
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+            c = {64 * i + b for i, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1} & allowed
+            if c and len(c) < len(allowed):
+                cand, src = c, 'nvml affinity'
+        if cand is None:
+            return 'not narrowed: all %d allowed cpus are local to GPU %d (single NUMA domain)' % (len(allowed), index)
+        os.sched_setaffinity(0, cand)
+        return '%d of %d cpus (%s)' % (len(cand), ncpu, src)
     except Exception as ex:      # diagnostics only; never take the measurement down
         return 'unavailable (%s)' % type(ex).__name__
-    return 'unavailable'
 
 
 class ClockSampler:
@@ -151,33 +206,61 @@ class ClockSampler:
         return out
 
 
+def resolve_workload(args, world=1):
+    shape = 'dsec' if args.workload in ('supervised', 'dsec', 'uda') else args.workload
+    sh = SHAPES[shape]
+    B = args.batch
+    scaling = 'weak'
+    if args.global_batch:
+        if args.global_batch % world:
+            raise ValueError('--global-batch %d is not divisible by %d ranks' % (args.global_batch, world))
+        B, scaling = args.global_batch // world, 'strong'
+    return dict(shape=shape, B=B, T=args.windows, C=args.bins, H=sh['H'], W=sh['W'], K=sh['K']), scaling
+
+
 # ------------------------------------------------------------------------------------ CPU reference arm
-CPU_SAMPLE_B = 2     # samples of the bounded CPU run (full T = 20 windows each, no extrapolation)
-CPU_SAMPLE_NOTE = ('B=%d samples of the workload, all T=20 event windows (image decoder on the last one) + SemSeg decoder '
-                   'forward/backward + loss at 440x640 through oracle/ess_oracle.py (the reference\'s own PyTorch CPU ops), '
-                   'all host threads' % CPU_SAMPLE_B)
+CPU_SAMPLE_B = 1     # samples per CPU step (full T windows each, no extrapolation)
 
 
-def cpu_reference_sample(threads=None, batch=CPU_SAMPLE_B):
-    """Times the oracle (CPU restatement of the reference path: the same PyTorch/MKL-DNN operators the reference
-    calls) on a bounded sample of the workload: `batch` samples through one complete supervised iteration -- the
-    T-window unroll, image decoder on the last window, decoder forward, Dice+CE, backward.  No extrapolation.
-    Returns (samples/s, parts)."""
-    from oracle import ess_oracle as O
-    w = WORK
-    if threads:
-        torch.set_num_threads(threads)
-    torch.manual_seed(6)
+def _cpu_modules(w):
     import ess_b200
-    m = ess_b200.E2VIDRecurrent(dict(E2VID_CFG), mode='fp32')      # parameter container only (CPU tensors)
+    torch.manual_seed(6)
+    cfg = dict(E2VID_CFG, num_bins=w['C'])
+    m = ess_b200.E2VIDRecurrent(cfg, mode='fp32')      # parameter container only (CPU tensors)
     randomize_bn_(m)
     dec = ess_b200.SemSegE2VID(256, w['K'], skip_connect=True, skip_type='concat')
-    e_sd = {k: v.detach() for k, v in m.state_dict().items()}
-    d_sd = {k: v.detach() for k, v in dec.state_dict().items()}
-    data, labels = synth_inputs(batch, w['T'], w['C'], w['H'], w['W'], w['K'], 1234)
+    return cfg, {k: v.detach() for k, v in m.state_dict().items()}, {k: v.detach() for k, v in dec.state_dict().items()}
+
+
+def cpu_sample_note(w, contract, batch):
+    return ('B=%d sample(s) of the workload per step, all T=%d event windows (E2VID image decoder on %s) + SemSeg decoder '
+            'forward/backward + loss at %dx%d through oracle/ess_oracle.py (the reference\'s own PyTorch CPU operators), all '
+            'host threads; no extrapolation' % (batch, w['T'], 'every window' if contract == 'A' else 'the last one',
+                                                 w['H'], w['W']))
+
+
+def cpu_reference_sample(w, contract='B', threads=None, batch=CPU_SAMPLE_B, state=None):
+    """Times the oracle (CPU restatement of the reference path: the same PyTorch/oneDNN operators the reference calls)
+    on a bounded sample of the workload: `batch` samples through one complete supervised iteration -- the T-window
+    unroll, image decoder per the contract, decoder forward, Dice+CE, backward.  Returns (samples/s, parts)."""
+    from oracle import ess_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    if state is None:
+        state = {}
+    if 'mods' not in state:
+        state['mods'] = _cpu_modules(w)
+        state['inputs'] = synth_inputs(batch, w['T'], w['C'], w['H'], w['W'], w['K'], 1234)
+    cfg, e_sd, d_sd = state['mods']
+    data, labels = state['inputs']
     t0 = time.perf_counter()
     with torch.no_grad():
-        _, _, latent = O.encoder_unroll(e_sd, E2VID_CFG, data, w['T'], w['C'], with_image_last=True)
+        if contract == 'A':
+            st = None
+            for i in range(w['T']):
+                _, st, latent = O.reconstructor_step(e_sd, cfg, data[:, i * w['C']:(i + 1) * w['C']], st, with_image=True)
+        else:
+            _, _, latent = O.encoder_unroll(e_sd, cfg, data, w['T'], w['C'], with_image_last=True)
     t_enc = time.perf_counter() - t0
     t0 = time.perf_counter()
     params = {k: v.clone().requires_grad_(True) for k, v in d_sd.items()}
@@ -188,32 +271,227 @@ def cpu_reference_sample(threads=None, batch=CPU_SAMPLE_B):
     return batch / (t_enc + t_dec), dict(batch=batch, t_unroll_s=t_enc, t_decoder_fwd_bwd_s=t_dec)
 
 
+def cpu_uda_sample(w, threads=None, batch=1):
+    """One UDA iteration (oracle.uda_step = ESSModel.train_step, DSEC branch) on `batch` (image, event-stack) pairs."""
+    from oracle import ess_oracle as O
+    import ess_b200
+    if threads:
+        torch.set_num_threads(threads)
+    cfg, e_sd, d_sd = _cpu_modules(w)
+    torch.manual_seed(3)
+    enc = ess_b200.StyleEncoderE2VID(1, skip_connect=True)
+    enc_sd = {k: v.detach() for k, v in enc.state_dict().items()}
+    g = torch.Generator().manual_seed(1234)
+    img = torch.rand(batch, 1, w['H'], w['W'], generator=g)
+    data, labels = synth_inputs(batch, w['T'], w['C'], w['H'], w['W'], w['K'], 1234)
+    t0 = time.perf_counter()
+    O.uda_step(e_sd, cfg, enc_sd, d_sd, img, labels, data, w['T'], w['C'], w['K'])
+    dt = time.perf_counter() - t0
+    return batch / dt, dict(batch=batch, t_iteration_s=dt)
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
+    world = max(1, args.gpus)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    vals = []
+    w, scaling = resolve_workload(args, world)
+    uda = args.workload == 'uda'
+    vals, state, parts = [], {}, None
     for i in range(args.warmup + args.steps):
-        v, parts = cpu_reference_sample()
+        if uda:
+            v, parts = cpu_uda_sample(w)
+        else:
+            v, parts = cpu_reference_sample(w, args.contract, state=state)
         if i >= args.warmup:
             vals.append(v)
     value = sum(vals) / len(vals)
-    sample = CPU_SAMPLE_NOTE
-    line = dict(impl='reference', metric=METRIC, value=value, unit='samples/s', n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1000.0 / value, higher_is_better=True, scaling='weak',
-                vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload='DSEC 440x640, C=5 bins, T=20 windows, K=11, ess_supervised (contract B: image on '
-                                     'last window)', batch_per_gpu=WORK['B'], parallelism='cpu'),
-                cpu_baseline=dict(value=value, unit='samples/s', cores=torch.get_num_threads(), kind='port',
-                                  sample=sample, parts=parts),
-                e2e=dict(value=value, unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    kind = 'ess UDA (ESSModel.train_step, DSEC branch)' if uda else 'ess_supervised'
+    sample = ('one full UDA iteration on B=1 (image, event-stack) pair through oracle.uda_step, all host threads' if uda
+              else cpu_sample_note(w, args.contract, CPU_SAMPLE_B))
+    unit = 'pairs/s' if uda else 'samples/s'
+    line = dict(impl='reference', metric=UDA_METRIC if uda else METRIC, value=value, unit=unit, n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup,
+                ms_per_step=1000.0 * w['B'] / value,      # time of one B-sample step of the workload at this throughput
+                higher_is_better=True, scaling=scaling, vs_baseline=None, dtype='f32', data='synthetic',
+                config=bench_config(w, args.contract, world, kind),
+                impl_config=dict(parallelism='cpu', threads=torch.get_num_threads(), sample_batch=CPU_SAMPLE_B,
+                                 ms_per_cpu_step=1000.0 * CPU_SAMPLE_B / value),
+                cpu_baseline=dict(value=value, unit=unit, cores=torch.get_num_threads(), kind='port', sample=sample,
+                                  batch=CPU_SAMPLE_B, parts=parts),
+                e2e=dict(value=value, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
     return 0
 
 
+# ---------------------------------------------------------------------------- product arm: shared helpers
+def device_timer(dev, world):
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms)
+    return barrier, timed
+
+
+def lstm_roofline(prof, peaks, ms_dev, steps, mode, work_is_default):
+    """roofline of the dominant kernel (the fused tcgen05 ConvLSTM cell): algorithmic FLOPs per launch / mean launch
+    duration from CUDA events recorded on the launching stream inside the timed region."""
+    by_tag = {}
+    for tag, fl, a, b, nsteps in prof:
+        t = by_tag.setdefault(tag, [0.0, 0.0, 0, nsteps])
+        t[0] += fl
+        t[1] += a.elapsed_time(b) / 1e3
+        t[2] += 1
+    if 'lstm_tc' not in by_tag:
+        if mode == 'fp32':
+            return dict(kernel='conv_fp32_kernel', bound='tensor', achieved=None, peak=peaks['bf16'], unit='TFLOP/s',
+                        frac=None, traffic=None)
+        return None
+    fl, sec, n, _ = by_tag['lstm_tc']
+    ach = fl / sec / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tpath) and work_is_default:
+        traffic = json.load(open(tpath)).get('lstm_tc', {}).get('mean_dram_bytes_per_launch')
+    roof = dict(kernel='conv_tc_kernel<LSTM> (fused ConvLSTM cell, %d launches)' % n, bound='tensor', achieved=ach,
+                peak=peaks['bf16'], unit='TFLOP/s', frac=ach / peaks['bf16'], traffic=traffic,
+                traffic_note='mean DRAM bytes per launch from the committed ncu --set full capture '
+                             '(profiles/ncu_traffic.json); algorithmic bytes are 865/433/216 MB for the 3 levels',
+                peak_source='%s bf16 dense sustained (MEASURED_PEAKS.json)' % peaks['source'],
+                note='algorithmic FLOPs (2*MAC, no credit for the 3 split passes): in bf16x3 mode the tensor pipe '
+                     'executes 3x this, so the mode ceiling is peak/3',
+                mean_launch_ms=sec / n * 1e3, share_of_step=sec * 1e3 / ms_dev,
+                mma_frac_of_peak=ach * (3 if mode == 'bf16x3' else 1) / peaks['bf16'])
+    roof['other_tc_kernels'] = {
+        tag: dict(achieved=fl2 / sec2 / 1e12, mean_launch_ms=sec2 / n2 * 1e3, launches_per_step=n2 // ns2,
+                  share_of_step=(sec2 * 1e3 / ns2) / (ms_dev / steps))
+        for tag, (fl2, sec2, n2, ns2) in sorted(by_tag.items()) if tag != 'lstm_tc'}
+    return roof
+
+
+def torch_gpu_baseline(e2vid, dec, cfg, w, contract, data, labels):
+    """Secondary baseline of SURVEY.md s8d: the reference's op stream (the oracle's functions on CUDA tensors ->
+    PyTorch/ATen/cuDNN on this B200), full batch, full T, no extrapolation, 1 warm-up + 2 timed iterations, with
+    TF32 on (cudnn.allow_tf32 = True, torch's default; matmul TF32 on) and off (strict fp32)."""
+    from oracle import ess_oracle as O
+    e_sd = {k: v.detach() for k, v in e2vid.state_dict().items()}
+    d_sd = {k: v.detach() for k, v in dec.state_dict().items()}
+    T, C, K = w['T'], w['C'], w['K']
+
+    def step():
+        with torch.no_grad():
+            st = None
+            for i in range(T):
+                _, st, lat = O.reconstructor_step(e_sd, cfg, data[:, i * C:(i + 1) * C], st,
+                                                  with_image=(contract == 'A' or i == T - 1))
+        params = {k: v.clone().requires_grad_(True) for k, v in d_sd.items()}
+        pred = O.semseg_forward(params, {k: v.detach() for k, v in lat.items()})
+        torch.autograd.grad(O.task_loss(pred[1], labels, K), list(params.values()))
+
+    def tm(n=2):
+        step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    out = {}
+    try:
+        torch.backends.cudnn.benchmark = True
+        for name, flag in (('tf32', True), ('fp32', False)):
+            torch.backends.cudnn.allow_tf32 = flag
+            torch.backends.cuda.matmul.allow_tf32 = flag
+            ms = tm()
+            out[name] = dict(value=w['B'] / (ms / 1e3), unit='samples/s', ms_per_step=ms)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    out['kind'] = ('oracle ops (the reference\'s op stream: PyTorch/ATen/cuDNN, cudnn.benchmark on) on this GPU, same '
+                   'batch, all T windows, no extrapolation; includes the reference\'s per-window host sync '
+                   '(inference_utils.py:100) but not its CudaTimer syncs')
+    out['sample'] = 'B=%d, T=%d, 1 warm-up + 2 timed iterations per precision setting' % (w['B'], T)
+    return out
+
+
+def dp_self_check(rank, world, dev, mode):
+    """Data-parallel correctness evidence carried by every N > 1 bench line: at a tiny shape every rank computes the
+    single-process step at the GLOBAL batch (redundantly) and then its shard of the N-rank step with the global-batch
+    hooks (ess_b200/dp.py); per-sample logits, the loss and the all-reduced gradients must agree (logits
+    1e-5, gradients <= 2e-3 -- split-K order differs).  Returns the worst deviation over ranks."""
+    import ess_b200
+    from ess_b200 import dp
+    Bg, T, C, H, W, K = 2 * world, 2, 5, 64, 96, 6
+    torch.manual_seed(6)
+    e2vid = ess_b200.E2VIDRecurrent(dict(E2VID_CFG), mode=mode)
+    randomize_bn_(e2vid)
+    e2vid = e2vid.to(dev).eval()
+    dec = ess_b200.SemSegE2VID(256, K, skip_connect=True, skip_type='concat').to(dev)
+    crit = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255)
+    rec = ess_b200.ImageReconstructor(e2vid, H, W, C, dev)
+    data, labels = synth_inputs(Bg, T, C, H, W, K, 99)
+    data, labels = data.to(dev), labels.to(dev)
+
+    def run(d, l, bucket=None):
+        if bucket is not None:
+            bucket.zero_()
+        else:
+            for p in dec.parameters():
+                p.grad = None
+        _, _, latent = rec.unroll(d, T, C)
+        pred = dec({k: v.detach() for k, v in latent.items()})
+        loss = crit(pred[1], l)
+        loss.backward()
+        if bucket is not None:
+            bucket.allreduce_()
+        return pred[1].detach(), loss.detach()
+
+    logits_g, loss_g = run(data, labels)
+    grads_g = {n: p.grad.clone() for n, p in dec.named_parameters()}
+    dp.attach(rec, crit)
+    bucket = dp.GradBucket(dec.parameters())
+    lo, hi = dp.shard_batch(Bg, rank, world)
+    logits_l, loss_l = run(data[lo:hi].contiguous(), labels[lo:hi].contiguous(), bucket)
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp(min=1e-30))
+
+    dev_ = torch.tensor([rel(logits_l, logits_g[lo:hi]), abs(float(loss_l) - float(loss_g)) / abs(float(loss_g)),
+                         max(rel(p.grad, grads_g[n]) for n, p in dec.named_parameters() if n.endswith('weight'))],
+                        device=dev, dtype=torch.float64)
+    torch.distributed.all_reduce(dev_, op=torch.distributed.ReduceOp.MAX)
+    lg, ls, gr = (float(x) for x in dev_)
+    for p in dec.parameters():
+        p.grad = None
+    return dict(shape='global B=%d (2 per rank), T=2, 64x96, K=6' % Bg, logits_rel=lg, loss_rel=ls, grads_rel=gr,
+                ok=bool(lg < 1e-5 and ls < 1e-5 and gr < 2e-3),
+                criterion='N-rank sharded step == single-process step at the global batch: logits 1e-5, loss 1e-5, '
+                          'summed gradients 2e-3 (max over ranks)')
+
+
 # ----------------------------------------------------------------------- optional workload: UDA iteration
+UDA_METRIC = '(image, event-stack) pairs/sec of one UDA iteration, 640x440x5bin voxel grids'
+
+
 def run_uda(args):
     """`--workload uda`: BASELINE.json configs[3] -- one `ESSModel.train_step` (training/ess_trainer.py:103-148, DSEC
     branch: image-encoder task step, T-window event unroll, cycle + task-consistency losses, two backward passes
@@ -230,10 +508,11 @@ def run_uda(args):
         raise RuntimeError('--workload uda is a single-GPU line')
     dev = torch.device('cuda', 0)
     _lib.check(_lib.lib().essb_device_check(), 'device check')
-    w = dict(WORK, B=args.batch, T=args.windows)
+    w, _ = resolve_workload(args, 1)
     B, T, C, H, W, K = w['B'], w['T'], w['C'], w['H'], w['W'], w['K']
     torch.manual_seed(6)
-    e2vid = ess_b200.E2VIDRecurrent(dict(E2VID_CFG), mode=args.mode)
+    cfg = dict(E2VID_CFG, num_bins=C)
+    e2vid = ess_b200.E2VIDRecurrent(cfg, mode=args.mode)
     randomize_bn_(e2vid)
     e2vid = e2vid.to(dev).eval()
     for p in e2vid.parameters():
@@ -286,23 +565,18 @@ def run_uda(args):
         opt_b.step()
         return t_img.detach() + e_loss.detach() + t_loss.detach()
 
-    def timed(fn, steps):
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1)
-
-    for i in range(max(args.warmup, 3)):
+    _, timed = device_timer(dev, 1)
+    warm = max(args.warmup, 3)
+    for i in range(warm):
         step(*devb[i & 1])
     clocks = ClockSampler(0)
     clocks.start()
+    _lib.PROFILE, _lib.PROFILE_TAGS = [], {'lstm_tc'}
     l0 = _lib.launch_count
     ms_dev = timed(lambda i: step(*devb[i & 1]), args.steps)
     launches = _lib.launch_count - l0
+    prof = [(t, fl, a, b, args.steps) for (t, fl, a, b) in _lib.PROFILE]
+    _lib.PROFILE, _lib.PROFILE_TAGS = None, None
 
     def e2e_step(i):
         h = host[i & 1]
@@ -314,20 +588,34 @@ def run_uda(args):
     clk = clocks.stop()
     value = args.steps * B / (ms_dev / 1e3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
-    line = dict(metric='(image, event-stack) pairs/sec of one UDA iteration, 640x440x5bin voxel grids', value=value,
-                unit='pairs/s', n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_dev / args.steps,
-                higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype={'bf16x3': 'bf16x3-split (f32 accumulate, f32 epilogues)', 'bf16': 'bf16 (f32 accumulate)',
-                       'fp32': 'f32'}[args.mode],
-                data='synthetic',
-                config=dict(workload='DSEC 440x640 UDA (ESSModel.train_step, DSEC branch): %d images + %d event stacks, '
-                                     'C=5 bins, T=%d windows, K=11' % (B, B, T), batch_per_gpu=B, mode=args.mode,
-                            l2_policy='two alternating input batches (larger than the 126 MB L2)'),
+    peaks = load_peaks()
+    # algorithmic FLOPs of one pair (SURVEY.md s8d cfg 4, contract B): the supervised sample's encoder unroll + image
+    # decoder, image encoder 2 x fwd + 2 x (dgrad + wgrad), decoder 5 forward + 5 backward units
+    Hp, Wp = padded_hw(H, W)
+    P = Hp * Wp
+    f_seg = (331776 + 64 * K) * P
+    f_pair = T * (1600 * C + 519168) * P + 150592 * P + 6 * 58.11e9 * (P / 281600.0) + 10 * f_seg
+    cfgd = bench_config(w, 'B', 1, 'ess UDA (ESSModel.train_step, DSEC branch)')
+    cfgd['gflop_per_sample'] = f_pair / 1e9
+    line = dict(metric=UDA_METRIC, value=value, unit='pairs/s', n_gpus=1, steps=args.steps, warmup=warm,
+                ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype=DTYPES[args.mode], data='synthetic', config=cfgd,
+                impl_config=dict(parallelism='dp1', mode=args.mode, optimizer='2 x RAdam (fused kernel)',
+                                 l2_policy='two alternating input batches (larger than the 126 MB L2)'),
+                tflops=value * f_pair / 1e12,
                 e2e=dict(value=args.steps * B / (ms_e2e / 1e3), unit='pairs/s', ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
                 gpu_launches=launches,
                 clocks=dict(sm_mhz=clk['sm_mhz'], sm_max_mhz=clk['sm_max_mhz'], reasons=clk['reasons'], samples=clk['samples']),
-                roofline=None, cpu_baseline=None)
+                roofline=lstm_roofline(prof, peaks, ms_dev, args.steps, args.mode, False))
+    if not args.no_cpu_baseline:
+        try:
+            v, parts = cpu_uda_sample(w, threads=os.cpu_count() or 1)
+            line['cpu_baseline'] = dict(value=v, unit='pairs/s', cores=torch.get_num_threads(), kind='port',
+                                        sample='one full UDA iteration on B=1 (image, event-stack) pair through '
+                                               'oracle.uda_step, all host threads', parts=parts)
+        except Exception as ex:
+            line['cpu_baseline'] = dict(value=None, error=repr(ex))
     emit(line)
     return 0
 
@@ -341,15 +629,23 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--mode', default=os.environ.get('ESS_B200_MODE', 'bf16x3'), choices=['bf16x3', 'bf16', 'fp32'])
     ap.add_argument('--batch', type=int, default=WORK['B'], help='samples per GPU')
+    ap.add_argument('--global-batch', type=int, default=0,
+                    help='total samples over all ranks (strong scaling, BASELINE.json configs[4]: 64); overrides --batch')
     ap.add_argument('--windows', type=int, default=WORK['T'])
+    ap.add_argument('--bins', type=int, default=WORK['C'], help='voxel-grid channels per window (C); configs[4] uses 10')
+    ap.add_argument('--contract', default='B', choices=['A', 'B'],
+                    help='B (default): fused unroll, E2VID image decoder on the last window; A: the unmodified trainer\'s '
+                         'per-window update_reconstruction with the image on every window')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-optimizer', action='store_true')
     ap.add_argument('--profile-all', action='store_true',
                     help='bracket every tcgen05 launch (not only the ConvLSTM cell) with CUDA events inside the timed region')
-    ap.add_argument('--workload', default='supervised', choices=['supervised', 'uda'],
-                    help="'supervised' (default, the BASELINE.json metric) or 'uda' (configs[3]: one ESSModel.train_step; single GPU)")
-    ap.add_argument('--torch-gpu-baseline', action='store_true',
-                    help='also time the oracle (the reference op stream as plain PyTorch/cuDNN ops, TF32 default) on this GPU')
+    ap.add_argument('--workload', default='supervised', choices=['supervised', 'dsec', 'ddd17', 'uda'],
+                    help="'supervised'/'dsec' (default, the BASELINE.json metric), 'ddd17' (configs[1]) or 'uda' "
+                         "(configs[3]: one ESSModel.train_step; single GPU)")
+    ap.add_argument('--no-torch-gpu-baseline', action='store_true',
+                    help='skip the PyTorch/cuDNN-on-this-GPU baseline (TF32 on and off) that the N=1 line carries')
+    ap.add_argument('--no-overlap', action='store_true', help='N > 1: one blocking gradient all-reduce after the backward')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -369,11 +665,15 @@ def main():
         raise RuntimeError('bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product arm')
     dev = torch.device('cuda', local)
     _lib.check(_lib.lib().essb_device_check(), 'device check')
-    w = dict(WORK, B=args.batch, T=args.windows)
+    w, scaling = resolve_workload(args, world)
     B, T, C, H, W, K = w['B'], w['T'], w['C'], w['H'], w['W'], w['K']
+    contract = args.contract
+
+    dp_check = dp_self_check(rank, world, dev, args.mode) if world > 1 else None
 
     torch.manual_seed(6)
-    e2vid = ess_b200.E2VIDRecurrent(dict(E2VID_CFG), mode=args.mode)
+    cfg = dict(E2VID_CFG, num_bins=C)
+    e2vid = ess_b200.E2VIDRecurrent(cfg, mode=args.mode)
     randomize_bn_(e2vid)
     e2vid = e2vid.to(dev).eval()
     for p in e2vid.parameters():
@@ -381,18 +681,17 @@ def main():
     dec = ess_b200.SemSegE2VID(256, K, skip_connect=True, skip_type='concat').to(dev)
     crit = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], gamma=2.0, num_classes=K, ignore_index=255)
     rec = ess_b200.ImageReconstructor(e2vid, H, W, C, dev)
+    opt = None if args.no_optimizer else RAdam([p for p in dec.parameters() if p.requires_grad], lr=5e-4,
+                                               weight_decay=0., betas=(0., 0.999))
     bucket = None
     if world > 1:
         dp.attach(rec, crit)
-        bucket = dp.GradBucket(dec.parameters())
-    opt = None if args.no_optimizer else RAdam([p for p in dec.parameters() if p.requires_grad], lr=5e-4,
-                                               weight_decay=0., betas=(0., 0.999))
+        bucket = dp.GradBucket(dec.parameters(), module=None if args.no_overlap else dec)
 
-    # two distinct device-resident batches (901 MB each >> 126 MB L2) alternate between timed steps
+    # two distinct device-resident batches (901 MB each at the default size >> 126 MB L2) alternate between timed steps
     host = [synth_inputs(B, T, C, H, W, K, 1234 + 17 * rank + i) for i in range(2)]
     # Pinned staging memory is allocated from threads bound to the GPU's own NUMA node (what `numactl
-    # --cpunodebind` does for a DataLoader process): on a two-socket host a far-node buffer halves the H2D rate,
-    # and at 70 ms per step the 919 MB of inputs need > 13 GB/s to stay hidden behind the compute.
+    # --cpunodebind` does for a DataLoader process): on a two-socket host a far-node buffer halves the H2D rate.
     affinity_all = os.sched_getaffinity(0) if hasattr(os, 'sched_getaffinity') else None
     numa = bind_to_gpu_numa_node(local)
     host = [(d.pin_memory(), l.pin_memory()) for d, l in host]
@@ -406,36 +705,24 @@ def main():
         else:
             for p in dec.parameters():
                 p.grad = None
-        _, _, latent = rec.unroll(data, T, C)                     # ess_supervised_trainer.py:126-130
-        latent = {k: v.detach() for k, v in latent.items()}       # :145-146
-        pred = dec(latent)                                        # :148
-        loss = crit(pred[1], labels)                              # :149
-        loss.backward()                                           # :103
+        if contract == 'A':                                           # ess_supervised_trainer.py:124-130, verbatim
+            rec.last_states_for_each_channel = {'grayscale': None}
+            for i in range(T):
+                event_tensor = data[:, i * C:(i + 1) * C, :, :]
+                img_fake, states_real, latent = rec.update_reconstruction(event_tensor)
+        else:
+            _, _, latent = rec.unroll(data, T, C)                     # the fused form of the same loop
+        latent = {k: v.detach() for k, v in latent.items()}           # :145-146
+        pred = dec(latent)                                            # :148
+        loss = crit(pred[1], labels)                                  # :149
+        loss.backward()                                               # :103
         if bucket is not None:
-            bucket.allreduce_()
+            bucket.allreduce_()                                       # (waits for the per-stage exchanges when overlapped)
         if opt is not None:
-            opt.step()                                            # :106
+            opt.step()                                                # :106
         return loss
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-        return float(ms)
-
+    barrier, timed = device_timer(dev, world)
     for i in range(args.warmup):
         step(*devb[i & 1])
     clocks = ClockSampler(local)
@@ -515,120 +802,47 @@ def main():
     value = samples / (ms_dev / 1e3)
     e2e_value = samples / (ms_e2e / 1e3)
     peaks = load_peaks()
-
-    # roofline of the dominant kernel (the fused tcgen05 ConvLSTM cell): algorithmic FLOPs per launch /
-    # mean launch duration from CUDA events recorded on the launching stream inside the timed region
-    roof = None
-    by_tag = {}
-    for tag, fl, a, b, nsteps in prof:
-        t = by_tag.setdefault(tag, [0.0, 0.0, 0, nsteps])
-        t[0] += fl
-        t[1] += a.elapsed_time(b) / 1e3
-        t[2] += 1
-    if 'lstm_tc' in by_tag:
-        fl, sec, n, _ = by_tag['lstm_tc']
-        ach = fl / sec / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
-        if os.path.exists(tpath) and (B, T, H, W) == (WORK['B'], WORK['T'], WORK['H'], WORK['W']):
-            traffic = json.load(open(tpath)).get('lstm_tc', {}).get('mean_dram_bytes_per_launch')
-        roof = dict(kernel='conv_tc_kernel<LSTM> (fused ConvLSTM cell, %d launches)' % n, bound='tensor', achieved=ach,
-                    peak=peaks['bf16'], unit='TFLOP/s', frac=ach / peaks['bf16'], traffic=traffic,
-                    traffic_note='mean DRAM bytes per launch from the committed ncu --set full capture '
-                                 '(profiles/ncu_traffic.json); algorithmic bytes are 865/433/216 MB for the 3 levels',
-                    peak_source='%s bf16 dense sustained (MEASURED_PEAKS.json)' % peaks['source'],
-                    note='algorithmic FLOPs (2*MAC, no credit for the 3 split passes): in bf16x3 mode the tensor pipe '
-                         'executes 3x this, so the mode ceiling is peak/3',
-                    mean_launch_ms=sec / n * 1e3, share_of_step=sec * 1e3 / ms_dev,
-                    mma_frac_of_peak=ach * (3 if args.mode == 'bf16x3' else 1) / peaks['bf16'])
-        # the other tcgen05 launches of the step, by role (algorithmic TFLOP/s, share of the timed region)
-        roof['other_tc_kernels'] = {
-            tag: dict(achieved=fl2 / sec2 / 1e12, mean_launch_ms=sec2 / n2 * 1e3, launches_per_step=n2 // ns2,
-                      share_of_step=(sec2 * 1e3 / ns2) / (ms_dev / args.steps))
-            for tag, (fl2, sec2, n2, ns2) in sorted(by_tag.items()) if tag != 'lstm_tc'}
-    elif args.mode == 'fp32':
-        roof = dict(kernel='conv_fp32_kernel', bound='tensor', achieved=None, peak=peaks['bf16'], unit='TFLOP/s',
-                    frac=None, traffic=None)
-
+    is_default = (B, T, C, H, W) == (WORK['B'], WORK['T'], WORK['C'], WORK['H'], WORK['W'])
+    roof = lstm_roofline(prof, peaks, ms_dev, args.steps, args.mode, is_default)
+    fps = flops_per_sample(T, C, H, W, K, contract)
     line = dict(metric=METRIC, value=value, unit='samples/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype={'bf16x3': 'bf16x3-split (f32 accumulate, f32 epilogues)', 'bf16': 'bf16 (f32 accumulate)',
-                       'fp32': 'f32'}[args.mode],
-                data='synthetic',
-                config=dict(workload='DSEC 440x640, C=5 bins, T=%d windows, K=11, ess_supervised (contract B: E2VID image '
-                                     'decoder on the last window only)' % T,
-                            batch_per_gpu=B, global_batch=B * world, parallelism='dp%d' % world, mode=args.mode,
-                            optimizer='none' if opt is None else 'RAdam (fused kernel)',
-                            l2_policy='two alternating 901 MB input batches (inputs larger than the 126 MB L2)',
-                            gflop_per_sample=flops_per_sample(T, C, H, W, K) / 1e9),
-                tflops=value * flops_per_sample(T, C, H, W, K) / 1e12,
+                ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling=scaling, vs_baseline=None,
+                dtype=DTYPES[args.mode], data='synthetic', config=bench_config(w, contract, world),
+                impl_config=dict(parallelism='dp%d' % world, mode=args.mode,
+                                 optimizer='none' if opt is None else 'RAdam (multi-tensor fused kernel)',
+                                 grad_exchange=(None if world == 1 else
+                                                ('one flat all-reduce after the backward' if args.no_overlap else
+                                                 'per-stage buckets all-reduced on a side stream as their gradients complete')),
+                                 l2_policy='two alternating %d MB input batches (inputs larger than the 126 MB L2)' %
+                                           (devb[0][0].numel() * 4 // 1000000)),
+                tflops=value * fps / 1e12,
+                step_frac_of_bf16_peak=value * fps / 1e12 / (peaks['bf16'] * world),
                 e2e=dict(value=e2e_value, unit='samples/s', ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=stage_d.numel() * 4 + stage_l.numel() * 8, d2h_bytes_per_step=4,
                          h2d_gb_per_s=h2d_gbs, host_numa_binding=numa),
                 gpu_launches=launches, clocks=dict(sm_mhz=clk['sm_mhz'], sm_max_mhz=clk['sm_max_mhz'],
                                                    reasons=clk['reasons'], samples=clk['samples']),
                 roofline=roof)
+    if dp_check is not None:
+        line['dp_check'] = dp_check
     if affinity_all is not None:
         try:
             os.sched_setaffinity(0, affinity_all)       # the CPU baseline gets every host core back
         except Exception:
             pass
+    if rank == 0 and world == 1 and not args.no_torch_gpu_baseline:
+        try:
+            line['torch_gpu_baseline'] = torch_gpu_baseline(e2vid, dec, cfg, w, contract, *devb[0])
+        except Exception as ex:   # a baseline must never take the measurement down
+            line['torch_gpu_baseline'] = dict(value=None, error=repr(ex))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cores = os.cpu_count() or 1
-            v, parts = cpu_reference_sample(threads=cores)
+            v, parts = cpu_reference_sample(w, contract, threads=cores)
             line['cpu_baseline'] = dict(value=v, unit='samples/s', cores=torch.get_num_threads(), kind='port',
-                                        sample=CPU_SAMPLE_NOTE,
-                                        parts=parts)
-        except Exception as ex:   # the baseline must never take the measurement down
-            line['cpu_baseline'] = dict(value=None, error=repr(ex))
-    if rank == 0 and world == 1 and args.torch_gpu_baseline:
-        # Secondary baseline of SURVEY.md s8d: the reference's op stream through PyTorch/ATen/cuDNN on this B200
-        # (cudnn.allow_tf32 = True, torch's default): the oracle's functions run on CUDA tensors.  Bounded
-        # sample: B=8, 3 windows (+ image decoder once) + decoder fwd/bwd, extrapolated linearly in T.
-        try:
-            from oracle import ess_oracle as O
-            e_sd = {k: v.detach() for k, v in e2vid.state_dict().items()}
-            d_sd = {k: v.detach() for k, v in dec.state_dict().items()}
-            d0, l0 = devb[0]
-
-            def enc_windows(nw, with_img):
-                st = None
-                for i in range(nw):
-                    _, st, lat = O.reconstructor_step(e_sd, E2VID_CFG, d0[:, i * C:(i + 1) * C], st,
-                                                      with_image=(with_img and i == nw - 1))
-                return lat
-
-            def dec_step(lat):
-                params = {k: v.clone().requires_grad_(True) for k, v in d_sd.items()}
-                pred = O.semseg_forward(params, {k: v.detach() for k, v in lat.items()})
-                torch.autograd.grad(O.task_loss(pred[1], l0, K), list(params.values()))
-
-            def tm(fn, n=3):
-                fn()
-                torch.cuda.synchronize()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                for _ in range(n):
-                    fn()
-                b.record()
-                torch.cuda.synchronize()
-                return a.elapsed_time(b) / n
-
-            with torch.no_grad():
-                t3 = tm(lambda: enc_windows(3, False))
-                t1 = tm(lambda: enc_windows(1, False))
-                t3i = tm(lambda: enc_windows(3, True))
-                lat = enc_windows(2, False)
-            t_win = (t3 - t1) / 2.0
-            t_dec = tm(lambda: dec_step(lat))
-            ms = T * t_win + (t3i - t3) + t_dec
-            line['torch_gpu_baseline'] = dict(value=B / (ms / 1e3), unit='samples/s', ms_per_step=ms,
-                                              kind='oracle ops (PyTorch/ATen/cuDNN, allow_tf32 default) on this GPU',
-                                              parts=dict(ms_window=t_win, ms_image_decoder=t3i - t3, ms_decoder_fwd_bwd=t_dec),
-                                              sample='B=%d: 3 windows + image decoder once + decoder fwd/bwd, linear in T' % B)
+                                        sample=cpu_sample_note(w, contract, CPU_SAMPLE_B), parts=parts)
         except Exception as ex:
-            line['torch_gpu_baseline'] = dict(value=None, error=repr(ex))
+            line['cpu_baseline'] = dict(value=None, error=repr(ex))
     if rank == 0:
         emit(line)
     if world > 1:

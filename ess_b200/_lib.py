@@ -80,6 +80,16 @@ class WgradTc(C.Structure):
                 ('dy', C.c_int8 * MAX_TAPS), ('dx', C.c_int8 * MAX_TAPS)]
 
 
+RADAM_MAX = 48
+
+
+class RadamMulti(C.Structure):
+    _fields_ = [('p', C.c_void_p * RADAM_MAX), ('g', C.c_void_p * RADAM_MAX), ('m', C.c_void_p * RADAM_MAX),
+                ('v', C.c_void_p * RADAM_MAX), ('n', C.c_int64 * RADAM_MAX), ('count', C.c_int32),
+                ('beta1', C.c_float), ('beta2', C.c_float), ('step_lr', C.c_float), ('eps', C.c_float),
+                ('wd_lr', C.c_float), ('rectified', C.c_int32)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes): every symbol include/ess_b200.h declares
@@ -131,6 +141,7 @@ SIGNATURES = {
     'essb_voxel_grid_dsec': (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P, _P]),
     'essb_voxel_grid_ddd17': (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
     'essb_radam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P]),
+    'essb_radam_multi_step': (_I, [C.POINTER(RadamMulti), _P]),
     'essb_event_prepare_planes': (_I, [_P, _L, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'essb_split_bf16': (_I, [C.POINTER(Src), _I, _I, _I, _P, _P, _I, _I, _I, _P]),
     'essb_pack_weight_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

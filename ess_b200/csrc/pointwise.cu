@@ -514,9 +514,87 @@ __global__ void radam_kernel(float* __restrict__ p, const float* __restrict__ g,
   p[i] = pi;
 }
 
+// Multi-tensor form: ONE launch updates up to ESSB_RADAM_MAX tensors (the 34 decoder tensors of the supervised step).
+// Block b works on a 4096-element chunk of the tensor whose block range [blk0[t], blk0[t+1]) contains b.
+struct RadamMultiParams {
+  essb_radam_multi d;
+  int blk0[ESSB_RADAM_MAX + 1];
+};
+constexpr int RADAM_CHUNK = 4096;
+__global__ void __launch_bounds__(256) radam_multi_kernel(const __grid_constant__ RadamMultiParams P) {
+  __shared__ int s_t;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = P.d.count;              // largest t with blk0[t] <= blockIdx.x
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (P.blk0[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+    }
+    s_t = lo;
+  }
+  __syncthreads();
+  const int t = s_t;
+  const long long n = P.d.n[t];
+  const long long base = (long long)(blockIdx.x - P.blk0[t]) * RADAM_CHUNK;
+  float* __restrict__ p = P.d.p[t];
+  const float* __restrict__ g = P.d.g[t];
+  float* __restrict__ m = P.d.m[t];
+  float* __restrict__ v = P.d.v[t];
+  const float beta1 = P.d.beta1, beta2 = P.d.beta2, step_lr = P.d.step_lr, eps = P.d.eps, wd_lr = P.d.wd_lr;
+  const int rectified = P.d.rectified;
+  auto upd = [&](float gi, float& mi, float& vi, float& pi) {
+    vi = beta2 * vi + (1.f - beta2) * gi * gi;
+    mi = beta1 * mi + (1.f - beta1) * gi;
+    if (wd_lr != 0.f) pi += -wd_lr * pi;
+    if (rectified) pi += -step_lr * (mi / (sqrtf(vi) + eps));
+    else pi += -step_lr * mi;
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15u) == 0 && (n & 3) == 0;
+  if (vec) {
+#pragma unroll
+    for (int r = 0; r < RADAM_CHUNK / (256 * 4); ++r) {
+      const long long i = base + ((long long)r * 256 + threadIdx.x) * 4;
+      if (i >= n) break;
+      const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+      float4 m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
+      float4 p4 = *reinterpret_cast<float4*>(p + i);
+      upd(g4.x, m4.x, v4.x, p4.x); upd(g4.y, m4.y, v4.y, p4.y); upd(g4.z, m4.z, v4.z, p4.z); upd(g4.w, m4.w, v4.w, p4.w);
+      *reinterpret_cast<float4*>(m + i) = m4;
+      *reinterpret_cast<float4*>(v + i) = v4;
+      *reinterpret_cast<float4*>(p + i) = p4;
+    }
+  } else {
+    for (int r = 0; r < RADAM_CHUNK / 256; ++r) {
+      const long long i = base + (long long)r * 256 + threadIdx.x;
+      if (i >= n) break;
+      float mi = m[i], vi = v[i], pi = p[i];
+      upd(g[i], mi, vi, pi);
+      m[i] = mi; v[i] = vi; p[i] = pi;
+    }
+  }
+}
+
 }  // namespace
 
 // =================================================================================== C ABI
+extern "C" int essb_radam_multi_step(const essb_radam_multi* d, void* stream) {
+  ESSB_REQUIRE(d && d->count > 0 && d->count <= ESSB_RADAM_MAX, "essb_radam_multi_step: count must be in [1, %d]", ESSB_RADAM_MAX);
+  static thread_local RadamMultiParams P;
+  P.d = *d;
+  int blocks = 0;
+  for (int t = 0; t < d->count; ++t) {
+    ESSB_REQUIRE(d->p[t] && d->g[t] && d->m[t] && d->v[t] && d->n[t] > 0, "essb_radam_multi_step: bad tensor %d", t);
+    P.blk0[t] = blocks;
+    const long long nb = (d->n[t] + RADAM_CHUNK - 1) / RADAM_CHUNK;
+    ESSB_REQUIRE(blocks + nb < (1ll << 30), "essb_radam_multi_step: too many elements");
+    blocks += (int)nb;
+  }
+  P.blk0[d->count] = blocks;
+  radam_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
+  ESSB_LAUNCH_CHECK("essb_radam_multi_step");
+  return ESSB_OK;
+}
+
 extern "C" int essb_radam_step(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2,
                                float step_lr, float eps, float wd_lr, int rectified, void* stream) {
   ESSB_REQUIRE(p && g && m && v && n > 0, "essb_radam_step: bad arguments");

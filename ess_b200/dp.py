@@ -67,26 +67,104 @@ def attach(reconstructor=None, task_loss=None):
 class GradBucket:
     """One flat fp32 buffer holding every trainable parameter's gradient.
 
-    `p.grad` of each parameter is a view into the buffer, so autograd accumulates straight into it
-    and the exchange is a single all-reduce launch with no packing copy."""
+    `p.grad` of each parameter is a view into the buffer, so there is no packing copy and the exchange needs no
+    unpacking.  Two modes:
 
-    def __init__(self, params):
+    * `module=None`: autograd accumulates into the views; `allreduce_()` is ONE all-reduce after the backward.
+    * `module=<SemSegE2VID>`: the decoder's hand-scheduled backward hands every weight gradient
+      to `_sink` the moment its wgrad launch is queued (deepest node last: completion order is the reverse of the
+      parameter order, so a stage is a contiguous slice of the buffer).  When a stage of >= `stage_floats` floats is
+      complete, its slice is all-reduced on a side stream while the backward keeps computing the next layers;
+      `allreduce_()` then only flushes the last stage and makes the compute stream wait for the side stream.
+    """
+
+    def __init__(self, params, module=None, stage_floats=1 << 20):
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.offsets = []
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.offsets.append(off)
             off += p.numel()
+        self.module = module
+        self.stages = []
+        if module is not None:
+            ids = {id(p): i for i, p in enumerate(self.params)}
+            self.index = {n: ids[id(p)] for n, p in module.named_parameters() if id(p) in ids}
+            if len(self.index) != len(self.params):
+                raise ValueError('GradBucket(module=...): params must be exactly the module\'s trainable parameters')
+            # stages = contiguous parameter ranges, cut walking BACKWARDS (the order the backward completes them)
+            hi = len(self.params)
+            while hi > 0:
+                lo, n = hi, 0
+                while lo > 0 and n < stage_floats:
+                    lo -= 1
+                    n += self.params[lo].numel()
+                self.stages.append([lo, hi])
+                hi = lo
+            self.stage_of = {}
+            for si, (lo, hi) in enumerate(self.stages):
+                for i in range(lo, hi):
+                    self.stage_of[i] = si
+            self.side = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None
+            self._reset_stage_state()
+            module._grad_sink = self._sink
+
+    def _reset_stage_state(self):
+        self.pending = [hi - lo for lo, hi in self.stages]
+        self.sent = [False] * len(self.stages)
+        self.touched = set()
 
     def zero_(self):
         self.flat.zero_()
-        off = 0
-        for p in self.params:      # re-attach in case an optimizer replaced .grad (zero_grad(set_to_none))
+        for p, off in zip(self.params, self.offsets):   # re-attach in case an optimizer replaced .grad (set_to_none)
             if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * off:
                 p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        if self.module is not None:
+            self._reset_stage_state()
+
+    def _launch(self, si):
+        lo, hi = self.stages[si]
+        a = self.offsets[lo]
+        b = self.offsets[hi - 1] + self.params[hi - 1].numel()
+        view = self.flat[a:b]
+        self.sent[si] = True
+        if world_size() == 1:
+            return
+        if self.side is None:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM)
+            return
+        self.side.wait_stream(torch.cuda.current_stream(self.flat.device))
+        with torch.cuda.stream(self.side):
+            dist.all_reduce(view, op=dist.ReduceOp.SUM)
+
+    def _sink(self, name, grad):
+        """Called by _DecoderFn.backward with a finished parameter gradient; returns True when it took it (autograd
+        then gets None for that parameter: the view already holds the value)."""
+        i = self.index.get(name)
+        if i is None:
+            return False
+        dst = self.params[i].grad
+        if i in self.touched:
+            dst.add_(grad.view_as(dst))
+        else:
+            dst.copy_(grad.view_as(dst))
+            self.touched.add(i)
+            si = self.stage_of[i]
+            self.pending[si] -= 1
+            if self.pending[si] == 0 and not self.sent[si]:
+                self._launch(si)
+        return True
 
     def allreduce_(self):
-        return allreduce_sum_(self.flat)
+        if self.module is None:
+            return allreduce_sum_(self.flat)
+        for si in range(len(self.stages)):
+            if not self.sent[si]:
+                self._launch(si)
+        if self.side is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self.side)
+        return self.flat

@@ -278,14 +278,14 @@ class E2VIDRecurrent(nn.Module):
         """event_tensor [N, num_bins, H, W] (H, W multiples of 2^num_encoders), prev_states None or a
         list of (hidden, cell) tuples (ConvLSTM) / tensors (ConvGRU).  Returns (img [N,1,H,W] or None
         when with_image=False, states, latent {1,2,4,8}) exactly as unet.py:145-181."""
-        ops.require_cuda(event_tensor)
+        ops.require_cuda_any(event_tensor)
         N, Cb, H, W = event_tensor.shape
         if Cb != self.num_bins:
             raise RuntimeError('expected %d input channels, got %d' % (self.num_bins, Cb))
         f = 2 ** self.num_encoders
         if H % f or W % f:
             raise RuntimeError('H, W must be multiples of %d (CropParameters pads to this)' % f)
-        with torch.no_grad():
+        with torch.no_grad(), ops.on_device_of(event_tensor):
             buf = self.head_planes_buffer(N, H, W, event_tensor.device)
             if buf is not None:      # tensor-core head: convert straight into its operand format
                 ev = event_tensor.float().contiguous()
@@ -344,6 +344,10 @@ class E2VIDRecurrent(nn.Module):
         ops.conv_tc(d, tag='head_tc', device=head.device if head is not None else planes[0].device)
 
     def _forward_impl(self, x, in_planes, N, H, W, prev_states, with_image, want_head=True):
+        with ops.on_device_of(x if x is not None else in_planes[0]):
+            return self._forward_on_device(x, in_planes, N, H, W, prev_states, with_image, want_head)
+
+    def _forward_on_device(self, x, in_planes, N, H, W, prev_states, with_image, want_head=True):
         P = self._pack()
         u = self.unetrecurrent
         ne = self.num_encoders

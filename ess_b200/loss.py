@@ -15,12 +15,23 @@ class _TaskLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, predict, target, K, ignore_index, use_dice, use_ce, reduce_fn):
         ops.require_cuda(predict, target)
-        if predict.shape[1] != K:
+        if predict.dim() != 4 or predict.shape[1] != K:
             raise AssertionError('predict & target shape do not match')      # loss_functions.py:120
+        # the kernels read `target` as int64 [N*H*W] matching the logits pixel for pixel: validate instead of
+        # misreading (torch's CrossEntropyLoss raises on both conditions, loss_functions.py:15)
+        if target.is_floating_point() or target.dtype == torch.bool:
+            raise RuntimeError('TaskLoss: expected integer class labels, got %s' % target.dtype)
+        if tuple(target.shape) != (predict.shape[0], predict.shape[2], predict.shape[3]):
+            raise ValueError('TaskLoss: expected target of shape %s for logits %s, got %s' %
+                             ((predict.shape[0], predict.shape[2], predict.shape[3]), tuple(predict.shape), tuple(target.shape)))
         logits = predict.detach().float().permute(0, 2, 3, 1)
         if not logits.is_contiguous():
             logits = logits.contiguous()
-        target = target.contiguous()
+        target = target.long().contiguous()
+        if TaskLoss.check_labels:
+            bad = (target != ignore_index) & ((target < 0) | (target >= K))
+            if bool(bad.any()):
+                raise IndexError('TaskLoss: labels outside [0, %d) that are not ignore_index=%d' % (K, ignore_index))
         sums = ops.task_loss_sums(logits, target, K, ignore_index)
         if reduce_fn is not None:
             sums = reduce_fn(sums)
@@ -39,6 +50,10 @@ class _TaskLossFn(torch.autograd.Function):
 
 
 class TaskLoss(torch.nn.Module):
+    # debug switch: verify on the device that every label is in [0, K) or == ignore_index (one reduction + a host
+    # sync per call, so off on the hot path; torch's CrossEntropyLoss device-asserts on such labels)
+    check_labels = False
+
     def __init__(self, losses=['cross_entropy'], gamma=2.0, num_classes=13, alpha=None, weight=None,
                  ignore_index=None, reduction='mean'):
         super().__init__()
@@ -55,4 +70,8 @@ class TaskLoss(torch.nn.Module):
         if not (use_dice or use_ce):
             return 0                                                            # loss_functions.py:18-24
         ign = self.ignore_index if self.ignore_index is not None else -100   # CrossEntropyLoss default
-        return _TaskLossFn.apply(predict, target, self.num_classes, int(ign), use_dice, use_ce, self.reduce_fn)
+        ops.require_cuda_any(predict, target)
+        if target.device != predict.device:
+            raise RuntimeError('TaskLoss: predict on %s but target on %s' % (predict.device, target.device))
+        with ops.on_device_of(predict):
+            return _TaskLossFn.apply(predict, target, self.num_classes, int(ign), use_dice, use_ce, self.reduce_fn)

@@ -16,12 +16,12 @@ def semseg_compute_confusion(y_hat_lbl, y_lbl, num_classes, ignore_label, out=No
         raise TypeError('Inputs must be torch tensors')
     if y_hat_lbl.device != y_lbl.device:
         raise ValueError('Input tensors have different device placement')
-    ops.require_cuda(y_hat_lbl)
-    pred = y_hat_lbl.reshape(-1).long().contiguous()
-    gt = y_lbl.reshape(-1).long().contiguous()
-    if pred.numel() != gt.numel():
-        raise ValueError('prediction / label size mismatch')
-    return ops.confusion_labels(pred, gt, num_classes, ignore_label, conf=out)
+    with ops.on_device_of(y_hat_lbl):
+        pred = y_hat_lbl.reshape(-1).long().contiguous()
+        gt = y_lbl.reshape(-1).long().contiguous()
+        if pred.numel() != gt.numel():
+            raise ValueError('prediction / label size mismatch')
+        return ops.confusion_labels(pred, gt, num_classes, ignore_label, conf=out)
 
 
 def _iou_acc(conf):

@@ -18,8 +18,25 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, EPI_GRU_OUT, EPI_GRU_UR, EPI
 IN_EPS = 1e-5
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """The launching stream: the CURRENT device's current stream.  Every module entry point runs under
+    `on_device_of(operand)`, and `require_cuda` refuses operands of another device, so the current device is the
+    operands' device and kernels never launch with foreign pointers."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def on_device_of(t):
+    """Context manager making `t`'s CUDA device current (the reference places its modules with
+    `settings.gpu_device = 'cuda:1'` and never calls torch.cuda.set_device).  Raises for CPU tensors: no fallback."""
+    require_cuda_any(t)
+    return torch.cuda.device(t.device)
+
+
+def require_cuda_any(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('ess_b200 runs on CUDA (sm_100a) only; got a %s tensor -- there is no CPU '
+                               'fallback' % t.device)
 
 
 def _p(t, offset_elems=0):
@@ -29,10 +46,17 @@ def _p(t, offset_elems=0):
 
 
 def require_cuda(*ts):
+    """Operands must be CUDA tensors of the CURRENT device (see _stream / on_device_of)."""
+    require_cuda_any(*ts)
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
-            raise RuntimeError('ess_b200 runs on CUDA (sm_100a) only; got a %s tensor -- there is no CPU '
-                               'fallback' % t.device)
+        if t is None:
+            continue
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError('ess_b200: operand on %s but the current CUDA device is cuda:%d (module entry points '
+                               'switch to their operands\' device; mixed-device operands are not supported)' % (t.device, cur))
 
 
 @dataclass

@@ -78,9 +78,8 @@ class ImageReconstructor:
         return t.contiguous()
 
     def update_reconstruction(self, event_tensor, event_tensor_id=None, stamp=None, with_image=True):
-        with torch.no_grad():
-            ev = event_tensor if event_tensor.is_cuda else event_tensor.to(self.device)
-            ops.require_cuda(ev)
+        ev = event_tensor if event_tensor.is_cuda else event_tensor.to(self.device)
+        with torch.no_grad(), ops.on_device_of(ev):
             ev = self._per_sample_contiguous(ev.float())
             B, C, H, W = ev.shape
             if self.hot_pixels is not None:
@@ -102,8 +101,7 @@ class ImageReconstructor:
 
     def unroll(self, data, num_windows, channels, image_on_last_only=True):
         """data [B, T*C, H, W] -> (img, states, latent) of the last window; resets the state first."""
-        with torch.no_grad():
-            ops.require_cuda(data)
+        with torch.no_grad(), ops.on_device_of(data):
             data = self._per_sample_contiguous(data.float())
             self.last_states_for_each_channel = {'grayscale': None}
             if self.hot_pixels is not None:

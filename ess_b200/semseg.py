@@ -156,14 +156,15 @@ class SemSegE2VID(nn.Module):
     def forward(self, input_dict):
         sz_in = input_dict[1].shape[3]        # input_dict[1] is used for its width only (:70)
         x8 = input_dict[8]
-        ops.require_cuda(x8)
+        ops.require_cuda_any(x8)
         names = [n for n, _ in self.named_parameters()]
         params = [p for _, p in self.named_parameters()]
         if self.skip_connect:
             ins = (x8, input_dict[4], input_dict[2])
         else:
             ins = (x8, None, None)
-        res = _DecoderFn.apply(self, names, ins[0], ins[1], ins[2], *params)
+        with ops.on_device_of(x8):
+            res = _DecoderFn.apply(self, names, ins[0], ins[1], ins[2], *params)
         out = {8: x8}
         for t in res:
             self.update_skip_dict(out, t, sz_in)
@@ -224,6 +225,7 @@ class _DecoderFn(torch.autograd.Function):
         # activation; ~1.7 GB at B=8 DSEC) instead of being re-created in the backward pass
         keep_planes = any(ctx.needs_input_grad[5:])
         ctx.planes = {}
+        probe = module.__dict__.get('_probe')    # test hook (teacher forcing, tests/test_gpu_teacher.py); None in use
         for nd in nodes:
             if isinstance(nd, _Conv):
                 first = T[nd.srcs[0][0]]
@@ -253,6 +255,8 @@ class _DecoderFn(torch.autograd.Function):
                     if keep_planes:
                         ctx.planes[nd.out] = (hi, lo)
                     del hi, lo
+                    if probe is not None:
+                        y = probe.fwd(nd.out, y)
                     T[nd.out] = y
                     if nd.stats:
                         S[nd.out] = ops.in_stats(y)
@@ -260,17 +264,25 @@ class _DecoderFn(torch.autograd.Function):
                     # 1x1 classifier (style_networks.py:34,88): HBM-bound, dedicated streaming kernel
                     T[nd.out] = ops.pw_conv_fwd(segs[0], w.detach().float().reshape(nd.cout, cin_total), bias, N, H, W,
                                                 nd.cout)
+                    if probe is not None:
+                        T[nd.out] = probe.fwd(nd.out, T[nd.out])
                 else:
                     wp = ops.pack_weight(w)
                     y, _, st, _ = ops.conv(segs, wp, bias, N, H, W, H, W, nd.cout, _taps(nd.k), epilogue=EPI_LINEAR,
                                            act=ACT_NONE, want_stats=nd.stats)
+                    if probe is not None:
+                        y2 = probe.fwd(nd.out, y)
+                        if y2 is not y:
+                            y, st = y2, None
                     T[nd.out] = y
                     if nd.stats:
-                        S[nd.out] = ops.in_finalize(st, H * W)
+                        S[nd.out] = ops.in_finalize(st, H * W) if st is not None else ops.in_stats(y)
             else:
                 src = T[nd.src]
                 T[nd.out] = ops.norm_act_add(src, S[nd.src][0], S[nd.src][1], relu=nd.relu,
                                              res=T[nd.res] if nd.res is not None else None)
+                if probe is not None:
+                    T[nd.out] = probe.fwd(nd.out, T[nd.out])
         ctx.module, ctx.names = module, names
         ctx.T, ctx.S = T, S
         ctx.set_materialize_grads(False)     # unused outputs (out[4], out[2] in the supervised step) stay None
@@ -280,6 +292,11 @@ class _DecoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *gouts):
+        with ops.on_device_of(ctx.T[0]):
+            return _DecoderFn._backward(ctx, *gouts)
+
+    @staticmethod
+    def _backward(ctx, *gouts):
         module, names = ctx.module, ctx.names
         nodes = module._nodes
         params = ctx.saved_tensors
@@ -298,6 +315,7 @@ class _DecoderFn(torch.autograd.Function):
                 need[nd.out] = need[nd.src] or (nd.res is not None and need[nd.res])
 
         G = {}   # tensor id -> [grad NHWC fp32 tensor | None, owned, bf16 (hi, lo) planes | None]
+        probe = module.__dict__.get('_probe')
         conv_of = {nd.out: nd for nd in nodes if isinstance(nd, _Conv)}
 
         def planes_spec(tid):
@@ -345,6 +363,8 @@ class _DecoderFn(torch.autograd.Function):
             if nd.out not in G:
                 continue
             gy, _, gy_planes = G.pop(nd.out)
+            if probe is not None:
+                gy, gy_planes = probe.bwd(nd.out, gy, gy_planes)
             if isinstance(nd, _Mat):
                 y = T[nd.src]
                 mean, rstd = S[nd.src]
@@ -412,6 +432,10 @@ class _DecoderFn(torch.autograd.Function):
                         grads[nd.w] = dw.view(w.shape)
                     if need_p[nd.b]:
                         grads[nd.b] = db
+                if sink is not None:       # hand the finished gradients over now: their exchange overlaps what follows
+                    for key in (nd.w, nd.b):
+                        if key in grads and sink(key, grads[key]):
+                            del grads[key]
             c_off = 0
             dtaps = [(-dy, -dx, wi) for (dy, dx, wi) in taps]
             for (sid, xf, ups) in nd.srcs:

@@ -178,7 +178,10 @@ class StyleEncoderE2VID(nn.Module):
         return _bn_apply(y, blk.bn2, identity, True, tr)
 
     def forward(self, x):
-        ops.require_cuda(x)
+        with ops.on_device_of(x):
+            return self._forward(x)
+
+    def _forward(self, x):
         out = {1: x}
         sz_in = x.shape[3]
         if x.shape[2] % 8 or x.shape[3] % 8:

@@ -41,7 +41,8 @@ class L1Loss(torch.nn.Module):
     """torch.nn.L1Loss(reduction='mean')."""
 
     def forward(self, input, target):
-        return _L1Fn.apply(input, target)
+        with ops.on_device_of(input):
+            return _L1Fn.apply(input, target)
 
 
 class _JSFn(torch.autograd.Function):
@@ -69,4 +70,5 @@ class _JSFn(torch.autograd.Function):
 
 class symJSDivLoss(torch.nn.Module):
     def forward(self, predict, target):
-        return _JSFn.apply(predict, target)
+        with ops.on_device_of(predict):
+            return _JSFn.apply(predict, target)

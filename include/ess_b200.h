@@ -289,6 +289,20 @@ int essb_voxel_grid_ddd17(const double* events, int64_t n, int C, int H, int W, 
  * with step_lr = step_size*lr and wd_lr = weight_decay*lr computed on the host exactly as radam.py:53-75. */
 int essb_radam_step(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2,
                     float step_lr, float eps, float wd_lr, int rectified, void* stream);
+/* Multi-tensor form of the same update (the reference loops over `group['params']` in Python, utils/radam.py:25-78):
+ * up to ESSB_RADAM_MAX tensors that share the hyper-parameters and the step count are updated by ONE launch. */
+#define ESSB_RADAM_MAX 48
+typedef struct essb_radam_multi {
+  float* p[ESSB_RADAM_MAX];
+  const float* g[ESSB_RADAM_MAX];
+  float* m[ESSB_RADAM_MAX];
+  float* v[ESSB_RADAM_MAX];
+  int64_t n[ESSB_RADAM_MAX];
+  int32_t count;
+  float beta1, beta2, step_lr, eps, wd_lr;
+  int32_t rectified;
+} essb_radam_multi;
+int essb_radam_multi_step(const essb_radam_multi* d, void* stream);
 
 /* ---- tcgen05 / TMA tensor-core path (sm_100a) --------------------------------------------- */
 /* Split an fp32 tensor into bf16 hi/lo planes: hi = bf16(x), lo = bf16(x - hi)  (x ~= hi + lo to

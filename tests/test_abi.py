@@ -34,14 +34,15 @@ def test_ctypes_struct_sizes_match_header():
     from ess_b200 import _lib
     prog = ('#include <stdio.h>\n#include "ess_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(essb_src),'
             ' sizeof(essb_conv), sizeof(essb_wgrad), sizeof(essb_tc_view), sizeof(essb_conv_tc)); '
-            'printf("%zu\\n", sizeof(essb_wgrad_tc)); return 0;}')
+            'printf("%zu %zu\\n", sizeof(essb_wgrad_tc), sizeof(essb_radam_multi)); return 0;}')
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, 's.c')
         open(c, 'w').write(prog)
         exe = os.path.join(d, 's')
         subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), c, '-o', exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
-    mine = [ctypes.sizeof(t) for t in (_lib.Src, _lib.Conv, _lib.Wgrad, _lib.TcView, _lib.ConvTc, _lib.WgradTc)]
+    mine = [ctypes.sizeof(t) for t in (_lib.Src, _lib.Conv, _lib.Wgrad, _lib.TcView, _lib.ConvTc, _lib.WgradTc,
+                                      _lib.RadamMulti)]
     assert sizes == mine, (sizes, mine)
 
 

@@ -76,6 +76,37 @@ def _worker(rank, world, port, q):
     lin2(x).sum().backward()
     assert torch.allclose(lin.weight.grad, lin2.weight.grad) and torch.allclose(lin.bias.grad, lin2.bias.grad)
     assert lin.weight.grad.data_ptr() == bucket.flat.data_ptr()
+    # (4) overlapped exchange: gradients are handed to the bucket's sink in COMPLETION order (reverse parameter order,
+    # as _DecoderFn.backward does); each stage's slice is all-reduced as soon as it is complete, the rest at the end
+    net = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.Linear(4, 4), torch.nn.Linear(4, 2))
+    with torch.no_grad():
+        for i, p_ in enumerate(net.parameters()):
+            p_.copy_(torch.linspace(-1, 1, p_.numel()).view_as(p_) * (i + 1) * 0.1)
+    ob = dp.GradBucket(net.parameters(), module=net, stage_floats=10)
+    assert net._grad_sink == ob._sink and len(ob.stages) >= 2
+    assert sorted(i for lo_, hi_ in ob.stages for i in range(lo_, hi_)) == list(range(6))
+    for rep in range(2):
+        ob.zero_()
+        loss = net(x[lo:hi]).pow(2).sum()
+        gs = torch.autograd.grad(loss, list(net.parameters()))
+        names = [n for n, _ in net.named_parameters()]
+        sent_before_flush = 0
+        for n, g_ in reversed(list(zip(names, gs))):
+            assert ob._sink(n, g_) is True
+        sent_before_flush = sum(ob.sent)
+        assert sent_before_flush == len(ob.stages)          # every stage left as soon as its last gradient arrived
+        assert ob._sink('not_a_parameter', gs[0]) is False
+        ob.allreduce_()
+        ref_net = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.Linear(4, 4), torch.nn.Linear(4, 2))
+        ref_net.load_state_dict(net.state_dict())
+        ref_g = torch.autograd.grad(ref_net(x).pow(2).sum(), list(ref_net.parameters()))
+        for p_, rg in zip(net.parameters(), ref_g):
+            assert torch.allclose(p_.grad, rg, rtol=1e-6, atol=1e-6)
+    # a gradient delivered twice in one step (UDA: two backward passes) accumulates
+    ob.zero_()
+    ob._sink(names[-1], gs[-1])
+    ob._sink(names[-1], gs[-1])
+    assert torch.allclose(list(net.parameters())[-1].grad, 2 * gs[-1])
     torch.distributed.destroy_process_group()
     q.put((rank, 'ok'))
 

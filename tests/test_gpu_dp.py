@@ -69,6 +69,14 @@ def _worker(rank, world, port, q):
 
     res = dict(rank=rank, logits=rel(logits_l, logits_g[lo:hi]), loss=abs(float(loss_l) - float(loss_g)),
                grads=max(rel(p.grad, grads_g[n]) for n, p in dec.named_parameters() if n.endswith('weight')))
+    # overlapped exchange (per-stage slices all-reduced on a side stream while the backward continues): same result
+    grads_flat = bucket.flat.clone()
+    ob = dp.GradBucket(dec.parameters(), module=dec, stage_floats=1 << 19)
+    _run_step(dec, crit, rec, data[lo:hi].contiguous(), labels[lo:hi].contiguous(), T, C, ob)
+    torch.cuda.synchronize()
+    res['overlap_stages'] = len(ob.stages)
+    res['overlap_vs_flat'] = rel(ob.flat, grads_flat)
+    res['overlap_grads'] = max(rel(p.grad, grads_g[n]) for n, p in dec.named_parameters() if n.endswith('weight'))
     torch.distributed.destroy_process_group()
     q.put(res)
 
@@ -91,3 +99,4 @@ def test_dp2_matches_single_process_global_batch():
         assert r['logits'] < 1e-5, r          # same kernels, same global statistics: per-sample logits agree
         assert r['loss'] < 1e-5, r            # every rank holds the GLOBAL-batch loss
         assert r['grads'] < 2e-3, r           # SUM of shard gradients == global gradient (split-K order differs)
+        assert r['overlap_stages'] >= 3 and r['overlap_vs_flat'] < 1e-6 and r['overlap_grads'] < 2e-3, r

@@ -266,6 +266,52 @@ def test_radam_kernel_vs_oracle():
         assert rel_err(w.detach(), w2) < 1e-6, i
 
 
+def test_radam_multi_tensor_exponential_lr_and_state_roundtrip():
+    """The multi-tensor launch over a realistic parameter set (60 tensors of mixed sizes incl. sizes that are not
+    multiples of 4 -> two launches, vector and scalar paths), with gradient views into ONE flat bucket (ess_b200.dp)
+    whose slices are not 16 B aligned, driven through torch's ExponentialLR exactly as the reference does
+    (training/base_trainer.py:64-66: one scheduler step per epoch) and a state_dict save / load in the middle
+    (utils/saver.py) -- against the oracle's per-tensor restatement of utils/radam.py:15-80."""
+    import ess_b200.optim
+    g = torch.Generator().manual_seed(1)
+    shapes = [(256, 256, 3, 3), (256,), (11, 32, 1, 1), (11,), (7, 5), (3,), (130,)] + [(64, 9), (33,)] * 26 + [(1,)]
+    assert len(shapes) == 60
+    params = [torch.nn.Parameter((torch.randn(s, generator=g) * 0.1).cuda()) for s in shapes]
+    ref = [p.detach().cpu().clone() for p in params]
+    states = [{} for _ in params]
+    total = sum(p.numel() for p in params)
+    flat = torch.zeros(total, device='cuda')
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    opt = ess_b200.optim.RAdam(params, lr=5e-4, weight_decay=1e-2, betas=(0., 0.999))
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.5)
+    lr = 5e-4
+    from ess_b200 import _lib
+    for epoch in range(3):
+        for it in range(4):
+            gs = [torch.randn(s, generator=g) for s in shapes]
+            flat.copy_(torch.cat([x.flatten() for x in gs]).cuda())
+            l0 = _lib.launch_count
+            opt.step()
+            assert _lib.launch_count - l0 == 2                      # 60 tensors -> 48 + 12
+            for r, x, st in zip(ref, gs, states):
+                O.radam_step(r, x, st, lr, (0., 0.999), weight_decay=1e-2)
+        sched.step()
+        lr *= 0.5
+        assert abs(opt.param_groups[0]['lr'] - lr) < 1e-12
+        if epoch == 0:      # checkpoint round trip: a fresh optimizer continues from the saved state
+            sd = opt.state_dict()
+            opt = ess_b200.optim.RAdam(params, lr=5e-4, weight_decay=1e-2, betas=(0., 0.999))
+            opt.load_state_dict(sd)
+            sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.5, last_epoch=0)
+            assert abs(opt.param_groups[0]['lr'] - lr) < 1e-12
+    for p, r in zip(params, ref):
+        assert rel_err(p.detach(), r) < 1e-5, tuple(p.shape)
+    assert all(p._version > 0 for p in params)                      # packed-weight caches see the update
+
+
 def test_voxel_grids():
     from ess_b200.voxel import VoxelGrid, generate_voxel_grid
     g = torch.Generator().manual_seed(0)

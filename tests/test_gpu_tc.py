@@ -182,3 +182,68 @@ def test_wgrad_tc_stride2(Cin, Cout, k):
     dw = ops.wgrad_tc(xp, gp, Cin, Cout, ops.taps_conv(k, pad), N, OH, OW, 3, stride=2)
     torch.cuda.synchronize()
     assert rel_err(dw.view(Cout, Cin, k, k).cpu(), w.grad) < 1e-3
+
+
+@pytest.mark.parametrize('passes,tol', [(3, 1e-3), (1, 3e-2)])
+@pytest.mark.parametrize('N,H,W,Cin,Cout,c_off,cs', [
+    (2, 12, 20, 256, 256, 0, 256),     # INSResBlock convs (style_networks.py:174-183)
+    (1, 55, 80, 256, 128, 0, 256),     # decoder_scale_1.5 at the odd DSEC 1/8 extent
+    (2, 16, 24, 256, 128, 0, 128),     # decoder_scale_2.0: first concat segment (upsampled x) ...
+    (2, 16, 24, 256, 128, 128, 128),   # ... and the skip segment in[4]
+    (1, 32, 48, 128, 64, 64, 64),      # decoder_scale_3.0: skip segment in[2]
+    (2, 40, 56, 64, 64, 0, 64),        # decoder_scale_3.1
+    (2, 64, 96, 64, 32, 0, 64),        # decoder_scale_4.0: Cout = 32 -> dY K-padded to 64
+    (1, 110, 160, 64, 32, 0, 64),
+])
+def test_dgrad_tc(passes, tol, N, H, W, Cin, Cout, c_off, cs):
+    """tcgen05 input gradient exactly as ess_b200.semseg._DecoderFn.backward launches it: dY planes (channel-padded
+    to a multiple of 64 with zeros) x the [c_off, c_off+cs) input-channel slice of the weight packed with
+    swap_io=True / kin_pad, mirrored taps -- vs autograd of F.conv2d (fp64)."""
+    from ess_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, Cin, H, W, generator=g).double().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * 0.05)
+    dy = torch.randn(N, Cout, H, W, generator=g)
+    gx, = torch.autograd.grad(F.conv2d(x, w.double(), None, padding=1), [x], dy.double())
+    kinp = (Cout + 63) // 64 * 64
+    gh, gl = ops.split_bf16(ops.Seg(nhwc(dy)), N, H, W, c_pad=kinp)
+    assert gh.shape[-1] == kinp
+    wseg = w.cuda()[:, c_off:c_off + cs].contiguous()
+    w_hi, w_lo, _ = ops.pack_weight_tc(wseg, swap_io=True, kin_pad=kinp)
+    dtaps = [(-dy_, -dx_, wi) for (dy_, dx_, wi) in ops.taps_conv(3, 1)]
+    dA = ops.conv_tc_dense((gh, gl), w_hi, w_lo, kinp, dtaps, N, H, W, cs, passes)
+    torch.cuda.synchronize()
+    err = rel_err(nchw(dA), gx[:, c_off:c_off + cs])
+    assert err < tol, err
+
+
+@pytest.mark.parametrize('relu,ups', [(True, 0), (False, 0), (True, 1)])
+@pytest.mark.parametrize('N,H,W,C', [(2, 12, 20, 64), (1, 55, 80, 128), (2, 32, 48, 32), (1, 16, 24, 256)])
+def test_in_backward_to_planes(relu, ups, N, H, W, C):
+    """InstanceNorm(+ReLU)(+nearest x2 upsample) backward writing the gradient ONLY as the bf16 hi/lo operand planes of
+    the tcgen05 dgrad / wgrad kernels (planes_ld = C rounded up to 64, zero padded; no fp32 copy) vs autograd (fp64)."""
+    from ess_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    y = (torch.randn(N, C, H, W, generator=g) * 2 + 0.3).double().requires_grad_(True)
+    a = F.instance_norm(y, eps=1e-5)
+    if relu:
+        a = torch.relu(a)
+    if ups:
+        a = a.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    dA = torch.randn(a.shape, generator=g)
+    gy, = torch.autograd.grad(a, [y], dA.double())
+    yd = nhwc(y.detach().float())
+    mean, rstd = ops.in_stats(yd)
+    ld = (C + 63) // 64 * 64
+    d32, planes = ops.in_backward(nhwc(dA), yd, mean, rstd, relu=relu, ups=ups, planes_ld=ld, want_fp32=False)
+    torch.cuda.synchronize()
+    assert d32 is None and planes[0].shape == (N, H, W, ld)
+    got = planes[0].float() + planes[1].float()
+    if ld > C:
+        assert float(got[..., C:].abs().max()) == 0.0
+    keep = (F.instance_norm(y.detach(), eps=1e-5).abs() > 1e-4) if relu else torch.ones_like(gy, dtype=torch.bool)
+    err = float(((nchw(got[..., :C]).double() - gy).abs() * keep).max() / gy.abs().max())
+    assert err < 1e-3, err
+    # and both outputs together agree with each other to the bf16x2 rounding (2^-16)
+    d32b, planes_b = ops.in_backward(nhwc(dA), yd, mean, rstd, relu=relu, ups=ups, planes_ld=ld, want_fp32=True)
+    assert rel_err(planes_b[0].float()[..., :C] + planes_b[1].float()[..., :C], d32b) < 2 ** -15

@@ -129,3 +129,27 @@ def test_shard_batch_partitions_the_global_batch():
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     with pytest.raises(ValueError):
         dp.shard_batch(10, 0, 4)
+
+
+@pytest.mark.parametrize('skip_connect', [True, False])
+def test_decoder_program_equals_oracle(skip_connect):
+    """The static node program of ess_b200.SemSegE2VID, interpreted with plain torch ops (helpers.program_forward,
+    the teacher of tests/test_gpu_teacher.py), reproduces the reference restatement O.semseg_forward -- outputs and
+    every parameter gradient -- in fp64: the wiring of the executor's graph is pinned on CPU."""
+    from helpers import O, make_labels, make_latents, make_semseg, program_forward
+    K, B, H, W = 5, 1, 16, 24
+    kw = dict(skip_connect=True, skip_type='concat') if skip_connect else dict(skip_connect=False, skip_type='sum')
+    dec = make_semseg(K, input_c=64, **kw)
+    lat = {k: v.double() for k, v in make_latents(B, H, W, base=8).items()}
+    labels = make_labels(B, H, W, K)
+    sd = {k: v.detach().double().requires_grad_(True) for k, v in dec.state_dict().items()}
+    outs, _ = program_forward(dec, sd, lat)
+    ref = O.semseg_forward(sd, lat, **kw)
+    for k in (4, 2, 1):
+        assert torch.equal(outs[k], ref[k]) or float((outs[k] - ref[k]).abs().max()) < 1e-12
+    g_a = torch.autograd.grad(O.task_loss(outs[1], labels, K), list(sd.values()), allow_unused=True)
+    g_b = torch.autograd.grad(O.task_loss(ref[1], labels, K), list(sd.values()), allow_unused=True)
+    for n, a, b in zip(sd, g_a, g_b):
+        assert (a is None) == (b is None), n
+        if a is not None:
+            assert float((a - b).abs().max()) <= 1e-12 * max(1.0, float(b.abs().max())), n
