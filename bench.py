@@ -33,6 +33,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault('ESS_B200_PRETRAINED', '0')    # random-init weights of the reference architecture (no checkpoints)
 
 E2VID_CFG = dict(num_bins=5, skip_type='sum', recurrent_block_type='convlstm', num_encoders=3, base_num_channels=32,
                  num_residual_blocks=2, norm='BN', use_upsample_conv=False)

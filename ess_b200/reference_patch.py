@@ -32,6 +32,8 @@ def install(reconstructor=True, uda=True):
         if reconstructor:
             _swap(mod, 'ImageReconstructor', ess_b200.ImageReconstructor)
     if uda:
+        # NB: like the reference, ess_b200.StyleEncoderE2VID starts from ImageNet resnet18 weights (hub cache or
+        # download) and warns loudly when they cannot be obtained -- see ess_b200/style_encoder.py
         _swap(trainers[-1], 'StyleEncoderE2VID', ess_b200.StyleEncoderE2VID)
         _swap(trainers[-1], 'symJSDivLoss', ess_b200.symJSDivLoss)
     radam = importlib.import_module('utils.radam')

@@ -43,10 +43,14 @@ class _INSResBlock(nn.Module):        # style_networks.py:172-193
 
 
 class _Conv(object):
-    __slots__ = ('out', 'srcs', 'w', 'b', 'cout', 'k', 'stats')
+    """`cout` = channels of the node's output tensor.  `pad` = None, or (Cout, Cin) of the PARAMETER when the executor
+    runs the layer zero-padded to (cout, sum of source channels): input_index_map=True makes the first stage 258
+    channels wide, which is carried as 260 (vector-width multiple) with zero weights / zero activations in the pad."""
+    __slots__ = ('out', 'srcs', 'w', 'b', 'cout', 'k', 'stats', 'pad')
 
-    def __init__(self, out, srcs, w, b, cout, k, stats):
+    def __init__(self, out, srcs, w, b, cout, k, stats, pad=None):
         self.out, self.srcs, self.w, self.b, self.cout, self.k, self.stats = out, srcs, w, b, cout, k, stats
+        self.pad = pad
 
 
 class _Mat(object):
@@ -79,12 +83,15 @@ class SemSegE2VID(nn.Module):
             self.decoder_scale_4 = nn.Sequential(_ReLUINSConv2d(tch, tch // 2))
             tch //= 2
         else:
-            if input_index_map:
-                raise NotImplementedError('SemSegE2VID(input_index_map=True): the coordinate channels make C '
-                                          'not a multiple of 4; not built (unused by the reference YAMLs)')
+            if input_index_map:                                  # style_networks.py:36-50: two coordinate channels
+                tch += 2
             self.decoder_scale_1 = nn.Sequential(*[_INSResBlock(tch) for _ in range(3)])
-            self.decoder_scale_2 = nn.Sequential(nn.Identity(), _ReLUINSConv2d(tch, tch // 2))
-            tch //= 2
+            if input_index_map:
+                self.decoder_scale_2 = nn.Sequential(nn.Identity(), _ReLUINSConv2d(tch, (tch - 2) // 2))
+                tch = (tch - 2) // 2
+            else:
+                self.decoder_scale_2 = nn.Sequential(nn.Identity(), _ReLUINSConv2d(tch, tch // 2))
+                tch //= 2
             self.decoder_scale_3 = nn.Sequential(nn.Identity(), _ReLUINSConv2d(tch, tch // 2))
             tch //= 2
             self.decoder_scale_4 = nn.Sequential(nn.Identity(), _ReLUINSConv2d(tch, tch // 2))
@@ -106,9 +113,9 @@ class SemSegE2VID(nn.Module):
             nid[0] += 1
             return nid[0] - 1
 
-        def conv(srcs, prefix, cout, k=3, stats=True):
+        def conv(srcs, prefix, cout, k=3, stats=True, pad=None):
             o = new()
-            nodes.append(_Conv(o, srcs, prefix + '.weight', prefix + '.bias', cout, k, stats))
+            nodes.append(_Conv(o, srcs, prefix + '.weight', prefix + '.bias', cout, k, stats, pad))
             return o
 
         def mat(src, relu, res=None):
@@ -119,9 +126,13 @@ class SemSegE2VID(nn.Module):
         c = self.input_c
         x = 0
         nres = 5 if self.skip_connect else 3
+        cw, pad1 = c, None                                               # width of the first stage as executed
+        if self.input_index_map and not self.skip_connect:
+            cw = (c + 2 + 3) // 4 * 4                                    # 258 -> 260
+            pad1 = (c + 2, c + 2)
         for b in range(nres):                                            # INSResBlock
-            y1 = conv([(x, 'raw', 0)], 'decoder_scale_1.%d.model.0' % b, c)
-            y2 = conv([(y1, 'nr', 0)], 'decoder_scale_1.%d.model.3' % b, c)
+            y1 = conv([(x, 'raw', 0)], 'decoder_scale_1.%d.model.0' % b, cw, pad=pad1)
+            y2 = conv([(y1, 'nr', 0)], 'decoder_scale_1.%d.model.3' % b, cw, pad=pad1)
             x = mat(y2, False, x)
         if self.skip_connect:
             y = conv([(x, 'raw', 0)], 'decoder_scale_1.5.model.0', c // 2)
@@ -137,7 +148,7 @@ class SemSegE2VID(nn.Module):
             o1 = conv([(y, 'nr', 0)], 'decoder_scale_5.0', self.output_c, k=1, stats=False)
             outs.append(o1)
         else:
-            y = conv([(x, 'raw', 1)], 'decoder_scale_2.1.model.0', c // 2)
+            y = conv([(x, 'raw', 1)], 'decoder_scale_2.1.model.0', c // 2, pad=(c // 2, c + 2) if pad1 else None)
             o4 = mat(y, True)
             outs.append(o4)
             y = conv([(o4, 'raw', 1)], 'decoder_scale_3.1.model.0', c // 4)
@@ -163,6 +174,13 @@ class SemSegE2VID(nn.Module):
             ins = (x8, input_dict[4], input_dict[2])
         else:
             ins = (x8, None, None)
+        if self.input_index_map and not self.skip_connect:
+            # style_networks.py:90-97: x-coordinate = row index, y-coordinate = column index, cached on the module
+            if self.index_coords is None or self.index_coords.shape[0] != x8.shape[0] or \
+                    self.index_coords.shape[2:] != x8.shape[2:] or self.index_coords.device != x8.device:
+                xc = torch.arange(x8.size(2), device=x8.device, dtype=torch.float)
+                yc = torch.arange(x8.size(3), device=x8.device, dtype=torch.float)
+                self.index_coords = torch.stack(torch.meshgrid([xc, yc], indexing='ij'), 0)[None].repeat(x8.size(0), 1, 1, 1)
         with ops.on_device_of(x8):
             res = _DecoderFn.apply(self, names, ins[0], ins[1], ins[2], *params)
         out = {8: x8}
@@ -180,6 +198,42 @@ def _nhwc(t):
 
 def _taps(k):
     return ops.taps_conv(k, k // 2)
+
+
+def _weight(nd, w):
+    """The node's weight as executed: the parameter itself, or zero-padded to (nd.cout, padded Cin) -- see _Conv.pad"""
+    w = w.detach()
+    if nd.pad is None:
+        return w
+    cout, cin = nd.pad
+    cin_p = (cin + 3) // 4 * 4
+    wp = torch.zeros((nd.cout, cin_p) + tuple(w.shape[2:]), device=w.device, dtype=torch.float32)
+    wp[:cout, :cin] = w
+    return wp
+
+
+def _bias(nd, b):
+    b = b.detach().float()
+    if nd.pad is None or b.numel() == nd.cout:
+        return b.contiguous()
+    bp = torch.zeros((nd.cout,), device=b.device, dtype=torch.float32)
+    bp[:b.numel()] = b
+    return bp
+
+
+def _packed32(module, w, nd, c_off=None, cs=None):
+    """ops.pack_weight of the node's (padded) weight for the fp32 CUDA-core kernels -- forward layout, or, with
+    (c_off, cs), the swap_io layout of the input-channel slice used by the input gradient -- cached per parameter
+    version like the tensor-core packs (the UDA iteration runs the decoder 5x forward / 3x backward per step)."""
+    cache = module.__dict__.setdefault('_wcache', {})
+    key = (w.data_ptr(), 'fp32', c_off, cs)
+    ent = cache.get(key)
+    if ent is None or ent[0] != w._version or ent[1] != tuple(w.shape):
+        wx = _weight(nd, w)
+        packed = ops.pack_weight(wx) if c_off is None else ops.pack_weight(wx[:, c_off:c_off + cs].contiguous(), swap_io=True)
+        ent = (w._version, tuple(w.shape), packed)
+        cache[key] = ent
+    return ent[2]
 
 
 def _packed_tc(module, w, **kw):
@@ -217,6 +271,13 @@ class _DecoderFn(torch.autograd.Function):
         nodes = module._nodes
         P = dict(zip(names, params))
         T = {0: _nhwc(x8), 1: _nhwc(x4), 2: _nhwc(x2)}
+        if module.input_index_map and not module.skip_connect:
+            # x = cat([x, index_coords]) (style_networks.py:97), carried with zero channels up to a multiple of 4
+            cw = nodes[0].cout
+            x0 = torch.zeros(tuple(T[0].shape[:3]) + (cw,), device=x8.device, dtype=torch.float32)
+            x0[..., :module.input_c] = T[0]
+            x0[..., module.input_c:module.input_c + 2] = module.index_coords.permute(0, 2, 3, 1)
+            T[0] = x0
         S = {}
         tc = module.mode != 'fp32'
         passes = 3 if module.mode == 'bf16x3' else 1
@@ -239,9 +300,9 @@ class _DecoderFn(torch.autograd.Function):
                     else:
                         segs.append(Seg(T[sid], ups=ups))
                 w = P[nd.w]
-                bias = P[nd.b].detach().float().contiguous()
-                cin_total = w.shape[1]
-                if tc and nd.k == 3 and cin_total % 64 == 0 and nd.cout in (32, 64, 128, 256):
+                bias = _bias(nd, P[nd.b])
+                cin_total = w.shape[1] if nd.pad is None else (nd.pad[1] + 3) // 4 * 4
+                if tc and nd.k == 3 and nd.pad is None and cin_total % 64 == 0 and nd.cout in (32, 64, 128, 256):
                     # tensor-core path: operand planes = the transformed (IN/ReLU/upsample/concat) input
                     hi = torch.empty((N, H, W, cin_total), device=first.device, dtype=torch.bfloat16)
                     lo = torch.empty_like(hi)
@@ -267,7 +328,7 @@ class _DecoderFn(torch.autograd.Function):
                     if probe is not None:
                         T[nd.out] = probe.fwd(nd.out, T[nd.out])
                 else:
-                    wp = ops.pack_weight(w)
+                    wp = _packed32(module, w, nd)
                     y, _, st, _ = ops.conv(segs, wp, bias, N, H, W, H, W, nd.cout, _taps(nd.k), epilogue=EPI_LINEAR,
                                            act=ACT_NONE, want_stats=nd.stats)
                     if probe is not None:
@@ -316,6 +377,7 @@ class _DecoderFn(torch.autograd.Function):
 
         G = {}   # tensor id -> [grad NHWC fp32 tensor | None, owned, bf16 (hi, lo) planes | None]
         probe = module.__dict__.get('_probe')
+        sink = module.__dict__.get('_grad_sink')   # ess_b200.dp.GradBucket(module=...): overlapped gradient exchange
         conv_of = {nd.out: nd for nd in nodes if isinstance(nd, _Conv)}
 
         def planes_spec(tid):
@@ -380,7 +442,7 @@ class _DecoderFn(torch.autograd.Function):
             H, W = first.shape[1] << ups0, first.shape[2] << ups0
             w = P[nd.w]
             taps = _taps(nd.k)
-            tc = ctx.mode != 'fp32' and nd.k == 3 and nd.cout % 32 == 0
+            tc = ctx.mode != 'fp32' and nd.k == 3 and nd.cout % 32 == 0 and nd.pad is None
             passes = 3 if ctx.mode == 'bf16x3' else 1
             gplanes = gy_planes
 
@@ -399,7 +461,7 @@ class _DecoderFn(torch.autograd.Function):
                         segs.append(Seg(T[sid], ups=ups, mean=S[sid][0], rstd=S[sid][1], relu=True))
                     else:
                         segs.append(Seg(T[sid], ups=ups))
-                cin_total = w.shape[1]
+                cin_total = w.shape[1] if nd.pad is None else (nd.pad[1] + 3) // 4 * 4
                 if _pw_ok(nd, segs, cin_total):
                     dw, db = ops.pw_conv_wgrad(segs[0], gy, want_w=need_p[nd.w], want_b=need_p[nd.b])
                     if need_p[nd.w]:
@@ -428,6 +490,9 @@ class _DecoderFn(torch.autograd.Function):
                         grads[nd.b] = _bias_grad(nd, gy, w.device)
                 else:
                     dw, db = ops.wgrad(segs, gy, N, H, W, H, W, nd.cout, taps, want_bias=need_p[nd.b])
+                    if nd.pad is not None:            # drop the zero-padded rows / columns
+                        dw = dw[:nd.pad[0], :nd.pad[1]].contiguous()
+                        db = db[:nd.pad[0]].contiguous() if db is not None else None
                     if need_p[nd.w]:
                         grads[nd.w] = dw.view(w.shape)
                     if need_p[nd.b]:
@@ -442,7 +507,7 @@ class _DecoderFn(torch.autograd.Function):
                 src = T[sid]
                 cs = src.shape[-1]
                 if need[sid]:
-                    wseg = w.detach()[:, c_off:c_off + cs].contiguous()
+                    wseg = w.detach()[:, c_off:c_off + cs].contiguous() if nd.pad is None else None
                     if nd.k == 1 and len(nd.srcs) == 1 and cs in (32, 64) and nd.cout <= 16 and not ups:
                         dA = ops.pw_conv_dgrad(gy, wseg.float().reshape(nd.cout, cs), cs)
                     elif tc and cs in (64, 128, 256):
@@ -458,7 +523,7 @@ class _DecoderFn(torch.autograd.Function):
                         w_hi, w_lo, _ = ent[1]
                         dA = ops.conv_tc_dense(gplanes, w_hi, w_lo, kinp, dtaps, N, H, W, cs, passes, tag='seg_dgrad')
                     else:
-                        wp = ops.pack_weight(wseg, swap_io=True)
+                        wp = _packed32(module, w, nd, c_off, cs)
                         dA, _, _, _ = ops.conv([Seg(gy)], wp, None, N, H, W, H, W, cs, dtaps)
                     if xf == 'nr':
                         g32, gpl = in_bwd(sid, dA, src, S[sid][0], S[sid][1], True, ups=ups)
@@ -471,7 +536,10 @@ class _DecoderFn(torch.autograd.Function):
 
         def out_grad(tid, ref):
             if tid in G and ref is not None:
-                return ops.as_nchw(G[tid][0]).to(ref.dtype)
+                g = G[tid][0]
+                if tid == 0 and g.shape[-1] != module.input_c:      # input_index_map: drop coordinate / pad channels
+                    g = g[..., :module.input_c].contiguous()
+                return ops.as_nchw(g).to(ref.dtype)
             return None
 
         gx8 = out_grad(0, None if not nig[2] else T[0])

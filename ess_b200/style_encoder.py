@@ -4,9 +4,10 @@ ResNet-18 stem (conv7x7 s2 + BN + ReLU, no max-pool) + layer1..3 with BatchNorm 
 
 Same constructor (`input_dim`, `skip_connect`), `forward(x) -> {1: x, 2, 4, 8}` and `state_dict` keys
 (`encoder_scale_1.0.weight`, `encoder_scale_1.1.*`, `encoder_scale_1.3.{0,1}.*`, `encoder_scale_{2,3}.{0,1}.*`)
-as the reference.  The torchvision modules are parameter/buffer holders only.  The reference builds its
-holders from `resnet18(pretrained=True)` (ImageNet weights, needs network access); here they start from
-torchvision's random init -- load a checkpoint for pretrained weights.
+as the reference.  The torchvision modules are parameter/buffer holders only.  Like the reference
+(`resnet18(pretrained=True)`, style_networks.py:117-121) the holders start from the ImageNet weights: taken from
+the torch hub cache, else downloaded; when neither is possible (no network) a warning says so LOUDLY and the
+encoder keeps torchvision's random init (ESS_B200_PRETRAINED=0 opts out silently, e.g. for checkpoint loading).
 
 Execution: two small autograd Functions on pixel-major fp32 tensors -- a bias-free gather convolution
 (forward; input gradient as per-phase gather-convs over dY; weight gradient as split-K implicit GEMM)
@@ -16,6 +17,9 @@ runs on the tcgen05 kernels (stride 2 through parity views; input gradients of s
 gathers with strided stores); the 1-channel 7x7 stem has its own HBM-bound kernels (stem_conv.cu); the stride-2
 weight gradients read the input through parity planes on the tcgen05 wgrad kernel.
 """
+import os
+import warnings
+
 import torch
 import torch.nn as nn
 import torchvision.models as tvm
@@ -145,11 +149,45 @@ def _bn_apply(x, bn, res, relu, training):
     return ops.affine_act(x, a, b, res=res, relu=relu)
 
 
+_warned_pretrained = [False]
+
+
+def _resnet18_imagenet():
+    """torchvision resnet18 with the ImageNet weights the reference starts from (style_networks.py:117-121).
+    Returns (module, source) with source in {'cache', 'download', 'disabled', 'random-init'}."""
+    if os.environ.get('ESS_B200_PRETRAINED', '1') == '0':
+        return tvm.resnet18(weights=None), 'disabled'
+    w = tvm.ResNet18_Weights.IMAGENET1K_V1
+    ckpt = os.path.join(torch.hub.get_dir(), 'checkpoints', os.path.basename(w.url))
+    try:
+        if os.path.exists(ckpt):
+            r = tvm.resnet18(weights=None)
+            r.load_state_dict(torch.load(ckpt, map_location='cpu', weights_only=True))
+            return r, 'cache'
+        import socket
+        old = socket.getdefaulttimeout()
+        socket.setdefaulttimeout(10)
+        try:
+            return tvm.resnet18(weights=w, progress=False), 'download'
+        finally:
+            socket.setdefaulttimeout(old)
+    except Exception as ex:
+        if not _warned_pretrained[0]:
+            _warned_pretrained[0] = True
+            warnings.warn('ess_b200.StyleEncoderE2VID: ImageNet weights for resnet18 are NOT available (%s: %s); the '
+                          'image encoder starts from RANDOM init, unlike the reference (resnet18(pretrained=True), '
+                          'models/style_networks.py:117-121).  Put %s into %s, load a checkpoint, or set '
+                          'ESS_B200_PRETRAINED=0 to acknowledge.' % (type(ex).__name__, str(ex)[:80],
+                                                                      os.path.basename(w.url), os.path.dirname(ckpt)),
+                          RuntimeWarning, stacklevel=3)
+        return tvm.resnet18(weights=None), 'random-init'
+
+
 class StyleEncoderE2VID(nn.Module):
     def __init__(self, input_dim, skip_connect=False):
         super().__init__()
         self.skip_connect = skip_connect
-        r = tvm.resnet18(weights=None)
+        r, self.pretrained_source = _resnet18_imagenet()
         conv_list = [nn.Conv2d(input_dim, 64, kernel_size=(7, 7), stride=(2, 2), padding=(3, 3), bias=False)]
         conv_list += list(r.children())[1:3]          # bn1, relu
         conv_list += list(r.children())[4:5]          # layer1 (max-pool skipped, as in the reference)

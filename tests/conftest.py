@@ -4,6 +4,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# synthetic random-init weights by design (no network): skip the ImageNet download attempt of
+# ess_b200.StyleEncoderE2VID; tests/test_host_logic.py covers the attempt + warning path explicitly
+os.environ.setdefault('ESS_B200_PRETRAINED', '0')
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

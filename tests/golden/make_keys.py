@@ -30,10 +30,12 @@ def main():
                                          state_dict=listing(SemSegE2VID(256, 11, skip_connect=True, skip_type='concat')))
     out['semseg_no_skip_k6'] = dict(args=dict(input_c=256, output_c=6, skip_connect=False),
                                     state_dict=listing(SemSegE2VID(256, 6, skip_connect=False)))
+    out['semseg_no_skip_index_map_k5'] = dict(args=dict(input_c=256, output_c=5, skip_connect=False, input_index_map=True),
+                                              state_dict=listing(SemSegE2VID(256, 5, skip_connect=False, input_index_map=True)))
     out['style_encoder'] = dict(args=dict(input_dim=1, skip_connect=True),
                                 state_dict=listing(StyleEncoderE2VID(1, skip_connect=True)))
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'state_dict_keys.json')
-    json.dump(out, open(path, 'w'), indent=0)
+    json.dump(out, open(path, 'w'))
     print('wrote', path, {k: len(v['state_dict']) for k, v in out.items()})
 
 

@@ -24,7 +24,7 @@ def test_e2vid_state_dict_contract(name):
     assert m.num_bins == KEYS[name]['cfg']['num_bins'] and m.num_encoders == 3
 
 
-@pytest.mark.parametrize('name', ['semseg_skip_concat_k11', 'semseg_no_skip_k6'])
+@pytest.mark.parametrize('name', ['semseg_skip_concat_k11', 'semseg_no_skip_k6', 'semseg_no_skip_index_map_k5'])
 def test_semseg_state_dict_contract(name):
     import ess_b200
     m = ess_b200.SemSegE2VID(**KEYS[name]['args'])

@@ -206,6 +206,46 @@ def test_semseg_no_skip_variant():
     assert rel_err(dict(dec.named_parameters())[n].grad, g_r[n]) < 5e-3
 
 
+@pytest.mark.parametrize('mode', ['fp32', 'bf16x3'])
+def test_semseg_input_index_map_variant(mode):
+    """SemSegE2VID(skip_connect=False, input_index_map=True) (style_networks.py:35-62,89-106): two coordinate channels
+    are concatenated to in[8], the three INSResBlocks run 258 channels wide (executed zero-padded to 260), then
+    258 -> 128 -> 64 -> 32 -> K.  Forward at 1e-3, every parameter gradient and the input gradient by the flip-robust
+    norm criterion against the fp64 oracle; state_dict shapes are the reference's."""
+    import ess_b200
+    K, B, H, W = 5, 2, 32, 48
+    dec = make_semseg(K, skip_connect=False, skip_type='sum', input_index_map=True)
+    assert dec.decoder_scale_1[0].model[0].weight.shape == (258, 258, 3, 3)
+    assert dec.decoder_scale_2[1].model[0].weight.shape == (128, 258, 3, 3)
+    dec = dec.cuda()
+    dec.mode = mode
+    lat = make_latents(B, H, W, device='cuda')
+    labels = make_labels(B, H, W, K).cuda()
+    kw = dict(skip_connect=False, skip_type='sum', input_index_map=True)
+    pred_r, loss_r, g_r = _oracle_semseg_grads(dec, lat, labels, K, want_inputs=True, dtype=torch.float64, **kw)
+    lat_g = {k: v.clone().requires_grad_(k == 8) for k, v in lat.items()}
+    pred = dec(lat_g)
+    assert set(pred.keys()) == set(pred_r.keys())
+    for k in pred_r:
+        assert pred[k].shape == pred_r[k].shape and rel_err(pred[k], pred_r[k]) < TOL, k
+    crit = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255)
+    loss = crit(pred[1], labels)
+    assert abs(float(loss.detach()) - float(loss_r)) < TOL * abs(float(loss_r))
+    loss.backward()
+    for n, p in list(dec.named_parameters()) + [('in8', lat_g[8])]:
+        a, r = p.grad.detach().cpu().double().flatten(), g_r[n].flatten()
+        assert p.grad.shape == p.shape
+        if n.endswith('bias') and not n.startswith('decoder_scale_5'):
+            assert float((a - r).abs().max()) < 5e-6, n
+            continue
+        cos, l2 = float(a @ r / (a.norm() * r.norm())), float((a - r).norm() / r.norm())
+        assert cos > 0.999 and l2 < 3e-2, (n, cos, l2)
+    # second call re-uses the cached coordinates; a different batch size rebuilds them
+    assert rel_err(dec({k: v for k, v in lat.items()})[1], pred_r[1]) < TOL
+    lat1 = {k: v[:1].contiguous() for k, v in lat.items()}
+    assert dec(lat1)[1].shape[0] == 1
+
+
 def test_full_size_properties_dsec():
     """BASELINE.json full size (440x640, C=5): properties that need no CPU oracle -- the tcgen05 path
     agrees with the exact-fp32 path, states carry, an all-zero window leaves zero-input statistics."""

@@ -105,7 +105,8 @@ def test_oracle_vs_live_reference_semseg_variants():
     torch.manual_seed(3)
     lat = {1: torch.randn(2, 8, 32, 32), 2: torch.randn(2, 16, 16, 16), 4: torch.randn(2, 32, 8, 8),
            8: torch.randn(2, 64, 4, 4)}
-    for kw in (dict(skip_connect=True, skip_type='concat'), dict(skip_connect=False), ):
+    for kw in (dict(skip_connect=True, skip_type='concat'), dict(skip_connect=False),
+               dict(skip_connect=False, input_index_map=True)):
         dec = SemSegE2VID(input_c=64, output_c=5, **kw)
         out = dec(lat)
         out2 = O.semseg_forward(dec.state_dict(), lat, **kw)

@@ -7,6 +7,8 @@ import sys
 
 import torch
 
+os.environ.setdefault('ESS_B200_PRETRAINED', '0')
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
