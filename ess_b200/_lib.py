@@ -68,7 +68,7 @@ class ConvTc(C.Structure):
                 ('epilogue', C.c_int32), ('act', C.c_int32), ('passes', C.c_int32), ('bw_log2', C.c_int32),
                 ('ntaps', C.c_int32),
                 ('dy', C.c_int8 * MAX_TAPS), ('dx', C.c_int8 * MAX_TAPS), ('view', C.c_int8 * MAX_TAPS),
-                ('widx', C.c_int8 * MAX_TAPS)]
+                ('widx', C.c_int8 * MAX_TAPS), ('acc_scale', C.c_float), ('planes_fmt', C.c_int32)]
 
 
 class WgradTc(C.Structure):
@@ -144,7 +144,9 @@ SIGNATURES = {
     'essb_radam_multi_step': (_I, [C.POINTER(RadamMulti), _P]),
     'essb_event_prepare_planes': (_I, [_P, _L, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'essb_split_bf16': (_I, [C.POINTER(Src), _I, _I, _I, _P, _P, _I, _I, _I, _P]),
+    'essb_split_planes': (_I, [C.POINTER(Src), _I, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
     'essb_pack_weight_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'essb_pack_weight_tc_fmt': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'essb_conv_tc_run': (_I, [C.POINTER(ConvTc), _P]),
     'essb_wgrad_tc_workspace_bytes': (_L, [C.POINTER(WgradTc)]),
     'essb_wgrad_tc_run': (_I, [C.POINTER(WgradTc), _P]),

@@ -84,6 +84,8 @@ struct TcParams {
   // dynamic tile scheduler + split-K tail (see TcUnit)
   int tmem_cols, tmem_buf_stride;        // TMEM columns allocated per CTA (power of two) / column offset of accumulator buffer 1
   int fuse_b;                            // bf16x3 with 2*BN <= 256: A_hi x [B_hi; B_lo] is ONE MMA of N = 2*BN (see below)
+  float acc_scale;                       // the epilogue multiplies the raw accumulator by this (f16f8 mode: 2^-(w8+14))
+  int planes_fmt;                        // format of out_hi/out_lo: 0 = bf16 hi/lo, 2 = hf8 (tc_ptx.cuh)
   int* sched;                            // [0] next unit, [1] CTAs done; zero before the launch, reset by the last CTA
   int n_units, n_whole, split;           // units [0, n_whole) are whole tiles; the rest are 1/split K-slices of the tail tiles
   float* splitk_ws;                      // [tail tile][part][32-col chunk][128 rows][32] fp32 partial accumulators
@@ -165,6 +167,26 @@ __device__ __forceinline__ void tc_add_res(const TcParams& p, const float* src, 
   }
 }
 
+// 8 consecutive channels (co a multiple of 8) of output pixel `opix` -> the operand planes of the next tcgen05 launch
+__device__ __forceinline__ void tc_store_planes8(const TcParams& p, size_t opix, int co, const float (&v)[8]) {
+  if (p.planes_fmt == 2) {
+    uint32_t h[4];
+    uint16_t a[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_hf8x2(v[2 * e], v[2 * e + 1], h[e], a[e], l[e]);
+    *reinterpret_cast<uint4*>(p.out_hi + opix * p.ld_planes + co) = make_uint4(h[0], h[1], h[2], h[3]);
+    uint8_t* lo = reinterpret_cast<uint8_t*>(p.out_lo) + opix * (size_t)p.ld_planes * 2 + hf8_lo_off(co);
+    *reinterpret_cast<uint2*>(lo) = make_uint2((uint32_t)a[0] | ((uint32_t)a[1] << 16), (uint32_t)a[2] | ((uint32_t)a[3] << 16));
+    *reinterpret_cast<uint2*>(lo + 64) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+  } else {
+    bf16x8 hh, hl;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_bf16(v[e], hh.v[e], hl.v[e]);
+    *reinterpret_cast<bf16x8*>(p.out_hi + opix * p.ld_planes + co) = hh;
+    *reinterpret_cast<bf16x8*>(p.out_lo + opix * p.ld_planes + co) = hl;
+  }
+}
+
 // Fused epilogue of one 32-column chunk of an accumulator row (r = the fp32 accumulators of row `pix`, columns
 // n0 + c0 .. + 31): bias / gates / activation / residuals -> global stores.  cpj = previous cell state (LSTM).
 template <int EPI>
@@ -176,12 +198,12 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
     const int hidden = p.Cout >> 2;
     const int ch0 = (n0 + c0) >> 2;
     float hv[8], cv[8];
-    bf16x8 hh, hl;
+    const float sc = p.acc_scale;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int co = n0 + c0 + e * 4;
-      float gi = __uint_as_float(r[e * 4 + 0]), gf = __uint_as_float(r[e * 4 + 1]);
-      float go = __uint_as_float(r[e * 4 + 2]), gc = __uint_as_float(r[e * 4 + 3]);
+      float gi = __uint_as_float(r[e * 4 + 0]) * sc, gf = __uint_as_float(r[e * 4 + 1]) * sc;
+      float go = __uint_as_float(r[e * 4 + 2]) * sc, gc = __uint_as_float(r[e * 4 + 3]) * sc;
       if (s_bias) {
         const float4 b4 = *reinterpret_cast<const float4*>(s_bias + co);
         gi += b4.x; gf += b4.y; go += b4.z; gc += b4.w;
@@ -189,7 +211,6 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
       const float cell = sigmoid_fast(gf) * cpj[e] + sigmoid_fast(gi) * tanh_fast(gc);
       cv[e] = cell;
       hv[e] = sigmoid_fast(go) * tanh_fast(cell);
-      split_bf16(hv[e], hh.v[e], hl.v[e]);
     }
     float* ho = p.out + pix * hidden + ch0;
     float* co_ = p.out2 + pix * hidden + ch0;
@@ -202,10 +223,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
       *reinterpret_cast<float4*>(co_) = make_float4(cv[0], cv[1], cv[2], cv[3]);
       *reinterpret_cast<float4*>(co_ + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
     }
-    if (p.out_hi) {
-      *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0) = hh;
-      *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0) = hl;
-    }
+    if (p.out_hi) tc_store_planes8(p, pix, ch0, hv);
   } else if constexpr (EPI == ESSB_EPI_GRU_UR) {
     // ConvGRU update / reset gates (submodules.py:267-268): columns co = 2*ch + {update, reset};
     // 32 columns = 16 channels.  Writes update (fp32) and prev_state*reset as bf16 planes (the A
@@ -213,9 +231,10 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
     const int hidden = p.Cout >> 1;
     const int ch0 = (n0 + c0) >> 1;
 #pragma unroll
+    const float sc = p.acc_scale;
+#pragma unroll
     for (int g = 0; g < 2; ++g) {
-      float uv[8];
-      bf16x8 hh, hl;
+      float uv[8], hr[8];
       float hp[8];
       if (p.aux0) {
         const float4 a0 = *reinterpret_cast<const float4*>(p.aux0 + pix * hidden + ch0 + g * 8);
@@ -228,16 +247,15 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int col = g * 16 + e * 2;
-        float gu = __uint_as_float(r[col]), gr = __uint_as_float(r[col + 1]);
+        float gu = __uint_as_float(r[col]) * sc, gr = __uint_as_float(r[col + 1]) * sc;
         if (s_bias) { gu += s_bias[n0 + c0 + col]; gr += s_bias[n0 + c0 + col + 1]; }
         uv[e] = sigmoid_fast(gu);
-        split_bf16(hp[e] * sigmoid_fast(gr), hh.v[e], hl.v[e]);
+        hr[e] = hp[e] * sigmoid_fast(gr);
       }
       float* uo = p.out + pix * hidden + ch0 + g * 8;
       *reinterpret_cast<float4*>(uo) = make_float4(uv[0], uv[1], uv[2], uv[3]);
       *reinterpret_cast<float4*>(uo + 4) = make_float4(uv[4], uv[5], uv[6], uv[7]);
-      *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch0 + g * 8) = hh;
-      *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch0 + g * 8) = hl;
+      tc_store_planes8(p, pix, ch0 + g * 8, hr);
     }
   } else if constexpr (EPI == ESSB_EPI_GRU_OUT) {
     // ConvGRU out gate + blend (submodules.py:269-271): h' = h*(1-u) + tanh(acc + b)*u
@@ -258,21 +276,16 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
 #pragma unroll
         for (int e = 0; e < 8; ++e) hp[e] = 0.f;
       }
-      bf16x8 hh, hl;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        float x = __uint_as_float(r[g * 8 + e]);
+        float x = __uint_as_float(r[g * 8 + e]) * p.acc_scale;
         if (s_bias) x += s_bias[ch + e];
         hv[e] = hp[e] * (1.f - uu[e]) + tanh_fast(x) * uu[e];
-        split_bf16(hv[e], hh.v[e], hl.v[e]);
       }
       float* ho = p.out + pix * hidden + ch;
       *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
       *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
-      if (p.out_hi) {
-        *reinterpret_cast<bf16x8*>(p.out_hi + pix * p.ld_planes + ch) = hh;
-        *reinterpret_cast<bf16x8*>(p.out_lo + pix * p.ld_planes + ch) = hl;
-      }
+      if (p.out_hi) tc_store_planes8(p, pix, ch, hv);
     }
   } else {
     const size_t opix = ((size_t)n * p.OHf + (oy * p.osy + p.ooy)) * p.OWf + (ox * p.osx + p.oox);
@@ -281,7 +294,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
       const int co = n0 + c0 + g * 16;
       float v[2][8];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) v[e >> 3][e & 7] = __uint_as_float(r[g * 16 + e]);
+      for (int e = 0; e < 16; ++e) v[e >> 3][e & 7] = __uint_as_float(r[g * 16 + e]) * p.acc_scale;
       if (s_bias) {
 #pragma unroll
         for (int e4 = 0; e4 < 4; ++e4) {
@@ -312,7 +325,10 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
           }
         }
       }
-      if (p.out_hi) {
+      if (p.out_hi && p.planes_fmt == 2) {
+        tc_store_planes8(p, opix, co, v[0]);
+        tc_store_planes8(p, opix, co + 8, v[1]);
+      } else if (p.out_hi) {
         uint32_t ph[8], pl[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -524,7 +540,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     fence_barrier_init();
     tma_prefetch_desc(&p.tmB_hi);
-    if (p.passes == 3) tma_prefetch_desc(&p.tmB_lo);
+    if (p.passes != 1) tma_prefetch_desc(&p.tmB_lo);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -571,7 +587,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const int cx = x0 + p.dx[tap], cy = y0 + p.dy[tap];
           tma_load_4d(st, &p.tmA_hi[v], &full_bar[s], ch, cx, cy, n);
           tma_load_2d(st + p.off_bhi, &p.tmB_hi, &full_bar[s], kcoord, nt * p.BN);
-          if (p.passes == 3) {
+          if (p.passes != 1) {
             tma_load_4d(st + p.off_alo, &p.tmA_lo[v], &full_bar[s], ch, cx, cy, n);
             tma_load_2d(st + p.off_blo, &p.tmB_lo, &full_bar[s], kcoord, nt * p.BN);
           }
@@ -584,7 +600,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // ============================================================ MMA issuer (whole warp, convergent:
     // umma_bf16 / umma_commit elect the issuing lane themselves, everything else stays in uniform registers)
     {
-      const uint32_t idesc = make_idesc(TC_M, p.BN);
+      // kind::f16 operand format: bf16 (1) in the bf16 / bf16x3 modes, fp16 (0) in the f16f8 mode
+      const uint32_t idesc = p.passes == 2 ? make_idesc_fmt(TC_M, p.BN, 0u, 0u) : make_idesc(TC_M, p.BN);
+      const uint32_t idesc_f8 = make_idesc_fmt(TC_M, p.BN, 0u, 0u);   // kind::f8f6f4: e4m3 x e4m3
       int s = 0;
       uint32_t ph = 0;
       uint32_t tph[2] = {0, 0};
@@ -601,7 +619,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + (size_t)s * p.stage_bytes);
-          if (p.passes == 3) {
+          if (p.passes == 2) {
+            // f16f8: fp16 main product + ONE K = 128 e4m3 product over the [a8 | a8l] x [w8l | w8] pair rows (both cross
+            // terms): 8 MMAs per 64-channel stage instead of 12, same operand bytes
+            const UDesc a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + p.off_alo);
+            const UDesc b_hi = make_smem_desc(sa + p.off_bhi);
+            const UDesc b_lo = make_smem_desc(sa + p.off_blo);
+#pragma unroll
+            for (int k = 0; k < TC_KCH / 16; ++k) {
+              const uint32_t ko = (uint32_t)(k * 2);
+              umma_f8(d_tmem, a_lo + ko, b_lo + ko, idesc_f8, ((it - un.k0) | k) != 0);
+              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            }
+          } else if (p.passes == 3) {
             const UDesc a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + p.off_alo);
             const UDesc b_hi = make_smem_desc(sa + p.off_bhi);
             const UDesc b_lo = make_smem_desc(sa + p.off_blo);
@@ -714,7 +744,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __g
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t tx = (uint32_t)(p.passes == 3 ? 2 : 1) * (uint32_t)(p.halo_w * p.halo_h * 128);
+      const uint32_t tx = (uint32_t)(p.passes != 1 ? 2 : 1) * (uint32_t)(p.halo_w * p.halo_h * 128);
       for (int local = 0;; ++local) {
         const int item = tc_sched_fetch(p, local, sched_ring, sfull_bar, sempty_bar);   // whole tiles only
         if (item < 0) break;
@@ -731,7 +761,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __g
               uint8_t* st = a_base + (size_t)s * p.a_stage_bytes;
               mbar_expect_tx(&a_full[s], tx);
               tma_load_4d(st, &p.tmA_hi[v], &a_full[s], c * TC_KCH, cx, cy, n);
-              if (p.passes == 3) tma_load_4d(st + p.a_lo_off, &p.tmA_lo[v], &a_full[s], c * TC_KCH, cx, cy, n);
+              if (p.passes != 1) tma_load_4d(st + p.a_lo_off, &p.tmA_lo[v], &a_full[s], c * TC_KCH, cx, cy, n);
               if (++s == p.a_stages) { s = 0; ph ^= 1; }
             }
       }
@@ -742,7 +772,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __g
     {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t tx = (uint32_t)(p.passes == 3 ? 2 : 1) * (uint32_t)(p.BN * TC_KCH * 2);
+      const uint32_t tx = (uint32_t)(p.passes != 1 ? 2 : 1) * (uint32_t)(p.BN * TC_KCH * 2);
       for (int local = 0;; ++local) {
         const int item = tc_sched_read(local, lane, sched_ring, sfull_bar, sempty_bar);
         if (item < 0) break;
@@ -760,7 +790,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __g
                 for (int j = 0; j < nt_taps; ++j) {
                   const int kcoord = p.widx[t0 + j] * p.k_per_tap + p.seg_koff[seg] + c * TC_KCH;
                   tma_load_2d(st + j * p.b_tap_bytes, &p.tmB_hi, &b_full[s], kcoord, nt * p.BN);
-                  if (p.passes == 3)
+                  if (p.passes != 1)
                     tma_load_2d(st + j * p.b_tap_bytes + p.b_lo_off, &p.tmB_lo, &b_full[s], kcoord, nt * p.BN);
                 }
                 if (++s == p.b_stages) { s = 0; ph ^= 1; }
@@ -771,7 +801,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __g
   } else if (warp == 1) {
     // ============================================================ MMA issuer (whole warp, convergent)
     {
-      const uint32_t idesc = make_idesc(TC_M, p.BN);
+      const uint32_t idesc = p.passes == 2 ? make_idesc_fmt(TC_M, p.BN, 0u, 0u) : make_idesc(TC_M, p.BN);
+      const uint32_t idesc_f8 = make_idesc_fmt(TC_M, p.BN, 0u, 0u);
       const uint32_t idesc2 = make_idesc(TC_M, 2 * p.BN);
       const uint32_t sbo = (uint32_t)p.halo_w * 128u;
       int sa = 0, sb = 0;
@@ -803,7 +834,17 @@ __global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __g
                 const uint32_t a_off = (uint32_t)((p.dy[t] - p.hy0) * p.halo_w + (p.dx[t] - p.hx0)) * 128u;
                 const UDesc a_hi = make_smem_desc_sbo(a_addr + a_off, sbo);
                 const UDesc b_hi = make_smem_desc(b_addr);
-                if (p.passes == 3 && p.fuse_b) {
+                if (p.passes == 2) {
+                  const UDesc a_lo = make_smem_desc_sbo(a_addr + p.a_lo_off + a_off, sbo);
+                  const UDesc b_lo = make_smem_desc(b_addr + p.b_lo_off);
+#pragma unroll
+                  for (int k = 0; k < TC_KCH / 16; ++k) {
+                    const uint32_t ko = (uint32_t)(k * 2);
+                    umma_f8(d_tmem, a_lo + ko, b_lo + ko, idesc_f8, acc);
+                    umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+                    acc = 1u;
+                  }
+                } else if (p.passes == 3 && p.fuse_b) {
                   // B_hi and B_lo tiles are adjacent K-major tiles, i.e. ONE tile of 2*BN rows: A_hi x [B_hi; B_lo]
                   // is a single MMA of N = 2*BN whose upper BN accumulator columns collect the hi*lo products
                   // (added back by the epilogue).  Two MMAs and two A reads per K-step instead of three: the
@@ -865,15 +906,22 @@ __global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __g
 
 // --------------------------------------------------------------------------- fp32 -> bf16 hi/lo
 __global__ void split_bf16_kernel(essb_src s, int N, int H, int W, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, int ld_out, int c_off, int c_write, long long total) {
+                                  __nv_bfloat16* __restrict__ lo, int ld_out, int c_off, int c_write, long long total,
+                                  int fmt) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int CQ = c_write >> 2;
   const int c = (int)(idx % CQ) * 4;
   const long long pix = idx / CQ;
+  uint8_t* lo8 = reinterpret_cast<uint8_t*>(lo) + pix * (long long)ld_out * 2 + hf8_lo_off(c_off + c);   // fmt 2 only
   if (c >= s.C) {  // zero channel padding [C, c_write) (K padding of the tensor-core operand)
     *reinterpret_cast<uint2*>(hi + pix * ld_out + c_off + c) = make_uint2(0u, 0u);
-    *reinterpret_cast<uint2*>(lo + pix * ld_out + c_off + c) = make_uint2(0u, 0u);
+    if (fmt == 2) {
+      *reinterpret_cast<uint32_t*>(lo8) = 0u;
+      *reinterpret_cast<uint32_t*>(lo8 + 64) = 0u;
+    } else {
+      *reinterpret_cast<uint2*>(lo + pix * ld_out + c_off + c) = make_uint2(0u, 0u);
+    }
     return;
   }
   const long long P = (long long)H * W;
@@ -889,6 +937,16 @@ __global__ void split_bf16_kernel(essb_src s, int N, int H, int W, __nv_bfloat16
     v.x = (v.x - m.x) * r.x; v.y = (v.y - m.y) * r.y; v.z = (v.z - m.z) * r.z; v.w = (v.w - m.w) * r.w;
   }
   if (s.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  if (fmt == 2) {
+    uint32_t h2[2];
+    uint16_t a[2], l2[2];
+    split_hf8x2(v.x, v.y, h2[0], a[0], l2[0]);
+    split_hf8x2(v.z, v.w, h2[1], a[1], l2[1]);
+    *reinterpret_cast<uint2*>(hi + pix * ld_out + c_off + c) = make_uint2(h2[0], h2[1]);
+    *reinterpret_cast<uint32_t*>(lo8) = (uint32_t)a[0] | ((uint32_t)a[1] << 16);
+    *reinterpret_cast<uint32_t*>(lo8 + 64) = (uint32_t)l2[0] | ((uint32_t)l2[1] << 16);
+    return;
+  }
   __nv_bfloat16 h[4], l[4];
   split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
   __nv_bfloat16* ho = hi + pix * ld_out + c_off + c;
@@ -965,7 +1023,7 @@ __global__ void event_prepare_planes_kernel(const float* __restrict__ x, long lo
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Cout, int Cin,
                                       int T, int transposed_layout, int swap_io, int flip, int interleave, int KinP,
-                                      int NoutP) {
+                                      int NoutP, int fmt, int w8) {
   const int Kin = swap_io ? Cout : Cin;
   const int Nout = swap_io ? Cin : Cout;
   const long long total = (long long)NoutP * T * KinP;
@@ -991,6 +1049,17 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, const float* 
     const size_t src = transposed_layout ? ((size_t)ci * Cout + co) * T + ts : ((size_t)co * Cin + ci) * T + ts;
     v = w[src];
     if (scale && !swap_io) v *= scale[co];
+  }
+  if (fmt == 2) {   // hf8 weights: fp16(W * 2^(w8+8)) and the [w8l | w8] pair row (see tc_ptx.cuh)
+    const float sh = exp2f((float)(w8 + 8));
+    const __half wh = __float2half_rn(hf8_sat_f16(v * sh));
+    reinterpret_cast<__half*>(hi)[idx] = wh;
+    const float r = v - __half2float(wh) / sh;
+    const long long kk = (long long)t * KinP + k;
+    uint8_t* row = reinterpret_cast<uint8_t*>(lo) + (long long)np * T * KinP * 2 + ((kk >> 6) << 7) + (kk & 63);
+    row[0] = (uint8_t)__nv_cvt_float_to_fp8(r * exp2f((float)(w8 + 11)), __NV_SATFINITE, __NV_E4M3);
+    row[64] = (uint8_t)__nv_cvt_float_to_fp8(v * exp2f((float)w8), __NV_SATFINITE, __NV_E4M3);
+    return;
   }
   __nv_bfloat16 h, l;
   split_bf16(v, h, l);
@@ -1073,7 +1142,13 @@ int num_sms() {
 
 extern "C" int essb_split_bf16(const essb_src* src, int N, int H, int W, uint16_t* hi, uint16_t* lo, int ld_out,
                                int c_off, int c_pad, void* stream) {
+  return essb_split_planes(src, N, H, W, hi, lo, ld_out, c_off, c_pad, 0, stream);
+}
+
+extern "C" int essb_split_planes(const essb_src* src, int N, int H, int W, uint16_t* hi, uint16_t* lo, int ld_out,
+                                 int c_off, int c_pad, int fmt, void* stream) {
   ESSB_REQUIRE(src && src->ptr && hi && lo && N > 0 && H > 0 && W > 0, "essb_split_bf16: bad arguments");
+  ESSB_REQUIRE(fmt == 0 || (fmt == 2 && ld_out % 64 == 0), "essb_split_planes: fmt must be 0 (bf16 hi/lo) or 2 (hf8, ld_out %% 64 == 0)");
   ESSB_REQUIRE(src->C % 4 == 0 && src->ld % 4 == 0 && essb_aligned16(src->ptr) && ld_out % 4 == 0 && c_off % 4 == 0,
                "essb_split_bf16: C, ld, ld_out, c_off must be multiples of 4 and pointers 16B aligned");
   ESSB_REQUIRE((src->mean == nullptr) == (src->rstd == nullptr), "essb_split_bf16: mean/rstd must come together");
@@ -1082,7 +1157,7 @@ extern "C" int essb_split_bf16(const essb_src* src, int N, int H, int W, uint16_
   const long long total = (long long)N * H * W * (c_write / 4);
   split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       *src, N, H, W, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), ld_out, c_off, c_write,
-      total);
+      total, fmt);
   ESSB_LAUNCH_CHECK("essb_split_bf16");
   return ESSB_OK;
 }
@@ -1116,14 +1191,23 @@ extern "C" int essb_event_prepare_planes(const float* x, int64_t bstride, const 
 extern "C" int essb_pack_weight_tc(const float* w, const float* scale, uint16_t* hi, uint16_t* lo, int Cout, int Cin,
                                    int T, int transposed_layout, int swap_io, int flip, int interleave, int KinP,
                                    int NoutP, void* stream) {
+  return essb_pack_weight_tc_fmt(w, scale, hi, lo, Cout, Cin, T, transposed_layout, swap_io, flip, interleave, KinP, NoutP,
+                                 0, 0, stream);
+}
+
+extern "C" int essb_pack_weight_tc_fmt(const float* w, const float* scale, uint16_t* hi, uint16_t* lo, int Cout, int Cin,
+                                       int T, int transposed_layout, int swap_io, int flip, int interleave, int KinP,
+                                       int NoutP, int fmt, int w8, void* stream) {
   ESSB_REQUIRE(w && hi && lo && Cout > 0 && Cin > 0 && T > 0, "essb_pack_weight_tc: bad arguments");
+  ESSB_REQUIRE(fmt == 0 || fmt == 2, "essb_pack_weight_tc_fmt: fmt must be 0 (bf16 hi/lo) or 2 (hf8)");
+  ESSB_REQUIRE(w8 >= -20 && w8 <= 40, "essb_pack_weight_tc_fmt: w8 (log2 of the e4m3 weight scale) out of range");
   const int Kin = swap_io ? Cout : Cin, Nout = swap_io ? Cin : Cout;
   ESSB_REQUIRE(KinP >= Kin && KinP % TC_KCH == 0 && NoutP >= Nout, "essb_pack_weight_tc: bad padding");
   ESSB_REQUIRE(interleave <= 1 || (Cout % interleave == 0 && !swap_io), "essb_pack_weight_tc: bad interleave");
   const long long total = (long long)NoutP * T * KinP;
   pack_weight_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       w, scale, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), Cout, Cin, T,
-      transposed_layout, swap_io, flip, interleave, KinP, NoutP);
+      transposed_layout, swap_io, flip, interleave, KinP, NoutP, fmt, w8);
   ESSB_LAUNCH_CHECK("essb_pack_weight_tc");
   return ESSB_OK;
 }
@@ -1133,11 +1217,14 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   ESSB_REQUIRE(d->n_views >= 1 && d->n_views <= MAX_VIEWS, "essb_conv_tc_run: n_views=%d", d->n_views);
   ESSB_REQUIRE(d->nseg == 1 || d->nseg == 2, "essb_conv_tc_run: nseg=%d", d->nseg);
   ESSB_REQUIRE(d->ntaps >= 1 && d->ntaps <= ESSB_MAX_TAPS, "essb_conv_tc_run: ntaps=%d", d->ntaps);
-  ESSB_REQUIRE(d->passes == 1 || d->passes == 3, "essb_conv_tc_run: passes must be 1 or 3");
+  ESSB_REQUIRE(d->passes >= 1 && d->passes <= 3, "essb_conv_tc_run: passes must be 1 (bf16), 2 (f16f8) or 3 (bf16x3)");
   ESSB_REQUIRE(d->N > 0 && d->OH > 0 && d->OW > 0 && d->Cout > 0, "essb_conv_tc_run: bad dims");
   ESSB_REQUIRE(d->w_hi && (d->passes == 1 || d->w_lo), "essb_conv_tc_run: null weights");
   ESSB_REQUIRE(d->bw_log2 >= 0 && d->bw_log2 <= 7, "essb_conv_tc_run: bw_log2=%d", d->bw_log2);
   ESSB_REQUIRE(d->k_per_tap % TC_KCH == 0, "essb_conv_tc_run: k_per_tap must be a multiple of 64");
+  ESSB_REQUIRE(d->planes_fmt == 0 || d->planes_fmt == 2, "essb_conv_tc_run: planes_fmt must be 0 (bf16 hi/lo) or 2 (hf8)");
+  ESSB_REQUIRE(d->planes_fmt == 0 || !d->out_hi || d->ld_planes % 64 == 0,
+               "essb_conv_tc_run: hf8 output planes need ld_planes %% 64 == 0 (got %d)", d->ld_planes);
   const int Ngemm = d->Cout;
   int BN = Ngemm < 256 ? Ngemm : 256;
   ESSB_REQUIRE(BN % 32 == 0 && Ngemm % BN == 0, "essb_conv_tc_run: Cout=%d must be 32/64/128 or a multiple of 256", Ngemm);
@@ -1180,7 +1267,7 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
     }
     p.halo_w = 8 + (hx1 - hx0);
     p.halo_h = 16 + (hy1 - hy0);
-    const int planes = d->passes == 3 ? 2 : 1;
+    const int planes = d->passes != 1 ? 2 : 1;
     const int a_plane = (p.halo_w * p.halo_h * 128 + 1023) & ~1023;
     p.a_lo_off = a_plane;
     p.a_stage_bytes = planes * a_plane;
@@ -1233,11 +1320,11 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
                      essb_aligned16(vw.lo),
                  "essb_conv_tc_run: view %d strides must be multiples of 8 elements and bases 16B aligned", v);
     if ((rc = encode_a_map(&p.tmA_hi[v], vw.hi, vw, d->N, boxW, boxH)) != ESSB_OK) return rc;
-    if (d->passes == 3 && (rc = encode_a_map(&p.tmA_lo[v], vw.lo, vw, d->N, boxW, boxH)) != ESSB_OK) return rc;
+    if (d->passes != 1 && (rc = encode_a_map(&p.tmA_lo[v], vw.lo, vw, d->N, boxW, boxH)) != ESSB_OK) return rc;
   }
   const long long ktot = (long long)d->n_w_taps * d->k_per_tap;
   if ((rc = encode_b_map(&p.tmB_hi, d->w_hi, ktot, d->w_rows, BN)) != ESSB_OK) return rc;
-  if (d->passes == 3 && (rc = encode_b_map(&p.tmB_lo, d->w_lo, ktot, d->w_rows, BN)) != ESSB_OK) return rc;
+  if (d->passes != 1 && (rc = encode_b_map(&p.tmB_lo, d->w_lo, ktot, d->w_rows, BN)) != ESSB_OK) return rc;
 
   p.tiles_x = (d->OW + BW - 1) / BW;
   p.tiles_y = (d->OH + BH - 1) / BH;
@@ -1247,7 +1334,7 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   p.BN = BN;
   p.passes = d->passes;
   const int b_tile_bytes = BN * TC_KCH * 2;
-  if (d->passes == 3) {  // stage = [A_hi | A_lo | B_hi | B_lo]
+  if (d->passes != 1) {  // stage = [A_hi | A_lo | B_hi | B_lo]
     p.off_alo = A_TILE_BYTES;
     p.off_bhi = 2 * A_TILE_BYTES;
     p.off_blo = 2 * A_TILE_BYTES + b_tile_bytes;
@@ -1333,6 +1420,8 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   p.tmem_cols = 512;
   p.tmem_buf_stride = 256;
   p.fuse_b = (halo && halo_fuse) ? 1 : 0;
+  p.acc_scale = d->acc_scale != 0.f ? d->acc_scale : 1.f;
+  p.planes_fmt = d->planes_fmt;
   if (halo && halo_occ == 2) {
     const int stride = BN * (halo_fuse ? 2 : 1);
     int cols = 32;

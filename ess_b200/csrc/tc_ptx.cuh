@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 
 namespace {
@@ -74,6 +76,11 @@ __device__ __forceinline__ UDesc make_smem_desc(uint32_t saddr) { return make_ud
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Same descriptor with explicit operand formats (cute::UMMA::InstrDescriptor a_format_/b_format_, bits [7,10) / [10,13)):
+// kind::f16: 0 = F16, 1 = BF16; kind::f8f6f4: 0 = E4M3, 1 = E5M2.  D is always f32.
+__device__ __forceinline__ uint32_t make_idesc_fmt(int M, int N, uint32_t a_fmt, uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // tcgen05.mma / tcgen05.commit are issued by ONE lane, but the issuing warp stays convergent: the leader is
 // elected inside the asm (elect.sync is deterministic for a fixed member mask, so the commit tracks the MMAs
 // of the same lane).  Keeping all 32 lanes on the loop lets ptxas hold descriptors, TMEM addresses and
@@ -86,6 +93,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, UDesc a, UDesc b, uin
       "elect.sync _|e, 0xffffffff;\n\t"
       "setp.ne.b32 p, %6, 0;\n\t"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a.lo), "r"(a.hi), "r"(b.lo), "r"(b.hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 8-bit operands (e4m3 x e4m3 here): M128 x N x K32 per instruction, i.e. the same 32 operand bytes per row as one
+// K16 bf16 MMA at twice the MAC rate; accumulates into the same fp32 TMEM columns as the kind::f16 MMAs.
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, UDesc a, UDesc b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %5, p;\n\t}"
       ::"r"(tmem_d), "r"(a.lo), "r"(a.hi), "r"(b.lo), "r"(b.hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -114,6 +133,30 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+
+// ---- "hf8" operand format of the f16f8 mode (fp16 main product + two fp8 cross terms = 2 tensor-pass equivalents):
+//   hi  = fp16(x * 2^HF8_AH)                       (saturating; |x| < 1023 is exact-range)
+//   a8  = e4m3(x * 2^HF8_A8)                       (saturating at |x| = 56: only the 2^-11-sized cross terms degrade)
+//   a8l = e4m3((x - hi / 2^HF8_AH) * 2^(HF8_A8 + 11))
+// A 64-channel chunk of the lo plane is 128 bytes: [a8 of the 64 channels | a8l of the 64 channels]; the weights'
+// chunk is [w8l | w8], so ONE K = 128 e4m3 dot product per chunk yields  a8.w8l + a8l.w8  (both cross terms).
+// With w_hi = fp16(W * 2^(w8 + 8)), w8 = e4m3(W * 2^w8), w8l = e4m3((W - w_hi / 2^(w8+8)) * 2^(w8 + 11)) all three
+// products carry the factor 2^(w8 + 14), removed by the epilogue (TcParams::acc_scale).  Validated against the
+// 1e-3 contract by emulation in the oracle (tools/precision_emul.py: logits 1.2e-4 at T = 20 vs 1.0e-4 for bf16x3).
+constexpr int HF8_AH = 6, HF8_A8 = 3;
+__device__ __forceinline__ float hf8_sat_f16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+// two values -> (packed fp16x2 hi, packed e4m3x2 a8, packed e4m3x2 a8l)
+__device__ __forceinline__ void split_hf8x2(float x0, float x1, uint32_t& hi2, uint16_t& a8, uint16_t& a8l) {
+  const __half2 h = __floats2half2_rn(hf8_sat_f16(x0 * (float)(1 << HF8_AH)), hf8_sat_f16(x1 * (float)(1 << HF8_AH)));
+  hi2 = *reinterpret_cast<const uint32_t*>(&h);
+  const float2 hf = __half22float2(h);
+  const float r0 = x0 - hf.x * (1.f / (float)(1 << HF8_AH)), r1 = x1 - hf.y * (1.f / (float)(1 << HF8_AH));
+  a8 = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(x0 * (float)(1 << HF8_A8), x1 * (float)(1 << HF8_A8)), __NV_SATFINITE, __NV_E4M3);
+  a8l = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(r0 * (float)(1 << (HF8_A8 + 11)), r1 * (float)(1 << (HF8_A8 + 11))),
+                                           __NV_SATFINITE, __NV_E4M3);
+}
+// byte offset of channel `c` (any c) inside a pixel's lo-plane row: [a8 | a8l] per 64-channel chunk
+__device__ __forceinline__ int hf8_lo_off(int c) { return ((c >> 6) << 7) + (c & 63); }
 
 // fast gate non-linearities (MUFU.EX2 + MUFU.RCP; ~1e-6 absolute error, far inside the 1e-3 contract)
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }

@@ -9,6 +9,10 @@ only -- their forward is never called; all arithmetic runs in libess_b200.so:
   mode "fp32"   : every conv on the exact-fp32 CUDA-core implicit-GEMM kernel (conv_fp32.cu)
   mode "bf16x3" : encoder stride-2 convs and the fused ConvLSTM cells on the tcgen05/TMA kernel
                   (conv_tc.cu) with the 3-product bf16 split (fp32-level accuracy)
+  mode "f16f8"  : same kernels, operands in the "hf8" format: fp16 main product + two e4m3 cross terms issued as
+                  ONE K=128 fp8 product per 64-channel chunk -- 2 tensor-pass equivalents instead of 3 at
+                  fp32-level accuracy (tools/precision_emul.py; the head conv stays bf16x3: its overlapping-window
+                  operand view is incompatible with the paired fp8 layout)
   mode "bf16"   : same kernels, single bf16 pass (fast, ~1e-2 relative; reported separately)
 
 Inference only (the reference freezes this network and runs it under no_grad,
@@ -25,7 +29,7 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, EPI_GRU_OUT, EPI_GRU_UR, EPI
 from .ops import Seg
 
 BN_EPS = 1e-5
-MODES = ('fp32', 'bf16x3', 'bf16')
+MODES = ('fp32', 'bf16x3', 'bf16', 'f16f8')
 
 
 def default_mode():
@@ -175,6 +179,13 @@ class E2VIDRecurrent(nn.Module):
         wh[:, :self.num_bins] = u.head.conv2d.weight.detach().float()
         P['head'] = (ops.pack_weight(wh), u.head.conv2d.bias.detach().float().contiguous(), cpad)
         tc = self.mode != 'fp32'
+        hf8 = self.mode == 'f16f8'
+
+        def pk(w, scale=None, **kw):
+            """(hi, lo, KinP, acc_scale) in the mode's operand format"""
+            if hf8:
+                return ops.pack_weight_tc_hf8(w, scale, **kw)
+            return ops.pack_weight_tc(w, scale, **kw) + (0.0,)
         P['head_tc'] = None
         if tc and cpad in (8, 16) and self.base_num_channels % 32 == 0 and self.base_num_channels <= 256:
             # per kernel row ky the head conv reads the 8-pixel x cpad-channel window starting at x-2 as one
@@ -205,8 +216,8 @@ class E2VIDRecurrent(nn.Module):
                     w6 = torch.zeros((cout, cin, 5, 6), device=dev)
                     w6[..., :5] = w
                     w = w6.view(cout, cin, 5, 3, 2).permute(0, 4, 1, 2, 3).reshape(cout, 2 * cin, 5, 3).contiguous()
-                hi, lo, kinp = ops.pack_weight_tc(w, scale)
-                e['tc'] = dict(hi=hi, lo=lo, k_per_tap=kinp, fold=fold, T=w.shape[2] * w.shape[3])
+                hi, lo, kinp, sc = pk(w, scale)
+                e['tc'] = dict(hi=hi, lo=lo, k_per_tap=kinp, fold=fold, T=w.shape[2] * w.shape[3], sc=sc)
             rb = enc.recurrent_block
             C = cout
             if self.recurrent_block_type == 'convlstm':
@@ -216,8 +227,8 @@ class E2VIDRecurrent(nn.Module):
                 e['lstm_b'] = _interleave(rb.Gates.bias, 4)
                 e['lstm_tc'] = None
                 if tc and C % 64 == 0:
-                    hi, lo, kinp = ops.pack_weight_tc(W, interleave=4)
-                    e['lstm_tc'] = dict(hi=hi, lo=lo, k_per_tap=kinp)
+                    hi, lo, kinp, sc = pk(W, interleave=4)
+                    e['lstm_tc'] = dict(hi=hi, lo=lo, k_per_tap=kinp, sc=sc)
             else:
                 wur = torch.cat([rb.update_gate.weight, rb.reset_gate.weight], 0).detach()
                 bur = torch.cat([rb.update_gate.bias, rb.reset_gate.bias], 0).detach()
@@ -229,16 +240,16 @@ class E2VIDRecurrent(nn.Module):
                 e['gru_o_b'] = rb.out_gate.bias.detach().float().contiguous()
                 e['gru_tc'] = None
                 if tc and C % 64 == 0:
-                    uh, ul, kinp = ops.pack_weight_tc(wur, interleave=2)
-                    oh_, ol_, _ = ops.pack_weight_tc(rb.out_gate.weight)
-                    e['gru_tc'] = dict(ur_hi=uh, ur_lo=ul, o_hi=oh_, o_lo=ol_, k_per_tap=kinp)
+                    uh, ul, kinp, usc = pk(wur, interleave=2)
+                    oh_, ol_, _, osc = pk(rb.out_gate.weight)
+                    e['gru_tc'] = dict(ur_hi=uh, ur_lo=ul, o_hi=oh_, o_lo=ol_, k_per_tap=kinp, ur_sc=usc, o_sc=osc)
             P['enc%d' % i] = e
         for j, rbk in enumerate(u.resblocks):
             s1, b1 = _bn_fold(rbk.conv1.bias, getattr(rbk, 'bn1', None), None, dev)
             s2, b2 = _bn_fold(rbk.conv2.bias, getattr(rbk, 'bn2', None), None, dev)
             P['res%d' % j] = (ops.pack_weight(rbk.conv1.weight, s1), b1, ops.pack_weight(rbk.conv2.weight, s2), b2)
             if tc:
-                P['res%d_tc' % j] = ops.pack_weight_tc(rbk.conv1.weight, s1) + ops.pack_weight_tc(rbk.conv2.weight, s2)
+                P['res%d_tc' % j] = pk(rbk.conv1.weight, s1) + pk(rbk.conv2.weight, s2)
         for i, dec in enumerate(u.decoders):
             bn = getattr(dec, 'norm_layer', None)
             if self.use_upsample_conv:
@@ -249,7 +260,7 @@ class E2VIDRecurrent(nn.Module):
                 P['dec%d' % i] = (ops.pack_weight(dec.transposed_conv2d.weight, scale, transposed_layout=True), bias,
                                   dec.transposed_conv2d.out_channels)
                 if tc:
-                    P['dec%d_tc' % i] = ops.pack_weight_tc(dec.transposed_conv2d.weight, scale, transposed_layout=True)
+                    P['dec%d_tc' % i] = pk(dec.transposed_conv2d.weight, scale, transposed_layout=True)
         scale, bias = _bn_fold(u.pred.conv2d.bias, getattr(u.pred, 'norm_layer', None), None, dev)
         P['pred'] = (ops.pack_weight(u.pred.conv2d.weight, scale), bias)
         wp = u.pred.conv2d.weight.detach().float().reshape(1, -1)
@@ -271,7 +282,11 @@ class E2VIDRecurrent(nn.Module):
                 and ent[0].shape == h_nhwc.shape:
             return ent[1], ent[2]
         N, H, W, _ = h_nhwc.shape
-        return ops.split_bf16(Seg(h_nhwc), N, H, W)
+        return ops.split_bf16(Seg(h_nhwc), N, H, W, fmt=self._fmt())
+
+    def _fmt(self):
+        """operand-plane format of the activations that travel between the tcgen05 launches of this network"""
+        return ops.PLANES_HF8 if self.mode == 'f16f8' else ops.PLANES_BF16
 
     # --------------------------------------------------------------------------------------- forward
     def forward(self, event_tensor, prev_states, with_image=True):
@@ -337,7 +352,9 @@ class E2VIDRecurrent(nn.Module):
         d.out_hi, d.out_lo, d.ld_planes = ops._p(planes[0]), ops._p(planes[1]), base
         d.N, d.OH, d.OW, d.Cout = N, H, W, base
         d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = H, W, 1, 0, 1, 0
-        d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, ACT_RELU, passes, ops.pick_bw_log2(W, H)
+        # f16f8 mode: the head itself runs bf16x3 (its input planes are bf16 hi/lo) but emits hf8 planes for encoder 0
+        d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, ACT_RELU, (3 if passes == 2 else passes), ops.pick_bw_log2(W, H)
+        d.planes_fmt = self._fmt()
         d.ntaps = 5
         for ky in range(5):
             d.dy[ky], d.dx[ky], d.view[ky], d.widx[ky] = ky, 0, 0, ky
@@ -353,7 +370,7 @@ class E2VIDRecurrent(nn.Module):
         ne = self.num_encoders
         lstm = self.recurrent_block_type == 'convlstm'
         tc_mode = self.mode != 'fp32'
-        passes = 3 if self.mode == 'bf16x3' else 1
+        passes = ops.PASSES.get(self.mode, 1)
         if prev_states is None:
             prev_states = [None] * ne
         base = self.base_num_channels
@@ -370,8 +387,13 @@ class E2VIDRecurrent(nn.Module):
             head = torch.empty((N, H, W, base), device=dev, dtype=torch.float32) if (want_head or not want_planes) else None
             self._head_tc(P, in_planes, N, H, W, head, planes, passes)
         else:
+            hf8 = self._fmt() == ops.PLANES_HF8       # the fp32 kernel's epilogue only writes bf16 hi/lo planes
             head, _, _, _ = ops.conv([Seg(x, C=cpad)], wh, bh, N, H, W, H, W, base, ops.taps_conv(5, 2), act=ACT_RELU,
-                                     planes=planes)
+                                     planes=None if hf8 else planes)
+            if hf8 and planes is not None:
+                g = max(1, 64 // base)                # hf8 rows are 64 channels: fold g pixels (W % 8 == 0)
+                shp = (N, H, W // g, base * g)
+                ops.split_bf16(Seg(head.view(shp)), N, H, W // g, planes[0].view(shp), planes[1].view(shp), fmt=ops.PLANES_HF8)
 
         blocks, states = [], []
         cur, cur_planes = head, planes
@@ -457,6 +479,7 @@ class E2VIDRecurrent(nn.Module):
         cmax = base * 2 ** ne
         dev = head.device
         t3 = ops.taps_conv(3, 1)
+        fmt = self._fmt()
 
         def new_planes(hh, ww, c):
             return (torch.empty((N, hh, ww, c), device=dev, dtype=torch.bfloat16),
@@ -465,18 +488,18 @@ class E2VIDRecurrent(nn.Module):
         x, xp = blocks[-1], planes
         nres = self.num_residual_blocks
         for j in range(nres):
-            hi1, lo1, k1, hi2, lo2, k2 = P['res%d_tc' % j]
+            hi1, lo1, k1, sc1, hi2, lo2, k2, sc2 = P['res%d_tc' % j]
             b1, b2 = P['res%d' % j][1], P['res%d' % j][3]
             tp = new_planes(h, w, cmax)
             ops.conv_tc_dense(xp, hi1, lo1, k1, t3, N, h, w, cmax, passes, bias=b1, act=ACT_RELU, want_out=False,
-                              out_planes=tp, tag='img_tc')
+                              out_planes=tp, tag='img_tc', acc_scale=sc1, planes_fmt=fmt)
             post = blocks[ne - 1] if j == nres - 1 else None
             np_ = new_planes(h, w, cmax)
             x = ops.conv_tc_dense(tp, hi2, lo2, k2, t3, N, h, w, cmax, passes, bias=b2, act=ACT_RELU, res_pre=x,
-                                  res_post=post, out_planes=np_, tag='img_tc')
+                                  res_post=post, out_planes=np_, tag='img_tc', acc_scale=sc2, planes_fmt=fmt)
             xp = np_
         for i in range(ne):
-            hi, lo, k = P['dec%d_tc' % i]
+            hi, lo, k, sc = P['dec%d_tc' % i]
             bd, cout = P['dec%d' % i][1], P['dec%d' % i][2]
             skip_next = blocks[ne - i - 2] if i < ne - 1 else head
             out = torch.empty((N, 2 * h, 2 * w, cout), device=dev, dtype=torch.float32)
@@ -485,7 +508,7 @@ class E2VIDRecurrent(nn.Module):
                 for px in range(2):
                     ops.conv_tc_dense(xp, hi, lo, k, ops.taps_convT_phase(py, px), N, h, w, cout, passes, bias=bd,
                                       act=ACT_RELU, out=out, out_place=(2 * h, 2 * w, 2, py, 2, px), res_post=skip_next,
-                                      out_planes=op, tag='img_tc')
+                                      out_planes=op, tag='img_tc', acc_scale=sc, planes_fmt=fmt)
             x, xp = out, op
             h, w = 2 * h, 2 * w
         wp, bp = P['pred']
@@ -565,6 +588,7 @@ class E2VIDRecurrent(nn.Module):
         d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = oh, ow, 1, 0, 1, 0
         d.out_hi, d.out_lo, d.ld_planes = ops._p(out_hi), ops._p(out_lo), cout
         d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, ACT_RELU, passes, ops.pick_bw_log2(ow, oh)
+        d.acc_scale, d.planes_fmt = tcw.get('sc', 0.0), (ops.PLANES_HF8 if passes == 2 else ops.PLANES_BF16)
         d.ntaps = len(taps)
         for t, (dy, dx, v, wi) in enumerate(taps):
             d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, v, wi
@@ -591,6 +615,7 @@ class E2VIDRecurrent(nn.Module):
             d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = oh, ow, 1, 0, 1, 0
             d.ldo, d.ld_planes = C, C
             d.act, d.passes, d.bw_log2 = ACT_NONE, passes, ops.pick_bw_log2(ow, oh)
+            d.planes_fmt = ops.PLANES_HF8 if passes == 2 else ops.PLANES_BF16
             d.ntaps = len(taps)
             for t, (dy, dx, wi) in enumerate(taps):
                 d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, 0, wi
@@ -602,7 +627,7 @@ class E2VIDRecurrent(nn.Module):
         base(d, h_planes)
         d.w_hi, d.w_lo, d.w_rows, d.bias = ops._p(tcw['ur_hi']), ops._p(tcw['ur_lo']), tcw['ur_hi'].shape[0], ops._p(e['gru_ur_b'])
         d.aux0, d.out, d.out_hi, d.out_lo = ops._p(h_prev), ops._p(upd), ops._p(hr[0]), ops._p(hr[1])
-        d.Cout, d.epilogue = 2 * C, EPI_GRU_UR
+        d.Cout, d.epilogue, d.acc_scale = 2 * C, EPI_GRU_UR, tcw.get('ur_sc', 0.0)
         ops.conv_tc(d, tag='gru_tc', device=dev)
         h = torch.empty((N, oh, ow, C), device=dev, dtype=torch.float32)
         hh = torch.empty((N, oh, ow, C), device=dev, dtype=torch.bfloat16)
@@ -611,7 +636,7 @@ class E2VIDRecurrent(nn.Module):
         base(d, hr if h_planes is not None else None)          # prev_state = 0  =>  prev_state*reset = 0: skip that K half
         d.w_hi, d.w_lo, d.w_rows, d.bias = ops._p(tcw['o_hi']), ops._p(tcw['o_lo']), tcw['o_hi'].shape[0], ops._p(e['gru_o_b'])
         d.aux0, d.aux1, d.out, d.out_hi, d.out_lo = ops._p(h_prev), ops._p(upd), ops._p(h), ops._p(hh), ops._p(hl)
-        d.Cout, d.epilogue = C, EPI_GRU_OUT
+        d.Cout, d.epilogue, d.acc_scale = C, EPI_GRU_OUT, tcw.get('o_sc', 0.0)
         ops.conv_tc(d, tag='gru_tc', device=dev)
         return h, hh, hl
 
@@ -639,6 +664,7 @@ class E2VIDRecurrent(nn.Module):
         d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = oh, ow, 1, 0, 1, 0
         d.ldo = C
         d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LSTM, ACT_NONE, passes, ops.pick_bw_log2(ow, oh)
+        d.acc_scale, d.planes_fmt = tcw.get('sc', 0.0), (ops.PLANES_HF8 if passes == 2 else ops.PLANES_BF16)
         taps = ops.taps_conv(3, 1)
         d.ntaps = len(taps)
         for t, (dy, dx, wi) in enumerate(taps):

@@ -5,6 +5,7 @@ only to own device memory and streams; every arithmetic op on the hot path is a 
 library.  Nothing here falls back to torch ops: a missing library or a failing call raises.
 """
 import ctypes as C
+import math
 import os
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
@@ -376,17 +377,34 @@ def confusion_logits(logits, target, K, ignore_index, conf=None):
 
 
 # --------------------------------------------------------------------------- tensor-core path helpers
-def split_bf16(seg: Seg, N, H, W, hi=None, lo=None, c_off=0, ld_out=None, c_pad=0):
-    """fp32 (optionally normalised / ReLU'd / upsampled) -> bf16 hi/lo planes [N, H, W, ld_out]; channels
-    [C, c_pad) of the output are zero-filled by the same kernel (K padding of a tensor-core operand)."""
+PLANES_BF16, PLANES_HF8 = 0, 2     # operand plane formats (include/ess_b200.h: essb_split_planes)
+PASSES = {'bf16': 1, 'f16f8': 2, 'bf16x3': 3}
+
+
+def split_bf16(seg: Seg, N, H, W, hi=None, lo=None, c_off=0, ld_out=None, c_pad=0, fmt=PLANES_BF16):
+    """fp32 (optionally normalised / ReLU'd / upsampled) -> tensor-core operand planes [N, H, W, ld_out]; channels
+    [C, c_pad) of the output are zero-filled by the same kernel (K padding of a tensor-core operand).
+    fmt PLANES_BF16: bf16 hi/lo; PLANES_HF8: fp16 hi + e4m3 pair plane (the f16f8 mode's operands; ld_out % 64 == 0).
+    Both planes are carried as bfloat16-typed tensors of the same shape (2 bytes per element either way)."""
     s = Src()
     c = seg.fill(s)
     if hi is None:
         ld_out = ld_out or max(c, c_pad)
         hi = torch.empty((N, H, W, ld_out), device=seg.t.device, dtype=torch.bfloat16)
         lo = torch.empty_like(hi)
-    call('essb_split_bf16', C.byref(s), N, H, W, _p(hi), _p(lo), hi.shape[-1], c_off, c_pad, _stream())
+    call('essb_split_planes', C.byref(s), N, H, W, _p(hi), _p(lo), hi.shape[-1], c_off, c_pad, fmt, _stream())
     return hi, lo
+
+
+def decode_planes(hi, lo, fmt=PLANES_BF16):
+    """Operand planes -> the fp32 values they represent (diagnostics / tests; plain torch ops)."""
+    if fmt == PLANES_BF16:
+        return hi.float() + lo.float()
+    ld = hi.shape[-1]
+    x = hi.view(torch.float16).float() / 64.0
+    b = lo.view(torch.uint8).reshape(tuple(lo.shape[:-1]) + (ld // 64, 128))
+    a8l = b[..., 64:].contiguous().view(torch.float8_e4m3fn).float().reshape(tuple(lo.shape[:-1]) + (ld,))
+    return x + a8l / float(1 << 14)
 
 
 def pack_weight_tc(w, scale=None, transposed_layout=False, swap_io=False, flip=False, interleave=1, kin_pad=None,
@@ -406,6 +424,31 @@ def pack_weight_tc(w, scale=None, transposed_layout=False, swap_io=False, flip=F
     call('essb_pack_weight_tc', _p(w), _p(scale), _p(hi), _p(lo), cout, cin, T, int(transposed_layout), int(swap_io),
          int(flip), int(interleave), kinp, noutp, _stream())
     return hi, lo, kinp
+
+
+def pack_weight_tc_hf8(w, scale=None, transposed_layout=False, interleave=1, kin_pad=None, nout_pad=None):
+    """Conv weight -> hf8 operand planes of the f16f8 mode (essb_pack_weight_tc_fmt, fmt 2).  Returns
+    (hi, lo, KinP, acc_scale): the e4m3 scale 2^w8 is chosen so that max|W| (after the BN fold) lands in (64, 128];
+    acc_scale = 2^-(w8+14) must be handed to the convolution that uses these weights.  One host sync (max) per pack --
+    weights are packed once per parameter version."""
+    w = w.detach().contiguous().float()
+    if transposed_layout:
+        cin, cout = w.shape[0], w.shape[1]
+    else:
+        cout, cin = w.shape[0], w.shape[1]
+    ws = w
+    if scale is not None:
+        ws = w * (scale.view(1, -1, 1, 1) if transposed_layout else scale.view(-1, 1, 1, 1))
+    m = float(ws.abs().max())
+    w8 = int(math.floor(math.log2(128.0 / m))) if m > 0 and math.isfinite(m) else 0
+    T = w.shape[2] * w.shape[3]
+    kinp = kin_pad or (cin + 63) // 64 * 64
+    noutp = nout_pad or cout
+    hi = torch.empty((noutp, T * kinp), device=w.device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    call('essb_pack_weight_tc_fmt', _p(w), _p(scale), _p(hi), _p(lo), cout, cin, T, int(transposed_layout), 0, 0,
+         int(interleave), kinp, noutp, PLANES_HF8, w8, _stream())
+    return hi, lo, kinp, 2.0 ** -(w8 + 14)
 
 
 def dense_view(v: TcView, hi, lo, c_off=0, C_=None):
@@ -453,7 +496,8 @@ def in_stats(y, count=None):
 
 
 def conv_tc_dense(planes, w_hi, w_lo, k_per_tap, taps, N, H, W, Cout, passes, bias=None, out=None, act=ACT_NONE,
-                  tag=None, res_pre=None, res_post=None, out_planes=None, want_out=True, out_place=None):
+                  tag=None, res_pre=None, res_post=None, out_planes=None, want_out=True, out_place=None, acc_scale=0.0,
+                  planes_fmt=PLANES_BF16):
     """Stride-1 gather-convolution on the tcgen05 kernel over ONE dense bf16 hi/lo plane pair
     [N, H, W, Cin] (Cin a multiple of 64; concatenated inputs are laid out side by side by
     split_bf16(c_off=...)).  Returns the fp32 result [N, H, W, Cout] (None when want_out=False and
@@ -480,6 +524,7 @@ def conv_tc_dense(planes, w_hi, w_lo, k_per_tap, taps, N, H, W, Cout, passes, bi
     d.N, d.OH, d.OW, d.Cout = N, H, W, Cout
     d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = out_place
     d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, act, passes, pick_bw_log2(W, H)
+    d.acc_scale, d.planes_fmt = acc_scale, planes_fmt
     d.ntaps = len(taps)
     for t, (dy, dx, wi) in enumerate(taps):
         d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, 0, wi

@@ -280,7 +280,7 @@ class _DecoderFn(torch.autograd.Function):
             T[0] = x0
         S = {}
         tc = module.mode != 'fp32'
-        passes = 3 if module.mode == 'bf16x3' else 1
+        passes = 1 if module.mode == 'bf16' else 3      # 'f16f8' (an encoder mode) = bf16x3 here
         ctx.mode = module.mode
         # operand planes of every tensor-core conv are kept for its weight gradient (same bytes as the fp32
         # activation; ~1.7 GB at B=8 DSEC) instead of being re-created in the backward pass
@@ -443,7 +443,7 @@ class _DecoderFn(torch.autograd.Function):
             w = P[nd.w]
             taps = _taps(nd.k)
             tc = ctx.mode != 'fp32' and nd.k == 3 and nd.cout % 32 == 0 and nd.pad is None
-            passes = 3 if ctx.mode == 'bf16x3' else 1
+            passes = 1 if ctx.mode == 'bf16' else 3
             gplanes = gy_planes
 
             def dy_planes():

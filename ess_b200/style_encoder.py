@@ -46,7 +46,7 @@ class _ConvFn(torch.autograd.Function):
         N, H, W, Cin = x.shape
         Cout, _, k, _ = w.shape
         OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-        passes = 3 if mode == 'bf16x3' else 1
+        passes = 1 if mode == 'bf16' else 3      # 'f16f8' (an E2VID mode) = bf16x3 here
         if _tc_ok(mode, k, Cin, Cout) and (stride == 1 or (stride == 2 and H % 2 == 0 and W % 2 == 0)):
             planes = ops.split_bf16(Seg(x), N, H, W)
             w_hi, w_lo, kinp = ops.pack_weight_tc(w)
@@ -72,7 +72,7 @@ class _ConvFn(torch.autograd.Function):
         Cout, _, k, _ = w.shape
         gy = gy.contiguous()
         OH, OW = gy.shape[1], gy.shape[2]
-        passes = 3 if mode == 'bf16x3' else 1
+        passes = 1 if mode == 'bf16' else 3      # 'f16f8' (an E2VID mode) = bf16x3 here
         tc = _tc_ok(mode, k, Cin, Cout)
         gplanes = ops.split_bf16(Seg(gy), N, OH, OW) if tc else None          # Cout is a multiple of 64
         gx = gw = None

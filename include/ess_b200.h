@@ -310,6 +310,11 @@ int essb_radam_multi_step(const essb_radam_multi* d, void* stream);
 int essb_split_bf16(const essb_src* src, int N, int H, int W, uint16_t* hi, uint16_t* lo, int ld_out,
                     int c_off, int c_pad /* channels [C, c_pad) are written as zeros (K padding); 0 = none */,
                     void* stream);
+/* Same with the output format selectable: fmt 0 = bf16 hi/lo planes; fmt 2 = "hf8": hi = fp16(x * 2^6), and per 64-channel
+ * chunk of the lo plane 128 bytes [e4m3(x * 2^3) x 64 | e4m3((x - hi/2^6) * 2^14) x 64] (ld_out % 64 == 0).  The tcgen05
+ * kernels consume hf8 operands with passes == 2 (fp16 main product + e4m3 cross terms). */
+int essb_split_planes(const essb_src* src, int N, int H, int W, uint16_t* hi, uint16_t* lo, int ld_out,
+                      int c_off, int c_pad, int fmt, void* stream);
 /* Event pre-processing (same arithmetic as essb_event_prepare) written directly in the head
  * convolution's tensor-core operand format: bf16 hi/lo planes with `cpad` (8 or 16) channels per
  * pixel, stored at (off_y, off_x) inside a caller-zeroed bordered buffer [B][Hb][Wb][cpad].  With a
@@ -326,6 +331,12 @@ int essb_event_prepare_planes(const float* x, int64_t bstride, const double* sta
 int essb_pack_weight_tc(const float* w, const float* scale, uint16_t* hi, uint16_t* lo, int Cout,
                         int Cin, int T, int transposed_layout, int swap_io, int flip, int interleave,
                         int KinP, int NoutP, void* stream);
+/* fmt 2: hf8 weights for passes == 2: hi = fp16(W * 2^(w8+8)), lo = per 64-k chunk [e4m3((W - hi/2^(w8+8)) * 2^(w8+11)) x 64 |
+ * e4m3(W * 2^w8) x 64]; w8 = floor(log2(128 / max|W|)) (after the BN fold) is chosen by the caller, who passes
+ * acc_scale = 2^-(w8+14) to essb_conv_tc_run.  fmt 0 = essb_pack_weight_tc. */
+int essb_pack_weight_tc_fmt(const float* w, const float* scale, uint16_t* hi, uint16_t* lo, int Cout,
+                            int Cin, int T, int transposed_layout, int swap_io, int flip, int interleave,
+                            int KinP, int NoutP, int fmt, int w8, void* stream);
 
 /* One TMA view of an A operand: bf16 hi/lo NHWC planes addressed as view[n][y][x][c] with element
  * strides (stride_n, stride_y, stride_x, 1).  A dense NHWC tensor is one view; a stride-2 conv
@@ -377,13 +388,17 @@ typedef struct essb_conv_tc {
   int32_t OHf, OWf, osy, ooy, osx, oox;
   int32_t ldo, ld_res, ld_planes;
   int32_t epilogue, act;
-  int32_t passes;        /* 3 = bf16x3 split (fp32-parity mode), 1 = single bf16 pass */
+  int32_t passes;        /* 3 = bf16x3 split (fp32-parity mode), 1 = single bf16 pass, 2 = f16f8: operands in the hf8
+                            format (fp16 main product + e4m3 cross terms = 2 tensor-pass equivalents, fp32-parity) */
   int32_t bw_log2;       /* spatial tile: BW = 1<<bw_log2 columns x 128/BW rows */
   int32_t ntaps;
   int8_t dy[ESSB_MAX_TAPS];
   int8_t dx[ESSB_MAX_TAPS];
   int8_t view[ESSB_MAX_TAPS];
   int8_t widx[ESSB_MAX_TAPS];
+  float acc_scale;       /* the epilogue multiplies the accumulator by this first (0 = 1.0); passes == 2: the
+                            2^-(w8+14) that belongs to the packed weights */
+  int32_t planes_fmt;    /* format of out_hi / out_lo: 0 = bf16 hi/lo planes, 2 = hf8 (ld_planes % 64 == 0) */
 } essb_conv_tc;
 int essb_conv_tc_run(const essb_conv_tc* d, void* stream);
 

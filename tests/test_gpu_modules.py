@@ -56,9 +56,9 @@ def test_golden_end_to_end_fp32(golden):
     assert abs(float(s['mean_iou']) - float(golden['mean_iou'])) < 1e-9
 
 
-@pytest.mark.parametrize('mode,tol', [('fp32', 1e-3), ('bf16x3', 1e-3), ('bf16', 6e-2)])
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-3), ('bf16x3', 1e-3), ('f16f8', 1e-3), ('bf16', 6e-2)])
 def test_e2vid_lightweight_vs_oracle(mode, tol):
-    """E2VID-lightweight architecture (10.7 M params), 3 windows, all three precision modes."""
+    """E2VID-lightweight architecture (10.7 M params), 3 windows, all four precision modes."""
     import ess_b200
     B, T, C, H, W = 2, 3, 5, 64, 96
     m = make_e2vid(mode=mode)
@@ -74,6 +74,32 @@ def test_e2vid_lightweight_vs_oracle(mode, tol):
     errs['c2'] = rel_err(st[2][1], st_r[2][1])
     print(mode, errs)
     assert max(errs.values()) < tol, errs
+
+
+@pytest.mark.parametrize('mode', ['bf16x3', 'f16f8'])
+def test_full_length_unroll_logits_within_contract(mode):
+    """The contract end to end at the benchmark's recurrence depth: T = 20 windows through the recurrent encoder in the
+    tensor-core modes, then the decoder -- latents, image and LOGITS within 1e-3 of the fp32 oracle (the f16f8 operand
+    scheme was selected by CPU emulation, tools/precision_emul.py; this is its measurement on the device)."""
+    import ess_b200
+    B, T, C, H, W, K = 1, 20, 5, 64, 96, 11
+    m = make_e2vid(mode=mode)
+    sd = sd_cpu(m)
+    data = make_events(B, T, C, H, W)
+    img_r, st_r, lat_r = O.encoder_unroll(sd, E2VID_CFG, data, T, C)
+    dec = make_semseg(K)
+    with torch.no_grad():
+        logits_r = O.semseg_forward(sd_cpu(dec), lat_r)[1]
+    m, dec = m.cuda(), dec.cuda()
+    dec.mode = mode
+    rec = ess_b200.ImageReconstructor(m, H, W, C, 'cuda')
+    img, st, lat = rec.unroll(data.cuda(), T, C)
+    with torch.no_grad():
+        logits = dec({k: v for k, v in lat.items()})[1]
+    errs = {k: rel_err(lat[k], lat_r[k]) for k in (1, 2, 4, 8)}
+    errs.update(img=rel_err(img, img_r), c0=rel_err(st[0][1], st_r[0][1]), logits=rel_err(logits, logits_r))
+    print(mode, 'T=20:', {k: '%.1e' % v for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
 
 
 @pytest.mark.parametrize('variant', ['convgru', 'upsample_conv', 'no_norm', 'reflect_pad', 'concat'])
@@ -253,19 +279,20 @@ def test_full_size_properties_dsec():
     B, T, C, H, W = 1, 2, 5, 440, 640
     data = make_events(B, T, C, H, W).cuda()
     outs = {}
-    for mode in ('fp32', 'bf16x3'):
+    for mode in ('fp32', 'bf16x3', 'f16f8'):
         m = make_e2vid(mode=mode).cuda()
         rec = ess_b200.ImageReconstructor(m, H, W, C, 'cuda')
         img, st, lat = rec.unroll(data, T, C)
         outs[mode] = (img, st, lat)
         assert lat[8].shape == (B, 256, 55, 80) and lat[1].shape == (B, 32, 440, 640) and img.shape == (B, 1, H, W)
         assert bool(torch.isfinite(lat[8]).all()) and float(img.min()) >= 0 and float(img.max()) <= 1
-    for k in (1, 2, 4, 8):
-        assert rel_err(outs['bf16x3'][2][k], outs['fp32'][2][k]) < TOL, k
-    assert rel_err(outs['bf16x3'][0], outs['fp32'][0]) < TOL
+    for mode in ('bf16x3', 'f16f8'):
+        for k in (1, 2, 4, 8):
+            assert rel_err(outs[mode][2][k], outs['fp32'][2][k]) < TOL, (mode, k)
+        assert rel_err(outs[mode][0], outs['fp32'][0]) < TOL, mode
 
 
-@pytest.mark.parametrize('mode', ['fp32', 'bf16x3'])
+@pytest.mark.parametrize('mode', ['fp32', 'bf16x3', 'f16f8'])
 def test_e2vid_module_forward_signature(mode):
     """E2VIDRecurrent.forward(event_tensor NCHW, prev_states) itself (no reconstructor): two chained calls,
     states passed back in, outputs are logical-NCHW tensors of the reference's shapes."""
@@ -342,13 +369,14 @@ def test_training_trajectory_and_miou_parity():
     assert abs(miou - miou_ref) < 1.0                                             # mIoU in percent points
 
 
-def test_e2vid_ten_bins_config5():
+@pytest.mark.parametrize('mode', ['bf16x3', 'f16f8'])
+def test_e2vid_ten_bins_config5(mode):
     """BASELINE config 5 uses C=10 voxel bins: the tensor-core head conv then runs with 16-channel pixels
     (two 64-wide K chunks per kernel row)."""
     import ess_b200
     cfg = dict(E2VID_CFG, num_bins=10)
     B, T, C, H, W = 1, 2, 10, 32, 64
-    m = make_e2vid(cfg, mode='bf16x3')
+    m = make_e2vid(cfg, mode=mode)
     sd = sd_cpu(m)
     data = make_events(B, T, C, H, W)
     img_r, st_r, lat_r = O.encoder_unroll(sd, cfg, data, T, C)
@@ -360,12 +388,13 @@ def test_e2vid_ten_bins_config5():
         assert rel_err(lat[k], lat_r[k]) < TOL, k
 
 
-def test_ddd17_shape_config2():
+@pytest.mark.parametrize('mode', ['bf16x3', 'f16f8'])
+def test_ddd17_shape_config2(mode):
     """BASELINE config 2: raw DDD17 width 346 is reflect-padded to 352 (L3/R3) and the logits stay at the
     padded size; K=6.  Checked against the oracle at B=1, T=2 (CPU finishes in seconds)."""
     import ess_b200
     B, T, C, H, W, K = 1, 2, 5, 200, 346, 6
-    m = make_e2vid(mode='bf16x3')
+    m = make_e2vid(mode=mode)
     sd = sd_cpu(m)
     data = make_events(B, T, C, H, W)
     img_r, st_r, lat_r = O.encoder_unroll(sd, E2VID_CFG, data, T, C)
@@ -383,14 +412,15 @@ def test_ddd17_shape_config2():
     assert rel_err(pred[1], pred_r[1]) < TOL
 
 
-def test_convgru_in_tensor_core_mode():
+@pytest.mark.parametrize('mode', ['bf16x3', 'f16f8'])
+def test_convgru_in_tensor_core_mode(mode):
     """ConvGRU checkpoints (`recurrent_block_type='convgru'`, model.py:77-80) in bf16x3 mode: head and encoder convs on
     tcgen05, each GRU cell as two tcgen05 launches (GRU_UR epilogue: update gate + planes of prev_state*reset;
     GRU_OUT epilogue: out gate + blend), ess_b200.e2vid._gru_tc."""
     import ess_b200
     cfg = dict(E2VID_CFG, recurrent_block_type='convgru')
     B, T, C, H, W = 1, 2, 5, 32, 64
-    m = make_e2vid(cfg, mode='bf16x3')
+    m = make_e2vid(cfg, mode=mode)
     sd = sd_cpu(m)
     data = make_events(B, T, C, H, W)
     img_r, st_r, lat_r = O.encoder_unroll(sd, cfg, data, T, C)
@@ -403,7 +433,7 @@ def test_convgru_in_tensor_core_mode():
         assert rel_err(lat[k], lat_r[k]) < TOL, k
 
 
-@pytest.mark.parametrize('mode', ['fp32', 'bf16x3'])
+@pytest.mark.parametrize('mode', ['fp32', 'bf16x3', 'f16f8'])
 def test_reconstructor_flip_and_hot_pixels(mode, tmp_path):
     """ImageReconstructor with the EventPreprocessor options of e2vid/utils/inference_utils.py:73-93 (hot-pixel
     file, flip) on a width that needs reflect padding (30 -> 32), per-window and fused-unroll forms."""

@@ -18,11 +18,37 @@ def nchw(x):
     return x.float().permute(0, 3, 1, 2).cpu()
 
 
-def planes_of(x_nchw):
+def planes_of(x_nchw, passes=3):
+    """operand planes in the format the given pass count consumes (2 = f16f8 mode: hf8 planes)"""
     from ess_b200 import ops
     t = nhwc(x_nchw)
     N, H, W, C = t.shape
-    return ops.split_bf16(ops.Seg(t), N, H, W)
+    return ops.split_bf16(ops.Seg(t), N, H, W, fmt=ops.PLANES_HF8 if passes == 2 else ops.PLANES_BF16)
+
+
+def pack_for(w, passes, **kw):
+    """dict(hi, lo, k_per_tap, sc) of a weight in the operand format of the given pass count"""
+    from ess_b200 import ops
+    if passes == 2:
+        hi, lo, kinp, sc = ops.pack_weight_tc_hf8(w, **kw)
+    else:
+        (hi, lo, kinp), sc = ops.pack_weight_tc(w, **kw), 0.0
+    return dict(hi=hi, lo=lo, k_per_tap=kinp, sc=sc)
+
+
+def test_split_hf8_roundtrip():
+    """hf8 operand planes (fp16 hi + e4m3 [a8 | a8l] pair rows): hi + a8l reproduces x to ~2^-15; a8 is e4m3(8x)."""
+    from ess_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 128, 5, 7, generator=g) * 3
+    x[0, 0, 0, 0] = 100.0          # beyond the e4m3 range of the cross terms (56): hi still exact-range
+    hi, lo = planes_of(x, passes=2)
+    rec = ops.decode_planes(hi, lo, ops.PLANES_HF8)
+    assert rel_err(nchw(rec)[:, :, 1:], x[:, :, 1:]) < 2 ** -14
+    b = lo.view(torch.uint8).reshape(2, 5, 7, 2, 128)
+    a8 = b[..., :64].contiguous().view(torch.float8_e4m3fn).float().reshape(2, 5, 7, 128) / 8.0
+    ref8 = (nhwc(x) * 8).clamp(-448, 448).to(torch.float8_e4m3fn).float() / 8.0
+    assert float((a8 != ref8).float().mean()) < 1e-4       # same round-to-nearest-even conversion
 
 
 @pytest.fixture(autouse=True)
@@ -43,7 +69,7 @@ def test_split_bf16_roundtrip():
     assert rel_err(nchw(rec), x) < 2 ** -15
 
 
-@pytest.mark.parametrize('passes,tol', [(3, 1e-3), (1, 3e-2)])
+@pytest.mark.parametrize('passes,tol', [(3, 1e-3), (2, 1e-3), (1, 3e-2)])
 @pytest.mark.parametrize('N,H,W,C,with_state', [(1, 8, 16, 64, True), (2, 13, 20, 64, False), (1, 7, 10, 128, True),
                                                 (1, 55, 80, 64, True),
                                                 # 168 tiles on 148 SMs: a full wave + 20 tail tiles cut into 4 K-slices
@@ -61,19 +87,19 @@ def test_convlstm_tc(passes, tol, N, H, W, C, with_state):
     prev = (torch.randn(N, C, H, W, generator=g), torch.randn(N, C, H, W, generator=g)) if with_state else None
     h_ref, c_ref = O.convlstm(x, prev, {'p.Gates.weight': w, 'p.Gates.bias': b}, 'p')
     m = ess_b200.E2VIDRecurrent.__new__(ess_b200.E2VIDRecurrent)
-    hi, lo, kinp = ops.pack_weight_tc(w.cuda(), interleave=4)
-    e = dict(lstm_tc=dict(hi=hi, lo=lo, k_per_tap=kinp), lstm_b=_interleave(b.cuda(), 4))
-    xp = planes_of(x)
-    hp = planes_of(prev[0]) if with_state else None
+    e = dict(lstm_tc=pack_for(w.cuda(), passes, interleave=4), lstm_b=_interleave(b.cuda(), 4))
+    xp = planes_of(x, passes)
+    hp = planes_of(prev[0], passes) if with_state else None
     cp = nhwc(prev[1]) if with_state else None
     h, c, hh, hl = ess_b200.E2VIDRecurrent._lstm_tc(m, e, xp, hp, cp, N, H, W, C, passes)
     torch.cuda.synchronize()
     assert rel_err(nchw(h), h_ref) < tol, rel_err(nchw(h), h_ref)
     assert rel_err(nchw(c), c_ref) < tol
-    assert rel_err(nchw(hh.float() + hl.float()), h_ref) < max(tol, 1e-4)
+    fmt = ops.PLANES_HF8 if passes == 2 else ops.PLANES_BF16
+    assert rel_err(nchw(ops.decode_planes(hh, hl, fmt)), h_ref) < max(tol, 1e-4)
 
 
-@pytest.mark.parametrize('passes,tol', [(3, 1e-3), (1, 3e-2)])
+@pytest.mark.parametrize('passes,tol', [(3, 1e-3), (2, 1e-3), (1, 3e-2)])
 @pytest.mark.parametrize('Cin,Cout,H,W', [(32, 64, 16, 32), (64, 128, 24, 16), (128, 256, 14, 22), (32, 64, 110, 160)])
 def test_encoder_conv_tc(passes, tol, Cin, Cout, H, W):
     """conv5x5 stride 2 + folded BN + ReLU through parity views (and the 32-channel pixel-pair fold)."""
@@ -92,15 +118,20 @@ def test_encoder_conv_tc(passes, tol, Cin, Cout, H, W):
         w6 = torch.zeros((Cout, Cin, 5, 6), device='cuda')
         w6[..., :5] = wd
         wd = w6.view(Cout, Cin, 5, 3, 2).permute(0, 4, 1, 2, 3).reshape(Cout, 2 * Cin, 5, 3).contiguous()
-    hi, lo, kinp = ops.pack_weight_tc(wd, scale.cuda())
-    e = dict(tc=dict(hi=hi, lo=lo, k_per_tap=kinp, fold=fold, T=wd.shape[2] * wd.shape[3]), bias=bias.cuda())
+    e = dict(tc=dict(pack_for(wd, passes, scale=scale.cuda()), fold=fold, T=wd.shape[2] * wd.shape[3]), bias=bias.cuda())
     m = ess_b200.E2VIDRecurrent.__new__(ess_b200.E2VIDRecurrent)
     oh, ow = H // 2, W // 2
     out_hi = torch.empty((N, oh, ow, Cout), device='cuda', dtype=torch.bfloat16)
     out_lo = torch.empty_like(out_hi)
-    ess_b200.E2VIDRecurrent._enc_conv_tc(m, e, planes_of(x), N, H, W, Cout, out_hi, out_lo, passes)
+    xp = planes_of(x, passes)
+    if passes == 2 and fold:      # 32-channel hf8 planes pair two pixels per 64-channel row (as the head conv writes them)
+        t = nhwc(x)
+        shp = (N, H, W // 2, 64)
+        ph, pl = ops.split_bf16(ops.Seg(t.view(shp)), N, H, W // 2, fmt=ops.PLANES_HF8)
+        xp = (ph.view(N, H, W, 32), pl.view(N, H, W, 32))
+    ess_b200.E2VIDRecurrent._enc_conv_tc(m, e, xp, N, H, W, Cout, out_hi, out_lo, passes)
     torch.cuda.synchronize()
-    got = nchw(out_hi.float() + out_lo.float())
+    got = nchw(ops.decode_planes(out_hi, out_lo, ops.PLANES_HF8 if passes == 2 else ops.PLANES_BF16))
     assert rel_err(got, ref) < tol, rel_err(got, ref)
 
 
@@ -143,8 +174,7 @@ def test_convlstm_tc_splitk_is_deterministic_and_leaves_scratch_clean():
     b = torch.randn(4 * C, generator=g) * 0.1
     prev = (torch.randn(N, C, H, W, generator=g), torch.randn(N, C, H, W, generator=g))
     m = ess_b200.E2VIDRecurrent.__new__(ess_b200.E2VIDRecurrent)
-    hi, lo, kinp = ops.pack_weight_tc(w.cuda(), interleave=4)
-    e = dict(lstm_tc=dict(hi=hi, lo=lo, k_per_tap=kinp), lstm_b=_interleave(b.cuda(), 4))
+    e = dict(lstm_tc=pack_for(w.cuda(), 3, interleave=4), lstm_b=_interleave(b.cuda(), 4))
     xp, hp, cp = planes_of(x), planes_of(prev[0]), nhwc(prev[1])
     run = lambda: ess_b200.E2VIDRecurrent._lstm_tc(m, e, xp, hp, cp, N, H, W, C, 3)
     assert ops.SPLITK
