@@ -41,7 +41,8 @@ WORK = dict(B=8, T=20, C=5, H=440, W=640, K=11)
 SHAPES = {'dsec': dict(H=440, W=640, K=11, name='DSEC 440x640'),
           'ddd17': dict(H=200, W=346, K=6, name='DDD17 200x346 (reflect-padded to 200x352)')}
 METRIC = 'samples/sec fwd+bwd 640x440x5bin voxel grids'
-DTYPES = {'bf16x3': 'bf16x3-split (f32 accumulate, f32 epilogues)', 'bf16': 'bf16 (f32 accumulate)', 'fp32': 'f32'}
+DTYPES = {'bf16x3': 'bf16x3-split (f32 accumulate, f32 epilogues)', 'bf16': 'bf16 (f32 accumulate)', 'fp32': 'f32',
+          'f16f8': 'f16+2xe4m3 split in the recurrent encoder (fp32-parity; f32 accumulate, f32 epilogues), bf16x3 in the decoder'}
 
 
 # stdout must carry exactly ONE JSON line (the driver parses it): keep a private handle on the real stdout
@@ -375,10 +376,11 @@ def lstm_roofline(prof, peaks, ms_dev, steps, mode, work_is_default):
                 traffic_note='mean DRAM bytes per launch from the committed ncu --set full capture '
                              '(profiles/ncu_traffic.json); algorithmic bytes are 865/433/216 MB for the 3 levels',
                 peak_source='%s bf16 dense sustained (MEASURED_PEAKS.json)' % peaks['source'],
-                note='algorithmic FLOPs (2*MAC, no credit for the 3 split passes): in bf16x3 mode the tensor pipe '
-                     'executes 3x this, so the mode ceiling is peak/3',
+                note='algorithmic FLOPs (2*MAC, no credit for split passes): bf16x3 executes 3 bf16 passes (ceiling peak/3); '
+                     'f16f8 executes one fp16 pass + one e4m3 pass of twice the K at twice the rate (2 pass-equivalents, '
+                     'ceiling peak/2)',
                 mean_launch_ms=sec / n * 1e3, share_of_step=sec * 1e3 / ms_dev,
-                mma_frac_of_peak=ach * (3 if mode == 'bf16x3' else 1) / peaks['bf16'])
+                mma_frac_of_peak=ach * {'bf16x3': 3, 'f16f8': 2}.get(mode, 1) / peaks['bf16'])
     roof['other_tc_kernels'] = {
         tag: dict(achieved=fl2 / sec2 / 1e12, mean_launch_ms=sec2 / n2 * 1e3, launches_per_step=n2 // ns2,
                   share_of_step=(sec2 * 1e3 / ns2) / (ms_dev / steps))
@@ -628,7 +630,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mode', default=os.environ.get('ESS_B200_MODE', 'bf16x3'), choices=['bf16x3', 'bf16', 'fp32'])
+    ap.add_argument('--mode', default=os.environ.get('ESS_B200_MODE', 'bf16x3'), choices=['bf16x3', 'bf16', 'fp32', 'f16f8'])
     ap.add_argument('--batch', type=int, default=WORK['B'], help='samples per GPU')
     ap.add_argument('--global-batch', type=int, default=0,
                     help='total samples over all ranks (strong scaling, BASELINE.json configs[4]: 64); overrides --batch')
