@@ -84,6 +84,8 @@ struct TcParams {
   // dynamic tile scheduler + split-K tail (see TcUnit)
   int tmem_cols, tmem_buf_stride;        // TMEM columns allocated per CTA (power of two) / column offset of accumulator buffer 1
   int fuse_b;                            // bf16x3 with 2*BN <= 256: A_hi x [B_hi; B_lo] is ONE MMA of N = 2*BN (see below)
+  int pair;                              // conv_tc_pair_kernel: CTA pairs (cta_group::2), B maps carry BN/2-row boxes
+  int b_split;                           // wide halo tiles (BN = 256): a B stage is ONE plane of one tap (hi and lo planes behind separate barriers)
   float acc_scale;                       // the epilogue multiplies the raw accumulator by this (f16f8 mode: 2^-(w8+14))
   int planes_fmt;                        // format of out_hi/out_lo: 0 = bf16 hi/lo, 2 = hf8 (tc_ptx.cuh)
   int* sched;                            // [0] next unit, [1] CTAs done; zero before the launch, reset by the last CTA
@@ -289,6 +291,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
     }
   } else {
     const size_t opix = ((size_t)n * p.OHf + (oy * p.osy + p.ooy)) * p.OWf + (ox * p.osx + p.oox);
+    uint32_t q8[8], q8l[8];   // hf8 planes: the chunk's 32 e4m3 a8 / a8l bytes, stored as ONE 32 B sector each after the loop
 #pragma unroll
     for (int g = 0; g < 2; ++g) {  // 16 channels per group: 2 x 32 B of fp32, 32 B per bf16 plane
       const int co = n0 + c0 + g * 16;
@@ -326,8 +329,22 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
         }
       }
       if (p.out_hi && p.planes_fmt == 2) {
-        tc_store_planes8(p, opix, co, v[0]);
-        tc_store_planes8(p, opix, co + 8, v[1]);
+        uint32_t h[8];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          uint16_t a0, l0, a1, l1;
+          split_hf8x2(v[e >> 2][(e & 3) * 2], v[e >> 2][(e & 3) * 2 + 1], h[e], a0, l0);
+          split_hf8x2(v[(e + 1) >> 2][((e + 1) & 3) * 2], v[(e + 1) >> 2][((e + 1) & 3) * 2 + 1], h[e + 1], a1, l1);
+          q8[g * 4 + (e >> 1)] = (uint32_t)a0 | ((uint32_t)a1 << 16);
+          q8l[g * 4 + (e >> 1)] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        }
+        __nv_bfloat16* oh = p.out_hi + opix * p.ld_planes + co;
+        if (p.wide & TC_WIDE_PLANES) {
+          st_global_256(oh, h);
+        } else {
+          *reinterpret_cast<uint4*>(oh) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(oh + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+        }
       } else if (p.out_hi) {
         uint32_t ph[8], pl[8];
 #pragma unroll
@@ -349,6 +366,18 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
           *reinterpret_cast<uint4*>(ol) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
           *reinterpret_cast<uint4*>(ol + 8) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
         }
+      }
+    }
+    if (p.out_hi && p.planes_fmt == 2) {   // n0 + c0 is a multiple of 32: both 32 B pieces lie inside one 64-channel chunk row
+      uint8_t* lo = reinterpret_cast<uint8_t*>(p.out_lo) + opix * (size_t)p.ld_planes * 2 + hf8_lo_off(n0 + c0);
+      if (p.wide & TC_WIDE_PLANES) {
+        st_global_256(lo, q8);
+        st_global_256(lo + 64, q8l);
+      } else {
+        *reinterpret_cast<uint4*>(lo) = make_uint4(q8[0], q8[1], q8[2], q8[3]);
+        *reinterpret_cast<uint4*>(lo + 16) = make_uint4(q8[4], q8[5], q8[6], q8[7]);
+        *reinterpret_cast<uint4*>(lo + 64) = make_uint4(q8l[0], q8l[1], q8l[2], q8l[3]);
+        *reinterpret_cast<uint4*>(lo + 80) = make_uint4(q8l[4], q8l[5], q8l[6], q8l[7]);
       }
     }
   }
@@ -388,7 +417,8 @@ __device__ __forceinline__ void tc_load_cprev(const TcParams& p, bool valid, siz
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                                  uint64_t* tempty_bar, uint32_t (&tph)[2], int local, const TcUnit& un,
-                                                 int q, int half, int lane, const float* __restrict__ s_bias) {
+                                                 int q, int half, int lane, const float* __restrict__ s_bias,
+                                                 const uint32_t* tempty_cluster = nullptr) {
   const int BW = 1 << p.bw_log2, BH = TC_M >> p.bw_log2;
   const int buf = local & 1;
   const int item = un.item;
@@ -434,7 +464,10 @@ __device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tme
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    if (lane == 0) {
+      if (tempty_cluster) mbar_arrive_cluster(tempty_cluster[buf]);   // CTA pair: the accumulator barrier lives in the leader CTA
+      else mbar_arrive(&tempty_bar[buf]);
+    }
     return;
   }
   // ---- split-K slice
@@ -695,8 +728,8 @@ __device__ __forceinline__ UDesc make_smem_desc_sbo(uint32_t saddr, uint32_t sbo
   return make_udesc(saddr, 1u, sbo_bytes);
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __grid_constant__ TcParams p) {
+template <int EPI, int OCC>
+__global__ void __launch_bounds__(HALO_THREADS, OCC) conv_tc_halo_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_base = smem;
@@ -783,6 +816,16 @@ __global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __g
             for (int g = 0; g < p.n_groups; ++g) {
               const int t_end = p.grp_first[g] + p.grp_count[g];
               for (int t0 = p.grp_first[g]; t0 < t_end; t0 += p.b_taps_per_stage) {
+                if (p.b_split) {   // one plane of one tap per stage
+                  const int kcoord = p.widx[t0] * p.k_per_tap + p.seg_koff[seg] + c * TC_KCH;
+                  for (int pl = 0; pl < (p.passes != 1 ? 2 : 1); ++pl) {
+                    mbar_wait(&b_empty[s], ph ^ 1);
+                    mbar_expect_tx(&b_full[s], (uint32_t)(p.BN * TC_KCH * 2));
+                    tma_load_2d(b_base + (size_t)s * p.b_stage_bytes, pl ? &p.tmB_lo : &p.tmB_hi, &b_full[s], kcoord, nt * p.BN);
+                    if (++s == p.b_stages) { s = 0; ph ^= 1; }
+                  }
+                  continue;
+                }
                 const int nt_taps = min(p.b_taps_per_stage, t_end - t0);
                 mbar_wait(&b_empty[s], ph ^ 1);
                 uint8_t* st = b_base + (size_t)s * p.b_stage_bytes;
@@ -825,6 +868,44 @@ __global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __g
               const uint32_t a_addr = smem_u32(a_base + (size_t)sa * p.a_stage_bytes);
               const int t_end = p.grp_first[g] + p.grp_count[g];
               for (int t0 = p.grp_first[g]; t0 < t_end; t0 += p.b_taps_per_stage) {
+               if (p.b_split) {
+                 // wide tile: the hi-plane MMAs of the tap run from one B stage, the lo-plane MMAs from the next one
+                 const uint32_t a_off = (uint32_t)((p.dy[t0] - p.hy0) * p.halo_w + (p.dx[t0] - p.hx0)) * 128u;
+                 const UDesc a_hi = make_smem_desc_sbo(a_addr + a_off, sbo);
+                 const UDesc a_lo = make_smem_desc_sbo(a_addr + p.a_lo_off + a_off, sbo);
+                 mbar_wait(&b_full[sb], phb);
+                 tc_fence_after();
+                 {
+                   const UDesc b_hi = make_smem_desc(smem_u32(b_base + (size_t)sb * p.b_stage_bytes));
+#pragma unroll
+                   for (int k = 0; k < TC_KCH / 16; ++k) {
+                     const uint32_t ko = (uint32_t)(k * 2);
+                     if (p.passes == 3) {
+                       umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, acc);
+                       umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+                     } else {
+                       umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, acc);
+                     }
+                     acc = 1u;
+                   }
+                 }
+                 umma_commit(&b_empty[sb]);
+                 if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+                 if (p.passes != 1) {
+                   mbar_wait(&b_full[sb], phb);
+                   tc_fence_after();
+                   const UDesc b_lo = make_smem_desc(smem_u32(b_base + (size_t)sb * p.b_stage_bytes));
+#pragma unroll
+                   for (int k = 0; k < TC_KCH / 16; ++k) {
+                     const uint32_t ko = (uint32_t)(k * 2);
+                     if (p.passes == 2) umma_f8(d_tmem, a_lo + ko, b_lo + ko, idesc_f8, 1u);
+                     else umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                   }
+                   umma_commit(&b_empty[sb]);
+                   if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+                 }
+                 continue;
+               }
                const int nt_taps = min(p.b_taps_per_stage, t_end - t0);
                mbar_wait(&b_full[sb], phb);
                tc_fence_after();
@@ -901,6 +982,217 @@ __global__ void __launch_bounds__(HALO_THREADS, 2) conv_tc_halo_kernel(const __g
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+
+// ------------------------------------------------------------------------------ CTA-pair kernel (cta_group::2)
+// The N = 256 layers (ConvLSTM cells, deepest encoder conv, 256-wide decoder convs) with the halo-reuse operand scheme on
+// a CTA PAIR: the two SMs of a TPC compute two horizontally adjacent 16 x 8 output patches (M = 256) with ONE
+// tcgen05.mma.cta_group::2 per K-step.  Each CTA stages its own A halo tile but only HALF of the weight rows (128 of the
+// 256 N rows, 16 KB per plane and tap instead of 32 KB): the tensor cores read the other half from the peer's shared
+// memory.  Why: the single-CTA N = 256 kernels are bound by the SM's shared-memory port, which serves both the UMMA operand
+// reads (A 4 KB + B 8 KB per 128-cycle MMA = 96 B/clk) and the TMA fills (67-94 B/clk at full tensor rate in the f16f8
+// mode; ncu: tensor pipe 62-68 %).  The pair halves the B bytes on both paths (64 B/clk operand reads, ~36 B/clk fills).
+// Protocol (as CUTLASS's 2-SM UMMA pipelines): TMA loads of both CTAs complete on the LEADER's full barrier (the leader
+// arms it with the bytes of both CTAs); the leader issues every MMA and multicasts its commits to the empty / accumulator-
+// full barriers of both CTAs; the epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier.
+// Static schedule (pair p takes tile pairs p, p + #pairs, ...): the dynamic scheduler bought nothing on these layers.
+template <int EPI>
+__global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_pair_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_base = smem;
+  uint8_t* b_base = smem + (size_t)p.a_stages * p.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.b_stages * p.b_stage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + MAX_STAGES;
+  uint64_t* b_full = bars + 2 * MAX_STAGES;
+  uint64_t* b_empty = bars + 3 * MAX_STAGES;
+  uint64_t* tfull_bar = bars + 4 * MAX_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  constexpr int BW = 8, BH = 16;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 16); }   // 8 epilogue warps x 2 CTAs
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  float* s_bias_buf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  if (p.bias)
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias_buf[i] = p.bias[i];
+  const float* s_bias = p.bias ? s_bias_buf : nullptr;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive / multicast commit / 2-SM TMA
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+  const int tx2n = (p.tiles_x + 1) >> 1;
+  const int n_pair_items = p.N * p.tiles_y * tx2n * p.n_tiles;
+  const int planes = p.passes != 1 ? 2 : 1;
+
+  if (warp == 0) {
+    // ============================================================ A (halo tile) producer, both CTAs
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = (uint32_t)planes * (uint32_t)(p.halo_w * p.halo_h * 128);
+      for (int t = pair; t < n_pair_items; t += npairs) {
+        int mt = t / p.n_tiles;
+        const int txi = 2 * (mt % tx2n) + (int)rank; mt /= tx2n;
+        const int tyi = mt % p.tiles_y;
+        const int n = mt / p.tiles_y;
+        const int cx = txi * BW + p.hx0, cy = tyi * BH + p.hy0;
+        for (int seg = 0; seg < p.nseg; ++seg)
+          for (int c = 0; c < p.seg_chunks[seg]; ++c)
+            for (int g = 0; g < p.n_groups; ++g) {
+              const int v = p.seg_view0[seg] + p.grp_view[g];
+              mbar_wait(&a_empty[s], ph ^ 1);
+              uint8_t* st = a_base + (size_t)s * p.a_stage_bytes;
+              if (leader) mbar_expect_tx(&a_full[s], 2u * tx);       // the halo tiles of both CTAs
+              const uint32_t bar = mapa_u32(smem_u32(&a_full[s]), 0u);
+              tma_load_4d_2sm(st, &p.tmA_hi[v], bar, c * TC_KCH, cx, cy, n);
+              if (planes == 2) tma_load_4d_2sm(st + p.a_lo_off, &p.tmA_lo[v], bar, c * TC_KCH, cx, cy, n);
+              if (++s == p.a_stages) { s = 0; ph ^= 1; }
+            }
+      }
+    }
+  } else if (warp == 2) {
+    // ============================================================ B (weights) producer, both CTAs: this CTA's half of N
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const int half_n = p.BN >> 1;
+      const uint32_t tx = (uint32_t)(half_n * TC_KCH * 2);
+      for (int t = pair; t < n_pair_items; t += npairs) {
+        const int nt = t % p.n_tiles;
+        const int row0 = nt * p.BN + (int)rank * half_n;
+        for (int seg = 0; seg < p.nseg; ++seg)
+          for (int c = 0; c < p.seg_chunks[seg]; ++c)
+            for (int g = 0; g < p.n_groups; ++g) {
+              const int t_end = p.grp_first[g] + p.grp_count[g];
+              for (int t0 = p.grp_first[g]; t0 < t_end; ++t0) {
+                const int kcoord = p.widx[t0] * p.k_per_tap + p.seg_koff[seg] + c * TC_KCH;
+                for (int pl = 0; pl < planes; ++pl) {
+                  mbar_wait(&b_empty[s], ph ^ 1);
+                  if (leader) mbar_expect_tx(&b_full[s], 2u * tx);
+                  const uint32_t bar = mapa_u32(smem_u32(&b_full[s]), 0u);
+                  tma_load_2d_2sm(b_base + (size_t)s * p.b_stage_bytes, pl ? &p.tmB_lo : &p.tmB_hi, bar, kcoord, row0);
+                  if (++s == p.b_stages) { s = 0; ph ^= 1; }
+                }
+              }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer: leader CTA only (whole warp, convergent)
+    if (leader) {
+      const uint32_t idesc = p.passes == 2 ? make_idesc_fmt(2 * TC_M, p.BN, 0u, 0u) : make_idesc(2 * TC_M, p.BN);
+      const uint32_t idesc_f8 = make_idesc_fmt(2 * TC_M, p.BN, 0u, 0u);
+      const uint32_t sbo = (uint32_t)p.halo_w * 128u;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      uint32_t tph[2] = {0, 0};
+      int local = 0;
+      for (int t = pair; t < n_pair_items; t += npairs, ++local) {
+        const int buf = local & 1;
+        mbar_wait(&tempty_bar[buf], tph[buf] ^ 1);
+        tph[buf] ^= 1;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.tmem_buf_stride);
+        uint32_t acc = 0;
+        for (int seg = 0; seg < p.nseg; ++seg)
+          for (int c = 0; c < p.seg_chunks[seg]; ++c)
+            for (int g = 0; g < p.n_groups; ++g) {
+              mbar_wait(&a_full[sa], pha);
+              tc_fence_after();
+              const uint32_t a_addr = smem_u32(a_base + (size_t)sa * p.a_stage_bytes);
+              const int t_end = p.grp_first[g] + p.grp_count[g];
+              for (int t0 = p.grp_first[g]; t0 < t_end; ++t0) {
+                const uint32_t a_off = (uint32_t)((p.dy[t0] - p.hy0) * p.halo_w + (p.dx[t0] - p.hx0)) * 128u;
+                const UDesc a_hi = make_smem_desc_sbo(a_addr + a_off, sbo);
+                const UDesc a_lo = make_smem_desc_sbo(a_addr + p.a_lo_off + a_off, sbo);
+                mbar_wait(&b_full[sb], phb);
+                tc_fence_after();
+                {
+                  const UDesc b_hi = make_smem_desc(smem_u32(b_base + (size_t)sb * p.b_stage_bytes));
+#pragma unroll
+                  for (int k = 0; k < TC_KCH / 16; ++k) {
+                    const uint32_t ko = (uint32_t)(k * 2);
+                    if (p.passes == 3) {
+                      umma2_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, acc);
+                      umma2_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+                    } else {
+                      umma2_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, acc);
+                    }
+                    acc = 1u;
+                  }
+                }
+                umma2_commit_mc(&b_empty[sb]);
+                if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+                if (p.passes != 1) {
+                  mbar_wait(&b_full[sb], phb);
+                  tc_fence_after();
+                  const UDesc b_lo = make_smem_desc(smem_u32(b_base + (size_t)sb * p.b_stage_bytes));
+#pragma unroll
+                  for (int k = 0; k < TC_KCH / 16; ++k) {
+                    const uint32_t ko = (uint32_t)(k * 2);
+                    if (p.passes == 2) umma2_f8(d_tmem, a_lo + ko, b_lo + ko, idesc_f8, 1u);
+                    else umma2_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                  }
+                  umma2_commit_mc(&b_empty[sb]);
+                  if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+                }
+              }
+              umma2_commit_mc(&a_empty[sa]);
+              if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+            }
+        umma2_commit_mc(&tfull_bar[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================================================ epilogue warps, both CTAs (each drains its own TMEM)
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    uint32_t tph[2] = {0, 0};
+    const uint32_t tempty_cluster[2] = {mapa_u32(smem_u32(&tempty_bar[0]), 0u), mapa_u32(smem_u32(&tempty_bar[1]), 0u)};
+    int local = 0;
+    for (int t = pair; t < n_pair_items; t += npairs, ++local) {
+      const int nt = t % p.n_tiles;
+      int mt = t / p.n_tiles;
+      const int txi = 2 * (mt % tx2n) + (int)rank; mt /= tx2n;
+      if (txi >= p.tiles_x) {   // odd tile count per row: this CTA's half of the last pair lies outside the image
+        const int buf = local & 1;
+        mbar_wait(&tfull_bar[buf], tph[buf]);
+        tph[buf] ^= 1;
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_cluster[buf]);
+        continue;
+      }
+      const TcUnit un = {(mt * p.tiles_x + txi) * p.n_tiles + nt, 0, 0, 0, -1};
+      tc_epilogue_item<EPI>(p, tmem_base, tfull_bar, tempty_bar, tph, local, un, q, half, lane, s_bias, tempty_cluster);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer may still multicast into / arrive on this CTA's barriers until both are done
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -1253,9 +1545,28 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   //      gives wrong results -- tried, tests/test_gpu_tc.py fails).
   static const int halo_env = [] { const char* e = getenv("ESSB_TC_HALO"); return e ? atoi(e) : 1; }();
   static const int baseoff_env = 0;
-  bool halo = halo_env != 0 && BN <= 128 && d->ntaps >= 2;
+  // ESSB_TC_HALO256=0 keeps the N = 256 layers (ConvLSTM cells, deepest encoder conv) on the classic kernel.  Measured
+  // (ncu, profiles/r02c_window.txt): in the f16f8 mode the classic N = 256 kernel is bound by the SM's L2 -> shared-memory
+  // fill (58.6 B/clk/SM of ~64: every tap re-fetches its 32 KB A box next to the 64 KB of weights), tensor pipe 62 %; the
+  // halo tile cuts the A traffic 9x -> 1.4x (1728 -> 1244 KB per 128 x 256 tile of a 64-channel ConvLSTM).
+  // (read per call, not cached: tests/test_gpu_tc.py flips it to keep both kernels covered)
+  const int halo256_env = [] { const char* e = getenv("ESSB_TC_HALO256"); return e ? atoi(e) : 1; }();
+  bool halo = halo_env != 0 && d->ntaps >= 2 && (BN <= 128 || (halo256_env != 0 && BN == 256));
+  bool wide_halo = halo && BN == 256;
+  if (wide_halo) {
+    // the halo patch is fixed at 16 rows x 8 pixels; the classic kernel picks its patch shape per layer.  Stay classic when
+    // the fixed patch wastes too many more output pixels (ESSB_TC_HALO256_WASTE = max ratio of padded pixel counts)
+    const double waste_env = [] { const char* e = getenv("ESSB_TC_HALO256_WASTE"); return e ? atof(e) : 2.0; }();
+    const int cbw = 1 << d->bw_log2, cbh = TC_M >> d->bw_log2;
+    const double t_halo = (double)((d->OW + 7) / 8) * ((d->OH + 15) / 16);
+    const double t_classic = (double)((d->OW + cbw - 1) / cbw) * ((d->OH + cbh - 1) / cbh);
+    if (t_halo > waste_env * t_classic) { halo = false; wide_halo = false; }
+  }
   // shared-memory bias staging area: as small as the layer allows (it competes with pipeline stages at 2 CTAs/SM)
   const int bias_floats = d->bias ? ((d->Cout + 255) / 256) * 256 : 0;
+  // CTA pairs (cta_group::2) for the wide halo tiles; ESSB_TC_PAIR=0 keeps them on single CTAs (read per call, see above)
+  const int pair_env = [] { const char* e = getenv("ESSB_TC_PAIR"); return e ? atoi(e) : 1; }();
+  bool pair = wide_halo && pair_env != 0;
   int halo_occ = 1;
   bool halo_fuse = false;
   int hx0 = 0, hx1 = 0, hy0 = 0, hy1 = 0;
@@ -1271,7 +1582,7 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
     const int a_plane = (p.halo_w * p.halo_h * 128 + 1023) & ~1023;
     p.a_lo_off = a_plane;
     p.a_stage_bytes = planes * a_plane;
-    const int b_plane = BN * TC_KCH * 2;
+    const int b_plane = (pair ? BN / 2 : BN) * TC_KCH * 2;   // a CTA of a pair stages half of the N rows
     p.b_lo_off = b_plane;
     p.b_tap_bytes = planes * b_plane;
     // Two CTAs per SM (ESSB_TC_OCC=2, default) when the pipeline fits half an SM's shared memory: the narrow-N
@@ -1289,6 +1600,7 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
       const int half = 113 * 1024 - tail_bytes;   // 2 x (113 KB + 1 KB reserved per CTA) = the SM's 228 KB
       if (p.a_stage_bytes + 2 * p.b_tap_bytes <= half) { budget = half; halo_occ = 2; }
     }
+    if (wide_halo) budget = 227 * 1024 - tail_bytes;   // the whole SM: 2 halo tiles + 4 single-plane weight stages
     p.a_stages = (2 * p.a_stage_bytes + 3 * p.b_tap_bytes <= budget) ? 2 : 1;
     // Narrow tiles (N <= 64) are bound by the MMA thread's per-stage cost (barrier wait + fence + commit, ~200
     // cycles) rather than by tensor work (12 MMAs x N/2 cycles per tap): put G taps behind one barrier.
@@ -1303,11 +1615,21 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
     }
     p.b_taps_per_stage = G;
     p.b_stage_bytes = G * p.b_tap_bytes;
+    p.b_split = 0;
+    if (wide_halo) {   // B stage = one plane of one tap (32 KB): finer-grained than [hi | lo] pairs, same bytes in flight
+      p.b_split = 1;
+      p.b_taps_per_stage = 1;
+      p.b_stage_bytes = b_plane;
+      p.a_stages = (2 * p.a_stage_bytes + 4 * b_plane <= budget) ? 2 : 1;
+    }
     int nb = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
     if (nb > MAX_STAGES) nb = MAX_STAGES;
     p.b_stages = nb;
     if (nb < 2 || p.halo_w > 64 || p.halo_h > 64) halo = false;
+    if (wide_halo && (nb < 3 || p.a_stages < 2)) halo = false;
   }
+  pair = pair && halo;
+  p.pair = pair ? 1 : 0;
   const int bw_log2 = halo ? 3 : d->bw_log2;
   const int BW = 1 << bw_log2, BH = TC_M >> bw_log2;
   const int boxW = halo ? p.halo_w : BW, boxH = halo ? p.halo_h : BH;
@@ -1323,8 +1645,9 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
     if (d->passes != 1 && (rc = encode_a_map(&p.tmA_lo[v], vw.lo, vw, d->N, boxW, boxH)) != ESSB_OK) return rc;
   }
   const long long ktot = (long long)d->n_w_taps * d->k_per_tap;
-  if ((rc = encode_b_map(&p.tmB_hi, d->w_hi, ktot, d->w_rows, BN)) != ESSB_OK) return rc;
-  if (d->passes != 1 && (rc = encode_b_map(&p.tmB_lo, d->w_lo, ktot, d->w_rows, BN)) != ESSB_OK) return rc;
+  const int b_box_rows = pair ? BN / 2 : BN;
+  if ((rc = encode_b_map(&p.tmB_hi, d->w_hi, ktot, d->w_rows, b_box_rows)) != ESSB_OK) return rc;
+  if (d->passes != 1 && (rc = encode_b_map(&p.tmB_lo, d->w_lo, ktot, d->w_rows, b_box_rows)) != ESSB_OK) return rc;
 
   p.tiles_x = (d->OW + BW - 1) / BW;
   p.tiles_y = (d->OH + BH - 1) / BH;
@@ -1462,10 +1785,46 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   }
   p.n_units = p.n_whole + (p.n_items - p.n_whole) * p.split;
   cudaError_t e;
+  if (pair) {
+    const int n_pair_items = d->N * p.tiles_y * ((p.tiles_x + 1) / 2) * p.n_tiles;
+    int pairs = num_sms() / 2;
+    if (pairs > n_pair_items) pairs = n_pair_items;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(HALO_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#define ESSB_LAUNCH_PAIR(EPI)                                                                                       \
+  e = cudaFuncSetAttribute(conv_tc_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); \
+  if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<EPI>, p);
+    if (d->epilogue == ESSB_EPI_LSTM) { ESSB_LAUNCH_PAIR(ESSB_EPI_LSTM) }
+    else if (d->epilogue == ESSB_EPI_GRU_UR) { ESSB_LAUNCH_PAIR(ESSB_EPI_GRU_UR) }
+    else if (d->epilogue == ESSB_EPI_GRU_OUT) { ESSB_LAUNCH_PAIR(ESSB_EPI_GRU_OUT) }
+    else { ESSB_LAUNCH_PAIR(ESSB_EPI_LINEAR) }
+#undef ESSB_LAUNCH_PAIR
+    if (e != cudaSuccess) {
+      essb_set_error("essb_conv_tc_run: CTA-pair launch failed: %s", cudaGetErrorString(e));
+      return ESSB_ERR_LAUNCH;
+    }
+    ESSB_LAUNCH_CHECK("essb_conv_tc_run (pair)");
+    return ESSB_OK;
+  }
   if (halo) {
-#define ESSB_LAUNCH_HALO(EPI)                                                                                       \
-  e = cudaFuncSetAttribute(conv_tc_halo_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); \
-  if (e == cudaSuccess) conv_tc_halo_kernel<EPI><<<grid, HALO_THREADS, smem_bytes, st>>>(p);
+#define ESSB_LAUNCH_HALO(EPI)                                                                                            \
+  if (halo_occ == 2) {                                                                                                   \
+    e = cudaFuncSetAttribute(conv_tc_halo_kernel<EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); \
+    if (e == cudaSuccess) conv_tc_halo_kernel<EPI, 2><<<grid, HALO_THREADS, smem_bytes, st>>>(p);                        \
+  } else {                                                                                                               \
+    e = cudaFuncSetAttribute(conv_tc_halo_kernel<EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); \
+    if (e == cudaSuccess) conv_tc_halo_kernel<EPI, 1><<<grid, HALO_THREADS, smem_bytes, st>>>(p);                        \
+  }
     if (d->epilogue == ESSB_EPI_LSTM) { ESSB_LAUNCH_HALO(ESSB_EPI_LSTM) }
     else if (d->epilogue == ESSB_EPI_GRU_UR) { ESSB_LAUNCH_HALO(ESSB_EPI_GRU_UR) }
     else if (d->epilogue == ESSB_EPI_GRU_OUT) { ESSB_LAUNCH_HALO(ESSB_EPI_GRU_OUT) }

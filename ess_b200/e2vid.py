@@ -165,7 +165,7 @@ class E2VIDRecurrent(nn.Module):
 
     # ------------------------------------------------------------------------------ weight packing
     def _key(self):
-        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers())) + (self.mode,)
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers())) + (self.mode, self._enc0_hf8())
 
     def _pack(self):
         key = self._key()
@@ -216,8 +216,15 @@ class E2VIDRecurrent(nn.Module):
                     w6 = torch.zeros((cout, cin, 5, 6), device=dev)
                     w6[..., :5] = w
                     w = w6.view(cout, cin, 5, 3, 2).permute(0, 4, 1, 2, 3).reshape(cout, 2 * cin, 5, 3).contiguous()
-                hi, lo, kinp, sc = pk(w, scale)
-                e['tc'] = dict(hi=hi, lo=lo, k_per_tap=kinp, fold=fold, T=w.shape[2] * w.shape[3], sc=sc)
+                if i == 0 and hf8 and not self._enc0_hf8():
+                    # f16f8 mode, first encoder conv in bf16x3: its input planes come from the head conv, whose epilogue
+                    # is the head's bottleneck -- the cheaper bf16 hi/lo split wins there, and this N = 64 layer is bound
+                    # by the shared-memory operand feed, not by its MMA count (measured, profiles/r02_*)
+                    hi, lo, kinp = ops.pack_weight_tc(w, scale)
+                    e['tc'] = dict(hi=hi, lo=lo, k_per_tap=kinp, fold=fold, T=w.shape[2] * w.shape[3], sc=0.0, passes=3)
+                else:
+                    hi, lo, kinp, sc = pk(w, scale)
+                    e['tc'] = dict(hi=hi, lo=lo, k_per_tap=kinp, fold=fold, T=w.shape[2] * w.shape[3], sc=sc)
             rb = enc.recurrent_block
             C = cout
             if self.recurrent_block_type == 'convlstm':
@@ -283,6 +290,16 @@ class E2VIDRecurrent(nn.Module):
             return ent[1], ent[2]
         N, H, W, _ = h_nhwc.shape
         return ops.split_bf16(Seg(h_nhwc), N, H, W, fmt=self._fmt())
+
+    @staticmethod
+    def _enc0_hf8():
+        """f16f8 mode: does the first encoder conv consume hf8 planes (ESS_B200_F16F8_ENC0=hf8) or bf16 hi/lo planes
+        in three passes (default)?"""
+        return os.environ.get('ESS_B200_F16F8_ENC0', 'bf16x3') == 'hf8'
+
+    def _fmt_enc0(self):
+        """operand-plane format of the head conv's output (= the first encoder conv's input)"""
+        return ops.PLANES_HF8 if (self.mode == 'f16f8' and self._enc0_hf8()) else ops.PLANES_BF16
 
     def _fmt(self):
         """operand-plane format of the activations that travel between the tcgen05 launches of this network"""
@@ -354,7 +371,7 @@ class E2VIDRecurrent(nn.Module):
         d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = H, W, 1, 0, 1, 0
         # f16f8 mode: the head itself runs bf16x3 (its input planes are bf16 hi/lo) but emits hf8 planes for encoder 0
         d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, ACT_RELU, (3 if passes == 2 else passes), ops.pick_bw_log2(W, H)
-        d.planes_fmt = self._fmt()
+        d.planes_fmt = self._fmt_enc0()
         d.ntaps = 5
         for ky in range(5):
             d.dy[ky], d.dx[ky], d.view[ky], d.widx[ky] = ky, 0, 0, ky
@@ -387,7 +404,7 @@ class E2VIDRecurrent(nn.Module):
             head = torch.empty((N, H, W, base), device=dev, dtype=torch.float32) if (want_head or not want_planes) else None
             self._head_tc(P, in_planes, N, H, W, head, planes, passes)
         else:
-            hf8 = self._fmt() == ops.PLANES_HF8       # the fp32 kernel's epilogue only writes bf16 hi/lo planes
+            hf8 = self._fmt_enc0() == ops.PLANES_HF8  # the fp32 kernel's epilogue only writes bf16 hi/lo planes
             head, _, _, _ = ops.conv([Seg(x, C=cpad)], wh, bh, N, H, W, H, W, base, ops.taps_conv(5, 2), act=ACT_RELU,
                                      planes=None if hf8 else planes)
             if hf8 and planes is not None:
@@ -587,7 +604,8 @@ class E2VIDRecurrent(nn.Module):
         d.N, d.OH, d.OW, d.Cout = N, oh, ow, cout
         d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = oh, ow, 1, 0, 1, 0
         d.out_hi, d.out_lo, d.ld_planes = ops._p(out_hi), ops._p(out_lo), cout
-        d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, ACT_RELU, passes, ops.pick_bw_log2(ow, oh)
+        # `passes` = the mode's pass count (decides the OUTPUT plane format); a layer may consume another format (tcw['passes'])
+        d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, ACT_RELU, tcw.get('passes', passes), ops.pick_bw_log2(ow, oh)
         d.acc_scale, d.planes_fmt = tcw.get('sc', 0.0), (ops.PLANES_HF8 if passes == 2 else ops.PLANES_BF16)
         d.ntaps = len(taps)
         for t, (dy, dx, v, wi) in enumerate(taps):

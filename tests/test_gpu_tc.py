@@ -51,6 +51,16 @@ def test_split_hf8_roundtrip():
     assert float((a8 != ref8).float().mean()) < 1e-4       # same round-to-nearest-even conversion
 
 
+N256 = {'pair': ('1', '1'), 'halo': ('1', '0'), 'classic': ('0', '0')}   # (ESSB_TC_HALO256, ESSB_TC_PAIR)
+
+
+def set_n256(monkeypatch, n256):
+    """Which kernel runs the N = 256 tiles: 'pair' = CTA pairs (cta_group::2, M = 256, each CTA stages half the weight rows),
+    'halo' = single-CTA halo-reuse kernel with per-plane B stages, 'classic' = one TMA box per tap (incl. split-K tail)."""
+    monkeypatch.setenv('ESSB_TC_HALO256', N256[n256][0])
+    monkeypatch.setenv('ESSB_TC_PAIR', N256[n256][1])
+
+
 @pytest.fixture(autouse=True)
 def _splitk_on():
     """The split-K tail of the tile scheduler is opt-in (ESSB_TC_SPLITK=1); these kernel tests keep it covered."""
@@ -76,7 +86,9 @@ def test_split_bf16_roundtrip():
                                                 # (split-K path of the scheduler); 2 x 168 n-tiles, 40 tail tiles
                                                 (1, 112, 192, 64, True), (1, 112, 192, 128, True),
                                                 (2, 55, 80, 256, False)])
-def test_convlstm_tc(passes, tol, N, H, W, C, with_state):
+@pytest.mark.parametrize('n256', ['pair', 'halo', 'classic'])
+def test_convlstm_tc(passes, tol, N, H, W, C, with_state, n256, monkeypatch):
+    set_n256(monkeypatch, n256)
     import ess_b200
     from ess_b200.e2vid import _interleave
     from ess_b200 import ops
@@ -101,8 +113,12 @@ def test_convlstm_tc(passes, tol, N, H, W, C, with_state):
 
 @pytest.mark.parametrize('passes,tol', [(3, 1e-3), (2, 1e-3), (1, 3e-2)])
 @pytest.mark.parametrize('Cin,Cout,H,W', [(32, 64, 16, 32), (64, 128, 24, 16), (128, 256, 14, 22), (32, 64, 110, 160)])
-def test_encoder_conv_tc(passes, tol, Cin, Cout, H, W):
+@pytest.mark.parametrize('n256', ['pair', 'halo', 'classic'])
+def test_encoder_conv_tc(passes, tol, Cin, Cout, H, W, n256, monkeypatch):
     """conv5x5 stride 2 + folded BN + ReLU through parity views (and the 32-channel pixel-pair fold)."""
+    if n256 != 'pair' and Cout != 256:
+        pytest.skip('the N = 256 kernel choice only matters for N = 256 tiles')
+    set_n256(monkeypatch, n256)
     import ess_b200
     from ess_b200 import ops
     g = torch.Generator().manual_seed(2)
@@ -123,12 +139,13 @@ def test_encoder_conv_tc(passes, tol, Cin, Cout, H, W):
     oh, ow = H // 2, W // 2
     out_hi = torch.empty((N, oh, ow, Cout), device='cuda', dtype=torch.bfloat16)
     out_lo = torch.empty_like(out_hi)
-    xp = planes_of(x, passes)
     if passes == 2 and fold:      # 32-channel hf8 planes pair two pixels per 64-channel row (as the head conv writes them)
         t = nhwc(x)
         shp = (N, H, W // 2, 64)
         ph, pl = ops.split_bf16(ops.Seg(t.view(shp)), N, H, W // 2, fmt=ops.PLANES_HF8)
         xp = (ph.view(N, H, W, 32), pl.view(N, H, W, 32))
+    else:
+        xp = planes_of(x, passes)
     ess_b200.E2VIDRecurrent._enc_conv_tc(m, e, xp, N, H, W, Cout, out_hi, out_lo, passes)
     torch.cuda.synchronize()
     got = nchw(ops.decode_planes(out_hi, out_lo, ops.PLANES_HF8 if passes == 2 else ops.PLANES_BF16))

@@ -16,7 +16,8 @@ from ess_b200.optim import RAdam  # noqa: E402
 from helpers import make_e2vid, make_events, make_labels, make_semseg  # noqa: E402
 
 B, T, C, H, W, K = 8, 20, 5, 440, 640, 11
-e2vid = make_e2vid(mode='bf16x3').cuda()
+MODE = os.environ.get('ESS_B200_MODE', 'bf16x3')
+e2vid = make_e2vid(mode=MODE).cuda()
 dec = make_semseg(K).cuda()
 crit = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255)
 rec = ess_b200.ImageReconstructor(e2vid, H, W, C, 'cuda')
@@ -56,6 +57,7 @@ for e in ev:
     a[0] += 1
     a[1] += (t - s) / 1e3
 span = (last_end - first) / 1e3
+print('mode', MODE)
 print('one step: %d kernels, span %.2f ms, kernel time %.2f ms, idle gaps %.2f ms' % (len(ev), span, busy / 1e3, gap / 1e3))
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print('%-50s %4d %8.3f ms %5.1f%%' % (k, v[0], v[1], 100 * v[1] / span))
