@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the ESS hot path on B200 (contract: see the task statement).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--mode bf16x3|bf16|fp32]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--mode f16f8|bf16x3|bf16|fp32]
                     [--workload dsec|ddd17|uda] [--bins C] [--contract A|B] [--global-batch G]
 
 Metric (BASELINE.json): samples/s of one supervised training iteration -- frozen E2VID encoder unrolled over T
@@ -630,7 +630,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mode', default=os.environ.get('ESS_B200_MODE', 'bf16x3'), choices=['bf16x3', 'bf16', 'fp32', 'f16f8'])
+    ap.add_argument('--mode', default=os.environ.get('ESS_B200_MODE', 'f16f8'), choices=['bf16x3', 'bf16', 'fp32', 'f16f8'])
     ap.add_argument('--batch', type=int, default=WORK['B'], help='samples per GPU')
     ap.add_argument('--global-batch', type=int, default=0,
                     help='total samples over all ranks (strong scaling, BASELINE.json configs[4]: 64); overrides --batch')

@@ -33,7 +33,7 @@ MODES = ('fp32', 'bf16x3', 'bf16', 'f16f8')
 
 
 def default_mode():
-    m = os.environ.get('ESS_B200_MODE', 'bf16x3')
+    m = os.environ.get('ESS_B200_MODE', 'f16f8')
     if m not in MODES:
         raise ValueError('ESS_B200_MODE must be one of %s' % (MODES,))
     return m

@@ -16,7 +16,7 @@ from ess_b200.optim import RAdam  # noqa: E402
 from helpers import make_e2vid, make_events, make_labels, make_semseg  # noqa: E402
 
 B, T, C, H, W, K = 8, 20, 5, 440, 640, 11
-MODE = os.environ.get('ESS_B200_MODE', 'bf16x3')
+MODE = os.environ.get('ESS_B200_MODE', 'f16f8')
 e2vid = make_e2vid(mode=MODE).cuda()
 dec = make_semseg(K).cuda()
 crit = ess_b200.TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255)

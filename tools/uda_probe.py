@@ -18,7 +18,7 @@ from helpers import make_e2vid, make_events, make_labels, make_semseg  # noqa: E
 
 B = int(os.environ.get('PROBE_B', '8'))
 T, C, H, W, K = int(os.environ.get('PROBE_T', '20')), 5, 440, 640, 11
-mode = os.environ.get('ESS_B200_MODE', 'bf16x3')
+mode = os.environ.get('ESS_B200_MODE', 'f16f8')
 dev = 'cuda'
 e2vid = make_e2vid(mode=mode).to(dev)
 torch.manual_seed(3)
