@@ -131,6 +131,7 @@ SIGNATURES = {
     'essb_task_loss_bwd': (_I, [_P, _I, _P, _L, _I, _L, _P, _I, _I, _P, _P, _I, _P]),
     'essb_confusion': (_I, [_P, _I, _P, _L, _I, _L, _P, _P]),
     'essb_confusion_labels': (_I, [_P, _P, _L, _I, _L, _P, _P]),
+    'essb_bn_train_finalize': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _F, _F, _P]),
     'essb_affine_act': (_I, [_P, _I, _P, _P, _P, _I, _I, _P, _I, _L, _I, _P]),
     'essb_bn_bwd_blocks': (_I, [_L]),
     'essb_bn_bwd_pass1': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _L, _I, _P]),

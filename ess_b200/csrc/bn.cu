@@ -214,6 +214,28 @@ __global__ void __launch_bounds__(256) jsdiv_kernel(const float* __restrict__ pr
   }
 }
 
+// Train-mode BatchNorm bookkeeping in one launch (nn.BatchNorm2d forward, training=True): folded scale/shift of the
+// apply pass, and the running-statistics update with the UNBIASED batch variance (momentum form), num_batches_tracked += 1.
+__global__ void bn_train_finalize_kernel(const float* __restrict__ mean, const float* __restrict__ rstd,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float* __restrict__ a, float* __restrict__ b, float* __restrict__ running_mean,
+                                         float* __restrict__ running_var, long long* __restrict__ num_batches, int C,
+                                         float momentum, float eps, float unbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches) *num_batches += 1;
+  if (c >= C) return;
+  const float m = mean[c], r = rstd[c];
+  const float g = gamma ? gamma[c] : 1.f;
+  const float av = g * r;
+  a[c] = av;
+  b[c] = (beta ? beta[c] : 0.f) - m * av;
+  if (running_mean) {
+    const float var_b = 1.f / (r * r) - eps;
+    running_mean[c] = running_mean[c] * (1.f - momentum) + m * momentum;
+    running_var[c] = running_var[c] * (1.f - momentum) + var_b * unbias * momentum;
+  }
+}
+
 inline unsigned grid_for(long long n, int per_thread) {
   long long b = (n + 256LL * per_thread - 1) / (256LL * per_thread);
   if (b > 148 * 8) b = 148 * 8;
@@ -240,6 +262,20 @@ extern "C" int essb_affine_act(const float* x, int ld_x, const float* a, const f
   affine_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, ld_x, a, b, res, ld_res, relu,
                                                                                      out, ld_out, C, total);
   ESSB_LAUNCH_CHECK("essb_affine_act");
+  return ESSB_OK;
+}
+
+extern "C" int essb_bn_train_finalize(const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                      float* a, float* b, float* running_mean, float* running_var,
+                                      int64_t* num_batches_tracked, int C, int64_t rows, float momentum, float eps,
+                                      void* stream) {
+  ESSB_REQUIRE(mean && rstd && a && b && C > 0 && rows > 0, "essb_bn_train_finalize: bad arguments");
+  ESSB_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "essb_bn_train_finalize: running_mean / running_var must come together");
+  const float unbias = (float)((double)rows / (double)(rows > 1 ? rows - 1 : 1));
+  bn_train_finalize_kernel<<<(unsigned)((C + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      mean, rstd, gamma, beta, a, b, running_mean, running_var, reinterpret_cast<long long*>(num_batches_tracked), C,
+      momentum, eps, unbias);
+  ESSB_LAUNCH_CHECK("essb_bn_train_finalize");
   return ESSB_OK;
 }
 

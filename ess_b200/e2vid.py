@@ -32,6 +32,17 @@ BN_EPS = 1e-5
 MODES = ('fp32', 'bf16x3', 'bf16', 'f16f8')
 
 
+_WARNED = set()
+
+
+def _warn_once(msg):
+    """A configuration that leaves the tensor-core path is correct but ~10x slower: say so once per message."""
+    if msg not in _WARNED:
+        _WARNED.add(msg)
+        import warnings
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)
+
+
 def default_mode():
     m = os.environ.get('ESS_B200_MODE', 'f16f8')
     if m not in MODES:
@@ -262,11 +273,13 @@ class E2VIDRecurrent(nn.Module):
             if self.use_upsample_conv:
                 scale, bias = _bn_fold(dec.conv2d.bias, bn, None, dev)
                 P['dec%d' % i] = (ops.pack_weight(dec.conv2d.weight, scale), bias, dec.conv2d.out_channels)
+                if tc and dec.conv2d.in_channels % 64 == 0 and dec.conv2d.out_channels % 32 == 0:
+                    P['dec%d_tc' % i] = pk(dec.conv2d.weight, scale)
             else:
                 scale, bias = _bn_fold(dec.transposed_conv2d.bias, bn, None, dev)
                 P['dec%d' % i] = (ops.pack_weight(dec.transposed_conv2d.weight, scale, transposed_layout=True), bias,
                                   dec.transposed_conv2d.out_channels)
-                if tc:
+                if tc and dec.transposed_conv2d.in_channels % 64 == 0 and dec.transposed_conv2d.out_channels % 32 == 0:
                     P['dec%d_tc' % i] = pk(dec.transposed_conv2d.weight, scale, transposed_layout=True)
         scale, bias = _bn_fold(u.pred.conv2d.bias, getattr(u.pred, 'norm_layer', None), None, dev)
         P['pred'] = (ops.pack_weight(u.pred.conv2d.weight, scale), bias)
@@ -412,7 +425,7 @@ class E2VIDRecurrent(nn.Module):
                 shp = (N, H, W // g, base * g)
                 ops.split_bf16(Seg(head.view(shp)), N, H, W // g, planes[0].view(shp), planes[1].view(shp), fmt=ops.PLANES_HF8)
 
-        blocks, states = [], []
+        blocks, states, block_planes = [], [], []
         cur, cur_planes = head, planes
         new_planes = {}
         h_in, w_in = H, W
@@ -449,6 +462,10 @@ class E2VIDRecurrent(nn.Module):
             else:
                 if cur is None:
                     raise RuntimeError('internal: fp32 activation missing')
+                if tc_mode:
+                    _warn_once('E2VIDRecurrent(mode=%r): encoder level %d (%d -> %d channels) runs on the fp32 CUDA-core '
+                               'kernels (~10x slower; the tensor-core path needs base_num_channels %% 32 == 0 and '
+                               'num_bins <= 16)' % (self.mode, i, cin, cout))
                 xi, _, _, _ = ops.conv([Seg(cur)], e['w'], e['bias'], N, h_in, w_in, oh, ow, cout, ops.taps_conv(5, 2),
                                        stride=2, act=ACT_RELU)
                 t3 = ops.taps_conv(3, 1)
@@ -471,6 +488,8 @@ class E2VIDRecurrent(nn.Module):
                     state = ops.as_nchw(h)
                 cur, cur_planes = h, None
             blocks.append(cur)
+            if cur_planes is not None:
+                block_planes.append(cur_planes)
             states.append(state)
             h_in, w_in = oh, ow
         self._planes = new_planes
@@ -480,29 +499,37 @@ class E2VIDRecurrent(nn.Module):
         if not with_image:
             return None, states, latent
         cmax = base * 2 ** ne
-        if tc_mode and cur_planes is not None and self.skip_type == 'sum' and not self.use_upsample_conv \
-                and base % 32 == 0 and cmax <= 256 * 4 and base * 2 % 64 == 0:
-            img = self._image_decoder_tc(P, head, blocks, cur_planes, N, h_in, w_in, passes)
+        if tc_mode and len(block_planes) == ne and base % 32 == 0 and cmax <= 256 * 4 and base * 2 % 64 == 0 \
+                and all('dec%d_tc' % i in P for i in range(ne)):
+            img = self._image_decoder_tc(P, head, blocks, block_planes, N, h_in, w_in, passes)
         else:
+            if tc_mode:
+                _warn_once('E2VIDRecurrent(mode=%r): this configuration (base_num_channels=%d) runs its image decoder on '
+                           'the fp32 CUDA-core kernels (~10x slower than the tensor-core path; channel counts must be '
+                           'multiples of 32 with 64-wide decoder inputs)' % (self.mode, base))
             img = self._image_decoder(P, head, blocks, N, h_in, w_in)
         return ops.as_nchw(img), states, latent
 
     # --------------------------------------------------------- image decoder on the tcgen05 kernel
-    def _image_decoder_tc(self, P, head, blocks, planes, N, h, w, passes):
-        """2 ResidualBlocks + 3 TransposedConvLayers (4 sub-pixel phases each, strided epilogue stores) on the
-        tensor-core kernel; activations travel between layers as bf16 hi/lo planes written by the epilogues;
-        the skip sums (unet.py:175,179) are epilogue adds.  The 1x1 prediction conv stays on the fp32 kernel."""
+    def _image_decoder_tc(self, P, head, blocks, block_planes, N, h, w, passes):
+        """2 ResidualBlocks + 3 up-sampling layers on the tensor-core kernel; activations travel between layers as
+        operand planes written by the epilogues.  TransposedConvLayer (submodules.py:34-62) = 4 sub-pixel phases with
+        strided epilogue stores; UpsampleConvLayer (submodules.py:65-93) = bilinear x2 (HBM-bound kernel) -> planes ->
+        25-tap conv.  skip_type 'sum' (unet.py:175,179): epilogue adds; 'concat': the skip tensor's planes are a second
+        K segment of the same launch (no torch.cat).  The 1x1 prediction conv stays on the streaming / fp32 kernel."""
         ne, base = self.num_encoders, self.base_num_channels
         cmax = base * 2 ** ne
-        dev = head.device
+        dev = blocks[-1].device
         t3 = ops.taps_conv(3, 1)
         fmt = self._fmt()
+        concat = self.skip_type != 'sum'
+        up = self.use_upsample_conv
 
         def new_planes(hh, ww, c):
             return (torch.empty((N, hh, ww, c), device=dev, dtype=torch.bfloat16),
                     torch.empty((N, hh, ww, c), device=dev, dtype=torch.bfloat16))
 
-        x, xp = blocks[-1], planes
+        x, xp = blocks[-1], block_planes[-1]
         nres = self.num_residual_blocks
         for j in range(nres):
             hi1, lo1, k1, sc1, hi2, lo2, k2, sc2 = P['res%d_tc' % j]
@@ -510,7 +537,7 @@ class E2VIDRecurrent(nn.Module):
             tp = new_planes(h, w, cmax)
             ops.conv_tc_dense(xp, hi1, lo1, k1, t3, N, h, w, cmax, passes, bias=b1, act=ACT_RELU, want_out=False,
                               out_planes=tp, tag='img_tc', acc_scale=sc1, planes_fmt=fmt)
-            post = blocks[ne - 1] if j == nres - 1 else None
+            post = blocks[ne - 1] if (j == nres - 1 and not concat) else None
             np_ = new_planes(h, w, cmax)
             x = ops.conv_tc_dense(tp, hi2, lo2, k2, t3, N, h, w, cmax, passes, bias=b2, act=ACT_RELU, res_pre=x,
                                   res_post=post, out_planes=np_, tag='img_tc', acc_scale=sc2, planes_fmt=fmt)
@@ -519,19 +546,29 @@ class E2VIDRecurrent(nn.Module):
             hi, lo, k, sc = P['dec%d_tc' % i]
             bd, cout = P['dec%d' % i][1], P['dec%d' % i][2]
             skip_next = blocks[ne - i - 2] if i < ne - 1 else head
-            out = torch.empty((N, 2 * h, 2 * w, cout), device=dev, dtype=torch.float32)
-            op = new_planes(2 * h, 2 * w, cout) if i < ne - 1 else None
-            for py in range(2):
-                for px in range(2):
-                    ops.conv_tc_dense(xp, hi, lo, k, ops.taps_convT_phase(py, px), N, h, w, cout, passes, bias=bd,
-                                      act=ACT_RELU, out=out, out_place=(2 * h, 2 * w, 2, py, 2, px), res_post=skip_next,
-                                      out_planes=op, tag='img_tc', acc_scale=sc, planes_fmt=fmt)
-            x, xp = out, op
+            post = None if concat else skip_next
+            if up:
+                srcs = [x] + ([blocks[ne - i - 1]] if concat else [])
+                segs = [ops.split_bf16(Seg(ops.bilinear_up2(s_)), N, 2 * h, 2 * w, fmt=fmt) for s_ in srcs]
+                x = ops.conv_tc_dense(segs, hi, lo, k, ops.taps_conv(5, 2), N, 2 * h, 2 * w, cout, passes, bias=bd,
+                                      act=ACT_RELU, res_post=post, tag='img_tc', acc_scale=sc, planes_fmt=fmt)
+                xp = None
+            else:
+                segs = [xp] + ([block_planes[ne - i - 1]] if concat else [])
+                out = torch.empty((N, 2 * h, 2 * w, cout), device=dev, dtype=torch.float32)
+                op = new_planes(2 * h, 2 * w, cout) if i < ne - 1 else None
+                for py in range(2):
+                    for px in range(2):
+                        ops.conv_tc_dense(segs, hi, lo, k, ops.taps_convT_phase(py, px), N, h, w, cout, passes, bias=bd,
+                                          act=ACT_RELU, out=out, out_place=(2 * h, 2 * w, 2, py, 2, px), res_post=post,
+                                          out_planes=op, tag='img_tc', acc_scale=sc, planes_fmt=fmt)
+                x, xp = out, op
             h, w = 2 * h, 2 * w
         wp, bp = P['pred']
-        if P['pred_pw'] is not None and x.shape[-1] == P['pred_pw'].shape[1]:
+        if not concat and P['pred_pw'] is not None and x.shape[-1] == P['pred_pw'].shape[1]:
             return ops.pw_conv_fwd(Seg(x), P['pred_pw'], bp, N, h, w, 1, act=ACT_SIGMOID)                  # unet.py:179
-        img, _, _, _ = ops.conv([Seg(x)], wp, bp, N, h, w, h, w, 1, ops.taps_conv(1, 0), act=ACT_SIGMOID)  # unet.py:179
+        segs = [Seg(x)] + ([Seg(head)] if concat else [])
+        img, _, _, _ = ops.conv(segs, wp, bp, N, h, w, h, w, 1, ops.taps_conv(1, 0), act=ACT_SIGMOID)      # unet.py:179
         return img
 
     # ----------------------------------------------------------------- image decoder (fp32 kernels)

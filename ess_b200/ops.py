@@ -498,16 +498,22 @@ def in_stats(y, count=None):
 def conv_tc_dense(planes, w_hi, w_lo, k_per_tap, taps, N, H, W, Cout, passes, bias=None, out=None, act=ACT_NONE,
                   tag=None, res_pre=None, res_post=None, out_planes=None, want_out=True, out_place=None, acc_scale=0.0,
                   planes_fmt=PLANES_BF16):
-    """Stride-1 gather-convolution on the tcgen05 kernel over ONE dense bf16 hi/lo plane pair
-    [N, H, W, Cin] (Cin a multiple of 64; concatenated inputs are laid out side by side by
-    split_bf16(c_off=...)).  Returns the fp32 result [N, H, W, Cout] (None when want_out=False and
+    """Stride-1 gather-convolution on the tcgen05 kernel over a dense operand plane pair [N, H, W, Cin] (Cin a
+    multiple of 64), or over a LIST of two such pairs = the channel concatenation of two tensors (each a
+    multiple of 64 channels; alternatively concatenated inputs are laid out side by side by split_bf16(c_off=...)).  Returns the fp32 result [N, H, W, Cout] (None when want_out=False and
     only the bf16 `out_planes` are produced).  out_place = (OHf, OWf, osy, ooy, osx, oox) scatters the
     result into a larger image (transposed-conv phases)."""
-    hi, lo = planes
+    segs = list(planes) if isinstance(planes, list) else [planes]
+    if not 1 <= len(segs) <= 2:
+        raise ValueError('conv_tc_dense: one or two channel segments')
+    hi, lo = segs[0]
     d = ConvTc()
-    dense_view(d.views[0], hi, lo)
-    d.n_views, d.nseg = 1, 1
-    d.seg_C[0], d.seg_view0[0], d.seg_koff[0] = hi.shape[-1], 0, 0
+    koff = 0
+    for s, (shi, slo) in enumerate(segs):       # concatenated inputs (torch.cat on dim 1) = K segments, no copy
+        dense_view(d.views[s], shi, slo)
+        d.seg_C[s], d.seg_view0[s], d.seg_koff[s] = shi.shape[-1], s, koff
+        koff += shi.shape[-1]
+    d.n_views = d.nseg = len(segs)
     d.k_per_tap, d.n_w_taps, d.w_rows = k_per_tap, w_hi.shape[1] // k_per_tap, w_hi.shape[0]
     d.w_hi, d.w_lo, d.bias = _p(w_hi), _p(w_lo), _p(bias)
     if out_place is None:
@@ -579,6 +585,28 @@ def dgrad_phase_taps(k, pad, stride):
                     taps.append(((py + pad - ky) // stride, (px + pad - kx) // stride, ky * k + kx))
             out[(py, px)] = taps
     return out
+
+
+def bn_train_finalize(mean, rstd, gamma, beta, rows, bn, momentum, eps):
+    """(a, b) of the BN apply pass; updates bn.running_mean / running_var / num_batches_tracked in place when `bn`
+    (an nn.BatchNorm2d with fp32 running statistics on this device) is given.  One launch (essb_bn_train_finalize)."""
+    Cc = mean.numel()
+    a = torch.empty((Cc,), device=mean.device, dtype=torch.float32)
+    b = torch.empty_like(a)
+    rm = rv = nb = None
+    if bn is not None:
+        rm, rv, nb = bn.running_mean, bn.running_var, bn.num_batches_tracked
+        if rm.dtype != torch.float32 or rv.dtype != torch.float32 or rm.device != mean.device or not rm.is_contiguous() \
+                or not rv.is_contiguous():
+            raise RuntimeError('bn_train_finalize: running statistics must be contiguous fp32 on the activation\'s device')
+        if nb is not None and (nb.dtype != torch.int64 or nb.device != mean.device):
+            nb += 1           # exotic placement: keep torch semantics
+            nb = None
+    call('essb_bn_train_finalize', _p(mean), _p(rstd), _p(gamma), _p(beta), _p(a), _p(b), _p(rm), _p(rv), _p(nb), Cc,
+         int(rows), float(momentum), float(eps), _stream())
+    if bn is not None:        # raw-pointer writes: keep autograd's / state_dict consumers' version counters honest
+        torch._C._increment_version([t for t in (rm, rv, nb) if t is not None])
+    return a, b
 
 
 def affine_act(x, a, b, res=None, relu=False, out=None):

@@ -116,19 +116,14 @@ class _BNFn(torch.autograd.Function):
         N, H, W, Cc = x.shape
         rows = N * H * W
         mean, rstd = ops.in_stats(x.view(1, 1, rows, Cc))          # biased variance, eps inside the sqrt
-        mean, rstd = mean.view(-1), rstd.view(-1)
-        if bn is not None and bn.track_running_stats:              # nn.BatchNorm2d running statistics update
-            with torch.no_grad():
-                var_b = 1.0 / (rstd * rstd) - BN_EPS
-                var_u = var_b * (rows / max(rows - 1, 1))
-                bn.running_mean.mul_(1 - BN_MOMENTUM).add_(mean, alpha=BN_MOMENTUM)
-                bn.running_var.mul_(1 - BN_MOMENTUM).add_(var_u, alpha=BN_MOMENTUM)
-                bn.num_batches_tracked += 1
-        g = gamma.detach().float()
-        a = (g * rstd).contiguous()
-        b = (beta.detach().float() - mean * a).contiguous()
+        mean, rstd = mean.view(-1).contiguous(), rstd.view(-1).contiguous()
+        g = gamma.detach().float().contiguous()
+        # folded scale/shift + nn.BatchNorm2d running-statistics update (unbiased variance, momentum form) +
+        # num_batches_tracked: ONE launch (was ~12 ATen launches per BatchNorm layer)
+        a, b = ops.bn_train_finalize(mean, rstd, g, beta.detach().float().contiguous(), rows,
+                                     bn if (bn is not None and bn.track_running_stats) else None, BN_MOMENTUM, BN_EPS)
         out = ops.affine_act(x, a, b, res=res, relu=relu)
-        ctx.save_for_backward(x, mean, rstd, g.contiguous(), out if relu else None)
+        ctx.save_for_backward(x, mean, rstd, g, out if relu else None)
         ctx.has_res = res is not None
         return out
 

@@ -257,6 +257,13 @@ int essb_confusion_labels(const int64_t* pred, const int64_t* target, int64_t np
 /* out = relu?(x * a[c] + b[c] + res)   (BN apply with folded gamma/beta, BasicBlock residual add) */
 int essb_affine_act(const float* x, int ld_x, const float* a, const float* b, const float* res, int ld_res,
                     int relu, float* out, int ld_out, int64_t rows, int C, void* stream);
+/* Train-mode nn.BatchNorm2d bookkeeping in one launch (torchvision resnet18 layers of StyleEncoderE2VID,
+ * models/style_networks.py:117-121 in .train()): a = gamma*rstd, b = beta - mean*a for essb_affine_act, and (when
+ * running_mean != NULL) running_* = (1-momentum)*running_* + momentum*{mean, unbiased batch variance},
+ * *num_batches_tracked += 1 (NULL = skip).  rows = N*H*W. */
+int essb_bn_train_finalize(const float* mean, const float* rstd, const float* gamma, const float* beta, float* a,
+                           float* b, float* running_mean, float* running_var, int64_t* num_batches_tracked, int C,
+                           int64_t rows, float momentum, float eps, void* stream);
 int essb_bn_bwd_blocks(int64_t rows);
 /* g = dout * (mask > 0) (mask = the block's post-ReLU output, or NULL); partial [blocks][C][2] = sums of
  * g and g*xhat per block.  dbeta = sum g, dgamma = sum g*xhat after essb_partial_reduce. */

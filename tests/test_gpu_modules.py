@@ -128,6 +128,49 @@ def test_e2vid_variants_fp32(variant):
     assert rel_err(img, img_r) < TOL and rel_err(lat[8], lat_r[8]) < TOL and rel_err(lat[1], lat_r[1]) < TOL
 
 
+@pytest.mark.parametrize('mode', ['bf16x3', 'f16f8'])
+@pytest.mark.parametrize('variant', ['upsample_conv', 'concat', 'upsample_concat', 'convgru_concat'])
+def test_e2vid_variants_tensor_core(variant, mode):
+    """UpsampleConvLayer (submodules.py:65-93: bilinear x2 + conv5x5) and skip_type='concat' (unet.py:175-179) image
+    decoders on the tcgen05 path (the concatenated skip tensor is a second K segment of the launch), at tensor-core
+    widths, vs the oracle: image and latents within 1e-3.  No fallback warning may fire."""
+    import warnings
+    import ess_b200
+    cfg = dict(E2VID_CFG)
+    if 'upsample' in variant:
+        cfg['use_upsample_conv'] = True
+    if 'concat' in variant:
+        cfg['skip_type'] = 'concat'
+    if 'convgru' in variant:
+        cfg['recurrent_block_type'] = 'convgru'
+    H, W = 48, 64
+    m = make_e2vid(cfg, mode=mode)
+    sd = sd_cpu(m)
+    data = make_events(2, 2, 5, H, W)
+    img_r, st_r, lat_r = O.encoder_unroll(sd, cfg, data, 2, 5)
+    m = m.cuda()
+    rec = ess_b200.ImageReconstructor(m, H, W, 5, 'cuda')
+    with warnings.catch_warnings():
+        warnings.simplefilter('error', RuntimeWarning)
+        img, st, lat = rec.unroll(data.cuda(), 2, 5)
+    assert img.shape == img_r.shape
+    errs = dict(img=rel_err(img, img_r), l8=rel_err(lat[8], lat_r[8]), l1=rel_err(lat[1], lat_r[1]))
+    print(variant, mode, {k: '%.1e' % v for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+
+
+def test_fallback_to_cuda_core_path_warns():
+    """A configuration outside the tensor-core path (base_num_channels = 8) still computes on the fp32 kernels, but says so."""
+    import ess_b200
+    cfg = dict(E2VID_CFG, base_num_channels=8, num_bins=3)
+    m = make_e2vid(cfg, mode='bf16x3').cuda()
+    rec = ess_b200.ImageReconstructor(m, 32, 40, 3, 'cuda')
+    from ess_b200 import e2vid as E
+    E._WARNED.clear()
+    with pytest.warns(RuntimeWarning, match='CUDA-core'):
+        rec.unroll(make_events(1, 1, 3, 32, 40).cuda(), 1, 3)
+
+
 def _oracle_semseg_grads(dec, lat, labels, K, want_inputs=False, dtype=torch.float32, **kw):
     params = {k: v.detach().cpu().to(dtype).clone().requires_grad_(True) for k, v in dec.state_dict().items()}
     lat_c = {k: v.detach().cpu().to(dtype).clone().requires_grad_(want_inputs) for k, v in lat.items()}
