@@ -68,7 +68,8 @@ class ConvTc(C.Structure):
                 ('epilogue', C.c_int32), ('act', C.c_int32), ('passes', C.c_int32), ('bw_log2', C.c_int32),
                 ('ntaps', C.c_int32),
                 ('dy', C.c_int8 * MAX_TAPS), ('dx', C.c_int8 * MAX_TAPS), ('view', C.c_int8 * MAX_TAPS),
-                ('widx', C.c_int8 * MAX_TAPS), ('acc_scale', C.c_float), ('planes_fmt', C.c_int32)]
+                ('widx', C.c_int8 * MAX_TAPS), ('acc_scale', C.c_float), ('planes_fmt', C.c_int32),
+                ('row_period', C.c_int32), ('rows_valid', C.c_int32)]
 
 
 class WgradTc(C.Structure):

@@ -88,6 +88,7 @@ struct TcParams {
   int b_split;                           // wide halo tiles (BN = 256): a B stage is ONE plane of one tap (hi and lo planes behind separate barriers)
   float acc_scale;                       // the epilogue multiplies the raw accumulator by this (f16f8 mode: 2^-(w8+14))
   int planes_fmt;                        // format of out_hi/out_lo: 0 = bf16 hi/lo, 2 = hf8 (tc_ptx.cuh)
+  int row_period, rows_valid;            // row-stacked batch (essb_conv_tc): rows with oy % row_period >= rows_valid are not stored
   int* sched;                            // [0] next unit, [1] CTAs done; zero before the launch, reset by the last CTA
   int n_units, n_whole, split;           // units [0, n_whole) are whole tiles; the rest are 1/split K-slices of the tail tiles
   float* splitk_ws;                      // [tail tile][part][32-col chunk][128 rows][32] fp32 partial accumulators
@@ -429,7 +430,7 @@ __device__ __forceinline__ void tc_epilogue_item(const TcParams& p, uint32_t tme
   const int n = mt / p.tiles_y;
   const int m = q * 32 + lane;
   const int oy = tyi * BH + (m >> p.bw_log2), ox = txi * BW + (m & (BW - 1));
-  const bool valid = oy < p.OH && ox < p.OW;
+  const bool valid = oy < p.OH && ox < p.OW && (p.row_period == 0 || (oy % p.row_period) < p.rows_valid);
   const int n0 = nt * p.BN;
   const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
   const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.tmem_buf_stride);
@@ -1745,6 +1746,10 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   p.fuse_b = (halo && halo_fuse) ? 1 : 0;
   p.acc_scale = d->acc_scale != 0.f ? d->acc_scale : 1.f;
   p.planes_fmt = d->planes_fmt;
+  ESSB_REQUIRE(d->row_period == 0 || (d->row_period > 0 && d->rows_valid > 0 && d->rows_valid <= d->row_period),
+               "essb_conv_tc_run: bad row_period / rows_valid (%d / %d)", d->row_period, d->rows_valid);
+  p.row_period = d->row_period;
+  p.rows_valid = d->rows_valid;
   if (halo && halo_occ == 2) {
     const int stride = BN * (halo_fuse ? 2 : 1);
     int cols = 32;

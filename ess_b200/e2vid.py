@@ -290,6 +290,48 @@ class E2VIDRecurrent(nn.Module):
         self._packed, self._packed_key = P, key
         return P
 
+    # ------------------------------------------------------------------------------ row-stacked levels
+    @staticmethod
+    def _stack_plan(N, H, W, ne):
+        """Per encoder level i (output oh x ow): rows per image `hp` of the level's buffers (hp > oh = row-stacked, see
+        essb_conv_tc.row_period) and whether the level's stride-2 conv runs on the tall view as well.  The tensor-core
+        kernels tile the output in 16-row patches PER IMAGE: a 55-row map (DSEC at 1/8 scale) pads to 64 rows (14 %), a
+        25-row map (DDD17) to 32.  Stacking the batch vertically with shared zero rows between the images (8 x 56 = 448 =
+        28 patches instead of 32) removes the rounding; the zero rows are the convolution's padding for both neighbours.
+        A level is stacked when that saves patches for its ConvLSTM, or lets the NEXT level's conv run tall
+        (its input period must be exactly twice its output period).  ESS_B200_STACK=0 disables it."""
+        if os.environ.get('ESS_B200_STACK', '1') == '0' or N < 2:
+            return [(H >> (i + 1), False) for i in range(ne)]
+        ohs = [H >> (i + 1) for i in range(ne)]
+        hp_last = ohs[-1] + 1
+        hps = [hp_last << (ne - 1 - i) for i in range(ne)]
+
+        def saves(i):
+            return -(-N * hps[i] // 16) < N * -(-ohs[i] // 16)
+        plan = []
+        for i in range(ne):
+            own = saves(i)
+            for_next = i + 1 < ne and saves(i + 1)
+            plan.append(hps[i] if (own or for_next) else ohs[i])
+        out = []
+        for i in range(ne):
+            stacked = plan[i] > ohs[i]
+            tall_conv = stacked and i > 0 and plan[i - 1] == 2 * plan[i] and plan[i - 1] > ohs[i - 1] and saves(i)
+            out.append((plan[i], tall_conv))
+        return out
+
+    def _zero_planes(self, key, shape, device, avoid=None):
+        """Persistent zero-initialised operand-plane pair (hi, lo) for a row-stacked level: its zero rows are never
+        written (masked stores), so it is cleared once.  Two alternating pairs per key; `avoid` = data_ptr of the pair
+        being READ by the launch that will write the returned one (the previous hidden state)."""
+        cache = self.__dict__.setdefault('_stack_bufs', {})
+        k = (key, tuple(shape), str(device))
+        ent = cache.get(k)
+        if ent is None:
+            ent = [tuple(torch.zeros(shape, device=device, dtype=torch.bfloat16) for _ in range(2)) for _ in range(2)]
+            cache[k] = ent
+        return ent[1] if ent[0][0].data_ptr() == avoid else ent[0]
+
     # --------------------------------------------------------------------------------- state helpers
     @staticmethod
     def _to_nhwc(t):
@@ -298,8 +340,8 @@ class E2VIDRecurrent(nn.Module):
 
     def _hidden_planes(self, h_nhwc):
         ent = self._planes.get(h_nhwc.data_ptr())
-        if ent is not None and ent[0].data_ptr() == h_nhwc.data_ptr() and ent[0]._version == ent[3] \
-                and ent[0].shape == h_nhwc.shape:
+        if ent is not None and len(ent) == 4 and ent[0].data_ptr() == h_nhwc.data_ptr() and ent[0]._version == ent[3] \
+                and ent[0].shape == h_nhwc.shape and h_nhwc.is_contiguous():
             return ent[1], ent[2]
         N, H, W, _ = h_nhwc.shape
         return ops.split_bf16(Seg(h_nhwc), N, H, W, fmt=self._fmt())
@@ -426,6 +468,8 @@ class E2VIDRecurrent(nn.Module):
                 ops.split_bf16(Seg(head.view(shp)), N, H, W // g, planes[0].view(shp), planes[1].view(shp), fmt=ops.PLANES_HF8)
 
         blocks, states, block_planes = [], [], []
+        plan = self._stack_plan(N, H, W, ne) if (tc_mode and lstm) else [(H >> (i + 1), False) for i in range(ne)]
+        prev_rows = H
         cur, cur_planes = head, planes
         new_planes = {}
         h_in, w_in = H, W
@@ -446,6 +490,33 @@ class E2VIDRecurrent(nn.Module):
                 new_planes[h.data_ptr()] = (h, hh, hl, h._version)
                 cur, cur_planes = h, (hh, hl)
                 state = ops.as_nchw(h)
+            elif use_tc and plan[i][0] > oh:
+                # row-stacked level (see _stack_plan): buffers [N, rows, ow, C] with rows - oh zero rows per image
+                rows, tall_conv = plan[i]
+                xh, xl = self._zero_planes(('x', i), (N, rows, ow, cout), dev)
+                self._enc_conv_tc(e, cur_planes, N, h_in, w_in, cout, xh, xl, passes, rows_out=rows,
+                                  tall=(prev_rows if tall_conv else 0))
+                h_full = c_full = hp_planes = None
+                if st is not None:
+                    ent = self._planes.get(st[0].data_ptr())
+                    if ent is not None and len(ent) == 6 and ent[5] == rows and ent[0]._version == ent[3] \
+                            and tuple(st[0].shape) == (N, cout, oh, ow) and st[1].data_ptr() == ent[4].data_ptr():
+                        hp_planes, c_full = (ent[1], ent[2]), ent[4]          # our own previous output: already stacked
+                    else:                                                      # foreign states: stack them once
+                        h_full = torch.zeros((N, rows, ow, cout), device=dev, dtype=torch.float32)
+                        c_full = torch.zeros_like(h_full)
+                        h_full[:, :oh] = self._to_nhwc(st[0])
+                        c_full[:, :oh] = self._to_nhwc(st[1])
+                        hp_planes = ops.split_bf16(Seg(h_full.view(1, N * rows, ow, cout)), 1, N * rows, ow, fmt=self._fmt())
+                        hp_planes = tuple(t.view(N, rows, ow, cout) for t in hp_planes)
+                out_planes = self._zero_planes(('h', i), (N, rows, ow, cout), dev,
+                                               avoid=hp_planes[0].data_ptr() if hp_planes is not None else None)
+                h_full, c_full, hh, hl = self._lstm_tc(e, (xh, xl), hp_planes, c_full, N, oh, ow, cout, passes,
+                                                       rows=rows, out_planes=out_planes)
+                h, c = h_full[:, :oh], c_full[:, :oh]
+                new_planes[h.data_ptr()] = (h, hh, hl, h_full._version, c_full, rows)
+                cur, cur_planes = h, (hh[:, :oh], hl[:, :oh])
+                state = (ops.as_nchw(h), ops.as_nchw(c))
             elif use_tc:
                 xh = torch.empty((N, oh, ow, cout), device=dev, dtype=torch.bfloat16)
                 xl = torch.empty_like(xh)
@@ -462,6 +533,8 @@ class E2VIDRecurrent(nn.Module):
             else:
                 if cur is None:
                     raise RuntimeError('internal: fp32 activation missing')
+                if not cur.is_contiguous():
+                    cur = cur.contiguous()
                 if tc_mode:
                     _warn_once('E2VIDRecurrent(mode=%r): encoder level %d (%d -> %d channels) runs on the fp32 CUDA-core '
                                'kernels (~10x slower; the tensor-core path needs base_num_channels %% 32 == 0 and '
@@ -491,6 +564,7 @@ class E2VIDRecurrent(nn.Module):
             if cur_planes is not None:
                 block_planes.append(cur_planes)
             states.append(state)
+            prev_rows = plan[i][0] if (use_tc and lstm) else oh
             h_in, w_in = oh, ow
         self._planes = new_planes
 
@@ -529,6 +603,7 @@ class E2VIDRecurrent(nn.Module):
             return (torch.empty((N, hh, ww, c), device=dev, dtype=torch.bfloat16),
                     torch.empty((N, hh, ww, c), device=dev, dtype=torch.bfloat16))
 
+        blocks = [b if b.is_contiguous() else b.contiguous() for b in blocks]   # residual / skip sources must be dense
         x, xp = blocks[-1], block_planes[-1]
         nres = self.num_residual_blocks
         for j in range(nres):
@@ -577,6 +652,7 @@ class E2VIDRecurrent(nn.Module):
         concat = self.skip_type != 'sum'
         base = self.base_num_channels
         cmax = base * 2 ** ne
+        blocks = [b if b.is_contiguous() else b.contiguous() for b in blocks]
         x = blocks[-1]
         t3 = ops.taps_conv(3, 1)
         nres = self.num_residual_blocks
@@ -610,12 +686,20 @@ class E2VIDRecurrent(nn.Module):
         return img
 
     # -------------------------------------------------------------------------- tcgen05 launches
-    def _enc_conv_tc(self, e, in_planes, N, h_in, w_in, cout, out_hi, out_lo, passes):
-        """conv5x5 stride 2 pad 2 + folded BN + ReLU (submodules.py:107,111) through parity views."""
+    def _enc_conv_tc(self, e, in_planes, N, h_in, w_in, cout, out_hi, out_lo, passes, rows_out=None, tall=0):
+        """conv5x5 stride 2 pad 2 + folded BN + ReLU (submodules.py:107,111) through parity views.
+        rows_out: rows per image of the output planes (row-stacked level; default dense).  tall = rows per image of the
+        INPUT buffer (= 2 * rows_out): run on the tall view of both (one image of N * rows rows, masked zero rows)."""
         tcw = e['tc']
         hi, lo = in_planes
         d = ConvTc()
         oh, ow = h_in // 2, w_in // 2
+        rows_out = rows_out or oh
+        if tall:
+            # in_planes are [:, :h_in] slices of [N, tall, w_in, C] buffers whose extra rows are zero
+            assert tall == 2 * rows_out and hi.stride(0) == tall * w_in * hi.shape[-1]
+            hi = hi.as_strided((1, N * tall, w_in, hi.shape[-1]), (N * hi.stride(0), hi.stride(1), hi.stride(2), 1))
+            lo = lo.as_strided((1, N * tall, w_in, lo.shape[-1]), (N * lo.stride(0), lo.stride(1), lo.stride(2), 1))
         taps = []
         if tcw['fold']:
             for py in range(2):
@@ -638,11 +722,16 @@ class E2VIDRecurrent(nn.Module):
         d.seg_C[0], d.seg_view0[0], d.seg_koff[0] = cin_eff, 0, 0
         d.k_per_tap, d.n_w_taps, d.w_rows = tcw['k_per_tap'], tcw['T'], tcw['hi'].shape[0]
         d.w_hi, d.w_lo, d.bias = ops._p(tcw['hi']), ops._p(tcw['lo']), ops._p(e['bias'])
-        d.N, d.OH, d.OW, d.Cout = N, oh, ow, cout
-        d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = oh, ow, 1, 0, 1, 0
+        if tall:
+            d.N, d.OH, d.OW, d.Cout = 1, N * rows_out, ow, cout
+            d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = N * rows_out, ow, 1, 0, 1, 0
+            d.row_period, d.rows_valid = rows_out, oh
+        else:
+            d.N, d.OH, d.OW, d.Cout = N, oh, ow, cout
+            d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = rows_out, ow, 1, 0, 1, 0
         d.out_hi, d.out_lo, d.ld_planes = ops._p(out_hi), ops._p(out_lo), cout
         # `passes` = the mode's pass count (decides the OUTPUT plane format); a layer may consume another format (tcw['passes'])
-        d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, ACT_RELU, tcw.get('passes', passes), ops.pick_bw_log2(ow, oh)
+        d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, ACT_RELU, tcw.get('passes', passes), ops.pick_bw_log2(ow, d.OH)
         d.acc_scale, d.planes_fmt = tcw.get('sc', 0.0), (ops.PLANES_HF8 if passes == 2 else ops.PLANES_BF16)
         d.ntaps = len(taps)
         for t, (dy, dx, v, wi) in enumerate(taps):
@@ -695,10 +784,20 @@ class E2VIDRecurrent(nn.Module):
         ops.conv_tc(d, tag='gru_tc', device=dev)
         return h, hh, hl
 
-    def _lstm_tc(self, e, x_planes, h_planes, c_prev, N, oh, ow, C, passes):
-        """Fused ConvLSTM cell (submodules.py:190-230): gates GEMM + sigma/tanh + state update."""
+    def _lstm_tc(self, e, x_planes, h_planes, c_prev, N, oh, ow, C, passes, rows=None, out_planes=None):
+        """Fused ConvLSTM cell (submodules.py:190-230): gates GEMM + sigma/tanh + state update.
+        rows > oh: row-stacked level -- every tensor is a full [N, rows, ow, C] buffer (zero rows in the planes) and the
+        launch sees ONE image of N * rows rows; h / c come back as full buffers too (rows >= oh of an image unwritten)."""
         tcw = e['lstm_tc']
         d = ConvTc()
+        n_img, img_rows = N, oh
+        if rows is not None and rows > oh:
+            tall = lambda t: t.view(1, N * rows, ow, t.shape[-1])
+            x_planes = (tall(x_planes[0]), tall(x_planes[1]))
+            if h_planes is not None:
+                h_planes = (tall(h_planes[0]), tall(h_planes[1]))
+            d.row_period, d.rows_valid = rows, oh
+            N, oh = 1, N * rows
         ops.dense_view(d.views[0], x_planes[0], x_planes[1])
         d.n_views, d.nseg = 1, 1
         d.seg_C[0], d.seg_view0[0], d.seg_koff[0] = C, 0, 0
@@ -709,10 +808,14 @@ class E2VIDRecurrent(nn.Module):
         d.k_per_tap, d.n_w_taps, d.w_rows = tcw['k_per_tap'], 9, tcw['hi'].shape[0]
         d.w_hi, d.w_lo, d.bias = ops._p(tcw['hi']), ops._p(tcw['lo']), ops._p(e['lstm_b'])
         dev = x_planes[0].device
-        h = torch.empty((N, oh, ow, C), device=dev, dtype=torch.float32)
+        full = (n_img, rows, ow, C) if d.row_period else (N, oh, ow, C)
+        h = torch.empty(full, device=dev, dtype=torch.float32)
         c = torch.empty_like(h)
-        hh = torch.empty((N, oh, ow, C), device=dev, dtype=torch.bfloat16)
-        hl = torch.empty_like(hh)
+        if out_planes is not None:
+            hh, hl = out_planes
+        else:
+            hh = torch.empty(full, device=dev, dtype=torch.bfloat16)
+            hl = torch.empty_like(hh)
         d.aux0, d.out, d.out2 = ops._p(c_prev), ops._p(h), ops._p(c)
         d.out_hi, d.out_lo, d.ld_planes = ops._p(hh), ops._p(hl), C
         d.N, d.OH, d.OW, d.Cout = N, oh, ow, 4 * C

@@ -451,11 +451,24 @@ def pack_weight_tc_hf8(w, scale=None, transposed_layout=False, interleave=1, kin
     return hi, lo, kinp, 2.0 ** -(w8 + 14)
 
 
+def _check_plane_strides(hi, lo):
+    """Operand planes are dense inside an image ([H, W, ld] contiguous); only the batch stride may be larger."""
+    N, H, W, ld = hi.shape
+    for t in (hi, lo):
+        if t is not None and (t.stride(3) != 1 or t.stride(2) != ld or t.stride(1) != W * ld or
+                              (N > 1 and t.stride(0) < H * W * ld)):
+            raise RuntimeError('operand planes must be pixel-major and dense inside each image (strides %s for shape %s)'
+                               % (tuple(t.stride()), tuple(t.shape)))
+    if lo is not None and (tuple(lo.shape) != tuple(hi.shape) or lo.stride(0) != hi.stride(0)):
+        raise RuntimeError('hi / lo operand planes must share shape and strides')
+
+
 def dense_view(v: TcView, hi, lo, c_off=0, C_=None):
     """TMA view of dense NHWC bf16 planes [N, H, W, ld]."""
     N, H, W, ld = hi.shape
+    _check_plane_strides(hi, lo)
     v.hi, v.lo = _p(hi, c_off), _p(lo, c_off)
-    v.stride_x, v.stride_y, v.stride_n = ld, W * ld, H * W * ld
+    v.stride_x, v.stride_y, v.stride_n = ld, W * ld, hi.stride(0)     # images may sit in a taller buffer (row-stacked levels)
     v.C, v.W, v.H = (C_ if C_ is not None else ld - c_off), W, H
 
 
@@ -463,15 +476,16 @@ def parity_view(v: TcView, hi, lo, py, px, fold_x=False):
     """View of the (py, px) parity plane of NHWC planes [N, H, W, ld] for stride-2 convolutions.
     fold_x: treat horizontal pixel pairs as one 2*ld-channel super-pixel (for ld = 32)."""
     N, H, W, ld = hi.shape
+    _check_plane_strides(hi, lo)
     if fold_x:
         off = py * W * ld
         v.hi, v.lo = _p(hi, off), _p(lo, off)
-        v.stride_x, v.stride_y, v.stride_n = 2 * ld, 2 * W * ld, H * W * ld
+        v.stride_x, v.stride_y, v.stride_n = 2 * ld, 2 * W * ld, hi.stride(0)
         v.C, v.W, v.H = 2 * ld, W // 2, H // 2
     else:
         off = (py * W + px) * ld
         v.hi, v.lo = _p(hi, off), _p(lo, off)
-        v.stride_x, v.stride_y, v.stride_n = 2 * ld, 2 * W * ld, H * W * ld
+        v.stride_x, v.stride_y, v.stride_n = 2 * ld, 2 * W * ld, hi.stride(0)
         v.C, v.W, v.H = ld, W // 2, H // 2
 
 

@@ -406,6 +406,12 @@ typedef struct essb_conv_tc {
   float acc_scale;       /* the epilogue multiplies the accumulator by this first (0 = 1.0); passes == 2: the
                             2^-(w8+14) that belongs to the packed weights */
   int32_t planes_fmt;    /* format of out_hi / out_lo: 0 = bf16 hi/lo planes, 2 = hf8 (ld_planes % 64 == 0) */
+  /* Row-stacked batches (0 = off): the caller presents a batch of images [N][row_period][W] (rows_valid image rows
+   * followed by row_period - rows_valid ZERO rows, which double as the convolution's zero padding between
+   * neighbours) as ONE tall image (N = 1, OH = N * row_period).  Output rows with oy % row_period >= rows_valid are
+   * computed but never stored, so the zero rows stay zero.  Removes the per-image rounding of the 16-row output
+   * patches (55-row maps: 8 x 4 patches per column -> 28). */
+  int32_t row_period, rows_valid;
 } essb_conv_tc;
 int essb_conv_tc_run(const essb_conv_tc* d, void* stream);
 

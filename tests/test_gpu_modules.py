@@ -456,6 +456,49 @@ def test_ddd17_shape_config2(mode):
 
 
 @pytest.mark.parametrize('mode', ['bf16x3', 'f16f8'])
+@pytest.mark.parametrize('B,H,W', [(3, 200, 346), (2, 48, 64), (4, 56, 80)])
+def test_row_stacked_levels_match_dense_and_oracle(mode, B, H, W, monkeypatch):
+    """Row-stacked levels (E2VIDRecurrent._stack_plan: the batch as ONE tall image with shared zero rows, masked stores,
+    tall stride-2 convs): (1) bit-identical to the dense layout (same K order per output pixel), (2) within 1e-3 of the
+    oracle over 3 windows incl. the image decoder, (3) the same through FOREIGN states (cloned tensors the module
+    has to re-stack) and through the per-window module call, (4) returned states / latents have the reference shapes."""
+    import ess_b200
+    from ess_b200.e2vid import E2VIDRecurrent as E
+    T, C = 3, 5
+    Hp, Wp = (H + 7) // 8 * 8, (W + 7) // 8 * 8
+    plan = E._stack_plan(B, Hp, Wp, 3)
+    assert any(rows > (Hp >> (i + 1)) for i, (rows, _) in enumerate(plan)), plan     # stacking is active at this shape
+    m = make_e2vid(mode=mode)
+    sd = sd_cpu(m)
+    data = make_events(B, T, C, H, W)
+    img_r, st_r, lat_r = O.encoder_unroll(sd, E2VID_CFG, data, T, C)
+    m = m.cuda()
+    rec = ess_b200.ImageReconstructor(m, H, W, C, 'cuda')
+    img, st, lat = rec.unroll(data.cuda(), T, C)
+    assert lat[8].shape == lat_r[8].shape and st[2][0].shape == st_r[2][0].shape
+    errs = dict(img=rel_err(img, img_r), **{'l%d' % k: rel_err(lat[k], lat_r[k]) for k in (1, 2, 4, 8)},
+                c2=rel_err(st[2][1], st_r[2][1]), c0=rel_err(st[0][1], st_r[0][1]))
+    print(mode, (B, H, W), plan, {k: '%.1e' % v for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+    # (1) dense layout, same kernels
+    monkeypatch.setenv('ESS_B200_STACK', '0')
+    img_d, st_d, lat_d = rec.unroll(data.cuda(), T, C)
+    monkeypatch.delenv('ESS_B200_STACK')
+    assert torch.equal(img_d, img) and all(torch.equal(lat_d[k], lat[k]) for k in (1, 2, 4, 8))
+    assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(st_d, st))
+    # (3) foreign states: two windows, the second one from clones of the first one's states
+    ev = data.cuda()
+    rec2 = ess_b200.ImageReconstructor(m, H, W, C, 'cuda')
+    _, s1, _ = rec2.update_reconstruction(ev[:, :C])
+    rec2.last_states_for_each_channel['grayscale'] = [(h.clone(), c.clone()) for h, c in s1]
+    img2, s2, lat2 = rec2.update_reconstruction(ev[:, C:2 * C])
+    rec3 = ess_b200.ImageReconstructor(m, H, W, C, 'cuda')
+    rec3.update_reconstruction(ev[:, :C])
+    img3, s3, lat3 = rec3.update_reconstruction(ev[:, C:2 * C])
+    assert torch.equal(img2, img3) and torch.equal(lat2[8], lat3[8]) and torch.equal(s2[1][1], s3[1][1])
+
+
+@pytest.mark.parametrize('mode', ['bf16x3', 'f16f8'])
 def test_convgru_in_tensor_core_mode(mode):
     """ConvGRU checkpoints (`recurrent_block_type='convgru'`, model.py:77-80) in bf16x3 mode: head and encoder convs on
     tcgen05, each GRU cell as two tcgen05 launches (GRU_UR epilogue: update gate + planes of prev_state*reset;
