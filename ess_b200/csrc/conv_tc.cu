@@ -1555,13 +1555,29 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   bool halo = halo_env != 0 && d->ntaps >= 2 && (BN <= 128 || (halo256_env != 0 && BN == 256));
   bool wide_halo = halo && BN == 256;
   if (wide_halo) {
-    // the halo patch is fixed at 16 rows x 8 pixels; the classic kernel picks its patch shape per layer.  Stay classic when
-    // the fixed patch wastes too many more output pixels (ESSB_TC_HALO256_WASTE = max ratio of padded pixel counts)
-    const double waste_env = [] { const char* e = getenv("ESSB_TC_HALO256_WASTE"); return e ? atof(e) : 2.0; }();
+    // The halo patch is fixed at 16 rows x 8 pixels and CTA pairs take tile pairs in whole rounds; the classic kernel picks
+    // its patch shape per layer.  Stay classic when that saves whole scheduling rounds: 256-channel decoder convs at 55 x 80,
+    // B = 8: 160 tile pairs on 74 CTA pairs = 3 rounds, classic 8 x 16 patches = 280 tiles on 148 CTAs = 2 rounds
+    // (measured, profiles/r02i_bench_dense_l2classic.json: 0.161 -> 0.140 ms per decoder conv).  A classic tile costs ~1.1x a
+    // pair tile (ConvLSTM cells: 0.54 vs 0.52 ms at equal rounds).  ESSB_TC_HALO256_WASTE (max ratio of padded pixel
+    // counts, default off) is the older A/B switch.
+    const double waste_env = [] { const char* e = getenv("ESSB_TC_HALO256_WASTE"); return e ? atof(e) : 0.0; }();
     const int cbw = 1 << d->bw_log2, cbh = TC_M >> d->bw_log2;
-    const double t_halo = (double)((d->OW + 7) / 8) * ((d->OH + 15) / 16);
-    const double t_classic = (double)((d->OW + cbw - 1) / cbw) * ((d->OH + cbh - 1) / cbh);
-    if (t_halo > waste_env * t_classic) { halo = false; wide_halo = false; }
+    const long long n_nt = Ngemm / BN;
+    const long long t_halo = (long long)((d->OW + 7) / 8) * ((d->OH + 15) / 16);
+    const long long t_classic = (long long)((d->OW + cbw - 1) / cbw) * ((d->OH + cbh - 1) / cbh);
+    const long long pair_items = (long long)d->N * ((d->OH + 15) / 16) * (((d->OW + 7) / 8 + 1) / 2) * n_nt;
+    const long long npairs = num_sms() / 2, nsm = num_sms();
+    const long long rounds_pair = (pair_items + npairs - 1) / npairs;
+    const long long rounds_classic = ((long long)d->N * t_classic * n_nt + nsm - 1) / nsm;
+    const int pair_mode = [] { const char* e = getenv("ESSB_TC_PAIR"); return e ? atoi(e) : 1; }();   // 0 off, 1 by rounds, 2 always
+    const bool pair_wanted = pair_mode != 0;
+    bool classic = false;
+    if (waste_env > 0.0) classic = (double)t_halo > waste_env * (double)t_classic;
+    else if (pair_mode >= 2) classic = false;
+    else if (pair_wanted) classic = 10 * rounds_pair > 11 * rounds_classic;
+    else classic = (double)t_halo > 2.0 * (double)t_classic;
+    if (classic) { halo = false; wide_halo = false; }
   }
   // shared-memory bias staging area: as small as the layer allows (it competes with pipeline stages at 2 CTAs/SM)
   const int bias_floats = d->bias ? ((d->Cout + 255) / 256) * 256 : 0;

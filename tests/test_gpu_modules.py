@@ -459,7 +459,7 @@ def test_ddd17_shape_config2(mode):
 @pytest.mark.parametrize('B,H,W', [(3, 200, 346), (2, 48, 64), (4, 56, 80)])
 def test_row_stacked_levels_match_dense_and_oracle(mode, B, H, W, monkeypatch):
     """Row-stacked levels (E2VIDRecurrent._stack_plan: the batch as ONE tall image with shared zero rows, masked stores,
-    tall stride-2 convs): (1) bit-identical to the dense layout (same K order per output pixel), (2) within 1e-3 of the
+    tall stride-2 convs): (1) equal to the dense layout up to the fp32 accumulation order (2e-5), (2) within 1e-3 of the
     oracle over 3 windows incl. the image decoder, (3) the same through FOREIGN states (cloned tensors the module
     has to re-stack) and through the per-window module call, (4) returned states / latents have the reference shapes."""
     import ess_b200
@@ -484,8 +484,11 @@ def test_row_stacked_levels_match_dense_and_oracle(mode, B, H, W, monkeypatch):
     monkeypatch.setenv('ESS_B200_STACK', '0')
     img_d, st_d, lat_d = rec.unroll(data.cuda(), T, C)
     monkeypatch.delenv('ESS_B200_STACK')
-    assert torch.equal(img_d, img) and all(torch.equal(lat_d[k], lat[k]) for k in (1, 2, 4, 8))
-    assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(st_d, st))
+    # same arithmetic per output pixel; only the fp32 accumulation ORDER may differ where the dispatcher picks another
+    # kernel variant for the other tiling (CTA pairs vs classic: tap-major vs chunk-major K loop)
+    same = dict(img=rel_err(img_d, img), **{'l%d' % k: rel_err(lat_d[k], lat[k]) for k in (1, 2, 4, 8)},
+                **{'s%d' % i: max(rel_err(a[0], b[0]), rel_err(a[1], b[1])) for i, (a, b) in enumerate(zip(st_d, st))})
+    assert max(same.values()) < 2e-5, same
     # (3) foreign states: two windows, the second one from clones of the first one's states
     ev = data.cuda()
     rec2 = ess_b200.ImageReconstructor(m, H, W, C, 'cuda')

@@ -51,7 +51,7 @@ def test_split_hf8_roundtrip():
     assert float((a8 != ref8).float().mean()) < 1e-4       # same round-to-nearest-even conversion
 
 
-N256 = {'pair': ('1', '1'), 'halo': ('1', '0'), 'classic': ('0', '0')}   # (ESSB_TC_HALO256, ESSB_TC_PAIR)
+N256 = {'pair': ('1', '2'), 'halo': ('1', '0'), 'classic': ('0', '0')}   # (ESSB_TC_HALO256, ESSB_TC_PAIR: 2 = always pairs)
 
 
 def set_n256(monkeypatch, n256):
