@@ -379,7 +379,7 @@ def lstm_roofline(prof, peaks, ms_dev, steps, mode, work_is_default):
                 note='algorithmic FLOPs (2*MAC, no credit for split passes): bf16x3 executes 3 bf16 passes (ceiling peak/3); '
                      'f16f8 executes one fp16 pass + one e4m3 pass of twice the K at twice the rate (2 pass-equivalents, '
                      'ceiling peak/2)',
-                mean_launch_ms=sec / n * 1e3, share_of_step=sec * 1e3 / ms_dev,
+                mean_launch_ms=sec / n * 1e3, share_of_step=(sec * 1e3 / by_tag['lstm_tc'][3]) / (ms_dev / steps),
                 mma_frac_of_peak=ach * {'bf16x3': 3, 'f16f8': 2}.get(mode, 1) / peaks['bf16'])
     roof['other_tc_kernels'] = {
         tag: dict(achieved=fl2 / sec2 / 1e12, mean_launch_ms=sec2 / n2 * 1e3, launches_per_step=n2 // ns2,
@@ -648,6 +648,8 @@ def main():
                          "(configs[3]: one ESSModel.train_step; single GPU)")
     ap.add_argument('--no-torch-gpu-baseline', action='store_true',
                     help='skip the PyTorch/cuDNN-on-this-GPU baseline (TF32 on and off) that the N=1 line carries')
+    ap.add_argument('--no-graph', action='store_true',
+                    help='contract B: issue the T encoder steps launch by launch instead of replaying their CUDA graph')
     ap.add_argument('--no-overlap', action='store_true', help='N > 1: one blocking gradient all-reduce after the backward')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -702,7 +704,9 @@ def main():
     stage_d = torch.empty_like(devb[0][0])
     stage_l = torch.empty_like(devb[0][1])
 
-    def step(data, labels):
+    use_graph = contract == 'B' and not args.no_graph
+
+    def step(data, labels, graph=None):
         if bucket is not None:
             bucket.zero_()
         else:
@@ -714,7 +718,7 @@ def main():
                 event_tensor = data[:, i * C:(i + 1) * C, :, :]
                 img_fake, states_real, latent = rec.update_reconstruction(event_tensor)
         else:
-            _, _, latent = rec.unroll(data, T, C)                     # the fused form of the same loop
+            _, _, latent = rec.unroll(data, T, C, graph=use_graph if graph is None else graph)   # the fused form of the same loop
         latent = {k: v.detach() for k, v in latent.items()}           # :145-146
         pred = dec(latent)                                            # :148
         loss = crit(pred[1], labels)                                  # :149
@@ -726,28 +730,43 @@ def main():
         return loss
 
     barrier, timed = device_timer(dev, world)
-    for i in range(args.warmup):
-        step(*devb[i & 1])
-    clocks = ClockSampler(local)
-    clocks.start()
     # Inside the timed region only the dominant kernel (fused ConvLSTM cell) is bracketed with CUDA events on its
     # launching stream (60 launches/step); bracketing all ~220 tcgen05 launches costs ~3 % of the step, so the
     # other roles are timed in an extra, untimed pass afterwards (--profile-all puts them back inside).
+    # With the unroll replayed as a CUDA graph the brackets are event-record NODES of the graph (created when the graph
+    # is captured, i.e. during the warm-up): after the timed region they hold the timestamps of the LAST replay of each
+    # of the two graphs (one per alternating input batch), i.e. of the last two timed steps.
     _lib.PROFILE = []
     _lib.PROFILE_TAGS = None if args.profile_all else {'lstm_tc'}
+    for i in range(max(args.warmup, 2 if use_graph else 0)):
+        step(*devb[i & 1])
+    torch.cuda.synchronize()
+    graph_prof = [e for e in _lib.PROFILE if len(e) == 5]
+    _lib.PROFILE = []
+    clocks = ClockSampler(local)
+    clocks.start()
     launches0 = _lib.launch_count
     ms_dev = timed(lambda i: step(*devb[i & 1]), args.steps)
     launches = _lib.launch_count - launches0
-    prof = _lib.PROFILE
+    prof = [(t, fl, a, b, args.steps) for (t, fl, a, b) in _lib.PROFILE]
+    n_graphs_timed = min(2, args.steps)
+    prof += [(t, fl, a, b, n_graphs_timed) for (t, fl, a, b, _) in graph_prof]
+    graph_launches = 0
+    if use_graph:      # kernels inside the replayed graphs do not pass through the ctypes launch counter: count them from
+        _lib.PROFILE, _lib.PROFILE_TAGS = None, None        # one eager unroll (same launch sequence)
+        c0 = _lib.launch_count
+        rec.unroll(devb[0][0], T, C, graph=False)
+        graph_launches = (_lib.launch_count - c0) * args.steps
+        launches += graph_launches
     if not args.profile_all:
         _lib.PROFILE, _lib.PROFILE_TAGS = [], None
         for i in range(2):
-            step(*devb[i & 1])
+            step(*devb[i & 1], graph=False)
         torch.cuda.synchronize()
         prof_other = [(t, fl, a, b, 2) for (t, fl, a, b) in _lib.PROFILE if t != 'lstm_tc']
     else:
         prof_other = []
-    prof = [(t, fl, a, b, args.steps) for (t, fl, a, b) in prof] + prof_other
+    prof = prof + prof_other
     _lib.PROFILE, _lib.PROFILE_TAGS = None, None
 
     # End-to-end: every step's events + labels come from pinned HOST memory and its loss is read back to the
@@ -766,11 +785,15 @@ def main():
             stage[i & 1][1].copy_(l, non_blocking=True)
             ready[i & 1].record(copy_stream)
 
+    e2e_step_ms = []
+
     def e2e_run(steps):
         for ev in freed:
             ev.record()
         prefetch(0)
         losses = []
+        del e2e_step_ms[:]
+        t_prev = time.perf_counter()
         for i in range(steps):
             if i + 1 < steps:
                 prefetch(i + 1)
@@ -778,6 +801,9 @@ def main():
             loss = step(*stage[i & 1])
             freed[i & 1].record()
             losses.append(float(loss.item()))               # D2H read of the step's result
+            t_now = time.perf_counter()
+            e2e_step_ms.append(round((t_now - t_prev) * 1e3, 2))   # host wall clock per step (diagnostic only)
+            t_prev = t_now
         return losses
 
     # plain H2D rate of the staging copy (diagnostic: explains an e2e value that falls below `value`)
@@ -817,12 +843,14 @@ def main():
                                                 ('one flat all-reduce after the backward' if args.no_overlap else
                                                  'per-stage buckets all-reduced on a side stream as their gradients complete')),
                                  l2_policy='two alternating %d MB input batches (inputs larger than the 126 MB L2)' %
-                                           (devb[0][0].numel() * 4 // 1000000)),
+                                           (devb[0][0].numel() * 4 // 1000000),
+                                 unroll=('CUDA graph replay (one graph per input buffer; %d of the counted launches per step are graph '
+                                         'nodes)' % (graph_launches // max(args.steps, 1))) if use_graph else 'launch by launch'),
                 tflops=value * fps / 1e12,
                 step_frac_of_bf16_peak=value * fps / 1e12 / (peaks['bf16'] * world),
                 e2e=dict(value=e2e_value, unit='samples/s', ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=stage_d.numel() * 4 + stage_l.numel() * 8, d2h_bytes_per_step=4,
-                         h2d_gb_per_s=h2d_gbs, host_numa_binding=numa),
+                         h2d_gb_per_s=h2d_gbs, host_numa_binding=numa, host_wall_ms_per_step=list(e2e_step_ms)),
                 gpu_launches=launches, clocks=dict(sm_mhz=clk['sm_mhz'], sm_max_mhz=clk['sm_max_mhz'],
                                                    reasons=clk['reasons'], samples=clk['samples']),
                 roofline=roof)

@@ -817,8 +817,11 @@ def conv_tc(d: ConvTc, tag=None, device=None):
         return
     k = sum(d.seg_C[s] for s in range(d.nseg)) * d.ntaps
     flops = 2.0 * d.N * d.OH * d.OW * d.Cout * k
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # under CUDA-graph capture the events become event-record NODES (external=True): after every replay they hold the
+    # timestamps of that replay, so a profile taken at capture time keeps measuring (entries carry a 5th field True)
+    cap = torch.cuda.is_current_stream_capturing()
+    e0, e1 = (torch.cuda.Event(enable_timing=True, external=cap), torch.cuda.Event(enable_timing=True, external=cap))
     e0.record()
     call('essb_conv_tc_run', C.byref(d), _stream())
     e1.record()
-    prof.append((tag or 'conv_tc', flops, e0, e1))
+    prof.append((tag or 'conv_tc', flops, e0, e1, True) if cap else (tag or 'conv_tc', flops, e0, e1))

@@ -13,6 +13,7 @@ the last window only (the trainers overwrite `img_fake` every iteration) -- cont
 `stats_reduce_fn` lets a data-parallel caller all-reduce the [T,3] statistics (global-batch semantics).
 """
 import math
+import os
 
 import torch
 
@@ -99,8 +100,18 @@ class ImageReconstructor:
                 img = out.view(b, 1, h, w)
         return img, states, latent
 
-    def unroll(self, data, num_windows, channels, image_on_last_only=True):
-        """data [B, T*C, H, W] -> (img, states, latent) of the last window; resets the state first."""
+    def unroll(self, data, num_windows, channels, image_on_last_only=True, graph=None):
+        """data [B, T*C, H, W] -> (img, states, latent) of the last window; resets the state first.
+
+        graph=True (default: env ESS_B200_GRAPH, off): the T encoder steps (~15 launches each) are captured ONCE per
+        input shape / input address into a CUDA graph and replayed -- the step is issued by one cudaGraphLaunch instead
+        of ~300 launches, which removes the host-side issue time (14 ms at DSEC size, more than the device time at the
+        DDD17 size) and the few-us device gaps between dependent kernels.  The statistics kernel (and its data-parallel
+        all-reduce) stay outside the graph and feed it through a fixed buffer.  Graph semantics: the returned tensors
+        live in the graph's memory pool and are OVERWRITTEN by the next graphed unroll of this reconstructor -- consume
+        them (decoder forward/backward) before the next call, as every trainer does; clone() what must survive."""
+        if graph is None:
+            graph = os.environ.get('ESS_B200_GRAPH', '0') == '1'
         with torch.no_grad(), ops.on_device_of(data):
             data = self._per_sample_contiguous(data.float())
             self.last_states_for_each_channel = {'grayscale': None}
@@ -111,14 +122,74 @@ class ImageReconstructor:
                 stats = ops.event_stats(data, num_windows, channels)
                 if self.stats_reduce_fn is not None:
                     stats = self.stats_reduce_fn(stats)
-            states = None
-            img = latent = None
-            for i in range(num_windows):
-                win = data[:, i * channels:(i + 1) * channels]
-                need_img = (i == num_windows - 1) or not image_on_last_only
-                img, states, latent = self._step(win, stats[i] if stats is not None else None, states, need_img,
-                                                 want_head=(i == num_windows - 1))
-                if self.no_recurrent:
-                    states = None
+            if graph:
+                img, states, latent = self._unroll_graphed(data, stats, num_windows, channels, image_on_last_only)
+            else:
+                img, states, latent = self._unroll_loop(data, stats, num_windows, channels, image_on_last_only)
             self.last_states_for_each_channel['grayscale'] = states
         return img, states, latent
+
+    def _unroll_loop(self, data, stats, num_windows, channels, image_on_last_only):
+        states = None
+        img = latent = None
+        for i in range(num_windows):
+            win = data[:, i * channels:(i + 1) * channels]
+            need_img = (i == num_windows - 1) or not image_on_last_only
+            img, states, latent = self._step(win, stats[i] if stats is not None else None, states, need_img,
+                                             want_head=(i == num_windows - 1))
+            if self.no_recurrent:
+                states = None
+        return img, states, latent
+
+    # ------------------------------------------------------------------------------------ CUDA graph of the unroll
+    MAX_ADDRESS_GRAPHS = 4
+
+    def _unroll_graphed(self, data, stats, num_windows, channels, image_on_last_only):
+        """Replay (capturing on first use) the graph of _unroll_loop for this input.  Graphs are keyed by everything
+        their recorded launches depend on: input address / shape / strides, the window split, the reconstructor's
+        options, the model's parameter versions and mode.  Up to MAX_ADDRESS_GRAPHS graphs read the caller's tensor in
+        place (a training loop's batches come back at the same one or two allocator addresses); further addresses
+        share one graph that reads a reconstructor-owned copy of the input (one extra device-to-device copy)."""
+        dev = data.device
+        base = (tuple(data.shape), tuple(data.stride()), num_windows, channels, bool(image_on_last_only), self.flip,
+                self.no_normalize, self.no_recurrent, self.standardization, self.model._key(),
+                os.environ.get('ESS_B200_STACK', '1'), str(dev))
+        G = self.__dict__.setdefault('_graphs', {})
+        if G and next(iter(G))[1:] != base:      # another shape / new weights: drop the stale graphs and their memory
+            G.clear()
+            self.__dict__.pop('_graph_static_in', None)
+        key = (data.data_ptr(),) + base
+        ent = G.get(key)
+        src = data
+        if ent is None and sum(1 for k in G if k[0] != 'static') >= self.MAX_ADDRESS_GRAPHS:
+            key = ('static',) + base
+            ent = G.get(key)
+            buf = self.__dict__.get('_graph_static_in')
+            if buf is None or buf.shape != data.shape or buf.device != dev:
+                buf = torch.empty(data.shape, device=dev, dtype=torch.float32)
+                self._graph_static_in = buf
+            buf.copy_(data)
+            src = buf
+        if ent is None:
+            cur = torch.cuda.current_stream(dev)
+            stream = self.__dict__.get('_graph_stream')
+            if stream is None or stream.device != dev:
+                stream = self._graph_stream = torch.cuda.Stream(device=dev)
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            st_buf = stats.clone() if stats is not None else None
+            # one eager pass on the capture stream first: every lazily created buffer (packed weights, scheduler slots
+            # of that stream, zero-bordered input planes, row-stacked plane buffers) must exist before the capture
+            stream.wait_stream(cur)
+            with torch.cuda.stream(stream):
+                self._unroll_loop(src, st_buf, num_windows, channels, image_on_last_only)
+            cur.wait_stream(stream)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._graph_pool, stream=stream):
+                out = self._unroll_loop(src, st_buf, num_windows, channels, image_on_last_only)
+            ent = (g, st_buf, out)
+            G[key] = ent
+        g, st_buf, out = ent
+        if st_buf is not None:
+            st_buf.copy_(stats)
+        g.replay()
+        return out

@@ -501,6 +501,41 @@ def test_row_stacked_levels_match_dense_and_oracle(mode, B, H, W, monkeypatch):
     assert torch.equal(img2, img3) and torch.equal(lat2[8], lat3[8]) and torch.equal(s2[1][1], s3[1][1])
 
 
+@pytest.mark.parametrize('mode', ['f16f8', 'fp32'])
+def test_unroll_cuda_graph_matches_launch_by_launch(mode):
+    """ImageReconstructor.unroll(graph=True): the T encoder steps replayed as ONE CUDA graph give bit-identical results
+    to the launch-by-launch loop -- on first use (capture + replay), on new data at the same address (replay only), at
+    further addresses (one graph each, then the shared static-input graph), and after the weights change (re-capture)."""
+    import ess_b200
+    B, T, C, H, W = 2, 3, 5, 48, 64
+    m = make_e2vid(mode=mode).cuda()
+    rec = ess_b200.ImageReconstructor(m, H, W, C, 'cuda')
+    ref = ess_b200.ImageReconstructor(m, H, W, C, 'cuda')
+
+    def check(x):
+        img, st, lat = rec.unroll(x, T, C, graph=True)
+        img_e, st_e, lat_e = ref.unroll(x.clone(), T, C, graph=False)
+        assert torch.equal(img, img_e) and all(torch.equal(lat[k], lat_e[k]) for k in (1, 2, 4, 8))
+        assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(st, st_e))
+        assert rec.last_states_for_each_channel['grayscale'] is st
+
+    x = make_events(B, T, C, H, W, seed=1).cuda()
+    check(x)
+    assert len(rec._graphs) == 1
+    x.copy_(make_events(B, T, C, H, W, seed=2).cuda())        # same address, new contents: replay only
+    check(x)
+    assert len(rec._graphs) == 1
+    keep = [x]
+    for seed in range(3, 3 + rec.MAX_ADDRESS_GRAPHS + 2):      # more addresses than address-keyed graphs
+        keep.append(make_events(B, T, C, H, W, seed=seed).cuda())
+        check(keep[-1])
+    assert len(rec._graphs) == rec.MAX_ADDRESS_GRAPHS + 1 and any(k[0] == 'static' for k in rec._graphs)
+    with torch.no_grad():
+        m.unetrecurrent.head.conv2d.bias.add_(0.01)            # new parameter version: stale graphs are dropped
+    check(x)
+    assert len(rec._graphs) == 1
+
+
 @pytest.mark.parametrize('mode', ['bf16x3', 'f16f8'])
 def test_convgru_in_tensor_core_mode(mode):
     """ConvGRU checkpoints (`recurrent_block_type='convgru'`, model.py:77-80) in bf16x3 mode: head and encoder convs on
