@@ -371,7 +371,7 @@ def lstm_roofline(prof, peaks, ms_dev, steps, mode, work_is_default):
     tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if os.path.exists(tpath) and work_is_default:
         traffic = json.load(open(tpath)).get('lstm_tc', {}).get('mean_dram_bytes_per_launch')
-    roof = dict(kernel='conv_tc_kernel<LSTM> (fused ConvLSTM cell, %d launches)' % n, bound='tensor', achieved=ach,
+    roof = dict(kernel='conv_tc_pair_kernel<LSTM> (fused ConvLSTM cell on CTA pairs, %d launches timed)' % n, bound='tensor', achieved=ach,
                 peak=peaks['bf16'], unit='TFLOP/s', frac=ach / peaks['bf16'], traffic=traffic,
                 traffic_note='mean DRAM bytes per launch from the committed ncu --set full capture '
                              '(profiles/ncu_traffic.json); algorithmic bytes are 865/433/216 MB for the 3 levels',
