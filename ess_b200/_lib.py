@@ -69,7 +69,7 @@ class ConvTc(C.Structure):
                 ('ntaps', C.c_int32),
                 ('dy', C.c_int8 * MAX_TAPS), ('dx', C.c_int8 * MAX_TAPS), ('view', C.c_int8 * MAX_TAPS),
                 ('widx', C.c_int8 * MAX_TAPS), ('acc_scale', C.c_float), ('planes_fmt', C.c_int32),
-                ('row_period', C.c_int32), ('rows_valid', C.c_int32)]
+                ('row_period', C.c_int32), ('rows_valid', C.c_int32), ('phase_cout', C.c_int32)]
 
 
 class WgradTc(C.Structure):

@@ -89,6 +89,7 @@ struct TcParams {
   int b_split;                           // wide halo tiles (BN = 256): a B stage is ONE plane of one tap (hi and lo planes behind separate barriers)
   float acc_scale;                       // the epilogue multiplies the raw accumulator by this (f16f8 mode: 2^-(w8+14))
   int planes_fmt;                        // format of out_hi/out_lo: 0 = bf16 hi/lo, 2 = hf8 (tc_ptx.cuh)
+  int phase_cout;                        // > 0: merged sub-pixel phases (essb_conv_tc.phase_cout): column block j of width phase_cout is phase (j >> 1, j & 1)
   int row_period, rows_valid;            // row-stacked batch (essb_conv_tc): rows with oy % row_period >= rows_valid are not stored
   int* sched;                            // [0] next unit, [1] CTAs done; zero before the launch, reset by the last CTA
   int n_units, n_whole, split;           // units [0, n_whole) are whole tiles; the rest are 1/split K-slices of the tail tiles
@@ -292,19 +293,29 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
       if (p.out_hi) tc_store_planes8(p, pix, ch, hv);
     }
   } else {
-    const size_t opix = ((size_t)n * p.OHf + (oy * p.osy + p.ooy)) * p.OWf + (ox * p.osx + p.oox);
+    // merged sub-pixel phases: this 32-column chunk belongs to phase ph = column / phase_cout, whose outputs live at
+    // pixel (oy * osy + (ph >> 1), ox * osx + (ph & 1)) and channel column % phase_cout (phase_cout is a multiple of 32)
+    int ccol = n0 + c0, ppy = p.ooy, ppx = p.oox;
+    if (p.phase_cout) {
+      const int ph = ccol / p.phase_cout;
+      ccol -= ph * p.phase_cout;
+      ppy = ph >> 1;
+      ppx = ph & 1;
+    }
+    const size_t opix = ((size_t)n * p.OHf + (oy * p.osy + ppy)) * p.OWf + (ox * p.osx + ppx);
     const bool do_st = !(p.base_offset_mode & 8);   // experiment flag: compute but do not store
     uint32_t q8[8], q8l[8];   // hf8 planes: the chunk's 32 e4m3 a8 / a8l bytes, stored as ONE 32 B sector each after the loop
 #pragma unroll
     for (int g = 0; g < 2; ++g) {  // 16 channels per group: 2 x 32 B of fp32, 32 B per bf16 plane
-      const int co = n0 + c0 + g * 16;
+      const int co = ccol + g * 16;          // output channel (bias is indexed by the GEMM column: cb)
+      const int cb = n0 + c0 + g * 16;
       float v[2][8];
 #pragma unroll
       for (int e = 0; e < 16; ++e) v[e >> 3][e & 7] = __uint_as_float(r[g * 16 + e]) * p.acc_scale;
       if (s_bias) {
 #pragma unroll
         for (int e4 = 0; e4 < 4; ++e4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + co + e4 * 4);
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cb + e4 * 4);
           float* vv = &v[e4 >> 1][(e4 & 1) * 4];
           vv[0] += b4.x; vv[1] += b4.y; vv[2] += b4.z; vv[3] += b4.w;
         }
@@ -376,7 +387,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
       }
     }
     if (p.out_hi && p.planes_fmt == 2 && do_st) {   // n0 + c0 is a multiple of 32: both 32 B pieces lie inside one 64-channel chunk row
-      uint8_t* lo = reinterpret_cast<uint8_t*>(p.out_lo) + opix * (size_t)p.ld_planes * 2 + hf8_lo_off(n0 + c0);
+      uint8_t* lo = reinterpret_cast<uint8_t*>(p.out_lo) + opix * (size_t)p.ld_planes * 2 + hf8_lo_off(ccol);
       if (p.wide & TC_WIDE_PLANES) {
         st_global_256(lo, q8);
         st_global_256(lo + 64, q8l);
@@ -1772,6 +1783,9 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   p.base_offset_mode = baseoff_env;
   ESSB_REQUIRE(d->row_period == 0 || (d->row_period > 0 && d->rows_valid > 0 && d->rows_valid <= d->row_period),
                "essb_conv_tc_run: bad row_period / rows_valid (%d / %d)", d->row_period, d->rows_valid);
+  ESSB_REQUIRE(d->phase_cout == 0 || (d->epilogue == ESSB_EPI_LINEAR && d->phase_cout % 32 == 0 && d->Cout == 4 * d->phase_cout),
+               "essb_conv_tc_run: phase_cout must be a multiple of 32 with Cout == 4 * phase_cout (LINEAR epilogue)");
+  p.phase_cout = d->phase_cout;
   p.row_period = d->row_period;
   p.rows_valid = d->rows_valid;
   if (halo && halo_occ == 2) {

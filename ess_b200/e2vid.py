@@ -176,7 +176,7 @@ class E2VIDRecurrent(nn.Module):
 
     # ------------------------------------------------------------------------------ weight packing
     def _key(self):
-        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers())) + (self.mode, self._enc0_hf8())
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers())) + (self.mode, self._enc0_hf8(), os.environ.get('ESS_B200_MERGE_PHASES', '1'))
 
     def _pack(self):
         key = self._key()
@@ -281,6 +281,11 @@ class E2VIDRecurrent(nn.Module):
                                   dec.transposed_conv2d.out_channels)
                 if tc and dec.transposed_conv2d.in_channels % 64 == 0 and dec.transposed_conv2d.out_channels % 32 == 0:
                     P['dec%d_tc' % i] = pk(dec.transposed_conv2d.weight, scale, transposed_layout=True)
+                    if os.environ.get('ESS_B200_MERGE_PHASES', '1') != '0' and 4 * dec.transposed_conv2d.out_channels <= 1024:
+                        # the four sub-pixel phases as ONE launch of N = 4 * Cout (essb_conv_tc.phase_cout)
+                        wm = ops.merge_convT_phases(dec.transposed_conv2d.weight)
+                        P['dec%d_tcm' % i] = pk(wm, scale.repeat(4) if scale is not None else None) + \
+                            (bias.repeat(4).contiguous() if bias is not None else None,)
         scale, bias = _bn_fold(u.pred.conv2d.bias, getattr(u.pred, 'norm_layer', None), None, dev)
         P['pred'] = (ops.pack_weight(u.pred.conv2d.weight, scale), bias)
         wp = u.pred.conv2d.weight.detach().float().reshape(1, -1)
@@ -632,6 +637,17 @@ class E2VIDRecurrent(nn.Module):
                 segs = [xp] + ([block_planes[ne - i - 1]] if concat else [])
                 out = torch.empty((N, 2 * h, 2 * w, cout), device=dev, dtype=torch.float32)
                 op = new_planes(2 * h, 2 * w, cout) if i < ne - 1 else None
+                merged = P.get('dec%d_tcm' % i)
+                if merged is not None:
+                    mhi, mlo, mk, msc, mb = merged
+                    cin_t = sum(sp[0].shape[-1] for sp in segs)
+                    ops.conv_tc_dense(segs, mhi, mlo, mk, t3, N, h, w, 4 * cout, passes, bias=mb, act=ACT_RELU, out=out,
+                                      out_place=(2 * h, 2 * w, 2, 0, 2, 0), res_post=post, out_planes=op, tag='img_tc',
+                                      acc_scale=msc, planes_fmt=fmt, phase_cout=cout,
+                                      flops=2.0 * N * h * w * cout * cin_t * 25)
+                    x, xp = out, op
+                    h, w = 2 * h, 2 * w
+                    continue
                 for py in range(2):
                     for px in range(2):
                         ops.conv_tc_dense(segs, hi, lo, k, ops.taps_convT_phase(py, px), N, h, w, cout, passes, bias=bd,

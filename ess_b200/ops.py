@@ -511,12 +511,14 @@ def in_stats(y, count=None):
 
 def conv_tc_dense(planes, w_hi, w_lo, k_per_tap, taps, N, H, W, Cout, passes, bias=None, out=None, act=ACT_NONE,
                   tag=None, res_pre=None, res_post=None, out_planes=None, want_out=True, out_place=None, acc_scale=0.0,
-                  planes_fmt=PLANES_BF16):
+                  planes_fmt=PLANES_BF16, phase_cout=0, flops=None):
     """Stride-1 gather-convolution on the tcgen05 kernel over a dense operand plane pair [N, H, W, Cin] (Cin a
     multiple of 64), or over a LIST of two such pairs = the channel concatenation of two tensors (each a
     multiple of 64 channels; alternatively concatenated inputs are laid out side by side by split_bf16(c_off=...)).  Returns the fp32 result [N, H, W, Cout] (None when want_out=False and
     only the bf16 `out_planes` are produced).  out_place = (OHf, OWf, osy, ooy, osx, oox) scatters the
-    result into a larger image (transposed-conv phases)."""
+    result into a larger image (transposed-conv phases).  phase_cout > 0: the four phases merged into ONE launch of
+    Cout = 4 * phase_cout GEMM columns (merge_convT_phases; `out` / `out_planes` / residuals are phase_cout wide);
+    `flops` = algorithmic FLOPs for the profile when they differ from the executed ones."""
     segs = list(planes) if isinstance(planes, list) else [planes]
     if not 1 <= len(segs) <= 2:
         raise ValueError('conv_tc_dense: one or two channel segments')
@@ -533,7 +535,7 @@ def conv_tc_dense(planes, w_hi, w_lo, k_per_tap, taps, N, H, W, Cout, passes, bi
     if out_place is None:
         out_place = (H, W, 1, 0, 1, 0)
     if out is None and want_out:
-        out = torch.empty((N, out_place[0], out_place[1], Cout), device=hi.device, dtype=torch.float32)
+        out = torch.empty((N, out_place[0], out_place[1], phase_cout or Cout), device=hi.device, dtype=torch.float32)
     if out is not None:
         d.out, d.ldo = _p(out), out.shape[-1]
     if out_planes is not None:
@@ -544,12 +546,28 @@ def conv_tc_dense(planes, w_hi, w_lo, k_per_tap, taps, N, H, W, Cout, passes, bi
     d.N, d.OH, d.OW, d.Cout = N, H, W, Cout
     d.OHf, d.OWf, d.osy, d.ooy, d.osx, d.oox = out_place
     d.epilogue, d.act, d.passes, d.bw_log2 = EPI_LINEAR, act, passes, pick_bw_log2(W, H)
-    d.acc_scale, d.planes_fmt = acc_scale, planes_fmt
+    d.acc_scale, d.planes_fmt, d.phase_cout = acc_scale, planes_fmt, phase_cout
     d.ntaps = len(taps)
     for t, (dy, dx, wi) in enumerate(taps):
         d.dy[t], d.dx[t], d.view[t], d.widx[t] = dy, dx, 0, wi
-    conv_tc(d, tag=tag, device=hi.device)
+    conv_tc(d, tag=tag, device=hi.device, flops=flops)
     return out
+
+
+def merge_convT_phases(wt):
+    """ConvTranspose2d(k5, s2, p2, output_padding 1) weight [Cin, Cout, 5, 5] -> the weight [4*Cout, Cin, 3, 3] of ONE
+    3x3 gather-convolution over the input whose output-channel block j holds sub-pixel phase (j >> 1, j & 1)
+    (taps_convT_phase); the 11 of 36 (phase, offset) pairs a phase does not use are zero."""
+    wt = wt.detach().float()
+    cin, cout = wt.shape[0], wt.shape[1]
+    wm = torch.zeros((4 * cout, cin, 3, 3), device=wt.device, dtype=torch.float32)
+    for py in range(2):
+        for px in range(2):
+            ph = py * 2 + px
+            for (dy, dx, widx) in taps_convT_phase(py, px):
+                ky, kx = divmod(widx, 5)
+                wm[ph * cout:(ph + 1) * cout, :, dy + 1, dx + 1] = wt[:, :, ky, kx].t()
+    return wm
 
 
 def wgrad_tc(a_planes, g_planes, Cin, Cout, taps, N, H, W, passes, tag='seg_wgrad', stride=1):
@@ -799,7 +817,7 @@ def _tc_workspace(device):
     return ent
 
 
-def conv_tc(d: ConvTc, tag=None, device=None):
+def conv_tc(d: ConvTc, tag=None, device=None, flops=None):
     """essb_conv_tc_run; when _lib.PROFILE is a list, brackets the launch with CUDA events on the
     launching stream and records (tag, algorithmic FLOPs, start, end).  `device`: the device the operands live
     on (scheduler slots / split-K scratch are allocated there; default = the current device)."""
@@ -816,7 +834,8 @@ def conv_tc(d: ConvTc, tag=None, device=None):
         call('essb_conv_tc_run', C.byref(d), _stream())
         return
     k = sum(d.seg_C[s] for s in range(d.nseg)) * d.ntaps
-    flops = 2.0 * d.N * d.OH * d.OW * d.Cout * k
+    if flops is None:
+        flops = 2.0 * d.N * d.OH * d.OW * d.Cout * k
     # under CUDA-graph capture the events become event-record NODES (external=True): after every replay they hold the
     # timestamps of that replay, so a profile taken at capture time keeps measuring (entries carry a 5th field True)
     cap = torch.cuda.is_current_stream_capturing()

@@ -412,6 +412,12 @@ typedef struct essb_conv_tc {
    * computed but never stored, so the zero rows stay zero.  Removes the per-image rounding of the 16-row output
    * patches (55-row maps: 8 x 4 patches per column -> 28). */
   int32_t row_period, rows_valid;
+  /* Merged sub-pixel phases (0 = off; LINEAR epilogue): the four output phases of a stride-2 transposed convolution
+   * (ConvTranspose2d(k5, s2, p2, output_padding 1), e2vid/model/submodules.py:39-40) as ONE launch of Cout = 4 * phase_cout
+   * GEMM columns over the union of their input offsets (weights of the taps a phase does not use are zero): column block
+   * j = co / phase_cout is phase (py, px) = (j >> 1, j & 1) and is stored at pixel (oy*osy + py, ox*osx + px), channel
+   * co % phase_cout (ooy / oox are ignored); bias has 4 * phase_cout entries.  phase_cout must be a multiple of 32. */
+  int32_t phase_cout;
 } essb_conv_tc;
 int essb_conv_tc_run(const essb_conv_tc* d, void* stream);
 
