@@ -1102,7 +1102,21 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_pair_kernel(const __g
           for (int c = 0; c < p.seg_chunks[seg]; ++c)
             for (int g = 0; g < p.n_groups; ++g) {
               const int t_end = p.grp_first[g] + p.grp_count[g];
-              for (int t0 = p.grp_first[g]; t0 < t_end; ++t0) {
+              for (int t0 = p.grp_first[g]; t0 < t_end; t0 += p.b_taps_per_stage) {
+                if (!p.b_split) {   // narrow tiles: a stage holds b_taps_per_stage taps, each [hi | lo]
+                  const int nt_taps = min(p.b_taps_per_stage, t_end - t0);
+                  mbar_wait(&b_empty[s], ph ^ 1);
+                  if (leader) mbar_expect_tx(&b_full[s], 2u * tx * (uint32_t)(planes * nt_taps));
+                  const uint32_t bar = mapa_u32(smem_u32(&b_full[s]), 0u);
+                  for (int j = 0; j < nt_taps; ++j) {
+                    const int kc = p.widx[t0 + j] * p.k_per_tap + p.seg_koff[seg] + c * TC_KCH;
+                    uint8_t* st = b_base + (size_t)s * p.b_stage_bytes + (size_t)j * p.b_tap_bytes;
+                    tma_load_2d_2sm(st, &p.tmB_hi, bar, kc, row0);
+                    if (planes == 2) tma_load_2d_2sm(st + p.b_lo_off, &p.tmB_lo, bar, kc, row0);
+                  }
+                  if (++s == p.b_stages) { s = 0; ph ^= 1; }
+                  continue;
+                }
                 const int kcoord = p.widx[t0] * p.k_per_tap + p.seg_koff[seg] + c * TC_KCH;
                 for (int pl = 0; pl < planes; ++pl) {
                   mbar_wait(&b_empty[s], ph ^ 1);
@@ -1139,7 +1153,38 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_pair_kernel(const __g
               tc_fence_after();
               const uint32_t a_addr = smem_u32(a_base + (size_t)sa * p.a_stage_bytes);
               const int t_end = p.grp_first[g] + p.grp_count[g];
-              for (int t0 = p.grp_first[g]; t0 < t_end; ++t0) {
+              for (int t0 = p.grp_first[g]; t0 < t_end; t0 += p.b_taps_per_stage) {
+                if (!p.b_split) {
+                  const int nt_taps = min(p.b_taps_per_stage, t_end - t0);
+                  mbar_wait(&b_full[sb], phb);
+                  tc_fence_after();
+                  for (int j = 0; j < nt_taps; ++j) {
+                    const int t = t0 + j;
+                    const uint32_t a_off = (uint32_t)((p.dy[t] - p.hy0) * p.halo_w + (p.dx[t] - p.hx0)) * 128u;
+                    const UDesc a_hi = make_smem_desc_sbo(a_addr + a_off, sbo);
+                    const UDesc a_lo = make_smem_desc_sbo(a_addr + p.a_lo_off + a_off, sbo);
+                    const uint32_t b_addr = smem_u32(b_base + (size_t)sb * p.b_stage_bytes) + (uint32_t)(j * p.b_tap_bytes);
+                    const UDesc b_hi = make_smem_desc(b_addr), b_lo = make_smem_desc(b_addr + p.b_lo_off);
+#pragma unroll
+                    for (int k = 0; k < TC_KCH / 16; ++k) {
+                      const uint32_t ko = (uint32_t)(k * 2);
+                      if (p.passes == 2) {
+                        umma2_f8(d_tmem, a_lo + ko, b_lo + ko, idesc_f8, acc);
+                        umma2_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+                      } else if (p.passes == 3) {
+                        umma2_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, acc);
+                        umma2_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                        umma2_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+                      } else {
+                        umma2_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, acc);
+                      }
+                      acc = 1u;
+                    }
+                  }
+                  umma2_commit_mc(&b_empty[sb]);
+                  if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+                  continue;
+                }
                 const uint32_t a_off = (uint32_t)((p.dy[t0] - p.hy0) * p.halo_w + (p.dx[t0] - p.hx0)) * 128u;
                 const UDesc a_hi = make_smem_desc_sbo(a_addr + a_off, sbo);
                 const UDesc a_lo = make_smem_desc_sbo(a_addr + p.a_lo_off + a_off, sbo);
@@ -1602,6 +1647,16 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
   // CTA pairs (cta_group::2) for the wide halo tiles; ESSB_TC_PAIR=0 keeps them on single CTAs (read per call, see above)
   const int pair_env = [] { const char* e = getenv("ESSB_TC_PAIR"); return e ? atoi(e) : 1; }();
   bool pair = wide_halo && pair_env != 0;
+  // CTA pairs for N = 128 tiles of the f16f8 mode (second encoder conv): OFF by default (ESSB_TC_PAIR128=1 enables, 2 = at any
+  // size).  The idea: a single CTA's UMMA operand reads of an M128 x N128 tile (A 4 KB + B 4 KB per 64-cycle MMA) fill the
+  // 128 B/clk shared-memory port (ncu: tensor pipe 49 % = tc_wavefronts_mem_shared 49 %), a pair reads and stages only half
+  // of the weight rows per SM.  Measured (profiles/r02s_bench_*.json): SLOWER -- encoder conv 1 0.121 -> 0.147 ms; one
+  // resident CTA per SM with a static schedule hides less latency than the two co-resident CTAs of the halo kernel.
+  const int pair128_env = [] { const char* e = getenv("ESSB_TC_PAIR128"); return e ? atoi(e) : 0; }();
+  const bool pair128 = halo && BN == 128 && d->passes == 2 && pair_env != 0 && pair128_env != 0 && d->ntaps >= 4 &&
+                       (pair128_env >= 2 ||     // 2 = always (tests); 1 = only when every CTA pair gets a tile pair
+                        (long long)d->N * ((d->OH + 15) / 16) * (((d->OW + 7) / 8 + 1) / 2) >= num_sms() / 2);
+  if (pair128) pair = true;
   int halo_occ = 1;
   bool halo_fuse = false;
   int hx0 = 0, hx1 = 0, hy0 = 0, hy1 = 0;
@@ -1635,7 +1690,7 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
       const int half = 113 * 1024 - tail_bytes;   // 2 x (113 KB + 1 KB reserved per CTA) = the SM's 228 KB
       if (p.a_stage_bytes + 2 * p.b_tap_bytes <= half) { budget = half; halo_occ = 2; }
     }
-    if (wide_halo) budget = 227 * 1024 - tail_bytes;   // the whole SM: 2 halo tiles + 4 single-plane weight stages
+    if (wide_halo || pair128) budget = 227 * 1024 - tail_bytes;   // the whole SM: 2 halo tiles + 4 single-plane weight stages
     p.a_stages = (2 * p.a_stage_bytes + 3 * p.b_tap_bytes <= budget) ? 2 : 1;
     // Narrow tiles (N <= 64) are bound by the MMA thread's per-stage cost (barrier wait + fence + commit, ~200
     // cycles) rather than by tensor work (12 MMAs x N/2 cycles per tap): put G taps behind one barrier.
@@ -1657,11 +1712,20 @@ extern "C" int essb_conv_tc_run(const essb_conv_tc* d, void* stream) {
       p.b_stage_bytes = b_plane;
       p.a_stages = (2 * p.a_stage_bytes + 4 * b_plane <= budget) ? 2 : 1;
     }
+    if (pair128) {     // B stage = G taps x [hi | lo] x 64 rows (16 KB per tap): >= 1024 MMA cycles per barrier round trip
+      halo_occ = 1;
+      halo_fuse = false;
+      p.a_stages = 2;
+      G = 2;
+      p.b_taps_per_stage = G;
+      p.b_stage_bytes = G * p.b_tap_bytes;
+    }
     int nb = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
     if (nb > MAX_STAGES) nb = MAX_STAGES;
     p.b_stages = nb;
     if (nb < 2 || p.halo_w > 64 || p.halo_h > 64) halo = false;
     if (wide_halo && (nb < 3 || p.a_stages < 2)) halo = false;
+    if (pair128 && nb < 3) halo = false;
   }
   pair = pair && halo;
   p.pair = pair ? 1 : 0;

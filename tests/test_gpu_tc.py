@@ -59,6 +59,7 @@ def set_n256(monkeypatch, n256):
     'halo' = single-CTA halo-reuse kernel with per-plane B stages, 'classic' = one TMA box per tap (incl. split-K tail)."""
     monkeypatch.setenv('ESSB_TC_HALO256', N256[n256][0])
     monkeypatch.setenv('ESSB_TC_PAIR', N256[n256][1])
+    monkeypatch.setenv('ESSB_TC_PAIR128', '2' if n256 == 'pair' else '0')    # N = 128 f16f8 tiles on CTA pairs, at any size
 
 
 @pytest.fixture(autouse=True)
@@ -112,12 +113,13 @@ def test_convlstm_tc(passes, tol, N, H, W, C, with_state, n256, monkeypatch):
 
 
 @pytest.mark.parametrize('passes,tol', [(3, 1e-3), (2, 1e-3), (1, 3e-2)])
-@pytest.mark.parametrize('Cin,Cout,H,W', [(32, 64, 16, 32), (64, 128, 24, 16), (128, 256, 14, 22), (32, 64, 110, 160)])
+@pytest.mark.parametrize('Cin,Cout,H,W', [(32, 64, 16, 32), (64, 128, 24, 16), (64, 128, 72, 100), (128, 256, 14, 22),
+                                          (32, 64, 110, 160)])
 @pytest.mark.parametrize('n256', ['pair', 'halo', 'classic'])
 def test_encoder_conv_tc(passes, tol, Cin, Cout, H, W, n256, monkeypatch):
     """conv5x5 stride 2 + folded BN + ReLU through parity views (and the 32-channel pixel-pair fold)."""
-    if n256 != 'pair' and Cout != 256:
-        pytest.skip('the N = 256 kernel choice only matters for N = 256 tiles')
+    if n256 != 'pair' and Cout != 256 and not (Cout == 128 and passes == 2 and n256 == 'halo'):
+        pytest.skip('the kernel choice only matters for N = 256 tiles and for N = 128 tiles of the f16f8 mode')
     set_n256(monkeypatch, n256)
     import ess_b200
     from ess_b200 import ops
