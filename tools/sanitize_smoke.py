@@ -1,7 +1,9 @@
 """Small-shape pass over every kernel family for compute-sanitizer (memcheck / initcheck):
     compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
-One supervised iteration (fused unroll with flip + hot pixels, decoder fwd/bwd, loss, RAdam) in bf16x3 mode with
-the split-K tail switched on, a ConvGRU encoder window, the UDA image encoder fwd/bwd, and the fp32 mode."""
+One supervised iteration (fused unroll with flip + hot pixels, decoder fwd/bwd, loss, RAdam) in the f16f8 (default), bf16x3
+and fp32 modes with the split-K tail switched on -- B = 2 at 48 x 80 makes the 1/8 level row-stacked (tall view, masked rows)
+and runs the CTA-pair, merged-phase and halo kernels -- then the same unroll replayed as a CUDA graph, the N = 128 CTA-pair
+variant, a ConvGRU encoder window, the UDA image encoder fwd/bwd."""
 import os
 import sys
 import types
@@ -20,7 +22,7 @@ from helpers import E2VID_CFG, make_e2vid, make_events, make_labels, make_semseg
 
 ops.SPLITK = True
 B, T, C, H, W, K = 2, 2, 5, 48, 80, 6
-for mode in ('bf16x3', 'fp32'):
+for mode in ('f16f8', 'bf16x3', 'fp32'):
     e2vid = make_e2vid(mode=mode).cuda()
     dec = make_semseg(K).cuda()
     dec.mode = mode
@@ -39,6 +41,15 @@ for mode in ('bf16x3', 'fp32'):
         opt.step()
     torch.cuda.synchronize()
     print(mode, 'supervised step ok, loss %.5f' % float(loss))
+    if mode == 'f16f8':
+        for _ in range(2):
+            rec.unroll(data, T, C, graph=True)          # capture + replay, then replay only
+        torch.cuda.synchronize()
+        os.environ['ESSB_TC_PAIR128'] = '2'             # opt-in CTA-pair kernel for the N = 128 tiles
+        rec.unroll(data, T, C)
+        os.environ['ESSB_TC_PAIR128'] = '0'
+        torch.cuda.synchronize()
+        print(mode, 'graphed unroll + N=128 pair kernel ok')
 # 168 tiles on 148 SMs: exercises the split-K tail of the scheduler
 m = ess_b200.E2VIDRecurrent(dict(E2VID_CFG), mode='bf16x3').cuda().eval()
 st = None
