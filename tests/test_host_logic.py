@@ -62,6 +62,50 @@ def test_transposed_conv_phases_reproduce_conv_transpose2d():
     assert n_taps == 25 and torch.allclose(out, ref, atol=1e-12)
 
 
+def test_merged_transposed_conv_phases_reproduce_conv_transpose2d():
+    """ops.merge_convT_phases: ONE 3x3 gather-convolution with 4*Cout output channels whose channel block j is sub-pixel
+    phase (j >> 1, j & 1) == ConvTranspose2d(k5, s2, p2, output_padding 1) (e2vid/model/submodules.py:39-40); the
+    placement rule is the one the tcgen05 epilogue applies (essb_conv_tc.phase_cout)."""
+    g = torch.Generator().manual_seed(5)
+    N, Cin, Cout, H, W = 2, 3, 4, 5, 6
+    x = torch.randn(N, Cin, H, W, generator=g, dtype=torch.float64)
+    wt = torch.randn(Cin, Cout, 5, 5, generator=g).double()        # fp32-representable: the merge keeps fp32 weights
+    ref = F.conv_transpose2d(x, wt, stride=2, padding=2, output_padding=1)
+    wm = ops.merge_convT_phases(wt.float()).double()            # [4*Cout, Cin, 3, 3]
+    assert wm.shape == (4 * Cout, Cin, 3, 3) and int((wm.abs().sum((1, 2, 3)) == 0).sum()) == 0
+    taps = ops.taps_conv(3, 1)
+    y = gather_conv(x, [wm[:, :, t // 3, t % 3] for t in range(9)], taps, H, W)
+    out = torch.zeros_like(ref)
+    for j in range(4):
+        out[:, :, (j >> 1)::2, (j & 1)::2] = y[:, j * Cout:(j + 1) * Cout]
+    assert float((out - ref).abs().max()) < 1e-12
+    used = sum(len(ops.taps_convT_phase(py, px)) for py in range(2) for px in range(2))
+    assert used == 25 and int((wm.abs().sum((0, 1)) > 0).sum()) == 9   # 25 of 36 (phase, offset) blocks carry weights
+
+
+@pytest.mark.parametrize('N,H,W,expect', [(8, 440, 640, [(220, False), (112, False), (56, True)]),
+                                          (8, 200, 352, [(104, False), (52, True), (26, True)]),
+                                          (1, 440, 640, [(220, False), (110, False), (55, False)]),
+                                          (2, 64, 96, [(32, False), (16, False), (8, False)])])
+def test_row_stack_plan(N, H, W, expect, monkeypatch):
+    """E2VIDRecurrent._stack_plan: a level is row-stacked (rows per image > its height) only when that saves 16-row output
+    patches for its ConvLSTM or lets the next level's stride-2 conv run on the tall view (input period = 2 x output
+    period); never for a single image; ESS_B200_STACK=0 switches it off."""
+    from ess_b200.e2vid import E2VIDRecurrent as E
+    monkeypatch.delenv('ESS_B200_STACK', raising=False)
+    plan = E._stack_plan(N, H, W, 3)
+    assert plan == expect
+    for i, (rows, tall) in enumerate(plan):
+        oh = H >> (i + 1)
+        assert rows >= oh
+        if tall:
+            assert i > 0 and plan[i - 1][0] == 2 * rows and rows > oh
+        if rows > oh:     # never more patches than the dense layout
+            assert -(-N * rows // 16) <= N * -(-oh // 16)
+    monkeypatch.setenv('ESS_B200_STACK', '0')
+    assert E._stack_plan(N, H, W, 3) == [(H >> (i + 1), False) for i in range(3)]
+
+
 @pytest.mark.parametrize('k,pad,stride', [(3, 1, 2), (1, 0, 2), (5, 2, 2), (3, 1, 1)])
 def test_dgrad_phase_taps_reproduce_the_input_gradient(k, pad, stride):
     g = torch.Generator().manual_seed(2)
