@@ -377,6 +377,11 @@ class E2VIDRecurrent(nn.Module):
         f = 2 ** self.num_encoders
         if H % f or W % f:
             raise RuntimeError('H, W must be multiples of %d (CropParameters pads to this)' % f)
+        if torch.is_grad_enabled() and self._wants_grad(event_tensor, prev_states):
+            if self.recurrent_block_type == 'convlstm':
+                return self._forward_bptt(event_tensor, prev_states, with_image)
+            _warn_once('E2VIDRecurrent(convgru): the differentiable path is built for ConvLSTM only -- running forward-only, '
+                       'the outputs carry no gradient')
         with torch.no_grad(), ops.on_device_of(event_tensor):
             buf = self.head_planes_buffer(N, H, W, event_tensor.device)
             if buf is not None:      # tensor-core head: convert straight into its operand format
@@ -386,6 +391,81 @@ class E2VIDRecurrent(nn.Module):
             cpad = (self.num_bins + 7) // 8 * 8
             x = ops.nchw_to_nhwc(event_tensor, cpad)
             return self.forward_nhwc(x, prev_states, with_image)
+
+    # ------------------------------------------------------- differentiable path (back-propagation through time)
+    def _wants_grad(self, event_tensor, prev_states):
+        if event_tensor.requires_grad or any(p.requires_grad for p in self.parameters()):
+            return True
+        for st in (prev_states or []):
+            for t in (st if isinstance(st, (tuple, list)) else (st,)):
+                if t is not None and t.requires_grad:
+                    return True
+        return False
+
+    def _forward_bptt(self, event_tensor, prev_states, with_image=True):
+        """forward() with autograd: gradients w.r.t. the parameters, the incoming states and the event tensor, so the
+        encoder can be trained THROUGH the recurrence like the reference module (SURVEY.md s8f "later": no reference
+        trainer does it -- they freeze the encoder and call it under no_grad, which takes the fused path).  Every
+        convolution runs on this library's kernels with its hand-written input / weight gradients (`style_encoder._ConvFn`:
+        tcgen05 for the 3x3 gate convolutions, in <= 256-output-channel slices, CUDA cores for the 5x5 ones); the gate
+        non-linearities, the eval-mode BatchNorm affine and the state update are autograd-recorded elementwise ops, and the
+        4C-channel gate tensor IS materialised (the backward needs it) -- this is the slow, memory-hungry path by design.
+        `img` is computed without gradient.  ConvLSTM + eval-mode BatchNorm only."""
+        import torch.nn.functional as F
+        from .style_encoder import _ConvFn
+        if any(isinstance(m_, nn.BatchNorm2d) and m_.training for m_ in self.modules()):
+            _warn_once('E2VIDRecurrent: BatchNorm layers are in training mode but this implementation always normalises with '
+                       'the running statistics (the reference trainers call .eval(), ess_supervised_trainer.py:47)')
+        _warn_once('E2VIDRecurrent: gradient mode is on and the encoder has trainable parameters / differentiable inputs -- '
+                   'taking the differentiable (BPTT) path, several times slower than the fused inference path; wrap the '
+                   'call in torch.no_grad() or freeze the parameters when no encoder gradient is needed')
+        mode = 'bf16x3' if self.mode == 'f16f8' else self.mode
+        u = self.unetrecurrent
+        ne = self.num_encoders
+        N, Cb, H, W = event_tensor.shape
+        prev_states = list(prev_states) if prev_states is not None else [None] * ne
+        with ops.on_device_of(event_tensor):
+            cpad = (Cb + 3) // 4 * 4
+            x = F.pad(event_tensor.float().permute(0, 2, 3, 1), (0, cpad - Cb)).contiguous()
+            wh = F.pad(u.head.conv2d.weight, (0, 0, 0, 0, 0, cpad - Cb))
+            head = torch.relu(_ConvFn.apply(x, wh, 1, 2, mode) + u.head.conv2d.bias)              # unet.py:131-132,153
+            cur = head
+            blocks, states = [], []
+            for i, enc in enumerate(u.encoders):
+                conv = enc.conv.conv2d
+                y = _ConvFn.apply(cur.contiguous(), conv.weight, 2, 2, mode)                      # submodules.py:7-31
+                if conv.bias is not None:
+                    y = y + conv.bias
+                bn = getattr(enc.conv, 'norm_layer', None)
+                if bn is not None:                                                                 # eval-mode BatchNorm2d
+                    y = (y - bn.running_mean) * (bn.weight / torch.sqrt(bn.running_var + BN_EPS)) + bn.bias
+                y = torch.relu(y)
+                C = conv.out_channels
+                st = prev_states[i]
+                if st is None:                                                                     # submodules.py:196-207
+                    h_prev = torch.zeros_like(y)
+                    c_prev = torch.zeros_like(y)
+                else:
+                    h_prev = st[0].float().permute(0, 2, 3, 1).contiguous()
+                    c_prev = st[1].float().permute(0, 2, 3, 1).contiguous()
+                xh = torch.cat([y, h_prev], -1)                                                    # :212
+                gw, gb = enc.recurrent_block.Gates.weight, enc.recurrent_block.Gates.bias
+                parts = [_ConvFn.apply(xh, gw[j:j + 256], 1, 1, mode) for j in range(0, 4 * C, 256)]
+                gates = (parts[0] if len(parts) == 1 else torch.cat(parts, -1)) + gb               # :213
+                g_in, g_rem, g_out, g_cell = gates.chunk(4, -1)                                    # :216
+                c = torch.sigmoid(g_rem) * c_prev + torch.sigmoid(g_in) * torch.tanh(g_cell)       # :219-227
+                h = torch.sigmoid(g_out) * torch.tanh(c)                                           # :228
+                blocks.append(h)
+                states.append((ops.as_nchw(h), ops.as_nchw(c)))
+                cur = h
+            latent = {1: ops.as_nchw(head), 2: ops.as_nchw(blocks[0]), 4: ops.as_nchw(blocks[1]), 8: ops.as_nchw(blocks[2])}
+            img = None
+            if with_image:
+                with torch.no_grad():
+                    P = self._pack()
+                    img = ops.as_nchw(self._image_decoder(P, head.detach().contiguous(), [b.detach().contiguous() for b in blocks],
+                                                          N, H >> ne, W >> ne))
+        return img, states, latent
 
     def head_planes_buffer(self, N, H, W, device):
         """Cached zero-bordered bf16 hi/lo input buffer of the tensor-core head conv for an [N, *, H, W]

@@ -346,8 +346,10 @@ def test_e2vid_module_forward_signature(mode):
     r1 = O.e2vid_recurrent_forward(sd, E2VID_CFG, ev[:, :C], None)
     r2 = O.e2vid_recurrent_forward(sd, E2VID_CFG, ev[:, C:], r1[1])
     m = m.cuda()
-    o1 = m(ev[:, :C].cuda(), None)
-    o2 = m(ev[:, C:].cuda(), o1[1])
+    with torch.no_grad():                 # as the reference trainers call it (frozen encoder): the fused inference path
+        o1 = m(ev[:, :C].cuda(), None)
+        o2 = m(ev[:, C:].cuda(), o1[1])
+    assert not o2[2][8].requires_grad
     assert o2[0].shape == (B, 1, H, W) and o2[2][8].shape == (B, 256, H // 8, W // 8)
     assert rel_err(o2[0], r2[0]) < TOL
     for k in (1, 2, 4, 8):
@@ -356,8 +358,67 @@ def test_e2vid_module_forward_signature(mode):
         assert rel_err(h, hr) < TOL and rel_err(c, cr) < TOL
     # states handed back as plain contiguous NCHW copies (not our channels_last views) also work
     st = [(h.contiguous(), c.contiguous()) for (h, c) in o1[1]]
-    o2b = m(ev[:, C:].cuda(), st)
+    with torch.no_grad():
+        o2b = m(ev[:, C:].cuda(), st)
     assert rel_err(o2b[2][8], r2[2][8]) < TOL
+
+
+@pytest.mark.parametrize('mode', ['f16f8', 'fp32'])
+def test_e2vid_backprop_through_time(mode):
+    """The differentiable path of E2VIDRecurrent (gradient mode + trainable encoder; SURVEY.md s8f 'later'): three
+    chained windows, a loss on the last window's latents and states, gradients w.r.t. EVERY encoder parameter (head,
+    three stride-2 convs + eval BatchNorm affine, three ConvLSTM gate convolutions) and w.r.t. the events of all
+    windows vs autograd through the oracle.  Forward values must agree with the fused inference path as well."""
+    import warnings
+    B, T, C, H, W = 2, 3, 5, 32, 48
+    m = make_e2vid(mode=mode)
+    sd = {k: (v.detach().clone().double().requires_grad_(v.is_floating_point() and 'running' not in k and 'num_batches' not in k)
+              if v.is_floating_point() else v.detach().clone()) for k, v in m.state_dict().items()}
+    ev = make_events(B, T, C, H, W)
+    ev64 = ev.double().requires_grad_(True)
+    g = torch.Generator().manual_seed(3)
+    wts = {k: torch.randn(1, generator=g).item() for k in (1, 2, 4, 8, 'h0', 'c2')}
+
+    def loss_of(lat, st):
+        return sum(wts[k] * lat[k].pow(2).mean() for k in (1, 2, 4, 8)) + wts['h0'] * st[0][0].sum() * 1e-3 + \
+            wts['c2'] * st[2][1].pow(2).mean()
+
+    st = None
+    for t in range(T):
+        _, st, lat = O.e2vid_recurrent_forward(sd, E2VID_CFG, ev64[:, t * C:(t + 1) * C], st, with_image=False)
+    loss_r = loss_of(lat, st)
+    names = [k for k, v in sd.items() if v.is_floating_point() and v.requires_grad and not k.startswith('unetrecurrent.resblocks')
+             and not k.startswith('unetrecurrent.decoders') and not k.startswith('unetrecurrent.pred')]
+    grads_r = torch.autograd.grad(loss_r, [sd[k] for k in names] + [ev64])
+    m = m.cuda()
+    evc = ev.cuda().requires_grad_(True)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', RuntimeWarning)
+        st = None
+        for t in range(T):
+            img, st, lat = m(evc[:, t * C:(t + 1) * C], st, with_image=(t == T - 1))
+    assert lat[8].requires_grad and img is not None and not img.requires_grad
+    loss = loss_of(lat, st)
+    assert abs(float(loss) - float(loss_r)) < 1e-3 * abs(float(loss_r))
+    loss.backward()
+    params = dict(m.named_parameters())
+    worst = 0.0
+    for k, gr in zip(names, grads_r[:-1]):
+        ga = params[k].grad
+        assert ga is not None, k
+        e = float((ga.detach().cpu().double() - gr).norm() / gr.norm().clamp_min(1e-30))
+        worst = max(worst, e)
+        assert e < 2e-3, (k, e)
+    e_in = float((evc.grad.cpu().double() - grads_r[-1]).norm() / grads_r[-1].norm())
+    print(mode, 'BPTT: loss %.6f (oracle %.6f), worst parameter-gradient rel-L2 %.1e, event-gradient %.1e'
+          % (float(loss), float(loss_r), worst, e_in))
+    assert e_in < 2e-3
+    # and the fused inference path computes the same forward
+    with torch.no_grad():
+        st2 = None
+        for t in range(T):
+            _, st2, lat2 = m(ev[:, t * C:(t + 1) * C].cuda(), st2, with_image=False)
+    assert rel_err(lat2[8], lat[8]) < TOL and rel_err(st2[2][1], st[2][1]) < TOL
 
 
 def test_training_trajectory_and_miou_parity():

@@ -55,13 +55,15 @@ m = ess_b200.E2VIDRecurrent(dict(E2VID_CFG), mode='bf16x3').cuda().eval()
 st = None
 ev = make_events(1, 2, 5, 224, 384).cuda()
 for i in range(2):
-    _, st, lat = m(ev[:, i * 5:(i + 1) * 5], st, with_image=False)
+    with torch.no_grad():
+        _, st, lat = m(ev[:, i * 5:(i + 1) * 5], st, with_image=False)
 torch.cuda.synchronize()
 print('large-tile LSTM windows ok')
 g = ess_b200.E2VIDRecurrent(dict(E2VID_CFG, recurrent_block_type='convgru'), mode='bf16x3').cuda().eval()
 st = None
 for i in range(2):
-    _, st, _ = g(ev[:, i * 5:(i + 1) * 5, :48, :80].contiguous(), st)
+    with torch.no_grad():
+        _, st, _ = g(ev[:, i * 5:(i + 1) * 5, :48, :80].contiguous(), st)
 torch.cuda.synchronize()
 print('ConvGRU windows ok')
 enc = ess_b200.StyleEncoderE2VID(1, skip_connect=True).cuda().train()
