@@ -378,10 +378,7 @@ class E2VIDRecurrent(nn.Module):
         if H % f or W % f:
             raise RuntimeError('H, W must be multiples of %d (CropParameters pads to this)' % f)
         if torch.is_grad_enabled() and self._wants_grad(event_tensor, prev_states):
-            if self.recurrent_block_type == 'convlstm':
-                return self._forward_bptt(event_tensor, prev_states, with_image)
-            _warn_once('E2VIDRecurrent(convgru): the differentiable path is built for ConvLSTM only -- running forward-only, '
-                       'the outputs carry no gradient')
+            return self._forward_bptt(event_tensor, prev_states, with_image)
         with torch.no_grad(), ops.on_device_of(event_tensor):
             buf = self.head_planes_buffer(N, H, W, event_tensor.device)
             if buf is not None:      # tensor-core head: convert straight into its operand format
@@ -410,7 +407,7 @@ class E2VIDRecurrent(nn.Module):
         tcgen05 for the 3x3 gate convolutions, in <= 256-output-channel slices, CUDA cores for the 5x5 ones); the gate
         non-linearities, the eval-mode BatchNorm affine and the state update are autograd-recorded elementwise ops, and the
         4C-channel gate tensor IS materialised (the backward needs it) -- this is the slow, memory-hungry path by design.
-        `img` is computed without gradient.  ConvLSTM + eval-mode BatchNorm only."""
+        `img` is computed without gradient.  ConvLSTM and ConvGRU; BatchNorm always uses its running statistics."""
         import torch.nn.functional as F
         from .style_encoder import _ConvFn
         if any(isinstance(m_, nn.BatchNorm2d) and m_.training for m_ in self.modules()):
@@ -442,6 +439,19 @@ class E2VIDRecurrent(nn.Module):
                 y = torch.relu(y)
                 C = conv.out_channels
                 st = prev_states[i]
+                if self.recurrent_block_type == 'convgru':                                         # submodules.py:255-273
+                    rb = enc.recurrent_block
+                    h_prev = torch.zeros_like(y) if st is None else st.float().permute(0, 2, 3, 1).contiguous()
+                    xh = torch.cat([y, h_prev], -1)
+                    upd = torch.sigmoid(_ConvFn.apply(xh, rb.update_gate.weight, 1, 1, mode) + rb.update_gate.bias)
+                    rst = torch.sigmoid(_ConvFn.apply(xh, rb.reset_gate.weight, 1, 1, mode) + rb.reset_gate.bias)
+                    out = torch.tanh(_ConvFn.apply(torch.cat([y, h_prev * rst], -1), rb.out_gate.weight, 1, 1, mode) +
+                                     rb.out_gate.bias)
+                    h = h_prev * (1 - upd) + out * upd
+                    blocks.append(h)
+                    states.append(ops.as_nchw(h))
+                    cur = h
+                    continue
                 if st is None:                                                                     # submodules.py:196-207
                     h_prev = torch.zeros_like(y)
                     c_prev = torch.zeros_like(y)

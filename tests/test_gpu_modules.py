@@ -363,15 +363,17 @@ def test_e2vid_module_forward_signature(mode):
     assert rel_err(o2b[2][8], r2[2][8]) < TOL
 
 
-@pytest.mark.parametrize('mode', ['f16f8', 'fp32'])
-def test_e2vid_backprop_through_time(mode):
+@pytest.mark.parametrize('mode,block', [('f16f8', 'convlstm'), ('fp32', 'convlstm'), ('f16f8', 'convgru')])
+def test_e2vid_backprop_through_time(mode, block):
     """The differentiable path of E2VIDRecurrent (gradient mode + trainable encoder; SURVEY.md s8f 'later'): three
     chained windows, a loss on the last window's latents and states, gradients w.r.t. EVERY encoder parameter (head,
-    three stride-2 convs + eval BatchNorm affine, three ConvLSTM gate convolutions) and w.r.t. the events of all
+    three stride-2 convs + eval BatchNorm affine, the gate convolutions of three ConvLSTM / ConvGRU cells) and w.r.t. the events of all
     windows vs autograd through the oracle.  Forward values must agree with the fused inference path as well."""
     import warnings
     B, T, C, H, W = 2, 3, 5, 32, 48
-    m = make_e2vid(mode=mode)
+    CFG = dict(E2VID_CFG, recurrent_block_type=block)
+    lstm = block == 'convlstm'
+    m = make_e2vid(CFG, mode=mode)
     sd = {k: (v.detach().clone().double().requires_grad_(v.is_floating_point() and 'running' not in k and 'num_batches' not in k)
               if v.is_floating_point() else v.detach().clone()) for k, v in m.state_dict().items()}
     ev = make_events(B, T, C, H, W)
@@ -380,12 +382,12 @@ def test_e2vid_backprop_through_time(mode):
     wts = {k: torch.randn(1, generator=g).item() for k in (1, 2, 4, 8, 'h0', 'c2')}
 
     def loss_of(lat, st):
-        return sum(wts[k] * lat[k].pow(2).mean() for k in (1, 2, 4, 8)) + wts['h0'] * st[0][0].sum() * 1e-3 + \
-            wts['c2'] * st[2][1].pow(2).mean()
+        h0, s2 = (st[0][0], st[2][1]) if lstm else (st[0], st[2])
+        return sum(wts[k] * lat[k].pow(2).mean() for k in (1, 2, 4, 8)) + wts['h0'] * h0.sum() * 1e-3 + wts['c2'] * s2.pow(2).mean()
 
     st = None
     for t in range(T):
-        _, st, lat = O.e2vid_recurrent_forward(sd, E2VID_CFG, ev64[:, t * C:(t + 1) * C], st, with_image=False)
+        _, st, lat = O.e2vid_recurrent_forward(sd, CFG, ev64[:, t * C:(t + 1) * C], st, with_image=False)
     loss_r = loss_of(lat, st)
     names = [k for k, v in sd.items() if v.is_floating_point() and v.requires_grad and not k.startswith('unetrecurrent.resblocks')
              and not k.startswith('unetrecurrent.decoders') and not k.startswith('unetrecurrent.pred')]
@@ -410,7 +412,7 @@ def test_e2vid_backprop_through_time(mode):
         worst = max(worst, e)
         assert e < 2e-3, (k, e)
     e_in = float((evc.grad.cpu().double() - grads_r[-1]).norm() / grads_r[-1].norm())
-    print(mode, 'BPTT: loss %.6f (oracle %.6f), worst parameter-gradient rel-L2 %.1e, event-gradient %.1e'
+    print(mode, block, 'BPTT: loss %.6f (oracle %.6f), worst parameter-gradient rel-L2 %.1e, event-gradient %.1e'
           % (float(loss), float(loss_r), worst, e_in))
     assert e_in < 2e-3
     # and the fused inference path computes the same forward
@@ -418,7 +420,7 @@ def test_e2vid_backprop_through_time(mode):
         st2 = None
         for t in range(T):
             _, st2, lat2 = m(ev[:, t * C:(t + 1) * C].cuda(), st2, with_image=False)
-    assert rel_err(lat2[8], lat[8]) < TOL and rel_err(st2[2][1], st[2][1]) < TOL
+    assert rel_err(lat2[8], lat[8]) < TOL and rel_err(st2[2][1] if lstm else st2[2], st[2][1] if lstm else st[2]) < TOL
 
 
 def test_training_trajectory_and_miou_parity():
