@@ -57,6 +57,8 @@ class _ConvLayer(nn.Module):          # e2vid/model/submodules.py:7-31
         self.conv2d = nn.Conv2d(cin, cout, k, stride, pad, bias=(norm != 'BN'))
         if norm == 'BN':
             self.norm_layer = nn.BatchNorm2d(cout)
+        elif norm == 'IN':                # submodules.py:21-22: running statistics, no affine parameters
+            self.norm_layer = nn.InstanceNorm2d(cout, track_running_stats=True)
 
 
 class _TransposedConvLayer(nn.Module):  # submodules.py:34-62
@@ -66,6 +68,8 @@ class _TransposedConvLayer(nn.Module):  # submodules.py:34-62
                                                     bias=(norm != 'BN'))
         if norm == 'BN':
             self.norm_layer = nn.BatchNorm2d(cout)
+        elif norm == 'IN':                # submodules.py:50-51
+            self.norm_layer = nn.InstanceNorm2d(cout, track_running_stats=True)
 
 
 class _ConvLSTM(nn.Module):           # submodules.py:175-188
@@ -101,6 +105,9 @@ class _ResidualBlock(nn.Module):      # submodules.py:140-155
         if norm == 'BN':
             self.bn1 = nn.BatchNorm2d(c)
             self.bn2 = nn.BatchNorm2d(c)
+        elif norm == 'IN':                # submodules.py:149-151: plain InstanceNorm2d (per-sample statistics, nothing stored)
+            self.bn1 = nn.InstanceNorm2d(c)
+            self.bn2 = nn.InstanceNorm2d(c)
         self.conv2 = nn.Conv2d(c, c, 3, 1, 1, bias=bias)
 
 
@@ -127,10 +134,14 @@ class _UNetRecurrent(nn.Module):      # unet.py:117-143
 
 def _bn_fold(conv_bias, bn, cout, device):
     """Eval-mode BatchNorm -> (scale, bias) per output channel (submodules.py:19-20,26-27)."""
-    if bn is None:
+    if bn is None or getattr(bn, 'running_var', None) is None:      # no norm, or a plain InstanceNorm2d (handled by its caller)
         return None, (conv_bias.detach().float().contiguous() if conv_bias is not None else None)
-    scale = (bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + BN_EPS))
-    bias = bn.bias.detach().float() - bn.running_mean.float() * scale
+    if isinstance(bn, nn.InstanceNorm2d):      # norm='IN' conv layers: eval-mode InstanceNorm2d(track_running_stats=True)
+        scale = 1.0 / torch.sqrt(bn.running_var.float() + BN_EPS)      # = (x - running_mean) / sqrt(running_var + eps)
+        bias = -bn.running_mean.float() * scale
+    else:
+        scale = (bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + BN_EPS))
+        bias = bn.bias.detach().float() - bn.running_mean.float() * scale
     if conv_bias is not None:
         bias = bias + conv_bias.detach().float() * scale
     return scale.contiguous(), bias.contiguous()
@@ -157,8 +168,8 @@ class E2VIDRecurrent(nn.Module):
         self.norm = str(config['norm']) if 'norm' in config else None
         self.use_upsample_conv = bool(config.get('use_upsample_conv', True))
         self.recurrent_block_type = str(config.get('recurrent_block_type', 'convlstm'))
-        if self.norm not in (None, 'BN'):
-            raise NotImplementedError("E2VIDRecurrent: norm=%r (only None and 'BN' are built)" % (self.norm,))
+        if self.norm not in (None, 'BN', 'IN'):
+            raise ValueError("E2VIDRecurrent: norm=%r (None, 'BN' or 'IN', submodules.py:19-22)" % (self.norm,))
         if self.recurrent_block_type not in ('convlstm', 'convgru'):
             raise ValueError(self.recurrent_block_type)
         if self.num_encoders < 3:
@@ -266,7 +277,7 @@ class E2VIDRecurrent(nn.Module):
             s1, b1 = _bn_fold(rbk.conv1.bias, getattr(rbk, 'bn1', None), None, dev)
             s2, b2 = _bn_fold(rbk.conv2.bias, getattr(rbk, 'bn2', None), None, dev)
             P['res%d' % j] = (ops.pack_weight(rbk.conv1.weight, s1), b1, ops.pack_weight(rbk.conv2.weight, s2), b2)
-            if tc:
+            if tc and self.norm != 'IN':      # norm='IN': the two resblocks normalise per sample -> fp32 image decoder
                 P['res%d_tc' % j] = pk(rbk.conv1.weight, s1) + pk(rbk.conv2.weight, s2)
         for i, dec in enumerate(u.decoders):
             bn = getattr(dec, 'norm_layer', None)
@@ -434,7 +445,9 @@ class E2VIDRecurrent(nn.Module):
                 if conv.bias is not None:
                     y = y + conv.bias
                 bn = getattr(enc.conv, 'norm_layer', None)
-                if bn is not None:                                                                 # eval-mode BatchNorm2d
+                if isinstance(bn, nn.InstanceNorm2d):                                              # norm='IN': running statistics
+                    y = (y - bn.running_mean) / torch.sqrt(bn.running_var + BN_EPS)
+                elif bn is not None:                                                               # eval-mode BatchNorm2d
                     y = (y - bn.running_mean) * (bn.weight / torch.sqrt(bn.running_var + BN_EPS)) + bn.bias
                 y = torch.relu(y)
                 C = conv.out_channels
@@ -669,13 +682,14 @@ class E2VIDRecurrent(nn.Module):
             return None, states, latent
         cmax = base * 2 ** ne
         if tc_mode and len(block_planes) == ne and base % 32 == 0 and cmax <= 256 * 4 and base * 2 % 64 == 0 \
-                and all('dec%d_tc' % i in P for i in range(ne)):
+                and all('dec%d_tc' % i in P for i in range(ne)) and 'res0_tc' in P:
             img = self._image_decoder_tc(P, head, blocks, block_planes, N, h_in, w_in, passes)
         else:
             if tc_mode:
-                _warn_once('E2VIDRecurrent(mode=%r): this configuration (base_num_channels=%d) runs its image decoder on '
-                           'the fp32 CUDA-core kernels (~10x slower than the tensor-core path; channel counts must be '
-                           'multiples of 32 with 64-wide decoder inputs)' % (self.mode, base))
+                _warn_once('E2VIDRecurrent(mode=%r): this configuration (base_num_channels=%d, norm=%r) runs its image decoder '
+                           'on the fp32 CUDA-core kernels (~10x slower than the tensor-core path; that one needs channel '
+                           'counts that are multiples of 32 with 64-wide decoder inputs and norm None / BN)'
+                           % (self.mode, base, self.norm))
             img = self._image_decoder(P, head, blocks, N, h_in, w_in)
         return ops.as_nchw(img), states, latent
 
@@ -764,8 +778,17 @@ class E2VIDRecurrent(nn.Module):
         nres = self.num_residual_blocks
         for j in range(nres):                                                      # submodules.py:157-172
             w1, b1, w2, b2 = P['res%d' % j]
-            t, _, _, _ = ops.conv([Seg(x)], w1, b1, N, h, w, h, w, cmax, t3, act=ACT_RELU)
             post = blocks[ne - 1] if (j == nres - 1 and not concat) else None      # skip_sum, unet.py:175
+            if self.norm == 'IN':
+                # conv1 -> InstanceNorm (per-sample statistics) -> ReLU -> conv2 -> InstanceNorm -> + x -> ReLU: the
+                # statistics come out of the conv epilogue, IN + ReLU are applied by the next conv's loader
+                t, _, st1, _ = ops.conv([Seg(x)], w1, b1, N, h, w, h, w, cmax, t3, want_stats=True)
+                m1, r1 = ops.in_finalize(st1, h * w)
+                y2, _, st2, _ = ops.conv([Seg(t, mean=m1, rstd=r1, relu=True)], w2, b2, N, h, w, h, w, cmax, t3, want_stats=True)
+                m2, r2 = ops.in_finalize(st2, h * w)
+                x = ops.norm_act_add(ops.norm_act_add(y2, m2, r2, relu=False, res=x), relu=True, res=post)
+                continue
+            t, _, _, _ = ops.conv([Seg(x)], w1, b1, N, h, w, h, w, cmax, t3, act=ACT_RELU)
             x, _, _, _ = ops.conv([Seg(t)], w2, b2, N, h, w, h, w, cmax, t3, act=ACT_RELU, res_pre=x, res_post=post)
         for i in range(ne):                                                        # unet.py:175-176
             wd, bd, cout = P['dec%d' % i]

@@ -76,12 +76,21 @@ def _bn_eval(x, sd, prefix):
                         sd[prefix + '.weight'], sd[prefix + '.bias'], training=False, eps=BN_EPS)
 
 
+def _in_eval(x, sd, prefix):
+    """nn.InstanceNorm2d(C, track_running_stats=True) in eval mode (submodules.py:21-22,50-51,80-81): F.instance_norm with
+    use_input_stats=False, i.e. the RUNNING statistics, no affine parameters."""
+    rm, rv = sd[prefix + '.running_mean'], sd[prefix + '.running_var']
+    return (x - rm.view(1, -1, 1, 1)) / torch.sqrt(rv.view(1, -1, 1, 1) + BN_EPS)
+
+
 def conv_layer(x, sd, prefix, stride, padding, norm, activation='relu'):
     """ConvLayer.forward (submodules.py:24-31): conv (+bias unless BN) -> norm -> activation."""
     out = F.conv2d(x, sd[prefix + '.conv2d.weight'], sd.get(prefix + '.conv2d.bias'),
                    stride=stride, padding=padding)
     if norm == 'BN':
         out = _bn_eval(out, sd, prefix + '.norm_layer')
+    elif norm == 'IN':
+        out = _in_eval(out, sd, prefix + '.norm_layer')
     elif norm is not None:
         raise NotImplementedError('norm=%r' % (norm,))
     if activation == 'relu':
@@ -126,10 +135,14 @@ def residual_block(x, sd, prefix, norm):
     out = F.conv2d(x, sd[prefix + '.conv1.weight'], sd.get(prefix + '.conv1.bias'), padding=1)
     if norm == 'BN':
         out = _bn_eval(out, sd, prefix + '.bn1')
+    elif norm == 'IN':                        # nn.InstanceNorm2d(C) WITHOUT running statistics (submodules.py:149-151):
+        out = F.instance_norm(out, eps=BN_EPS)  # per-sample statistics in train and eval mode alike
     out = torch.relu(out)
     out = F.conv2d(out, sd[prefix + '.conv2.weight'], sd.get(prefix + '.conv2.bias'), padding=1)
     if norm == 'BN':
         out = _bn_eval(out, sd, prefix + '.bn2')
+    elif norm == 'IN':
+        out = F.instance_norm(out, eps=BN_EPS)
     return torch.relu(out + x)
 
 
@@ -144,6 +157,8 @@ def upsample_layer(x, sd, prefix, norm, use_upsample_conv):
                                  stride=2, padding=2, output_padding=1)
     if norm == 'BN':
         out = _bn_eval(out, sd, prefix + '.norm_layer')
+    elif norm == 'IN':
+        out = _in_eval(out, sd, prefix + '.norm_layer')
     return torch.relu(out)
 
 

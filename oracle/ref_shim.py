@@ -138,6 +138,9 @@ def randomize_bn_(module, generator=None):
             with torch.no_grad():
                 m.weight.copy_(torch.rand(m.weight.shape, generator=generator) + 0.5)
                 m.bias.copy_(torch.randn(m.bias.shape, generator=generator) * 0.1)
+        elif isinstance(m, torch.nn.InstanceNorm2d) and m.track_running_stats:      # norm='IN' conv layers
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=generator) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=generator) + 0.5)
 
 
 def make_reference_e2vid(cfg=None, seed=6):

@@ -22,7 +22,8 @@ def main():
     from models.style_networks import SemSegE2VID, StyleEncoderE2VID
     out = {}
     for name, over in (('e2vid_lightweight_convlstm', {}), ('e2vid_convgru', dict(recurrent_block_type='convgru')),
-                       ('e2vid_upsample_conv_10bins', dict(use_upsample_conv=True, num_bins=10))):
+                       ('e2vid_upsample_conv_10bins', dict(use_upsample_conv=True, num_bins=10)),
+                       ('e2vid_instance_norm', dict(norm='IN'))):
         cfg = dict(ref_shim.E2VID_LIGHTWEIGHT_CFG, **over)
         out[name] = dict(cfg=cfg, state_dict=listing(ref_shim.make_reference_e2vid(cfg)))
     torch.manual_seed(0)

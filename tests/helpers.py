@@ -34,6 +34,9 @@ def randomize_bn_(module, seed=7):
             with torch.no_grad():
                 m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
                 m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+        elif isinstance(m, torch.nn.InstanceNorm2d) and m.track_running_stats:      # norm='IN' conv layers
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
 
 
 def make_e2vid(cfg=None, seed=6, mode='fp32'):

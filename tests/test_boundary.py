@@ -16,7 +16,8 @@ def listing(module):
     return [[k, list(v.shape), str(v.dtype)] for k, v in module.state_dict().items()]
 
 
-@pytest.mark.parametrize('name', ['e2vid_lightweight_convlstm', 'e2vid_convgru', 'e2vid_upsample_conv_10bins'])
+@pytest.mark.parametrize('name', ['e2vid_lightweight_convlstm', 'e2vid_convgru', 'e2vid_upsample_conv_10bins',
+                                  'e2vid_instance_norm'])
 def test_e2vid_state_dict_contract(name):
     import ess_b200
     m = ess_b200.E2VIDRecurrent(dict(KEYS[name]['cfg']), mode='fp32')

@@ -102,7 +102,7 @@ def test_full_length_unroll_logits_within_contract(mode):
     assert max(errs.values()) < TOL, errs
 
 
-@pytest.mark.parametrize('variant', ['convgru', 'upsample_conv', 'no_norm', 'reflect_pad', 'concat'])
+@pytest.mark.parametrize('variant', ['convgru', 'upsample_conv', 'no_norm', 'reflect_pad', 'concat', 'in_norm'])
 def test_e2vid_variants_fp32(variant):
     import ess_b200
     cfg = dict(E2VID_CFG, base_num_channels=8, num_bins=3)
@@ -115,6 +115,8 @@ def test_e2vid_variants_fp32(variant):
         cfg.pop('norm')
     elif variant == 'concat':
         cfg['skip_type'] = 'concat'
+    elif variant == 'in_norm':
+        cfg['norm'] = 'IN'
     else:
         H, W = 30, 43
     m = make_e2vid(cfg, mode='fp32')
@@ -156,6 +158,29 @@ def test_e2vid_variants_tensor_core(variant, mode):
     assert img.shape == img_r.shape
     errs = dict(img=rel_err(img, img_r), l8=rel_err(lat[8], lat_r[8]), l1=rel_err(lat[1], lat_r[1]))
     print(variant, mode, {k: '%.1e' % v for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+
+
+@pytest.mark.parametrize('mode', ['bf16x3', 'f16f8'])
+def test_e2vid_instance_norm_in_tensor_core_mode(mode):
+    """norm='IN' (submodules.py:21-22,149-151): the conv layers' InstanceNorm2d(track_running_stats=True) is folded like an
+    eval BatchNorm (running statistics, no affine) and the encoder stays on the tcgen05 kernels; the two resblocks use
+    per-sample statistics, so the image decoder takes the fp32 kernels (and says so)."""
+    import ess_b200
+    cfg = dict(E2VID_CFG, norm='IN')
+    H, W = 48, 64
+    m = make_e2vid(cfg, mode=mode)
+    sd = sd_cpu(m)
+    data = make_events(2, 2, 5, H, W)
+    img_r, st_r, lat_r = O.encoder_unroll(sd, cfg, data, 2, 5)
+    m = m.cuda()
+    rec = ess_b200.ImageReconstructor(m, H, W, 5, 'cuda')
+    from ess_b200 import e2vid as E
+    E._WARNED.clear()
+    with pytest.warns(RuntimeWarning, match='image decoder'):
+        img, st, lat = rec.unroll(data.cuda(), 2, 5)
+    errs = dict(img=rel_err(img, img_r), l8=rel_err(lat[8], lat_r[8]), l2=rel_err(lat[2], lat_r[2]), c2=rel_err(st[2][1], st_r[2][1]))
+    print(mode, {k: '%.1e' % v for k, v in errs.items()})
     assert max(errs.values()) < TOL, errs
 
 

@@ -72,7 +72,7 @@ def test_oracle_vs_live_reference_lightweight():
 
 
 @needs_ref
-@pytest.mark.parametrize('variant', ['convgru', 'upsample_conv', 'no_norm', 'reflect_pad'])
+@pytest.mark.parametrize('variant', ['convgru', 'upsample_conv', 'no_norm', 'reflect_pad', 'in_norm', 'in_norm_upsample'])
 def test_oracle_vs_live_reference_variants(variant):
     ref_shim.install()
     from e2vid.image_reconstructor import ImageReconstructor
@@ -84,6 +84,9 @@ def test_oracle_vs_live_reference_variants(variant):
         cfg['use_upsample_conv'] = True
     elif variant == 'no_norm':
         cfg.pop('norm')
+    elif variant.startswith('in_norm'):       # InstanceNorm2d(track_running_stats=True) in the conv layers, plain IN in the resblocks
+        cfg['norm'] = 'IN'
+        cfg['use_upsample_conv'] = variant.endswith('upsample')
     else:
         H, W = 30, 43
     m = ref_shim.make_reference_e2vid(cfg)
