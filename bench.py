@@ -850,7 +850,11 @@ def main():
                 step_frac_of_bf16_peak=value * fps / 1e12 / (peaks['bf16'] * world),
                 e2e=dict(value=e2e_value, unit='samples/s', ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=stage_d.numel() * 4 + stage_l.numel() * 8, d2h_bytes_per_step=4,
-                         h2d_gb_per_s=h2d_gbs, host_numa_binding=numa, host_wall_ms_per_step=list(e2e_step_ms)),
+                         h2d_gb_per_s=h2d_gbs, host_numa_binding=numa, host_wall_ms_per_step=list(e2e_step_ms),
+                         # diagnostic: the first timed step cannot hide its own H2D copy behind a previous step (pipeline
+                         # fill, part of `value` above); the remaining steps are the steady state of a training loop
+                         steady_state_value=((len(e2e_step_ms) - 1) * B * world / (sum(e2e_step_ms[1:]) / 1e3)
+                                             if len(e2e_step_ms) > 1 else None)),
                 gpu_launches=launches, clocks=dict(sm_mhz=clk['sm_mhz'], sm_max_mhz=clk['sm_max_mhz'],
                                                    reasons=clk['reasons'], samples=clk['samples']),
                 roofline=roof)
