@@ -173,6 +173,20 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_dgrad_kernel(const float* 
 // A warp instruction loads RPW = 128 / CIN consecutive pixel rows as float4 per lane (fully coalesced); lane =
 // (row within the group, 4-channel group).  Each lane keeps 4 x 16 accumulators; row groups are folded with
 // shuffles once at the end.
+__device__ __forceinline__ void pw_cp_async16(float* dst_smem, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void pw_cp_async4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void pw_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void pw_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Tiles of TROWS pixel rows (activation rows [TROWS][CIN] and dy rows [TROWS][Cout]) are staged in shared memory with
+// cp.async, double-buffered: the loads of tile t+1 are in flight while tile t is multiplied, at no register cost.  (With the
+// loads issued from registers the kernel sat at 25 % occupancy -- 64 + 16 accumulators per lane -- waiting on global memory:
+// ncu long-scoreboard 53 % of the stall samples, 1.2 TB/s; profiles/r02o_hbm_kernels.md.)
 template <int CIN>
 __global__ void __launch_bounds__(PW_THREADS) pw_conv_wgrad_kernel(essb_src s, const float* __restrict__ dy, int ld_dy,
                                                                    long long rows, long long P, int Cout,
@@ -180,8 +194,10 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_wgrad_kernel(essb_src s, c
   constexpr int C4 = CIN / 4;                          // lanes per pixel row
   constexpr int RPW = 32 / C4;                         // pixel rows per warp load (4 or 2)
   constexpr int GP = PW_MAX_COUT + 4;                  // dy row pitch in shared memory (conflict-free 128-bit reads)
-  constexpr int TROWS = PW_THREADS;                    // rows per staged dy tile
-  __shared__ __align__(16) float g_s[TROWS * GP];
+  constexpr int TROWS = PW_THREADS;                    // rows per staged tile
+  extern __shared__ __align__(16) float pw_dyn[];      // [2][TROWS * CIN] activation tiles, then [2][TROWS * GP] dy tiles
+  float* const x_s = pw_dyn;
+  float* const g_s = pw_dyn + 2 * TROWS * CIN;
   __shared__ float red[PW_MAX_COUT + 1][CIN];          // cross-warp reduction ([PW_MAX_COUT] row = bias partials)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cg = lane % C4, rg = lane / C4;
@@ -196,58 +212,82 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_wgrad_kernel(essb_src s, c
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j][k] = 0.f;
   }
-  for (long long t0 = r0; t0 < r1; t0 += TROWS) {
+  // the dy columns [Cout, 16) are never written by the copies: zero both stages once
+  for (int i = threadIdx.x; i < 2 * TROWS * GP; i += PW_THREADS) g_s[i] = 0.f;
+  __syncthreads();
+  auto issue = [&](int st, long long t0) {
     const long long left = r1 - t0;
     const int rows_here = left < TROWS ? (int)left : TROWS;
-    __syncthreads();
-    // stage the dy tile [rows_here][Cout] -> g_s[row][GP] (zero padded)
-    for (int i = threadIdx.x; i < TROWS * PW_MAX_COUT; i += PW_THREADS) {
-      const int r = i / PW_MAX_COUT, k = i - r * PW_MAX_COUT;
-      g_s[r * GP + k] = (r < rows_here && k < Cout) ? dy[(t0 + r) * ld_dy + k] : 0.f;
+    float* xs = x_s + st * (TROWS * CIN);
+    float* gs = g_s + st * (TROWS * GP);
+    for (int i = threadIdx.x; i < rows_here * C4; i += PW_THREADS) {
+      const int r = i / C4, c4 = i - r * C4;
+      pw_cp_async16(xs + r * CIN + c4 * 4, s.ptr + (t0 + r) * s.ld + c4 * 4);
+    }
+    for (int i = threadIdx.x; i < rows_here * Cout; i += PW_THREADS) {
+      const int r = i / Cout, k = i - r * Cout;
+      pw_cp_async4(gs + r * GP + k, dy + (t0 + r) * ld_dy + k);
+    }
+    pw_cp_async_commit();
+  };
+  int st = 0;
+  if (r0 < r1) issue(0, r0);
+  for (long long t0 = r0; t0 < r1; t0 += TROWS, st ^= 1) {
+    const long long left = r1 - t0;
+    const int rows_here = left < TROWS ? (int)left : TROWS;
+    if (t0 + TROWS < r1) {
+      issue(st ^ 1, t0 + TROWS);                       // stage st^1 was released by the barrier that ended the last iteration
+      pw_cp_async_wait<1>();
+    } else {
+      pw_cp_async_wait<0>();
     }
     __syncthreads();
+    const float* xs = x_s + st * (TROWS * CIN);
+    const float* gsb = g_s + st * (TROWS * GP);
     const int wr0 = warp * 32;                          // this warp's 32 rows of the tile
-    if (wr0 >= rows_here) continue;
-    const int wrows = min(32, rows_here - wr0);
-    const long long p0 = t0 + wr0;
-    const long long n_first = p0 / P, n_last = (p0 + wrows - 1) / P;
-    float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), rstd = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (s.mean) {
-      mean = *reinterpret_cast<const float4*>(s.mean + n_first * CIN + cg * 4);
-      rstd = *reinterpret_cast<const float4*>(s.rstd + n_first * CIN + cg * 4);
-    }
+    if (wr0 < rows_here) {
+      const int wrows = min(32, rows_here - wr0);
+      const long long p0 = t0 + wr0;
+      const long long n_first = p0 / P, n_last = (p0 + wrows - 1) / P;
+      float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), rstd = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (s.mean) {
+        mean = *reinterpret_cast<const float4*>(s.mean + n_first * CIN + cg * 4);
+        rstd = *reinterpret_cast<const float4*>(s.rstd + n_first * CIN + cg * 4);
+      }
 #pragma unroll 4
-    for (int i = 0; i < 32; i += RPW) {
-      const int r = i + rg;
-      if (r < wrows) {
-        const long long p = p0 + r;
-        float4 v = *reinterpret_cast<const float4*>(s.ptr + p * s.ld + cg * 4);
-        if (s.mean) {
-          float4 m = mean, q = rstd;
-          if (n_first != n_last && p / P != n_first) {    // the warp's rows straddle two samples (rare)
-            m = *reinterpret_cast<const float4*>(s.mean + n_last * CIN + cg * 4);
-            q = *reinterpret_cast<const float4*>(s.rstd + n_last * CIN + cg * 4);
+      for (int i = 0; i < 32; i += RPW) {
+        const int r = i + rg;
+        if (r < wrows) {
+          const long long p = p0 + r;
+          float4 v = *reinterpret_cast<const float4*>(xs + (wr0 + r) * CIN + cg * 4);
+          if (s.mean) {
+            float4 m = mean, q = rstd;
+            if (n_first != n_last && p / P != n_first) {    // the warp's rows straddle two samples (rare)
+              m = *reinterpret_cast<const float4*>(s.mean + n_last * CIN + cg * 4);
+              q = *reinterpret_cast<const float4*>(s.rstd + n_last * CIN + cg * 4);
+            }
+            v.x = (v.x - m.x) * q.x; v.y = (v.y - m.y) * q.y; v.z = (v.z - m.z) * q.z; v.w = (v.w - m.w) * q.w;
           }
-          v.x = (v.x - m.x) * q.x; v.y = (v.y - m.y) * q.y; v.z = (v.z - m.z) * q.z; v.w = (v.w - m.w) * q.w;
-        }
-        if (s.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        const float4* gr = reinterpret_cast<const float4*>(g_s + (wr0 + r) * GP);
+          if (s.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          const float4* gr = reinterpret_cast<const float4*>(gsb + (wr0 + r) * GP);
 #pragma unroll
-        for (int k4 = 0; k4 < PW_MAX_COUT / 4; ++k4) {
-          const float4 g = gr[k4];
-          const float gk[4] = {g.x, g.y, g.z, g.w};
+          for (int k4 = 0; k4 < PW_MAX_COUT / 4; ++k4) {
+            const float4 g = gr[k4];
+            const float gk[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int k = k4 * 4 + e;
-            acc[0][k] = fmaf(v.x, gk[e], acc[0][k]);
-            acc[1][k] = fmaf(v.y, gk[e], acc[1][k]);
-            acc[2][k] = fmaf(v.z, gk[e], acc[2][k]);
-            acc[3][k] = fmaf(v.w, gk[e], acc[3][k]);
-            if (cg == 0) accb[k] += gk[e];
+            for (int e = 0; e < 4; ++e) {
+              const int k = k4 * 4 + e;
+              acc[0][k] = fmaf(v.x, gk[e], acc[0][k]);
+              acc[1][k] = fmaf(v.y, gk[e], acc[1][k]);
+              acc[2][k] = fmaf(v.z, gk[e], acc[2][k]);
+              acc[3][k] = fmaf(v.w, gk[e], acc[3][k]);
+              if (cg == 0) accb[k] += gk[e];
+            }
           }
         }
       }
     }
+    __syncthreads();                                    // every warp is done with stage st before it is refilled
   }
   // fold the row groups of the warp (lanes with equal cg), then the warps one after the other (deterministic)
 #pragma unroll
@@ -305,7 +345,7 @@ __global__ void pw_conv_wgrad_reduce_kernel(const float* __restrict__ part, int 
 
 int pw_wgrad_blocks(long long rows) {
   long long nb = (rows + 2047) / 2048;
-  if (nb > 148 * 8) nb = 148 * 8;
+  if (nb > 148 * 2) nb = 148 * 2;      // two resident blocks per SM (104 KB of staging each): long tile loops keep the pipeline full
   if (nb < 1) nb = 1;
   return (int)nb;
 }
@@ -371,10 +411,19 @@ extern "C" int essb_pw_conv_wgrad(const essb_src* src, const float* dy, int ld_d
   }
   const long long rpb = (rows + nb - 1) / nb;
   cudaStream_t st = (cudaStream_t)stream;
-  if (src->C == 32)
-    pw_conv_wgrad_kernel<32><<<nb, PW_THREADS, 0, st>>>(*src, dy, ld_dy, rows, P, Cout, rpb, workspace);
-  else
-    pw_conv_wgrad_kernel<64><<<nb, PW_THREADS, 0, st>>>(*src, dy, ld_dy, rows, P, Cout, rpb, workspace);
+  const size_t smem = (size_t)2 * PW_THREADS * (src->C + PW_MAX_COUT + 4) * sizeof(float);   // two stages of (x tile + dy tile)
+  cudaError_t e;
+  if (src->C == 32) {
+    e = cudaFuncSetAttribute(pw_conv_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) pw_conv_wgrad_kernel<32><<<nb, PW_THREADS, smem, st>>>(*src, dy, ld_dy, rows, P, Cout, rpb, workspace);
+  } else {
+    e = cudaFuncSetAttribute(pw_conv_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) pw_conv_wgrad_kernel<64><<<nb, PW_THREADS, smem, st>>>(*src, dy, ld_dy, rows, P, Cout, rpb, workspace);
+  }
+  if (e != cudaSuccess) {
+    essb_set_error("essb_pw_conv_wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    return ESSB_ERR_LAUNCH;
+  }
   ESSB_LAUNCH_CHECK("essb_pw_conv_wgrad");
   const int total = Cout * src->C + Cout;
   pw_conv_wgrad_reduce_kernel<<<(total * 32 + 255) / 256, 256, 0, st>>>(workspace, nb, src->C, Cout, dw, dbias);
