@@ -1311,6 +1311,74 @@ __global__ void split_bf16_kernel(essb_src s, int N, int H, int W, __nv_bfloat16
   *reinterpret_cast<uint2*>(lo_) = *reinterpret_cast<uint2*>(l);
 }
 
+// Fast path of split_bf16_kernel: 8 channels per thread (two 128-bit loads, 128-bit plane stores), 32-bit index arithmetic,
+// the upsampling coordinates only when the source IS upsampled.  Same values as the general kernel.
+template <int UPS, int FMT>
+__global__ void __launch_bounds__(256) split_planes8_kernel(essb_src s, int H, int W, __nv_bfloat16* __restrict__ hi,
+                                                            __nv_bfloat16* __restrict__ lo, int ld_out, int c_off, int cq8,
+                                                            unsigned total) {
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const unsigned pix = idx / (unsigned)cq8;
+  const int c = (int)(idx - pix * (unsigned)cq8) * 8;
+  const unsigned P = (unsigned)(H * W);
+  __nv_bfloat16* ho = hi + (size_t)pix * ld_out + c_off + c;
+  if (c >= s.C) {  // zero channel padding [C, c_write)
+    *reinterpret_cast<uint4*>(ho) = make_uint4(0u, 0u, 0u, 0u);
+    if (FMT == 2) {
+      uint8_t* l8 = reinterpret_cast<uint8_t*>(lo) + (size_t)pix * ld_out * 2 + hf8_lo_off(c_off + c);
+      *reinterpret_cast<uint2*>(l8) = make_uint2(0u, 0u);
+      *reinterpret_cast<uint2*>(l8 + 64) = make_uint2(0u, 0u);
+    } else {
+      *reinterpret_cast<uint4*>(lo + (size_t)pix * ld_out + c_off + c) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    return;
+  }
+  const unsigned n = (s.mean || UPS) ? pix / P : 0u;
+  size_t sp = pix;
+  if (UPS) {
+    const unsigned pp = pix - n * P;
+    const unsigned y = pp / (unsigned)W, x = pp - y * (unsigned)W;
+    sp = ((size_t)n * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+  }
+  const float* src = s.ptr + sp * s.ld + c;
+  float v[8];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  if (s.mean) {
+    const float* mp = s.mean + (size_t)n * s.C + c;
+    const float* rp = s.rstd + (size_t)n * s.C + c;
+    const float4 m0 = *reinterpret_cast<const float4*>(mp), m1 = *reinterpret_cast<const float4*>(mp + 4);
+    const float4 q0 = *reinterpret_cast<const float4*>(rp), q1 = *reinterpret_cast<const float4*>(rp + 4);
+    const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    const float q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (v[e] - m[e]) * q[e];
+  }
+  if (s.relu) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+  }
+  if (FMT == 2) {
+    uint32_t h2[4];
+    uint16_t a[4], l2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_hf8x2(v[2 * e], v[2 * e + 1], h2[e], a[e], l2[e]);
+    *reinterpret_cast<uint4*>(ho) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+    uint8_t* l8 = reinterpret_cast<uint8_t*>(lo) + (size_t)pix * ld_out * 2 + hf8_lo_off(c_off + c);
+    *reinterpret_cast<uint2*>(l8) = make_uint2((uint32_t)a[0] | ((uint32_t)a[1] << 16), (uint32_t)a[2] | ((uint32_t)a[3] << 16));
+    *reinterpret_cast<uint2*>(l8 + 64) = make_uint2((uint32_t)l2[0] | ((uint32_t)l2[1] << 16), (uint32_t)l2[2] | ((uint32_t)l2[3] << 16));
+  } else {
+    bf16x8 hh, hl;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_bf16(v[e], hh.v[e], hl.v[e]);
+    *reinterpret_cast<bf16x8*>(ho) = hh;
+    *reinterpret_cast<bf16x8*>(lo + (size_t)pix * ld_out + c_off + c) = hl;
+  }
+}
+
 // Event pre-processing straight into the head convolution's operand format: normalise (as
 // event_prepare_kernel in pointwise.cu), reflect-pad to (Hp, Wp), NCHW -> pixel-major with `cpad`
 // channels, split to bf16 hi/lo, and store at offset (off_y, off_x) inside a zero-bordered buffer
@@ -1510,6 +1578,26 @@ extern "C" int essb_split_planes(const essb_src* src, int N, int H, int W, uint1
   ESSB_REQUIRE((src->mean == nullptr) == (src->rstd == nullptr), "essb_split_bf16: mean/rstd must come together");
   const int c_write = c_pad > src->C ? c_pad : src->C;
   ESSB_REQUIRE(c_write % 4 == 0 && c_off + c_write <= ld_out, "essb_split_bf16: c_off + max(C, c_pad) exceeds ld_out");
+  // fast path: 8 channels per thread, 32-bit indices (every shape of the decoder / encoder paths)
+  {
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const long long total8 = (long long)N * H * W * (c_write / 8);
+    if (src->C % 8 == 0 && c_write % 8 == 0 && c_off % 8 == 0 && ld_out % 8 == 0 && src->ld % 4 == 0 && al16(hi) && al16(lo) &&
+        (src->ups == 0 || (src->ups == 1 && H % 2 == 0 && W % 2 == 0)) && total8 < (1ll << 31) &&
+        (long long)N * H * W < (1ll << 31) && (!src->mean || (al16(src->mean) && al16(src->rstd)))) {
+      const unsigned blocks = (unsigned)((total8 + 255) / 256);
+      __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(hi);
+      __nv_bfloat16* l = reinterpret_cast<__nv_bfloat16*>(lo);
+      cudaStream_t st = (cudaStream_t)stream;
+      const int cq8 = c_write / 8;
+      if (src->ups == 0 && fmt == 0) split_planes8_kernel<0, 0><<<blocks, 256, 0, st>>>(*src, H, W, h, l, ld_out, c_off, cq8, (unsigned)total8);
+      else if (src->ups == 0) split_planes8_kernel<0, 2><<<blocks, 256, 0, st>>>(*src, H, W, h, l, ld_out, c_off, cq8, (unsigned)total8);
+      else if (fmt == 0) split_planes8_kernel<1, 0><<<blocks, 256, 0, st>>>(*src, H, W, h, l, ld_out, c_off, cq8, (unsigned)total8);
+      else split_planes8_kernel<1, 2><<<blocks, 256, 0, st>>>(*src, H, W, h, l, ld_out, c_off, cq8, (unsigned)total8);
+      ESSB_LAUNCH_CHECK("essb_split_planes (8 channels per thread)");
+      return ESSB_OK;
+    }
+  }
   const long long total = (long long)N * H * W * (c_write / 4);
   split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       *src, N, H, W, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), ld_out, c_off, c_write,
