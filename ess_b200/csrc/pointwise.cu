@@ -243,22 +243,25 @@ __global__ void __launch_bounds__(256) in_stats_kernel(const float* __restrict__
   }
 }
 
+// I = index type: unsigned when the element count fits 32 bits (every shape of the decoder: three 64-bit divisions per
+// thread made this memory-bound kernel instruction-bound), long long otherwise
+template <typename I>
 __global__ void in_bwd_pass2_kernel(const float* __restrict__ g, const float* __restrict__ y, int ld_y,
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                                    const float* __restrict__ gsum, float* __restrict__ dy, long long P, int C,
-                                    float inv_p, long long total, __nv_bfloat16* __restrict__ hi,
+                                    const float* __restrict__ gsum, float* __restrict__ dy, I P, int C,
+                                    float inv_p, I total, __nv_bfloat16* __restrict__ hi,
                                     __nv_bfloat16* __restrict__ lo, int ld_planes, int c_write) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const I idx = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x;
   if (idx >= total) return;
-  const int CQ = c_write >> 2;
-  const int c = (int)(idx % CQ) * 4;
-  const long long pix = idx / CQ;
+  const I CQ = (I)(c_write >> 2);
+  const size_t pix = (size_t)(idx / CQ);
+  const int c = (int)(idx - (I)pix * CQ) * 4;
   if (c >= C) {  // zero channel padding of the bf16 planes (K padding of the tensor-core operand)
     *reinterpret_cast<uint2*>(hi + pix * ld_planes + c) = make_uint2(0u, 0u);
     *reinterpret_cast<uint2*>(lo + pix * ld_planes + c) = make_uint2(0u, 0u);
     return;
   }
-  const int n = (int)(pix / P);
+  const int n = (int)((I)pix / P);
   const float4 gv = *reinterpret_cast<const float4*>(g + pix * C + c);
   const float4 yv = *reinterpret_cast<const float4*>(y + pix * ld_y + c);
   const float4 m = *reinterpret_cast<const float4*>(mean + (size_t)n * C + c);
@@ -707,9 +710,14 @@ extern "C" int essb_in_bwd_pass2(const float* g, const float* y, int ld_y, const
     return rc;
   const int c_write = dy_hi ? ld_planes : C;   // planes are written across their whole pitch (zeros beyond C)
   const long long total = (long long)N * P * (c_write / 4);
-  in_bwd_pass2_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      g, y, ld_y, mean, rstd, gsum, dy, P, C, 1.0f / (float)P, total, reinterpret_cast<__nv_bfloat16*>(dy_hi),
-      reinterpret_cast<__nv_bfloat16*>(dy_lo), ld_planes, c_write);
+  if (total < (1ll << 31))
+    in_bwd_pass2_kernel<unsigned><<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        g, y, ld_y, mean, rstd, gsum, dy, (unsigned)P, C, 1.0f / (float)P, (unsigned)total, reinterpret_cast<__nv_bfloat16*>(dy_hi),
+        reinterpret_cast<__nv_bfloat16*>(dy_lo), ld_planes, c_write);
+  else
+    in_bwd_pass2_kernel<long long><<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        g, y, ld_y, mean, rstd, gsum, dy, (long long)P, C, 1.0f / (float)P, total, reinterpret_cast<__nv_bfloat16*>(dy_hi),
+        reinterpret_cast<__nv_bfloat16*>(dy_lo), ld_planes, c_write);
   ESSB_LAUNCH_CHECK("essb_in_bwd_pass2");
   return ESSB_OK;
 }
