@@ -42,8 +42,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) task_loss_fwd_kernel(const float
   for (int k = 0; k < KMAX; ++k) { I[k] = 0.f; S[k] = 0.f; T[k] = 0.f; }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
        i += (long long)gridDim.x * blockDim.x) {
-    const long long t = target[i];
-    if (t == ignore_index) continue;
+    const long long t64 = target[i];
+    if (t64 == ignore_index) continue;
+    const int t = (t64 >= 0 && t64 < K) ? (int)t64 : -1;      // 32-bit compares in the unrolled class loop
     float p[KMAX], lse;
     const float* q = logits + i * ld;
     load_softmax<KMAX>(q, K, p, lse);
@@ -126,9 +127,10 @@ __global__ void __launch_bounds__(LOSS_THREADS) task_loss_bwd_kernel(
   const float ce_w = s_ce;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
        i += (long long)gridDim.x * blockDim.x) {
-    const long long t = target[i];
+    const long long t64 = target[i];
     float* o = dlogits + i * ld_d;
-    if (t == ignore_index) {
+    const int t = (t64 >= 0 && t64 < K) ? (int)t64 : -1;      // 32-bit compares in the unrolled class loops
+    if (t64 == ignore_index) {
 #pragma unroll
       for (int k = 0; k < KMAX; ++k)
         if (k < K) o[k] = 0.f;
@@ -198,10 +200,16 @@ inline unsigned loss_grid(long long npix) {
 
 }  // namespace
 
+// the class loops are fully unrolled over KM >= K and these kernels are instruction-bound (profiles/r02o_hbm_kernels.md):
+// KM close to K matters (K = 11 -> 12 instead of 16: a quarter fewer exp / compare / accumulate instructions)
 #define ESSB_DISPATCH_K(K, CALL)                      \
   do {                                                \
-    if ((K) <= 8) { constexpr int KM = 8; CALL; }     \
+    if ((K) <= 4) { constexpr int KM = 4; CALL; }     \
+    else if ((K) <= 6) { constexpr int KM = 6; CALL; } \
+    else if ((K) <= 8) { constexpr int KM = 8; CALL; } \
+    else if ((K) <= 12) { constexpr int KM = 12; CALL; } \
     else if ((K) <= 16) { constexpr int KM = 16; CALL; } \
+    else if ((K) <= 20) { constexpr int KM = 20; CALL; } \
     else { constexpr int KM = 32; CALL; }             \
   } while (0)
 
